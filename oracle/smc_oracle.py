@@ -1,0 +1,606 @@
+"""CPU oracle for the Sequential-Monte-Carlo inner loop of tingiskhan/pyfilter (reference v0.29.0).
+
+THIS FILE IS TEST INFRASTRUCTURE.  It restates, on torch-CPU / numpy, the algorithm behind
+``pyfilter.filters.particle.{SISR,APF}.batch_filter`` and ``pyfilter.resampling.{systematic,multinomial}``
+so that the CUDA path in ``pyfilter_b200`` can be checked against it.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it; the
+product path never does (it fails loudly when the CUDA library is missing).
+
+Pinning: ``tests/test_oracle_pinned.py`` checks every function below against (a) the unmodified reference
+package imported from /root/reference (build container only; needs the stand-ins under ``oracle/standins``),
+(b) the golden vectors under ``tests/golden/`` that ``oracle/make_golden.py`` generated from that same
+reference, and (c) the reference's own known-answer test ``tests/test_resampling.py:31-47``.
+The state-space-model arithmetic itself lives in the un-vendored dependency ``stochproc==0.3.0``
+(pyproject.toml:32) - its semantics (``x_t = loc + scale*eps``; Euler-Maruyama ``loc = x + f(x) dt``) are
+restated from its published behaviour and are pinned only through the stand-in, see DESIGN.md ("parity
+unpinned at the stochproc boundary").
+
+Layout follows the reference: particle-major ``x:(N,[B],[d])``, ``log w:(N,[B])``; float32 everywhere, int64
+ancestor indices.  All file:line citations are into /root/reference/pyfilter/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+INFTY = float("inf")
+_LOG_SQRT_2PI = math.log(math.sqrt(2.0 * math.pi))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# weights: normalize / ESS                                                                      utils.py:8-20, 49-64
+# ----------------------------------------------------------------------------------------------------------------------
+def normalize(weights: torch.Tensor) -> torch.Tensor:
+    """``utils.py:49-64``: NaN-safe softmax over dim 0.  Mutates ``weights`` in place exactly like the reference
+    (NaN and +inf become -inf, -inf becomes -FLT_MAX); columns whose soft-max sums to zero become uniform."""
+    weights = weights.nan_to_num_(-INFTY, posinf=-INFTY)
+    normalized = (weights - weights.max(dim=0)[0]).softmax(dim=0)
+    ax_sum = normalized.sum(dim=0)
+    normalized.masked_fill_(ax_sum == 0.0, 1.0 / normalized.shape[0])
+    return normalized
+
+
+def get_ess(weights: torch.Tensor, normalized: bool = False) -> torch.Tensor:
+    """``utils.py:8-20``: ``1 / sum_i W_i^2`` over dim 0."""
+    if not normalized:
+        weights = normalize(weights)
+    return weights.pow(2.0).sum(dim=0).reciprocal()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# resampling                                                                                     resampling.py:8-65
+# ----------------------------------------------------------------------------------------------------------------------
+def _wrapped(f, w: torch.Tensor, normalized: bool, **kwargs) -> torch.Tensor:
+    """``resampling.py:8-21``.  1-D input calls ``f(w, *kwargs)`` - i.e. keyword *names* are splatted
+    positionally, so ``u=`` is effectively ignored for 1-D input: the positional
+    argument that arrives is the string ``"u"`` bound to ``normalized`` and ``u`` stays ``None``."""
+    if not normalized:
+        w = normalize(w)
+    if w.dim() == 1:
+        return f(w)
+    return f(w.moveaxis(0, 1), **kwargs).moveaxis(0, 1)
+
+
+def _systematic_rows(w: torch.Tensor, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``resampling.py:35-52`` on a ``(B,N)`` (or ``(N,)``) tensor of normalised weights."""
+    is_1d = w.dim() == 1
+    if is_1d:
+        w = w.unsqueeze(0)
+    shape = (w.shape[0], 1)
+    u = u if u is not None else torch.empty(shape, device=w.device).uniform_()
+    n = w.shape[1]
+    index_range = torch.arange(n, dtype=u.dtype, device=w.device).unsqueeze(0)
+    probs = (index_range + u) / n
+    cumsum = w.cumsum(-1)
+    cumsum[..., -1] = 1.0
+    res = torch.searchsorted(cumsum, probs)
+    return res.squeeze(0) if is_1d else res
+
+
+def systematic(w: torch.Tensor, normalized: bool = False, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``pyfilter.resampling.systematic`` (``resampling.py:24-52``).  ``w``: ``(N,)`` or ``(N,B)``; ``u``: ``(B,1)``."""
+    return _wrapped(_systematic_rows, w, normalized, **({} if u is None else {"u": u}))
+
+
+def multinomial(w: torch.Tensor, normalized: bool = False) -> torch.Tensor:
+    """``pyfilter.resampling.multinomial`` (``resampling.py:55-65``): ``torch.multinomial(W, N, replacement=True)``."""
+    return _wrapped(lambda ww: torch.multinomial(ww, ww.shape[-1], replacement=True), w, normalized)
+
+
+def sequential_cumsum(w: np.ndarray, acc_dtype, out_dtype=np.float32) -> np.ndarray:
+    """Sequential prefix sum accumulated in ``acc_dtype`` and rounded to ``out_dtype`` per element.
+
+    ``acc_dtype=float64`` is what ``torch.cumsum`` does for float32 CPU tensors (ATen ``cumsum_cpu_kernel``
+    accumulates in ``acc_type<float>=double``; SURVEY.md Appendix A-5, measured).  ``acc_dtype=float32`` is the
+    prefix sum inside ``torch.multinomial``'s CPU kernel (Appendix A-6).  ``np.cumsum`` is a plain sequential loop
+    in the accumulator dtype, which is exactly these semantics."""
+    return np.cumsum(np.asarray(w).astype(acc_dtype), dtype=acc_dtype).astype(out_dtype)
+
+
+def systematic_probes(n: int, u: float) -> np.ndarray:
+    """``resampling.py:44-46``: ``p_i = fl32(fl32(i + u) / n)`` with true IEEE division (torch CPU ``div``)."""
+    i = np.arange(n, dtype=np.float32)
+    return ((i + np.float32(u)).astype(np.float32) / np.float32(n)).astype(np.float32)
+
+
+def systematic_restated(W: np.ndarray, u: float) -> np.ndarray:
+    """Numpy restatement of ``systematic`` for ONE column of normalised float32 weights (no torch ops):
+    sequential fp64-accumulated prefix sum, last element forced to 1, left-insertion search.  Used to pin what
+    the CUDA kernel must reproduce bit-for-bit."""
+    W = np.asarray(W, dtype=np.float32)
+    c = sequential_cumsum(W, np.float64)
+    c[-1] = np.float32(1.0)
+    return np.searchsorted(c, systematic_probes(W.shape[0], u), side="left").astype(np.int64)
+
+
+def multinomial_restated(W: np.ndarray, U: np.ndarray) -> np.ndarray:
+    """Numpy restatement of ``torch.multinomial(W, n, replacement=True)`` on CPU for one row, given the float64
+    uniforms ``U`` in draw order (ATen ``multinomial_with_replacement_kernel``):
+    sequential **float32** prefix sum, divided by its last element, then a left binary search evaluated in double."""
+    W = np.asarray(W, dtype=np.float32)
+    c = sequential_cumsum(W, np.float32)
+    c = (c / c[-1]).astype(np.float32)
+    return np.searchsorted(c.astype(np.float64), np.asarray(U, dtype=np.float64), side="left").astype(np.int64)
+
+
+def systematic_loop(W, u) -> np.ndarray:
+    """Pure-Python two-pointer walk (small inputs only): ancestor of probe i is the first j with c_j >= p_i."""
+    W = np.asarray(W, dtype=np.float32)
+    n = W.shape[0]
+    p = systematic_probes(n, u)
+    out = np.zeros(n, dtype=np.int64)
+    acc, j = np.float64(W[0]), 0
+    c = np.float32(acc) if n > 1 else np.float32(1.0)
+    for i in range(n):
+        while c < p[i]:
+            j += 1
+            acc = acc + np.float64(W[j])
+            c = np.float32(1.0) if j == n - 1 else np.float32(acc)
+        out[i] = j
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# estimators                                                                              filters/particle/utils.py
+# ----------------------------------------------------------------------------------------------------------------------
+def log_likelihood(importance_weights: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``filters/particle/utils.py:7-22``: ``max + log sum_i omega_i exp(w_i - max)``; ``omega = 1/N`` if omitted."""
+    max_w, _ = importance_weights.max(dim=0)
+    temp = (importance_weights - max_w).exp()
+    if weights is None:
+        weights = 1.0 / importance_weights.shape[0]
+    return max_w + (weights * temp).sum(dim=0).log()
+
+
+def filter_mean_and_variance(x: torch.Tensor, W: torch.Tensor, event_dims: int):
+    """``filters/particle/utils.py:26-65`` (``covariance=False, keep_dim=True``): two-pass weighted mean and
+    variance over dim 0; scalar states get a trailing axis of length 1."""
+    values = x.unsqueeze(-1) if event_dims == 0 else x
+    w = W.unsqueeze(-1)
+    mean = (w * values).sum(dim=0)
+    centered = values - mean
+    var = (w * centered.pow(2.0)).sum(dim=0)
+    return mean, var
+
+
+def normal_log_prob(value, loc, scale):
+    """``torch.distributions.Normal.log_prob`` (the density every reference model callable ends in)."""
+    scale = torch.as_tensor(scale, dtype=torch.float32)
+    var = scale**2
+    return -((value - loc) ** 2) / (2 * var) - scale.log() - _LOG_SQRT_2PI
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# model zoo (the four BASELINE.json state-space models)
+#   hidden process:  x_t = loc(x_{t-1}) + scale(x_{t-1}) * inc,   inc = inc_scale * z,  z ~ N(0, I)      [stochproc AffineProcess]
+#   observation:     log p(y | x)
+# ----------------------------------------------------------------------------------------------------------------------
+def _t(v):
+    return torch.as_tensor(v, dtype=torch.float32)
+
+
+@dataclass
+class Model:
+    """Base class.  Parameters are float32 tensors of shape ``()`` or ``(B,)`` (one value per parallel filter)."""
+
+    name: str = "model"
+    state_dim: int = 0  # 0 = scalar state (event_shape ()), else event_shape (state_dim,)
+    obs_dim: int = 0
+    inc_scale: float = 1.0  # std of the increment distribution: 1 for unit increments, sqrt(dt) for Euler-Maruyama
+    linear_obs: Optional[Tuple] = None  # (a, b, s) when the observation is y = b + a x + s nu (LinearStateSpaceModel)
+
+    def mean_scale(self, x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+        raise NotImplementedError
+
+    def obs_log_prob(self, y: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+        raise NotImplementedError
+
+    def initial_loc_scale(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        raise NotImplementedError
+
+    # -- helpers shared by all models
+    def initial_sample(self, shape: Tuple[int, ...], z: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``filters/particle/base.py:91``: ``x_0 = loc_0 + scale_0 * z`` with ``z ~ N(0,1)`` of shape ``(N,[B],[d])``."""
+        loc, scale = self.initial_loc_scale()
+        full = tuple(shape) + ((self.state_dim,) if self.state_dim else ())
+        if z is None:
+            z = torch.empty(full).normal_()
+        return loc + scale * z
+
+    def propagate(self, x: torch.Tensor, z: torch.Tensor) -> torch.Tensor:
+        """stochproc ``AffineProcess.propagate``: ``AffineTransform(loc, scale)(inc)`` = ``loc + scale * inc``."""
+        loc, scale = self.mean_scale(x)
+        inc = z * self.inc_scale if self.inc_scale != 1.0 else z
+        return loc + scale * inc
+
+    def simulate(self, T: int, generator: Optional[torch.Generator] = None):
+        """Draw one path ``(x_{1:T}, y_{1:T})`` from the model (synthetic data for tests and the bench)."""
+        g = generator
+        d = (self.state_dim,) if self.state_dim else ()
+        x = self.initial_sample((), torch.empty(d).normal_(generator=g))
+        xs, ys = [], []
+        for _ in range(T):
+            x = self.propagate(x, torch.empty(d).normal_(generator=g))
+            xs.append(x)
+            ys.append(self.sample_obs(x, g))
+        return torch.stack(xs), torch.stack(ys)
+
+    def sample_obs(self, x, g):
+        raise NotImplementedError
+
+
+@dataclass
+class LinearGaussianAR1(Model):
+    """Config 1 (reference ``tests/filters/models.py:12-16``): ``x_t = alpha + beta x_{t-1} + sigma eps``,
+    stationary ``x_0``; ``y_t = b + a x_t + s nu``."""
+
+    alpha: torch.Tensor = field(default_factory=lambda: _t(0.0))
+    beta: torch.Tensor = field(default_factory=lambda: _t(0.99))
+    sigma: torch.Tensor = field(default_factory=lambda: _t(0.05))
+    a: torch.Tensor = field(default_factory=lambda: _t(1.0))
+    b: torch.Tensor = field(default_factory=lambda: _t(0.0))
+    s: torch.Tensor = field(default_factory=lambda: _t(0.15))
+    name: str = "lg_ar1"
+
+    def __post_init__(self):
+        for k in ("alpha", "beta", "sigma", "a", "b", "s"):
+            setattr(self, k, _t(getattr(self, k)))
+        self.linear_obs = (self.a, self.b, self.s)
+
+    def mean_scale(self, x):
+        return torch.broadcast_tensors(self.alpha + self.beta * x, self.sigma)
+
+    def obs_log_prob(self, y, x):
+        return normal_log_prob(y, self.b + self.a * x, self.s)
+
+    def initial_loc_scale(self):
+        return self.alpha, self.sigma / (1.0 - self.beta**2.0).sqrt()
+
+    def sample_obs(self, x, g):
+        return self.b + self.a * x + self.s * torch.empty(()).normal_(generator=g)
+
+
+@dataclass
+class SineDiffusion(Model):
+    """Configs 2 and 5 (reference README.md:44-67): Euler-Maruyama of ``dx = sin(x - gamma) dt + sigma dW``,
+    ``x_0 ~ N(0,1)``; ``y_t = b + a x_t + s nu``."""
+
+    gamma: torch.Tensor = field(default_factory=lambda: _t(0.0))
+    sigma: torch.Tensor = field(default_factory=lambda: _t(1.0))
+    dt: float = 0.1
+    a: torch.Tensor = field(default_factory=lambda: _t(1.0))
+    b: torch.Tensor = field(default_factory=lambda: _t(0.0))
+    s: torch.Tensor = field(default_factory=lambda: _t(0.1))
+    name: str = "sine_em"
+
+    def __post_init__(self):
+        for k in ("gamma", "sigma", "a", "b", "s"):
+            setattr(self, k, _t(getattr(self, k)))
+        self.inc_scale = math.sqrt(self.dt)
+        self.linear_obs = (self.a, self.b, self.s)
+
+    def mean_scale(self, x):
+        return torch.broadcast_tensors(x + torch.sin(x - self.gamma) * _t(self.dt), self.sigma)
+
+    def obs_log_prob(self, y, x):
+        return normal_log_prob(y, self.b + self.a * x, self.s)
+
+    def initial_loc_scale(self):
+        return torch.zeros_like(self.gamma), torch.ones_like(self.gamma)
+
+    def sample_obs(self, x, g):
+        return self.b + self.a * x + self.s * torch.empty(()).normal_(generator=g)
+
+
+@dataclass
+class StochasticVolatility(Model):
+    """Config 3: ``x_t = mu + phi (x_{t-1} - mu) + sigma_v eps``, stationary ``x_0``; ``y_t ~ N(0, exp(x_t / 2))``."""
+
+    mu: torch.Tensor = field(default_factory=lambda: _t(-1.0))
+    phi: torch.Tensor = field(default_factory=lambda: _t(0.97))
+    sigma_v: torch.Tensor = field(default_factory=lambda: _t(0.2))
+    name: str = "sv_ar1"
+
+    def __post_init__(self):
+        for k in ("mu", "phi", "sigma_v"):
+            setattr(self, k, _t(getattr(self, k)))
+
+    def mean_scale(self, x):
+        return torch.broadcast_tensors(self.mu + self.phi * (x - self.mu), self.sigma_v)
+
+    def obs_log_prob(self, y, x):
+        return normal_log_prob(y, 0.0, (x / 2.0).exp())
+
+    def initial_loc_scale(self):
+        return self.mu, self.sigma_v / (1.0 - self.phi**2.0).sqrt()
+
+    def sample_obs(self, x, g):
+        return (x / 2.0).exp() * torch.empty(()).normal_(generator=g)
+
+
+@dataclass
+class Lorenz63(Model):
+    """Config 4 (reference examples/lorenz.ipynb:53-117): Euler-Maruyama of the Lorenz-63 drift, ``dt=0.01``, unit
+    diffusion, ``x_0 ~ N(m_0, sqrt(10) I)``; ``y_t = 0.8 (x^1, x^3) + sqrt(0.1) nu`` (2-D observation)."""
+
+    s: torch.Tensor = field(default_factory=lambda: _t(10.0))
+    r: torch.Tensor = field(default_factory=lambda: _t(28.0))
+    b: torch.Tensor = field(default_factory=lambda: _t(8.0 / 3.0))
+    sigma: torch.Tensor = field(default_factory=lambda: _t(1.0))
+    dt: float = 0.01
+    obs_a: float = 0.8
+    obs_s: torch.Tensor = field(default_factory=lambda: _t(0.1).sqrt())
+    name: str = "lorenz63_em"
+    state_dim: int = 3
+    obs_dim: int = 2
+
+    def __post_init__(self):
+        for k in ("s", "r", "b", "sigma", "obs_s"):
+            setattr(self, k, _t(getattr(self, k)))
+        self.inc_scale = math.sqrt(self.dt)
+        self.x0_mean = _t([-5.91652, -5.52332, 24.5723])
+        self.x0_scale = math.sqrt(10.0) * torch.ones(3)
+
+    def _p(self, p):  # parameter (B,) -> broadcast against (N,B)
+        return p
+
+    def mean_scale(self, x):
+        x0, x1, x2 = x[..., 0], x[..., 1], x[..., 2]
+        f0 = -self.s * (x0 - x1)
+        f1 = self.r * x0 - x1 - x0 * x2
+        f2 = x0 * x1 - self.b * x2
+        drift = torch.stack((f0, f1, f2), dim=-1)
+        sig = self.sigma.unsqueeze(-1) if self.sigma.dim() > 0 else self.sigma
+        return torch.broadcast_tensors(x + drift * _t(self.dt), sig)
+
+    def obs_loc(self, x):
+        return torch.stack((self.obs_a * x[..., 0], self.obs_a * x[..., 2]), dim=-1)
+
+    def obs_log_prob(self, y, x):
+        return normal_log_prob(y, self.obs_loc(x), self.obs_s).sum(-1)
+
+    def initial_loc_scale(self):
+        return self.x0_mean, self.x0_scale
+
+    def sample_obs(self, x, g):
+        return self.obs_loc(x) + self.obs_s * torch.empty(2).normal_(generator=g)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# proposals                                                               filters/particle/proposals/{bootstrap,linear}.py
+# ----------------------------------------------------------------------------------------------------------------------
+def bootstrap_sample_and_weight(model: Model, y, x_prev, z):
+    """``proposals/bootstrap.py:10-14``: propagate through the dynamics, weight by the observation density."""
+    x_new = model.propagate(x_prev, z)
+    return x_new, model.obs_log_prob(y, x_new)
+
+
+def affine_pre_weight(model: Model, y, x_prev):
+    """``proposals/base.py:69-85`` with ``pre_weight_funcs.py:9-11``: ``log p(y | loc(x_{t-1}))``."""
+    loc, _ = model.mean_scale(x_prev)
+    return model.obs_log_prob(y, loc)
+
+
+def lgo_sample_and_weight(model: Model, y, x_prev, z):
+    """``proposals/linear.py:38-55`` + ``proposals/utils.py:219-267`` + ``proposals/base.py:45-50`` for a SCALAR
+    state and observation: optimal Gaussian kernel ``N(k, P)``, ``P = 1/(sigma^-2 + a^2 s^-2)``,
+    ``k = P (sigma^-2 m + a s^-2 (y - b))``; weight ``log p(y|x') + log p(x'|x) - log N(x'; k, P)``."""
+    assert model.state_dim == 0 and model.obs_dim == 0 and model.linear_obs is not None
+    a, b, s = model.linear_obs
+    mean, scale = model.mean_scale(x_prev)
+    h_var_inv = scale.pow(-2.0)
+    o_var_inv = s.pow(-2.0)
+    # find_optimal_density, hidden_is_1d and obs_is_1d: 1x1 "matrices"
+    t_2 = a * o_var_inv * a
+    cov = (h_var_inv + t_2).reciprocal()  # .inverse() of a 1x1 matrix
+    t_1 = h_var_inv * mean
+    t_3 = a * (o_var_inv * (y - b))
+    k_mean = cov * (t_1 + t_3)
+    k_std = cov.sqrt()
+    x_new = z * k_std + k_mean  # torch.normal(mean, std)
+    # _weight_with_kernel
+    y_lp = normal_log_prob(y, b + a * x_new, s)
+    inc_std = _t(model.inc_scale)
+    # TransformedDistribution(inc, Affine(loc, scale)).log_prob(x) = inc.log_prob((x - loc)/scale) - log|scale|
+    x_lp = normal_log_prob((x_new - mean) / scale, 0.0, inc_std) - scale.abs().log()
+    k_lp = normal_log_prob(x_new, k_mean, k_std)
+    return x_new, y_lp + x_lp - k_lp
+
+
+def lgo_pre_weight(model: Model, y, x_prev):
+    """``proposals/linear.py:57-86`` for scalar state/observation: ``log N(y; b + a x_{t-1}, sqrt(s^2 + a^2 sigma^2))``
+    (centred on the PREVIOUS state, Appendix A-8)."""
+    a, b, s = model.linear_obs
+    _, h_scale = model.mean_scale(x_prev)
+    cov = s.pow(2.0) + a * h_scale.pow(2.0) * a
+    return normal_log_prob(y, b + a * x_prev, cov.sqrt())
+
+
+PROPOSALS = {
+    "bootstrap": (bootstrap_sample_and_weight, affine_pre_weight),
+    "linear_gaussian": (lgo_sample_and_weight, lgo_pre_weight),
+}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# one filter step, noise injected (teacher-forced parity protocol)
+# ----------------------------------------------------------------------------------------------------------------------
+def _gather0(x: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """``filters/utils.py:4-21``."""
+    if x.dim() > idx.dim():
+        idx = idx.unsqueeze(-1).expand_as(x)
+    return x.gather(0, idx)
+
+
+def _as_2d_resample(W: torch.Tensor, u, resampler: str, U=None) -> torch.Tensor:
+    """Resample every column of ``W`` (``(N,)`` or ``(N,B)``) with injected randomness."""
+    squeeze = W.dim() == 1
+    W2 = W.unsqueeze(-1) if squeeze else W
+    if resampler == "systematic":
+        uu = torch.as_tensor(u, dtype=torch.float32).reshape(-1, 1)
+        idx = _systematic_rows(W2.moveaxis(0, 1), uu).moveaxis(0, 1)
+    elif resampler == "multinomial":
+        cols = [torch.from_numpy(multinomial_restated(W2[:, b].numpy(), np.asarray(U)[..., b] if np.asarray(U).ndim > 1 else U))
+                for b in range(W2.shape[1])]
+        idx = torch.stack(cols, dim=1)
+    else:
+        raise ValueError(resampler)
+    return idx.squeeze(-1) if squeeze else idx
+
+
+def sisr_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, ess_threshold=0.9,
+              resampler="systematic", U=None) -> Dict[str, torch.Tensor]:
+    """One ``SISR`` move (``filters/particle/sisr.py:14-56``, ``filters/base.py:188-221``) with injected noise.
+
+    ``x:(N,[B],[d])``, ``lw:(N,[B])``, ``z`` unit normals shaped like ``x``, ``u:(B,)`` systematic offsets for ALL
+    columns (only the resampled ones are used).  A NaN ``y`` propagates only (``particle/state.py:38-42``)."""
+    lw = lw.clone()
+    n = lw.shape[0]
+    W = normalize(lw)  # sisr.py:16 (mutates lw like the reference)
+    ess = get_ess(W, normalized=True)
+    mask = ess < ess_threshold * n  # sisr.py:19, threshold base.py:42
+    inds = prev_inds.clone()
+    x_res, lw_res = x, lw
+    if bool(mask.any()):
+        all_idx = _as_2d_resample(W, u, resampler, U)
+        if W.dim() == 1:
+            inds, x_res = all_idx, _gather0(x, all_idx)
+            lw_res = torch.zeros_like(lw)
+            W = torch.full_like(W, 1.0 / n)
+        else:
+            um = mask.unsqueeze(0)
+            inds = torch.where(um, all_idx, prev_inds)
+            lw_res = lw.masked_fill(um, 0.0)
+            W = W.masked_fill(um, 1.0 / n)
+            sel = torch.where(um, all_idx, torch.arange(n).unsqueeze(-1).expand_as(all_idx))
+            x_res = _gather0(x, sel)
+    out = {"resampled": mask.clone(), "ess": ess, "prev_inds": inds, "x_resampled": x_res}
+    if bool(torch.isnan(torch.as_tensor(y)).all()):
+        x_new = model.propagate(x_res, z)
+        lw_new, ll = lw_res, torch.zeros(lw.shape[1:])
+    else:
+        x_new, inc = PROPOSALS[proposal][0](model, y, x_res, z)
+        lw_new = inc + lw_res  # sisr.py:52
+        ll = log_likelihood(inc, W)  # sisr.py:55
+    mean, var = filter_mean_and_variance(x_new, normalize(lw_new.clone()), model.state_dim)
+    out.update(x=x_new, lw=lw_new, ll=ll, mean=mean, var=var)
+    return out
+
+
+def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resampler="systematic", U=None):
+    """One ``APF`` move (``filters/particle/apf.py:16-46``) with injected noise; resamples every step."""
+    lw = lw.clone()
+    n = lw.shape[0]
+    W = normalize(lw)  # apf.py:17
+    if bool(torch.isnan(torch.as_tensor(y)).all()):  # filters/base.py:213, predict does not resample
+        x_new = model.propagate(x, z)
+        mean, var = filter_mean_and_variance(x_new, normalize(lw.clone()), model.state_dim)
+        idx = torch.arange(n) if lw.dim() == 1 else torch.arange(n).unsqueeze(-1).expand(lw.shape)
+        return {"x": x_new, "lw": lw, "ll": torch.zeros(lw.shape[1:]), "mean": mean, "var": var, "prev_inds": idx,
+                "resample_W": W}
+    sample_and_weight, pre_weight = PROPOSALS[proposal]
+    g = pre_weight(model, y, x)  # apf.py:27
+    rw = normalize(g + lw)  # apf.py:29-31 -> resampling.py:10-11
+    idx = _as_2d_resample(rw, u, resampler, U)
+    x_res = _gather0(x, idx)  # apf.py:34
+    x_new, inc = sample_and_weight(model, y, x_res, z)  # apf.py:41
+    lw_new = inc - g.gather(0, idx)  # apf.py:43
+    ll = log_likelihood(lw_new) + (W * g.exp()).sum(dim=0).log()  # apf.py:44
+    mean, var = filter_mean_and_variance(x_new, normalize(lw_new.clone()), model.state_dim)
+    return {"x": x_new, "lw": lw_new, "ll": ll, "mean": mean, "var": var, "prev_inds": idx, "resample_W": rw,
+            "pre_weight": g, "x_resampled": x_res}
+
+
+STEPS = {"sisr": sisr_step, "apf": apf_step}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# free-running driver (CPU baseline + statistical checks)                                   filters/base.py:140-158
+# ----------------------------------------------------------------------------------------------------------------------
+def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, particles: int,
+                 batch_shape: Tuple[int, ...] = (), resampler: str = "systematic", ess_threshold: float = 0.9,
+                 x0: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """``BaseFilter.batch_filter`` for SISR/APF using torch's global CPU generator in the reference's draw order
+    (Appendix A-15: ``u`` - only when something resamples - then the transition noise)."""
+    shape = (particles,) + tuple(batch_shape)
+    d = (model.state_dim,) if model.state_dim else ()
+    x = model.initial_sample(shape) if x0 is None else x0
+    lw = torch.zeros(shape)
+    n = particles
+    inds = torch.arange(n) if not batch_shape else torch.arange(n).unsqueeze(-1).expand(shape)
+    ll_total = torch.zeros(tuple(batch_shape))
+    mean, var = filter_mean_and_variance(x, normalize(lw.clone()), model.state_dim)
+    means, variances = [mean], [var]
+    nb = int(np.prod(batch_shape)) if batch_shape else 1
+    for y_t in y:
+        # which columns draw resampling randomness (reference order: u first, then the transition noise)
+        if algorithm == "sisr":
+            mask = (get_ess(normalize(lw.clone()), True) < ess_threshold * n).reshape(-1)  # sisr.py:16-19
+        else:
+            mask = torch.full((nb,), not bool(torch.isnan(y_t).all()))  # apf.py:29-31 resamples every observed step
+        u = U = None
+        if bool(mask.any()):
+            k = int(mask.sum())
+            if resampler == "systematic":
+                u = torch.zeros(nb)
+                u[mask] = torch.empty((k, 1)).uniform_().reshape(-1)  # resampling.py:40-41
+            else:
+                # torch.multinomial draws row by row (one row per resampled column), N float64 uniforms each
+                Uf = np.zeros((n, nb))
+                Uf[:, mask.numpy()] = torch.empty((k, n), dtype=torch.float64).uniform_().numpy().T
+                U = Uf if batch_shape else Uf[:, 0]
+        z = torch.empty(shape + d).normal_()
+        if algorithm == "sisr":
+            out = sisr_step(model, proposal, x, lw, inds, y_t, z, u, ess_threshold, resampler, U)
+        else:
+            out = apf_step(model, proposal, x, lw, inds, y_t, z, u, resampler, U)
+        x, lw, inds = out["x"], out["lw"], out["prev_inds"]
+        ll_total = ll_total + out["ll"]
+        means.append(out["mean"])
+        variances.append(out["var"])
+    return {"loglikelihood": ll_total, "filter_means": torch.stack(means), "filter_variance": torch.stack(variances),
+            "x": x, "lw": lw, "prev_inds": inds}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# closed-form Kalman filter for config 1 (replaces the absent pykalman in tests/filters/test_particle.py:64-111)
+# ----------------------------------------------------------------------------------------------------------------------
+def kalman_filter_1d(y: np.ndarray, alpha, beta, sigma, a, b, s, m0, p0):
+    """Scalar Kalman recursion; ``y`` may contain NaN (skipped).  Returns filtered means, variances, total log-lik."""
+    y = np.asarray(y, dtype=np.float64)
+    m, p = float(m0), float(p0)
+    means, variances, ll = [], [], 0.0
+    for yt in y:
+        m, p = alpha + beta * m, beta * beta * p + sigma * sigma
+        if not np.isnan(yt):
+            sv = a * a * p + s * s
+            resid = yt - (b + a * m)
+            ll += -0.5 * (math.log(2.0 * math.pi * sv) + resid * resid / sv)
+            k = p * a / sv
+            m, p = m + k * resid, (1.0 - k * a) * p
+        means.append(m)
+        variances.append(p)
+    return np.array(means), np.array(variances), ll
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# factory shared by tests / golden files / bench
+# ----------------------------------------------------------------------------------------------------------------------
+DEFAULT_PARAMS = {
+    "lg_ar1": dict(alpha=0.0, beta=0.99, sigma=0.05, a=1.0, b=0.0, s=0.15),
+    "sine_em": dict(gamma=0.0, sigma=1.0, dt=0.1, a=1.0, b=0.0, s=0.1),
+    "sv_ar1": dict(mu=-1.0, phi=0.97, sigma_v=0.2),
+    "lorenz63_em": dict(s=10.0, r=28.0, b=8.0 / 3.0, sigma=1.0, dt=0.01, obs_a=0.8, obs_s=math.sqrt(0.1)),
+}
+_CLASSES = {"lg_ar1": LinearGaussianAR1, "sine_em": SineDiffusion, "sv_ar1": StochasticVolatility,
+            "lorenz63_em": Lorenz63}
+
+
+def build_model(name: str, params: Optional[dict] = None) -> Model:
+    p = dict(DEFAULT_PARAMS[name])
+    p.update(params or {})
+    return _CLASSES[name](**p)

@@ -1,0 +1,128 @@
+"""Pin oracle/smc_oracle.py: against the golden vectors generated from the unmodified reference, against the
+reference's own known-answer test (tests/test_resampling.py:31-47 of the reference) and, where /root/reference
+is present (build container), against the reference package itself."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smc_oracle as O
+from oracle.ref_loader import reference_available
+from tests.golden_util import filter_cases, load_filter_case, load_resampling, model_params
+
+
+def test_resampling_golden_systematic():
+    g = load_resampling()
+    names = sorted({k[4:-2] for k in g if k.startswith("sys_") and k.endswith("_W")})
+    assert len(names) >= 7
+    for name in names:
+        W, u, idx = g[f"sys_{name}_W"], g[f"sys_{name}_u"], g[f"sys_{name}_idx"]
+        got = O.systematic(torch.from_numpy(W).clone(), normalized=True, u=torch.from_numpy(u))
+        assert np.array_equal(got.numpy(), idx), name
+        for b in range(W.shape[1]):  # torch-free restatements must agree bit for bit too
+            assert np.array_equal(O.systematic_restated(W[:, b], u[b, 0]), idx[:, b]), (name, b)
+            if W.shape[0] <= 1000:
+                assert np.array_equal(O.systematic_loop(W[:, b], u[b, 0]), idx[:, b]), (name, b)
+
+
+def test_resampling_golden_multinomial():
+    g = load_resampling()
+    for name in sorted({k[4:-2] for k in g if k.startswith("mul_") and k.endswith("_W")}):
+        W, U, idx = g[f"mul_{name}_W"], g[f"mul_{name}_U"], g[f"mul_{name}_idx"]
+        for b in range(W.shape[1]):
+            assert np.array_equal(O.multinomial_restated(W[:, b], U[:, b]), idx[:, b]), (name, b)
+
+
+def test_normalize_golden():
+    g = load_resampling()
+    W = O.normalize(torch.from_numpy(g["norm_in"]).clone())
+    assert np.array_equal(W.numpy(), g["norm_out"], equal_nan=True)
+    assert np.array_equal(O.get_ess(W, True).numpy(), g["norm_ess"], equal_nan=True)
+
+
+def test_reference_kat_systematic():
+    """Same construction as the reference's tests/test_resampling.py:31-47 (seed 123, fp64 weights (10,300), one
+    offset per element), checked against an independent two-pointer walk instead of the filterpy loop."""
+    torch.random.manual_seed(123)
+    weights = O.normalize(torch.randn((10, 300), dtype=torch.float64))
+    u = torch.rand(weights.shape)
+    inds = O.systematic(weights.moveaxis(0, 1), u=u, normalized=True).moveaxis(0, 1).numpy()
+    for i in range(weights.shape[0]):
+        w = weights[i].numpy()
+        positions = (u[i].numpy() + np.arange(300, dtype=np.float32)) / np.float32(300)
+        c = np.cumsum(w)
+        c[-1] = 1.0
+        j, exp = 0, np.zeros(300, dtype=np.int64)
+        for k in range(300):
+            while c[j] < positions[k]:
+                j += 1
+            exp[k] = j
+        assert (inds[i] == exp).all()
+
+
+@pytest.mark.parametrize("tag", filter_cases())
+def test_teacher_forced_steps_match_reference(tag):
+    g = load_filter_case(tag)
+    model = O.build_model(g["model"], model_params(g))
+    B = g["B"]
+    for t in range(g["T"]):
+        x, lw = torch.from_numpy(g["x_prev"][t]), torch.from_numpy(g["lw_prev"][t])
+        inds = torch.from_numpy(g["inds_prev"][t])
+        y = torch.as_tensor(g["y"][t])
+        z = torch.from_numpy(g["z"][t])
+        u = torch.from_numpy(g["u"][t])
+        U = g["U"][t]
+        U = (U if B else U[:, 0]) if U.size else None
+        kw = dict(u=u, resampler=g["resampler"], U=U)
+        out = O.STEPS[g["alg"]](model, g["proposal"], x, lw, inds, y, z, **kw)
+        assert torch.equal(out["prev_inds"], torch.from_numpy(g["prev_inds"][t])), (tag, t)
+        # the oracle is the same arithmetic on the same substrate: expect bit-for-bit agreement
+        for k in ("x", "lw", "ll", "mean", "var"):
+            a, b = out[k].numpy(), g[k][t]
+            assert np.array_equal(a.reshape(b.shape), b, equal_nan=True), (tag, t, k, np.abs(a.reshape(b.shape) - b).max())
+
+
+def test_kalman_agreement_config1():
+    """The reference's own accuracy criterion (tests/filters/test_particle.py:105-111) with a closed-form Kalman
+    filter in place of the absent pykalman: median relative deviation < 10 %."""
+    torch.manual_seed(123)
+    m = O.build_model("lg_ar1")
+    _, y = m.simulate(100)
+    res = O.batch_filter(m, "sisr", "bootstrap", y, 1500)
+    p = O.DEFAULT_PARAMS["lg_ar1"]
+    km, _, kll = O.kalman_filter_1d(y.numpy(), p["alpha"], p["beta"], p["sigma"], p["a"], p["b"], p["s"],
+                                    p["alpha"], p["sigma"] ** 2 / (1 - p["beta"] ** 2))
+    assert abs((kll - res["loglikelihood"].item()) / kll) < 0.1
+    means = res["filter_means"][1:, 0].numpy()
+    assert np.median(np.abs((km - means) / km)) < 0.1
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("alg,proposal,resampler,bshape", [
+    ("sisr", "bootstrap", "systematic", ()), ("sisr", "linear_gaussian", "multinomial", (3,)),
+    ("apf", "bootstrap", "systematic", (3,)), ("apf", "linear_gaussian", "systematic", ()),
+])
+def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape):
+    from oracle.ref_loader import load_reference
+    from oracle.ref_models import build_reference_model
+
+    load_reference()
+    from pyfilter import resampling as RR
+    from pyfilter.filters.particle import APF, SISR, proposals as pr
+
+    torch.manual_seed(5)
+    m = O.build_model("sine_em")
+    _, y = m.simulate(40)
+    ssm = build_reference_model("sine_em", O.DEFAULT_PARAMS["sine_em"])
+    cls = {"sisr": SISR, "apf": APF}[alg]
+    prop = {"bootstrap": pr.Bootstrap, "linear_gaussian": pr.LinearGaussianObservations}[proposal]()
+    f = cls(ssm, 300, proposal=prop, resampling=getattr(RR, resampler))
+    f.set_batch_shape(torch.Size(bshape))
+    torch.manual_seed(11)
+    r = f.batch_filter(y, bar=False)
+    torch.manual_seed(11)
+    o = O.batch_filter(m, alg, proposal, y, 300, bshape, resampler)
+    assert torch.equal(r.loglikelihood, o["loglikelihood"])
+    assert torch.equal(r.filter_means, o["filter_means"])
+    assert torch.equal(r.filter_variance, o["filter_variance"])
+    assert torch.equal(r.latest_state.timeseries_state.value, o["x"])
+    assert torch.equal(r.latest_state.previous_indices, o["prev_inds"])
