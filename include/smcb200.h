@@ -1,0 +1,157 @@
+/* smcb200 - B200-native Sequential-Monte-Carlo inner loop, C ABI.
+ *
+ * Drop-in boundary for the hot path of tingiskhan/pyfilter (reference v0.29.0, pure Python on PyTorch).  The reference has no
+ * FFI; its boundary is the Python plug-in surface.  Every entry point below names the reference
+ * interface it stands behind (paths relative to /root/reference/pyfilter/).  pyfilter_b200/ binds these with ctypes and
+ * re-creates the reference's classes on top (INTEGRATION.md shows the binding a pyfilter maintainer would add).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named *_dev is a CUDA device pointer, *_host a host pointer;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); work is enqueued on it, nothing synchronises
+ *     unless stated;
+ *   - functions return 0 on success, a negative SMCB_E* code otherwise; smcb_last_error() gives the message (thread local);
+ *   - a handle is not thread-safe; distinct handles are independent;
+ *   - device layout: one column per independent filter (the reference's batch dimension, filters/base.py:93-119); a column is
+ *     a contiguous row of `ld` elements (ld = particles rounded up to 4096); states are SoA x[dim][column][particle];
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SMCB_ENODEVICE.
+ */
+#ifndef SMCB200_H
+#define SMCB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SMCB_VERSION 100
+
+enum { SMCB_OK = 0, SMCB_EINVAL = -1, SMCB_ECUDA = -2, SMCB_ENODEVICE = -3, SMCB_EUNSUPPORTED = -4, SMCB_ESTATE = -5 };
+
+/* models: the user-supplied stochproc callables of the reference become a compiled zoo */
+enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3 };
+/* proposals: filters/particle/proposals/bootstrap.py:4-17, proposals/linear.py:13-89 */
+enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1 };
+/* filters: filters/particle/sisr.py:7-56, filters/particle/apf.py:9-46 */
+enum { SMCB_SISR = 0, SMCB_APF = 1 };
+/* resamplers: resampling.py:24-52 (systematic), :55-65 (multinomial) */
+enum { SMCB_SYSTEMATIC = 0, SMCB_MULTINOMIAL = 1 };
+
+#define SMCB_MAX_RAW_PARAMS 8
+
+/* Raw parameter order per model (float32, one value per column or one shared value):
+ *   SMCB_LG_AR1       alpha, beta, sigma, a, b, s             x' = alpha + beta x + sigma e ;       y = b + a x + s v
+ *   SMCB_SINE_EM      gamma, sigma, dt, a, b, s               x' = x + sin(x - gamma) dt + sigma sqrt(dt) e ; y = b + a x + s v
+ *   SMCB_SV_AR1       mu, phi, sigma_v                        x' = mu + phi (x - mu) + sigma_v e ;  y ~ N(0, exp(x/2))
+ *   SMCB_LORENZ63_EM  s, r, b, sigma, dt, obs_a, obs_s        Euler-Maruyama Lorenz-63 ;            y = obs_a (x1, x3) + obs_s v
+ */
+typedef struct smcb_config {
+  int32_t model;          /* SMCB_LG_AR1 ...                                              (the `model` argument, filters/base.py:22) */
+  int32_t proposal;       /* SMCB_BOOTSTRAP ...                                           (`proposal`, filters/particle/base.py:24) */
+  int32_t algorithm;      /* SMCB_SISR / SMCB_APF                                          (the filter class) */
+  int32_t resampler;      /* SMCB_SYSTEMATIC / SMCB_MULTINOMIAL                            (`resampling`, filters/particle/base.py:23) */
+  int64_t particles;      /* N                                                            (`particles`, filters/particle/base.py:22) */
+  int32_t batch;          /* B >= 1 independent filters                                    (set_batch_shape, filters/base.py:93-119) */
+  int32_t n_raw_params;   /* number of rows in `params_host` */
+  const float* params_host; /* (n_raw_params, param_cols) row-major, host memory */
+  int32_t param_cols;     /* 1 (shared) or `batch` (one value per column) */
+  float ess_threshold;    /* relative ESS threshold of SISR                               (`ess_threshold`, filters/particle/base.py:25,42) */
+  uint64_t seed;          /* Philox key */
+  int32_t history_rows;   /* rows kept for filter means / variances / log-likelihood increments (T + 1 for batch_filter) */
+  int32_t fold_lookahead; /* APF: fold log p(y_{t+1}|.) into the stored weights when y_{t+1} is known (saves one pass) */
+  int32_t exact_scan;     /* 1: ancestors bit-exact against torch.cumsum/searchsorted on CPU (default); 0 reserved */
+  int32_t reserved;
+} smcb_config;
+
+typedef struct smcb_filter smcb_filter;
+
+typedef struct smcb_info {
+  int64_t particles, ld;
+  int32_t batch, state_dim, obs_dim;
+  int32_t t;              /* filter moves completed */
+  int32_t history_rows;
+  int32_t slow_tiles;     /* exact-scan tiles that needed the sequential fallback so far (diagnostic; synchronises) */
+  int64_t kernel_launches;/* kernels launched by this handle so far */
+} smcb_info;
+
+/* library */
+int smcb_version(void);
+const char* smcb_last_error(void);
+int smcb_device_count(void);
+
+/* lifetime ............................................................ ParticleFilter.__init__ (filters/particle/base.py:19-48) */
+int smcb_filter_create(const smcb_config* cfg, smcb_filter** out);
+int smcb_filter_destroy(smcb_filter* f);
+/* new parameter values for an existing handle (SMC2 / PMMH rebuild the model per theta: filters/base.py:75-83) */
+int smcb_filter_set_params(smcb_filter* f, const float* params_host, int32_t n_raw_params, int32_t param_cols, void* stream);
+int smcb_filter_info(smcb_filter* f, smcb_info* out);
+
+/* ParticleFilter.initialize (filters/particle/base.py:87-103): x_0 ~ p_0, log w = 0, ll = 0, prev_inds = arange; history row 0 */
+int smcb_filter_initialize(smcb_filter* f, void* stream);
+/* init_state= of batch_filter (filters/base.py:141,152): the caller has written x / log w through the borrowed pointers below
+ * (smcb_filter_ptr); recompute normalisers, ESS and moments for that state and set the move counter to `t`. */
+int smcb_filter_refresh_state(smcb_filter* f, int32_t t, void* stream);
+
+/* observations for the coming moves: y_dev is (count, obs_dim) float32 on the device, y_dev[0] belongs to move `base_t` */
+int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, int32_t count, int32_t base_t, void* stream);
+
+/* BaseFilter.filter (filters/base.py:188-221) = predict (sisr.py:14-48 / apf.py:16-23) + correct (sisr.py:50-56 / apf.py:25-46)
+ * for the next `steps` observations set above; NaN observations propagate only (filters/base.py:213-214). */
+int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream);
+
+/* measurement aid: runs `steps` moves like smcb_filter_run with CUDA events around every kernel group and returns the summed
+ * device time in milliseconds: out_ms_host[0..4] = {APF pre-weight (+finalize), tile sums, scan + ancestors, fused step,
+ * finalize}.  Synchronises the stream. */
+int smcb_filter_profile(smcb_filter* f, int32_t steps, float* out_ms_host, void* stream);
+
+/* BaseFilter.batch_filter (filters/base.py:140-158) end to end on HOST buffers: initialises, copies y (T, obs_dim) to the
+ * device, runs T moves, copies back filter means / variances ((T+1, B, D) each), per-move log-likelihood increments (T+1, B)
+ * (row 0 is zero) and the total log-likelihood (B).  Any output pointer may be NULL.  Synchronises the stream. */
+int smcb_filter_batch_filter_host(smcb_filter* f, const float* y_host, int32_t T, float* means_host, float* vars_host,
+                                  float* ll_steps_host, float* ll_total_host, void* stream);
+
+/* parity hooks: inject the transition noise (D, B, ld) / systematic offsets (B) / multinomial uniforms
+ * (B, ld) float64, or dump the ones the kernels generated and the normalised weights (B, ld) the resampler consumed.  NULL
+ * switches a hook off. */
+int smcb_filter_set_noise(smcb_filter* f, const float* eps_dev, const float* u_dev, const double* U_dev);
+int smcb_filter_dump_noise(smcb_filter* f, float* eps_dev, float* u_dev, float* w_dev);
+
+/* borrowed device pointers into the handle's state (valid until destroy) ........ ParticleFilterCorrection (particle/state.py:72-211) */
+enum {
+  SMCB_PTR_X = 0,          /* float (D, B, ld)  current particles           `_x`                                            */
+  SMCB_PTR_LOGW = 1,       /* float (B, ld)     log-weights                 `_w`                                            */
+  SMCB_PTR_PREV_INDS = 2,  /* int32 (B, ld)     ancestors of the last move  `_prev_inds` (widen to int64 on the host side)  */
+  SMCB_PTR_MEAN = 3,       /* float (B, D)      latest filter mean          `_mean`                                         */
+  SMCB_PTR_VAR = 4,        /* float (B, D)      latest filter variance      `_var`                                          */
+  SMCB_PTR_LL = 5,         /* float (B)         latest log p(y_t|y_{1:t-1}) `_ll`                                           */
+  SMCB_PTR_LL_TOTAL = 6,   /* float (B)         running log-likelihood      FilterResult.loglikelihood (filters/result.py:42-48) */
+  SMCB_PTR_HIST_MEAN = 7,  /* float (rows,B,D)  FilterResult.filter_means   (filters/result.py:50-57)                        */
+  SMCB_PTR_HIST_VAR = 8,   /* float (rows,B,D)  FilterResult.filter_variance                                                */
+  SMCB_PTR_HIST_LL = 9,    /* float (rows,B)    per-move increments                                                         */
+  SMCB_PTR_ESS = 10,       /* float (B) packed copy refreshed by smcb_filter_sync_stats                                     */
+  SMCB_PTR_X_OTHER = 11    /* float (D, B, ld)  the ping-pong twin of SMCB_PTR_X (previous particles)                       */
+};
+int smcb_filter_ptr(smcb_filter* f, int32_t what, void** ptr_dev);
+/* gathers ESS / resample flags of every column into the packed SMCB_PTR_ESS buffer (get_ess, utils.py:8-20) */
+int smcb_filter_sync_stats(smcb_filter* f, void* stream);
+
+/* stand-alone operators ......................................................................................................
+ * All take a weight matrix with element strides (stride_n, stride_b): the reference's particle-major (N,B) tensor has
+ * (B, 1); a single column has (1, 0).  `out_dev` strides are given the same way. */
+/* pyfilter.utils.normalize (utils.py:49-64): NaN-safe soft-max over the particle axis; does NOT mutate the input */
+int smcb_normalize(const float* logw_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, float* out_dev,
+                   int64_t out_stride_n, int64_t out_stride_b, float* ess_out_dev, void* stream);
+/* pyfilter.resampling.systematic (resampling.py:24-52): int64 ancestors; `u_dev` (B) overrides the sampled offsets (the
+ * reference's testing hook `u=`); `normalized` mirrors the keyword of the same name */
+int smcb_systematic(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, int32_t normalized,
+                    const float* u_dev, uint64_t seed, int64_t* out_dev, int64_t out_stride_n, int64_t out_stride_b,
+                    void* stream);
+/* pyfilter.resampling.multinomial (resampling.py:55-65): `U_dev` (B, n) float64 uniforms in draw order override Philox */
+int smcb_multinomial(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, int32_t normalized,
+                     const double* U_dev, uint64_t seed, int64_t* out_dev, int64_t out_stride_n, int64_t out_stride_b,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB200_H */

@@ -1,0 +1,155 @@
+"""ctypes binding of ``libsmcb200.so`` (C ABI in ``include/smcb200.h``).
+
+The shared library is built IN-TREE by ``build_library()`` (``nvcc -gencode arch=compute_100a,code=sm_100a``) so that it
+travels with the repository snapshot to the GPU box.  There is no CPU fallback: every compute entry point raises when the
+library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsmcb200.so")
+_SOURCES = ["smcb_api.cu", "resample.cuh", "step.cuh", "operators.cuh", "common.cuh", "models.h", "philox.h", "scan_tile.h",
+            "exact_scan.h"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+              "-diag-suppress", "128"]
+
+
+class SmcbError(RuntimeError):
+    pass
+
+
+class smcb_config(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("proposal", C.c_int32), ("algorithm", C.c_int32), ("resampler", C.c_int32),
+        ("particles", C.c_int64), ("batch", C.c_int32), ("n_raw_params", C.c_int32),
+        ("params_host", C.POINTER(C.c_float)), ("param_cols", C.c_int32), ("ess_threshold", C.c_float),
+        ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_scan", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class smcb_info(C.Structure):
+    _fields_ = [
+        ("particles", C.c_int64), ("ld", C.c_int64), ("batch", C.c_int32), ("state_dim", C.c_int32), ("obs_dim", C.c_int32),
+        ("t", C.c_int32), ("history_rows", C.c_int32), ("slow_tiles", C.c_int32), ("kernel_launches", C.c_int64),
+    ]
+
+
+# every symbol include/smcb200.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("smcb_version", C.c_int, []),
+    ("smcb_last_error", C.c_char_p, []),
+    ("smcb_device_count", C.c_int, []),
+    ("smcb_filter_create", C.c_int, [C.POINTER(smcb_config), C.POINTER(_P)]),
+    ("smcb_filter_destroy", C.c_int, [_P]),
+    ("smcb_filter_set_params", C.c_int, [_P, C.POINTER(C.c_float), C.c_int32, C.c_int32, _P]),
+    ("smcb_filter_info", C.c_int, [_P, C.POINTER(smcb_info)]),
+    ("smcb_filter_initialize", C.c_int, [_P, _P]),
+    ("smcb_filter_refresh_state", C.c_int, [_P, C.c_int32, _P]),
+    ("smcb_filter_set_observations", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
+    ("smcb_filter_run", C.c_int, [_P, C.c_int32, _P]),
+    ("smcb_filter_profile", C.c_int, [_P, C.c_int32, _P, _P]),
+    ("smcb_filter_batch_filter_host", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    ("smcb_filter_set_noise", C.c_int, [_P, _P, _P, _P]),
+    ("smcb_filter_dump_noise", C.c_int, [_P, _P, _P, _P]),
+    ("smcb_filter_ptr", C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
+    ("smcb_filter_sync_stats", C.c_int, [_P, _P]),
+    ("smcb_normalize", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P]),
+    ("smcb_systematic", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64,
+                                  C.c_int64, _P]),
+    ("smcb_multinomial", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64,
+                                   C.c_int64, _P]),
+]
+
+PTR_X, PTR_LOGW, PTR_PREV_INDS, PTR_MEAN, PTR_VAR, PTR_LL, PTR_LL_TOTAL, PTR_HIST_MEAN, PTR_HIST_VAR, PTR_HIST_LL, PTR_ESS, \
+    PTR_X_OTHER = range(12)
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    built = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(_HERE, "csrc", s) for s in _SOURCES] + [os.path.join(os.path.dirname(_HERE), "include", "smcb200.h")]
+    return any(os.path.exists(s) and os.path.getmtime(s) > built for s in srcs)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compiles ``csrc/smcb_api.cu`` for sm_100a into ``pyfilter_b200/libsmcb200.so`` (nvcc cross-compiles without a GPU)."""
+    if not force and not _stale():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(_HERE, "csrc", "smcb_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise SmcbError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+def load_library():
+    """Loads the shared library (building it when nvcc is available and the sources are newer) and binds every symbol."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if _stale():
+            try:
+                build_library()
+            except (SmcbError, FileNotFoundError) as e:
+                if not os.path.exists(LIB_PATH):
+                    raise SmcbError(f"libsmcb200.so is missing and could not be built ({e}); pyfilter_b200 has no CPU fallback")
+        lib = C.CDLL(LIB_PATH)
+        for name, restype, argtypes in SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load_library().smcb_last_error().decode()
+        if rc == -4:
+            raise NotImplementedError(msg)
+        if rc == -1:
+            raise ValueError(msg)
+        raise SmcbError(f"libsmcb200 error {rc}: {msg}")
+
+
+def require_cuda():
+    import torch
+
+    if not torch.cuda.is_available() or load_library().smcb_device_count() < 1:
+        raise SmcbError("pyfilter_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def current_stream() -> int:
+    import torch
+
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DeviceView:
+    """Zero-copy ``__cuda_array_interface__`` wrapper of a borrowed device pointer; ``owner`` keeps the handle alive."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(s) for s in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+        self._owner = owner
+
+
+def as_tensor(ptr: int, shape, typestr: str, owner):
+    import torch
+
+    t = torch.as_tensor(DeviceView(ptr, shape, typestr, owner), device="cuda")
+    t._smcb_owner = owner
+    return t

@@ -1,0 +1,99 @@
+// Shared device-side plumbing: per-column statistics, block partial records, warp/block reductions, acquire/release.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include "models.h"
+
+#define SMCB_FLT_MAX 3.402823466e+38f
+
+// Per-column summary written by the finalize kernel and read by the next step's kernels (all on device, no host sync).
+struct ColStats {
+  float m_lw, z_lw, inv_z_lw;   // max, sum exp(lw - max) and its reciprocal for the log-weights (filters/particle/state.py:148)
+  float m_rw, z_rw, inv_z_rw;   // the same for the APF resampling log-weights  g + lw   (filters/particle/apf.py:29)
+  float ess;                    // 1 / sum W^2                                            (utils.py:8-20)
+  int32_t resample;             // 1 when the coming step resamples this column            (sisr.py:19 / apf.py:31)
+  float shift[3];               // moment shift (= latest filter mean) used to accumulate the variance in one pass
+  float ll_aux;                 // log sum_i W_i exp(g_i)  (second term of apf.py:44), valid for the coming step
+  int32_t fold_valid;           // 1 when rw already holds g_{t+1} + lw_t for the coming step (look-ahead folded by the step kernel)
+  float pad[3];
+};
+
+// One record per (column, block) of the step / pre-weight / init kernels: soft-max partials.
+struct Partial {
+  float m1, z1, zz1;            // over lw:  max, sum e, sum e^2          (e = exp(lw - m1))
+  float sx[3], sxx[3];          // sum e (x - shift), sum e (x - shift)^2
+  float m2, z2;                 // over rw (APF look-ahead folded)
+  float m3, z3;                 // SISR likelihood increment: max inc, sum W_prev exp(inc - m3)   (filters/particle/utils.py:16-22)
+};
+
+// Device control block: lets one captured CUDA graph serve every time step (no per-step kernel arguments change).
+struct Ctrl {
+  int32_t t;            // number of completed filter moves (row index into the moment history is t + 1)
+  int32_t y_base;       // time index of y[0]
+  int32_t y_count;      // observations available at y
+  int32_t ticket;       // last-block-done counter of the finalize kernel
+  uint32_t epoch;       // bumped once per resampling launch; tags the look-back slots so they never need clearing
+  uint32_t tile_counter;
+  int32_t slow_tiles;   // diagnostics: tiles that took the sequential fallback of the exact scan
+  int32_t pad;
+  const float* y;       // (y_count, OD) observations on device
+};
+
+__device__ __forceinline__ float smcb_sanitize(float w) {
+  // utils.py:57 nan_to_num_(nan=-inf, posinf=-inf) with neginf left at its default (lowest finite float)
+  if (w != w || w == INFINITY) return -INFINITY;
+  if (w == -INFINITY) return -SMCB_FLT_MAX;
+  return w;
+}
+
+// normalised weight exactly as every kernel of this library evaluates it (must be ONE function: the tile-sum pre-pass and the
+// scan kernel have to see identical bits).  Differs from the reference's exp(v)/sum by at most a few ulp (tolerance 1e-6).
+__device__ __forceinline__ float smcb_weight(float lw, float m, float inv_z) {
+  return __fmul_rn(expf(__fsub_rn(lw, m)), inv_z);
+}
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide max / sum for blockDim.x == NT (multiple of 32, <= 1024); result broadcast to every thread.  `scratch` holds
+// at least 33 elements.  Deterministic (fixed tree).
+template <int NT, typename T, typename Op>
+__device__ __forceinline__ T block_allreduce(T v, T ident, Op op, T* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // protect scratch reuse
+  if (lane == 0) scratch[wid] = v;
+  __syncthreads();
+  T r = (lane < NT / 32) ? scratch[lane] : ident;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+struct OpMaxF { __device__ __forceinline__ float operator()(float a, float b) const { return fmaxf(a, b); } };
+struct OpSumF { __device__ __forceinline__ float operator()(float a, float b) const { return a + b; } };
+struct OpSumD { __device__ __forceinline__ double operator()(double a, double b) const { return a + b; } };
+struct OpSumI { __device__ __forceinline__ int operator()(int a, int b) const { return a + b; } };

@@ -1,0 +1,118 @@
+// Compiled model zoo: the four state-space models of BASELINE.json, as device functions.
+//
+// In the reference the model is a Python callable (stochproc AffineProcess.mean_scale / StateSpaceModel.build_density,
+// SURVEY.md Appendix C); a fused kernel cannot call that, so each model is a struct with
+//     loc_scale(x_prev, P) -> (loc[D], scale)        x_t = loc + scale * (inc_scale * z)            [AffineProcess.propagate]
+//     obs_lp(y, x, P)                                 log p(y | x)                                    [build_density().log_prob]
+// P is the per-column parameter row (raw parameters first, then host-precomputed constants), see smcb_param_layout in
+// smcb_api.cu and pyfilter_b200/timeseries.py.  Arithmetic is written with explicit round-to-nearest intrinsics so that every
+// call site produces identical bits (the APF recomputes the look-ahead weight of the ancestor instead of gathering it).
+#pragma once
+#include <cuda_runtime.h>
+
+#define SMCB_NPARAM 28
+#define SMCB_LOG_SQRT_2PI 0.9189385332046727f
+
+enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_NUM_MODELS = 4 };
+enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1 };
+enum { SMCB_ALG_SISR = 0, SMCB_ALG_APF = 1 };
+enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
+
+// Parameter row layout (per column).  Slots 0..7: model parameters and observation constants; 8..19: constants of the
+// LinearGaussianObservations proposal; 20..26: increment scale and initial distribution.
+// linear-Gaussian observation slots (lg_ar1, sine_em):   y = b + a x + s nu
+#define P_OBS_A 3
+#define P_OBS_B 4
+#define P_OBS_S 5
+#define P_OBS_INV2VAR 6    // 1 / (2 s^2)
+#define P_OBS_LOGNORM 7    // log s + log sqrt(2 pi)
+// LinearGaussianObservations constants (proposals/linear.py:38-86, proposals/utils.py:219-267), scalar state/observation
+#define P_LGO_HVI 8          // sigma^-2
+#define P_LGO_COV 9          // P = 1 / (sigma^-2 + a^2 s^-2)
+#define P_LGO_KSTD 10        // sqrt(P)
+#define P_LGO_K_INV2VAR 11   // 1 / (2 P)
+#define P_LGO_K_LOGNORM 12   // log sqrt(P) + log sqrt(2 pi)
+#define P_LGO_PRE_INV2VAR 13 // 1 / (2 (s^2 + a^2 sigma^2))
+#define P_LGO_PRE_LOGNORM 14 // log sqrt(s^2 + a^2 sigma^2) + log sqrt(2 pi)
+#define P_LGO_INC_INV2VAR 15 // 1 / (2 inc_scale^2)
+#define P_LGO_INC_LOGNORM 16 // log inc_scale + log sqrt(2 pi) + log sigma   (increment density + log|d inc / d x|)
+#define P_LGO_INV_SIGMA 17   // 1 / sigma
+#define P_LGO_OVI 18         // s^-2
+#define P_INC_SCALE 20       // std of the increment distribution (1 or sqrt(dt))
+#define P_X0_LOC 21          // .. +2 (three dims)
+#define P_X0_SCALE 24        // .. +2
+
+__device__ __forceinline__ float smcb_normal_lp(float v, float loc, float inv2var, float lognorm) {
+  float d = __fsub_rn(v, loc);
+  return __fsub_rn(__fmul_rn(-__fmul_rn(d, d), inv2var), lognorm);
+}
+// Normal(loc, scale).log_prob(v) with scale given directly (used where scale is not a per-column constant)
+__device__ __forceinline__ float smcb_normal_lp_scale(float v, float loc, float scale) {
+  float d = __fsub_rn(v, loc);
+  float var2 = __fmul_rn(2.0f, __fmul_rn(scale, scale));
+  return __fsub_rn(__fsub_rn(__fdiv_rn(-__fmul_rn(d, d), var2), logf(scale)), SMCB_LOG_SQRT_2PI);
+}
+
+template <int MODEL> struct Model;
+
+// ---- config 1: x_t = alpha + beta x_{t-1} + sigma eps;  y = b + a x + s nu          (reference tests/filters/models.py:12-16)
+template <> struct Model<SMCB_MODEL_LG_AR1> {
+  static constexpr int D = 1, OD = 1;
+  static constexpr bool LINEAR_OBS = true;
+  __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
+    loc[0] = __fadd_rn(P[0], __fmul_rn(P[1], x[0]));
+    scale = P[2];
+  }
+  __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
+    return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
+  }
+};
+
+// ---- configs 2 and 5: Euler-Maruyama of dx = sin(x - gamma) dt + sigma dW;  y = b + a x + s nu      (reference README.md:44-67)
+template <> struct Model<SMCB_MODEL_SINE_EM> {
+  static constexpr int D = 1, OD = 1;
+  static constexpr bool LINEAR_OBS = true;
+  __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
+    loc[0] = __fadd_rn(x[0], __fmul_rn(sinf(__fsub_rn(x[0], P[0])), P[2]));
+    scale = P[1];
+  }
+  __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
+    return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
+  }
+};
+
+// ---- config 3: x_t = mu + phi (x_{t-1} - mu) + sigma_v eps;  y ~ N(0, exp(x/2))
+template <> struct Model<SMCB_MODEL_SV_AR1> {
+  static constexpr int D = 1, OD = 1;
+  static constexpr bool LINEAR_OBS = false;
+  __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
+    loc[0] = __fadd_rn(P[0], __fmul_rn(P[1], __fsub_rn(x[0], P[0])));
+    scale = P[2];
+  }
+  __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
+    // Normal(0, exp(x/2)).log_prob(y) = -y^2 / (2 exp(x)) - x/2 - log sqrt(2 pi)
+    float hy2 = __fmul_rn(0.5f, __fmul_rn(y[0], y[0]));
+    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, expf(-x[0])), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
+  }
+};
+
+// ---- config 4: Euler-Maruyama Lorenz-63, y = obs_a (x^1, x^3) + obs_s nu                      (reference examples/lorenz.ipynb:53-117)
+//      P: 0 s, 1 r, 2 b, 3 sigma, 4 dt, 5 obs_a, 6 inv2var, 7 lognorm (per component)
+template <> struct Model<SMCB_MODEL_LORENZ63_EM> {
+  static constexpr int D = 3, OD = 2;
+  static constexpr bool LINEAR_OBS = false;
+  __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
+    float f0 = __fmul_rn(-P[0], __fsub_rn(x[0], x[1]));
+    float f1 = __fsub_rn(__fsub_rn(__fmul_rn(P[1], x[0]), x[1]), __fmul_rn(x[0], x[2]));
+    float f2 = __fsub_rn(__fmul_rn(x[0], x[1]), __fmul_rn(P[2], x[2]));
+    loc[0] = __fadd_rn(x[0], __fmul_rn(f0, P[4]));
+    loc[1] = __fadd_rn(x[1], __fmul_rn(f1, P[4]));
+    loc[2] = __fadd_rn(x[2], __fmul_rn(f2, P[4]));
+    scale = P[3];
+  }
+  __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
+    float l0 = smcb_normal_lp(y[0], __fmul_rn(P[5], x[0]), P[6], P[7]);
+    float l1 = smcb_normal_lp(y[1], __fmul_rn(P[5], x[2]), P[6], P[7]);
+    return __fadd_rn(l0, l1);
+  }
+};

@@ -1,0 +1,234 @@
+// Launch helpers and the small kernels behind the stand-alone operators (pyfilter.utils.normalize / get_ess,
+// pyfilter.resampling.systematic / multinomial) - the same resampling kernels the filter handle uses, fed from a caller tensor
+// with arbitrary (particle, column) strides.
+#pragma once
+#include "resample.cuh"
+
+// ---- layout adapters ---------------------------------------------------------------------------------------------------------
+// in[i*sn + b*sb]  ->  rows[b*ld + i]   (32x32 shared-memory transpose so both sides stay coalesced for particle-major input)
+__global__ void gather_rows_kernel(const float* __restrict__ in, int64_t n, int B, int64_t sn, int64_t sb, float* __restrict__ rows, int64_t ld) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // (32, 8)
+  if (sn == 1) {  // rows already contiguous: plain copy, x along particles
+    for (int k = ty; k < 32; k += 8) {
+      const int b = b0 + k;
+      const int64_t i = i0 + tx;
+      if (b < B && i < n) rows[(int64_t)b * ld + i] = in[i + (int64_t)b * sb];
+    }
+    return;
+  }
+  for (int k = ty; k < 32; k += 8) {  // read with x along columns
+    const int64_t i = i0 + k;
+    const int b = b0 + tx;
+    if (i < n && b < B) tile[k][tx] = in[i * sn + (int64_t)b * sb];
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {  // write with x along particles
+    const int b = b0 + k;
+    const int64_t i = i0 + tx;
+    if (b < B && i < n) rows[(int64_t)b * ld + i] = tile[tx][k];
+  }
+}
+
+// rows[b*ld + i] (int32)  ->  out[i*sn + b*sb] (int64)     (torch.searchsorted / torch.multinomial return int64)
+__global__ void scatter_i64_kernel(const int32_t* __restrict__ rows, int64_t n, int B, int64_t ld, int64_t* __restrict__ out, int64_t sn, int64_t sb) {
+  __shared__ int32_t tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  if (sn == 1) {
+    for (int k = ty; k < 32; k += 8) {
+      const int b = b0 + k;
+      const int64_t i = i0 + tx;
+      if (b < B && i < n) out[i + (int64_t)b * sb] = (int64_t)rows[(int64_t)b * ld + i];
+    }
+    return;
+  }
+  for (int k = ty; k < 32; k += 8) {
+    const int b = b0 + k;
+    const int64_t i = i0 + tx;
+    if (b < B && i < n) tile[k][tx] = rows[(int64_t)b * ld + i];
+  }
+  __syncthreads();
+  for (int k = ty; k < 32; k += 8) {
+    const int64_t i = i0 + k;
+    const int b = b0 + tx;
+    if (i < n && b < B) out[i * sn + (int64_t)b * sb] = (int64_t)tile[tx][k];
+  }
+}
+
+static inline void op_launch_gather_rows(const float* in, int64_t n, int B, int64_t sn, int64_t sb, float* rows, int64_t ld, cudaStream_t s) {
+  dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
+  gather_rows_kernel<<<g, dim3(32, 8), 0, s>>>(in, n, B, sn, sb, rows, ld);
+}
+static inline void op_launch_scatter_i64(const int32_t* rows, int64_t n, int B, int64_t ld, int64_t* out, int64_t sn, int64_t sb, cudaStream_t s) {
+  dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
+  scatter_i64_kernel<<<g, dim3(32, 8), 0, s>>>(rows, n, B, ld, out, sn, sb);
+}
+
+// ---- normalisers of a matrix of log-weights (utils.py:49-64, 8-20) --------------------------------------------------------------
+struct NormPartial { float m, z, zz; };
+
+__global__ void __launch_bounds__(RS_NT) colstats_partial_kernel(const float* __restrict__ rows, int64_t n, int64_t ld, int nblk, NormPartial* parts) {
+  __shared__ float scratch[33];
+  const int col = blockIdx.y, blk = blockIdx.x;
+  const float* src = rows + (int64_t)col * ld + (int64_t)blk * RS_TILE;
+  float v[RS_ITEMS];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {  // striped: coalesced
+    const int64_t i = (int64_t)blk * RS_TILE + j * RS_NT + threadIdx.x;
+    v[j] = (i < n) ? smcb_sanitize(src[j * RS_NT + threadIdx.x]) : -INFINITY;
+    m = fmaxf(m, v[j]);
+  }
+  m = block_allreduce<RS_NT>(m, -INFINITY, OpMaxF(), scratch);
+  float z = 0.f, zz = 0.f;
+  if (m > -INFINITY) {
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      const float e = (v[j] == -INFINITY) ? 0.f : expf(v[j] - m);
+      z += e; zz += e * e;
+    }
+  }
+  z = block_allreduce<RS_NT>(z, 0.f, OpSumF(), scratch);
+  zz = block_allreduce<RS_NT>(zz, 0.f, OpSumF(), scratch);
+  if (threadIdx.x == 0) { NormPartial p; p.m = m; p.z = z; p.zz = zz; parts[(int64_t)col * nblk + blk] = p; }
+}
+
+__global__ void __launch_bounds__(128) colstats_final_kernel(const NormPartial* parts, int nblk, int64_t n, ColStats* stats) {
+  __shared__ float scratch[33];
+  const int col = blockIdx.x;
+  float m = -INFINITY;
+  for (int b = threadIdx.x; b < nblk; b += 128) m = fmaxf(m, parts[(int64_t)col * nblk + b].m);
+  m = block_allreduce<128>(m, -INFINITY, OpMaxF(), scratch);
+  float z = 0.f, zz = 0.f;
+  for (int b = threadIdx.x; b < nblk; b += 128) {
+    const NormPartial p = parts[(int64_t)col * nblk + b];
+    if (p.m > -INFINITY) {
+      const float sc = expf(p.m - m);
+      z += p.z * sc; zz += p.zz * sc * sc;
+    }
+  }
+  z = block_allreduce<128>(z, 0.f, OpSumF(), scratch);
+  zz = block_allreduce<128>(zz, 0.f, OpSumF(), scratch);
+  if (threadIdx.x == 0) {
+    ColStats st;
+    memset(&st, 0, sizeof(st));
+    st.m_lw = m; st.z_lw = z; st.inv_z_lw = 1.0f / z;
+    st.ess = (z * z) / zz;
+    st.resample = 1;
+    stats[col] = st;
+  }
+}
+
+// out[i*sn + b*sb] = normalised weight; all-(-inf) columns (max == -inf, i.e. every entry NaN/+inf) give NaN like the reference
+__global__ void apply_weights_kernel(const float* __restrict__ rows, const ColStats* stats, int64_t n, int B, int64_t ld, float* out, int64_t sn, int64_t sb) {
+  __shared__ float tile[32][33];
+  const int64_t i0 = (int64_t)blockIdx.x * 32;
+  const int b0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int k = ty; k < 32; k += 8) {
+    const int b = b0 + k;
+    const int64_t i = i0 + tx;
+    if (b < B && i < n) {
+      const ColStats st = stats[b];
+      tile[k][tx] = smcb_weight(smcb_sanitize(rows[(int64_t)b * ld + i]), st.m_lw, st.inv_z_lw);
+    }
+  }
+  __syncthreads();
+  if (sn == 1) {
+    for (int k = ty; k < 32; k += 8) {
+      const int b = b0 + k;
+      const int64_t i = i0 + tx;
+      if (b < B && i < n) out[i + (int64_t)b * sb] = tile[k][tx];
+    }
+  } else {
+    for (int k = ty; k < 32; k += 8) {
+      const int64_t i = i0 + k;
+      const int b = b0 + tx;
+      if (i < n && b < B) out[i * sn + (int64_t)b * sb] = tile[tx][k];
+    }
+  }
+}
+
+__global__ void copy_ess_kernel(const ColStats* st, float* out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) out[b] = st[b].ess;
+}
+
+static inline void op_launch_colstats(const float* rows, int64_t n, int B, int64_t ld, int nblk, NormPartial* parts, ColStats* stats, cudaStream_t s) {
+  colstats_partial_kernel<<<dim3(nblk, B), RS_NT, 0, s>>>(rows, n, ld, nblk, parts);
+  colstats_final_kernel<<<B, 128, 0, s>>>(parts, nblk, n, stats);
+}
+static inline void op_launch_apply_weights(const float* rows, const ColStats* stats, int64_t n, int B, int64_t ld, float* out, int64_t sn, int64_t sb, cudaStream_t s) {
+  dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
+  apply_weights_kernel<<<g, dim3(32, 8), 0, s>>>(rows, stats, n, B, ld, out, sn, sb);
+}
+static inline void op_launch_copy_ess(const ColStats* st, float* out, int B, cudaStream_t s) {
+  copy_ess_kernel<<<(B + 127) / 128, 128, 0, s>>>(st, out, B);
+}
+
+// ---- systematic ------------------------------------------------------------------------------------------------------------------
+static inline void op_launch_systematic(const ResampleArgs& r, cudaStream_t s) {
+  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+}
+
+// ---- multinomial (resampling.py:55-65 -> ATen multinomial_with_replacement_kernel on CPU) --------------------------------------------
+//   c32_k = fl32(c32_{k-1} + W_k)  (sequential float32 prefix, reproduced exactly by the transducer scan with a 24-bit mantissa),
+//   cn_k = fl32(c32_k / c32_{n-1});  draw i:  ancestor = first k with (double)cn_k >= U_i,  U_i float64 uniforms in draw order.
+struct MultinomialArgs {
+  const float* c;          // (B, ld) sequential float32 prefix sums
+  int64_t n, ld;
+  int32_t B;
+  const ColStats* stats;   // resample flags (may be NULL)
+  const double* U;         // optional injected uniforms (B, U_pitch)
+  int64_t U_pitch;
+  uint64_t seed;
+  const Ctrl* ctrl;
+  int32_t* anc;            // (B, ld)
+};
+
+__global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a) {
+  const int col = blockIdx.y;
+  if (a.stats && !a.stats[col].resample) return;
+  const float* c = a.c + (int64_t)col * a.ld;
+  const float total = c[a.n - 1];
+  const int t = a.ctrl->t;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+    double U;
+    if (a.U) U = a.U[(int64_t)col * a.U_pitch + i];
+    else {
+      Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)col, (uint32_t)t, SMCB_RNG_MULTINOMIAL, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      U = smcb_u01_double(r.x, r.y);
+    }
+    int64_t lo = 0, hi = a.n;
+    while (hi - lo > 0) {
+      const int64_t mid = lo + (hi - lo) / 2;
+      const float cn = __fdiv_rn(__ldg(c + mid), total);
+      if ((double)cn < U) lo = mid + 1; else hi = mid;
+    }
+    a.anc[(int64_t)col * a.ld + i] = (int32_t)(lo < a.n ? lo : a.n - 1);
+  }
+}
+
+// r.c_out must point at a (B, ld) float scratch buffer owned by the caller; tile_sum_kernel has already been enqueued
+static inline void op_launch_multinomial_after_tilesum(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
+  systematic_kernel<24, RS_OUT_CUMSUM><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+  MultinomialArgs m;
+  m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
+  m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc;
+  int bx = (int)((r.n + 255) / 256);
+  const int cap = (148 * 8 + r.B - 1) / r.B;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  multinomial_draw_kernel<<<dim3(bx, r.B), 256, 0, s>>>(m);
+}
+static inline int op_launch_multinomial(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
+  if (!r.c_out) return SMCB_EINVAL;
+  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  op_launch_multinomial_after_tilesum(r, U, U_pitch, s);
+  return SMCB_OK;
+}

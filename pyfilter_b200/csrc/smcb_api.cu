@@ -1,0 +1,584 @@
+// C ABI of libsmcb200 (include/smcb200.h): handle management, kernel dispatch over the compiled model zoo, the time loop.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/smcb200.h"
+#include "resample.cuh"
+#include "step.cuh"
+#include "operators.cuh"
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call)                                                                                            \
+  do {                                                                                                      \
+    cudaError_t e_ = (call);                                                                                \
+    if (e_ != cudaSuccess)                                                                                  \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? SMCB_ENODEVICE : SMCB_ECUDA, \
+                  std::string(#call) + ": " + cudaGetErrorString(e_));                                      \
+  } while (0)
+
+extern "C" int smcb_version(void) { return SMCB_VERSION; }
+extern "C" const char* smcb_last_error(void) { return g_err.c_str(); }
+extern "C" int smcb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+static const int kDims[SMCB_NUM_MODELS][2] = {{1, 1}, {1, 1}, {1, 1}, {3, 2}};
+static const int kRaw[SMCB_NUM_MODELS] = {6, 6, 3, 7};
+
+// ---- host-side parameter row (layout in models.h) -------------------------------------------------------------------------
+static void derive_params(int model, const double* r, float* P) {
+  const double c = 0.91893853320467274178;  // log sqrt(2 pi)
+  for (int i = 0; i < SMCB_NPARAM; ++i) P[i] = 0.f;
+  double inc = 1.0, sigma = 1.0, a = 0, s = 1;
+  bool linear = false;
+  switch (model) {
+    case SMCB_MODEL_LG_AR1:
+      for (int i = 0; i < 6; ++i) P[i] = (float)r[i];
+      sigma = r[2]; a = r[3]; s = r[5]; linear = true;
+      P[P_X0_LOC] = (float)r[0];
+      P[P_X0_SCALE] = (float)(r[2] / sqrt(1.0 - r[1] * r[1]));
+      break;
+    case SMCB_MODEL_SINE_EM:
+      for (int i = 0; i < 6; ++i) P[i] = (float)r[i];
+      sigma = r[1]; a = r[3]; s = r[5]; linear = true; inc = sqrt(r[2]);
+      P[P_X0_LOC] = 0.f; P[P_X0_SCALE] = 1.f;
+      break;
+    case SMCB_MODEL_SV_AR1:
+      for (int i = 0; i < 3; ++i) P[i] = (float)r[i];
+      P[P_X0_LOC] = (float)r[0];
+      P[P_X0_SCALE] = (float)(r[2] / sqrt(1.0 - r[1] * r[1]));
+      break;
+    case SMCB_MODEL_LORENZ63_EM: {
+      for (int i = 0; i < 6; ++i) P[i] = (float)r[i];
+      const double os = r[6];
+      P[6] = (float)(1.0 / (2.0 * os * os));
+      P[7] = (float)(log(os) + c);
+      inc = sqrt(r[4]);
+      const float m0[3] = {-5.91652f, -5.52332f, 24.5723f};
+      for (int d = 0; d < 3; ++d) { P[P_X0_LOC + d] = m0[d]; P[P_X0_SCALE + d] = (float)sqrt(10.0); }
+      break;
+    }
+  }
+  P[P_INC_SCALE] = (float)inc;
+  if (linear) {
+    P[P_OBS_INV2VAR] = (float)(1.0 / (2.0 * s * s));
+    P[P_OBS_LOGNORM] = (float)(log(s) + c);
+    const double hvi = 1.0 / (sigma * sigma), ovi = 1.0 / (s * s);
+    const double cov = 1.0 / (hvi + a * a * ovi);
+    const double pre = s * s + a * a * sigma * sigma;
+    P[P_LGO_HVI] = (float)hvi;
+    P[P_LGO_OVI] = (float)ovi;
+    P[P_LGO_COV] = (float)cov;
+    P[P_LGO_KSTD] = (float)sqrt(cov);
+    P[P_LGO_K_INV2VAR] = (float)(1.0 / (2.0 * cov));
+    P[P_LGO_K_LOGNORM] = (float)(0.5 * log(cov) + c);
+    P[P_LGO_PRE_INV2VAR] = (float)(1.0 / (2.0 * pre));
+    P[P_LGO_PRE_LOGNORM] = (float)(0.5 * log(pre) + c);
+    P[P_LGO_INC_INV2VAR] = (float)(1.0 / (2.0 * inc * inc));
+    P[P_LGO_INC_LOGNORM] = (float)(log(inc) + c + log(fabs(sigma)));
+    P[P_LGO_INV_SIGMA] = (float)(1.0 / sigma);
+  }
+}
+
+struct smcb_filter {
+  smcb_config cfg;
+  int D, OD, B, tiles_per_col, blocks_per_col, iters;
+  int64_t n, ld;
+  float* P_dev = nullptr;
+  float* xbuf[2] = {nullptr, nullptr};
+  float *lw = nullptr, *rw = nullptr;
+  int32_t *anc = nullptr, *prev_inds = nullptr;
+  ColStats* stats = nullptr;
+  Partial* partials = nullptr;
+  Ctrl* ctrl = nullptr;
+  double* tilesum = nullptr;
+  TileSlot* slots = nullptr;
+  float *hist_mean = nullptr, *hist_var = nullptr, *hist_ll = nullptr;
+  float *latest_mean = nullptr, *latest_var = nullptr, *latest_ll = nullptr, *ll_total = nullptr, *ess_packed = nullptr;
+  float* y_own = nullptr;
+  int y_own_cap = 0;
+  float* cbuf = nullptr;  // multinomial: sequential float32 prefix sums (B, ld)
+  const float *eps_in = nullptr, *u_in = nullptr;
+  const double* U_in = nullptr;
+  float *eps_out = nullptr, *u_out = nullptr, *w_out = nullptr;
+  int t_host = 0, y_base = 0, y_count = 0;
+  bool folded_for_next = false;
+  int64_t launches = 0;
+};
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+  cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, count * sizeof(T));
+  return e;
+}
+
+static int upload_params(smcb_filter* f, const float* params_host, int n_raw, int cols, cudaStream_t s) {
+  if (n_raw != kRaw[f->cfg.model]) return fail(SMCB_EINVAL, "wrong number of raw parameters for this model");
+  if (cols != 1 && cols != f->B) return fail(SMCB_EINVAL, "param_cols must be 1 or the batch size");
+  std::vector<float> P((size_t)f->B * SMCB_NPARAM);
+  for (int b = 0; b < f->B; ++b) {
+    double r[SMCB_MAX_RAW_PARAMS];
+    for (int k = 0; k < n_raw; ++k) r[k] = params_host[(size_t)k * cols + (cols == 1 ? 0 : b)];
+    derive_params(f->cfg.model, r, &P[(size_t)b * SMCB_NPARAM]);
+  }
+  CU(cudaMemcpyAsync(f->P_dev, P.data(), P.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+  CU(cudaStreamSynchronize(s));  // P is a stack/heap temporary
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_destroy(smcb_filter* f) {
+  if (!f) return SMCB_OK;
+  void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
+                  f->tilesum, f->slots, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
+                  f->ll_total, f->ess_packed, f->y_own, f->cbuf};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete f;
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
+  if (!cfg || !out) return fail(SMCB_EINVAL, "null argument");
+  if (cfg->model < 0 || cfg->model >= SMCB_NUM_MODELS) return fail(SMCB_EUNSUPPORTED, "unknown model id (only the compiled zoo is supported; there is no CPU fallback)");
+  if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS) return fail(SMCB_EUNSUPPORTED, "unknown proposal");
+  if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM))
+    return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
+  if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
+  if (cfg->resampler != SMCB_SYSTEMATIC && cfg->resampler != SMCB_MULTINOMIAL) return fail(SMCB_EUNSUPPORTED, "unknown resampler");
+  if (cfg->particles < 1 || cfg->particles >= ((int64_t)1 << 31) - RS_TILE) return fail(SMCB_EINVAL, "particles out of range");
+  if (cfg->resampler == SMCB_MULTINOMIAL && cfg->particles > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");  // torch.multinomial's limit
+  if (cfg->batch < 1) return fail(SMCB_EINVAL, "batch must be >= 1");
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  smcb_filter* f = new smcb_filter();
+  f->cfg = *cfg;
+  f->cfg.params_host = nullptr;
+  f->D = kDims[cfg->model][0];
+  f->OD = kDims[cfg->model][1];
+  f->B = cfg->batch;
+  f->n = cfg->particles;
+  f->tiles_per_col = (int)((f->n + RS_TILE - 1) / RS_TILE);
+  f->ld = (int64_t)f->tiles_per_col * RS_TILE;
+  {
+    const int64_t chunk = ST_NT * ST_VEC;
+    const int64_t nchunks = (f->n + chunk - 1) / chunk;
+    int64_t cap = (148 * 8) / f->B;
+    if (cap < 1) cap = 1;
+    f->iters = (int)((nchunks + cap - 1) / cap);
+    f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);
+  }
+  const size_t cells = (size_t)f->B * f->ld;
+  const int rows = cfg->history_rows > 0 ? cfg->history_rows : 1;
+  f->cfg.history_rows = rows;
+  cudaError_t e = cudaSuccess;
+#define A_(call) if (e == cudaSuccess) e = (call)
+  A_(dalloc(&f->P_dev, (size_t)f->B * SMCB_NPARAM));
+  A_(dalloc(&f->xbuf[0], cells * f->D));
+  A_(dalloc(&f->xbuf[1], cells * f->D));
+  A_(dalloc(&f->lw, cells));
+  A_(dalloc(&f->rw, cells));
+  A_(dalloc(&f->anc, cells));
+  A_(dalloc(&f->prev_inds, cells));
+  A_(dalloc(&f->stats, (size_t)f->B));
+  A_(dalloc(&f->partials, (size_t)f->B * f->blocks_per_col));
+  A_(dalloc(&f->ctrl, (size_t)1));
+  A_(dalloc(&f->tilesum, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->slots, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
+  A_(dalloc(&f->hist_var, (size_t)rows * f->B * f->D));
+  A_(dalloc(&f->hist_ll, (size_t)rows * f->B));
+  A_(dalloc(&f->latest_mean, (size_t)f->B * f->D));
+  A_(dalloc(&f->latest_var, (size_t)f->B * f->D));
+  A_(dalloc(&f->latest_ll, (size_t)f->B));
+  A_(dalloc(&f->ll_total, (size_t)f->B));
+  A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
+  if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
+#undef A_
+  if (e != cudaSuccess) {
+    smcb_filter_destroy(f);
+    return fail(SMCB_ECUDA, std::string("device allocation failed: ") + cudaGetErrorString(e));
+  }
+  int rc = upload_params(f, cfg->params_host, cfg->n_raw_params, cfg->param_cols, 0);
+  if (rc != SMCB_OK) { smcb_filter_destroy(f); return rc; }
+  *out = f;
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_set_params(smcb_filter* f, const float* params_host, int32_t n_raw, int32_t cols, void* stream) {
+  if (!f || !params_host) return fail(SMCB_EINVAL, "null argument");
+  return upload_params(f, params_host, n_raw, cols, (cudaStream_t)stream);
+}
+
+extern "C" int smcb_filter_info(smcb_filter* f, smcb_info* o) {
+  if (!f || !o) return fail(SMCB_EINVAL, "null argument");
+  o->particles = f->n; o->ld = f->ld; o->batch = f->B; o->state_dim = f->D; o->obs_dim = f->OD;
+  o->t = f->t_host; o->history_rows = f->cfg.history_rows; o->kernel_launches = f->launches;
+  Ctrl c;
+  CU(cudaMemcpy(&c, f->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
+  o->slow_tiles = c.slow_tiles;
+  return SMCB_OK;
+}
+
+// ---- kernel dispatch ------------------------------------------------------------------------------------------------------------
+static StepArgs make_args(smcb_filter* f) {
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n = f->n; a.ld = f->ld; a.B = f->B; a.blocks_per_col = f->blocks_per_col; a.iters = f->iters;
+  a.P = f->P_dev; a.xbuf[0] = f->xbuf[0]; a.xbuf[1] = f->xbuf[1]; a.lw = f->lw; a.rw = f->rw;
+  a.anc = f->anc; a.prev_inds = f->prev_inds; a.stats = f->stats; a.partials = f->partials; a.ctrl = f->ctrl;
+  a.eps_in = f->eps_in; a.eps_out = f->eps_out; a.seed = f->cfg.seed;
+  a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
+  a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
+  a.latest_mean = f->latest_mean; a.latest_var = f->latest_var; a.latest_ll = f->latest_ll; a.ll_total = f->ll_total;
+  return a;
+}
+
+#define FOR_MODEL(M, BODY)                                                  \
+  switch (M) {                                                              \
+    case 0: { constexpr int MODEL = 0; BODY; } break;                        \
+    case 1: { constexpr int MODEL = 1; BODY; } break;                        \
+    case 2: { constexpr int MODEL = 2; BODY; } break;                        \
+    case 3: { constexpr int MODEL = 3; BODY; } break;                        \
+  }
+
+template <int MODEL, int PROP>
+static void launch_step_alg(int alg, dim3 g, cudaStream_t s, const StepArgs& a) {
+  if (alg == SMCB_SISR) step_kernel<MODEL, PROP, SMCB_ALG_SISR><<<g, ST_NT, 0, s>>>(a);
+  else step_kernel<MODEL, PROP, SMCB_ALG_APF><<<g, ST_NT, 0, s>>>(a);
+}
+
+static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
+  dim3 g(f->blocks_per_col, f->B);
+  const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
+  switch (f->cfg.model) {
+    case 0: if (prop) launch_step_alg<0, 1>(alg, g, s, a); else launch_step_alg<0, 0>(alg, g, s, a); break;
+    case 1: if (prop) launch_step_alg<1, 1>(alg, g, s, a); else launch_step_alg<1, 0>(alg, g, s, a); break;
+    case 2: launch_step_alg<2, 0>(alg, g, s, a); break;
+    case 3: launch_step_alg<3, 0>(alg, g, s, a); break;
+  }
+  f->launches++;
+}
+
+static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
+  dim3 g(f->blocks_per_col, f->B);
+  const int prop = f->cfg.proposal;
+  switch (f->cfg.model) {
+    case 0: if (prop) preweight_kernel<0, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<0, 0><<<g, ST_NT, 0, s>>>(a); break;
+    case 1: if (prop) preweight_kernel<1, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<1, 0><<<g, ST_NT, 0, s>>>(a); break;
+    case 2: preweight_kernel<2, 0><<<g, ST_NT, 0, s>>>(a); break;
+    case 3: preweight_kernel<3, 0><<<g, ST_NT, 0, s>>>(a); break;
+  }
+  f->launches++;
+}
+
+static void launch_state(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
+  dim3 g(f->blocks_per_col, f->B);
+  FOR_MODEL(f->cfg.model, (state_kernel<MODEL><<<g, ST_NT, 0, s>>>(a)));
+  f->launches++;
+}
+
+static void launch_finalize(smcb_filter* f, StepArgs a, int mode, cudaStream_t s) {
+  a.fin_mode = mode;
+  const bool apf = f->cfg.algorithm == SMCB_APF;
+  if (f->D == 1) {
+    if (apf) finalize_kernel<1, 1, SMCB_ALG_APF><<<f->B, 128, 0, s>>>(a);
+    else finalize_kernel<1, 1, SMCB_ALG_SISR><<<f->B, 128, 0, s>>>(a);
+  } else {
+    if (apf) finalize_kernel<3, 2, SMCB_ALG_APF><<<f->B, 128, 0, s>>>(a);
+    else finalize_kernel<3, 2, SMCB_ALG_SISR><<<f->B, 128, 0, s>>>(a);
+  }
+  f->launches++;
+}
+
+static int push_ctrl(smcb_filter* f, const float* y_dev, cudaStream_t s) {
+  // only the fields the host owns: t, y_base, y_count, y (the device owns ticket/epoch/tile_counter/slow_tiles)
+  struct { int32_t t, y_base, y_count; } head = {f->t_host, f->y_base, f->y_count};
+  CU(cudaMemcpyAsync(f->ctrl, &head, sizeof(head), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync((char*)f->ctrl + offsetof(Ctrl, y), &y_dev, sizeof(y_dev), cudaMemcpyHostToDevice, s));
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_initialize(smcb_filter* f, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  f->t_host = 0; f->folded_for_next = false;
+  const float* ynull = nullptr;
+  f->y_count = 0; f->y_base = 0;
+  int rc = push_ctrl(f, ynull, s);
+  if (rc) return rc;
+  CU(cudaMemsetAsync(f->ll_total, 0, sizeof(float) * f->B, s));
+  CU(cudaMemsetAsync(f->stats, 0, sizeof(ColStats) * f->B, s));
+  StepArgs a = make_args(f);
+  a.sample_x0 = 1;
+  launch_state(f, a, s);
+  launch_finalize(f, a, FIN_STATE, s);
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_refresh_state(smcb_filter* f, int32_t t, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  f->t_host = t; f->folded_for_next = false;
+  struct { int32_t t; } head = {t};
+  CU(cudaMemcpyAsync(f->ctrl, &head, sizeof(head), cudaMemcpyHostToDevice, s));
+  StepArgs a = make_args(f);
+  a.sample_x0 = 0;
+  launch_state(f, a, s);
+  launch_finalize(f, a, FIN_STATE, s);
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, int32_t count, int32_t base_t, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  if (count < 0) return fail(SMCB_EINVAL, "negative count");
+  f->y_base = base_t; f->y_count = count;
+  return push_ctrl(f, y_dev, (cudaStream_t)stream);
+}
+
+// one filter move; `ev` (optional) receives 6 events bracketing the 5 kernel groups
+static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
+  const bool apf = f->cfg.algorithm == SMCB_APF;
+  const int t = f->t_host;
+  if (t - f->y_base < 0 || t - f->y_base >= f->y_count) return fail(SMCB_ESTATE, "no observation set for this move");
+  StepArgs a = make_args(f);
+  if (ev) cudaEventRecord(ev[0], s);
+  if (apf && !f->folded_for_next) {  // apf.py:27-29 evaluated now because the previous move could not fold it
+    launch_preweight(f, a, s);
+    launch_finalize(f, a, FIN_PREWEIGHT, s);
+  }
+  if (ev) cudaEventRecord(ev[1], s);
+  ResampleArgs r;
+  memset(&r, 0, sizeof(r));
+  r.w = apf ? f->rw : f->lw;
+  r.n = f->n; r.ld = f->ld; r.B = f->B; r.tiles_per_col = f->tiles_per_col;
+  r.input_is_w = 0; r.use_rw = apf ? 1 : 0; r.stats = f->stats;
+  r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed;
+  r.tilesum = f->tilesum; r.slots = f->slots; r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
+  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  f->launches++;
+  if (ev) cudaEventRecord(ev[2], s);
+  if (f->cfg.resampler == SMCB_SYSTEMATIC) {
+    systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+    f->launches++;
+  } else {
+    r.c_out = f->cbuf;
+    op_launch_multinomial_after_tilesum(r, f->U_in, f->ld, s);
+    f->launches += 2;
+  }
+  if (ev) cudaEventRecord(ev[3], s);
+  launch_step(f, a, s);
+  if (ev) cudaEventRecord(ev[4], s);
+  launch_finalize(f, a, FIN_STEP, s);
+  if (ev) cudaEventRecord(ev[5], s);
+  f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
+  f->t_host = t + 1;
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  for (int k = 0; k < steps; ++k) {
+    int rc = run_one(f, s, nullptr);
+    if (rc) return rc;
+  }
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_profile(smcb_filter* f, int32_t steps, float* out_ms_host, void* stream) {
+  if (!f || !out_ms_host || steps < 1) return fail(SMCB_EINVAL, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  std::vector<cudaEvent_t> ev((size_t)steps * 6);
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  int rc = SMCB_OK;
+  for (int k = 0; k < steps && rc == SMCB_OK; ++k) rc = run_one(f, s, &ev[(size_t)k * 6]);
+  cudaError_t e2 = cudaStreamSynchronize(s);
+  for (int g = 0; g < 5; ++g) out_ms_host[g] = 0.f;
+  if (rc == SMCB_OK && e2 == cudaSuccess)
+    for (int k = 0; k < steps; ++k)
+      for (int g = 0; g < 5; ++g) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[(size_t)k * 6 + g], ev[(size_t)k * 6 + g + 1]);
+        out_ms_host[g] += ms;
+      }
+  for (auto& e : ev) cudaEventDestroy(e);
+  if (e2 != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e2));
+  return rc;
+}
+
+extern "C" int smcb_filter_batch_filter_host(smcb_filter* f, const float* y_host, int32_t T, float* means_host, float* vars_host,
+                                             float* ll_steps_host, float* ll_total_host, void* stream) {
+  if (!f || !y_host) return fail(SMCB_EINVAL, "null argument");
+  if (T + 1 > f->cfg.history_rows && (means_host || vars_host || ll_steps_host))
+    return fail(SMCB_EINVAL, "history_rows of the handle is smaller than T + 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (f->y_own_cap < T * f->OD) {
+    if (f->y_own) cudaFree(f->y_own);
+    f->y_own = nullptr; f->y_own_cap = 0;
+    CU(cudaMalloc((void**)&f->y_own, sizeof(float) * (size_t)T * f->OD));
+    f->y_own_cap = T * f->OD;
+  }
+  CU(cudaMemcpyAsync(f->y_own, y_host, sizeof(float) * (size_t)T * f->OD, cudaMemcpyHostToDevice, s));
+  int rc = smcb_filter_initialize(f, stream);
+  if (rc) return rc;
+  rc = smcb_filter_set_observations(f, f->y_own, T, 0, stream);
+  if (rc) return rc;
+  rc = smcb_filter_run(f, T, stream);
+  if (rc) return rc;
+  const size_t rows = (size_t)T + 1;
+  if (means_host) CU(cudaMemcpyAsync(means_host, f->hist_mean, sizeof(float) * rows * f->B * f->D, cudaMemcpyDeviceToHost, s));
+  if (vars_host) CU(cudaMemcpyAsync(vars_host, f->hist_var, sizeof(float) * rows * f->B * f->D, cudaMemcpyDeviceToHost, s));
+  if (ll_steps_host) CU(cudaMemcpyAsync(ll_steps_host, f->hist_ll, sizeof(float) * rows * f->B, cudaMemcpyDeviceToHost, s));
+  if (ll_total_host) CU(cudaMemcpyAsync(ll_total_host, f->ll_total, sizeof(float) * f->B, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_set_noise(smcb_filter* f, const float* eps_dev, const float* u_dev, const double* U_dev) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  f->eps_in = eps_dev; f->u_in = u_dev; f->U_in = U_dev;
+  return SMCB_OK;
+}
+extern "C" int smcb_filter_dump_noise(smcb_filter* f, float* eps_dev, float* u_dev, float* w_dev) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  f->eps_out = eps_dev; f->u_out = u_dev; f->w_out = w_dev;
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_ptr(smcb_filter* f, int32_t what, void** p) {
+  if (!f || !p) return fail(SMCB_EINVAL, "null argument");
+  switch (what) {
+    case SMCB_PTR_X: *p = f->xbuf[f->t_host & 1]; break;
+    case SMCB_PTR_X_OTHER: *p = f->xbuf[(f->t_host + 1) & 1]; break;
+    case SMCB_PTR_LOGW: *p = f->lw; break;
+    case SMCB_PTR_PREV_INDS: *p = f->prev_inds; break;
+    case SMCB_PTR_MEAN: *p = f->latest_mean; break;
+    case SMCB_PTR_VAR: *p = f->latest_var; break;
+    case SMCB_PTR_LL: *p = f->latest_ll; break;
+    case SMCB_PTR_LL_TOTAL: *p = f->ll_total; break;
+    case SMCB_PTR_HIST_MEAN: *p = f->hist_mean; break;
+    case SMCB_PTR_HIST_VAR: *p = f->hist_var; break;
+    case SMCB_PTR_HIST_LL: *p = f->hist_ll; break;
+    case SMCB_PTR_ESS: *p = f->ess_packed; break;
+    default: return fail(SMCB_EINVAL, "unknown pointer id");
+  }
+  return SMCB_OK;
+}
+
+__global__ void pack_stats_kernel(const ColStats* st, float* out, int B) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) { out[b] = st[b].ess; out[B + b] = (float)st[b].resample; }
+}
+extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  pack_stats_kernel<<<(f->B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(f->stats, f->ess_packed, f->B);
+  f->launches++;
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+// ---- stand-alone operators ---------------------------------------------------------------------------------------------------------
+struct OpWorkspace {
+  float* w = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; TileSlot* slots = nullptr; Ctrl* ctrl = nullptr;
+  ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
+  int64_t ld = 0; int tiles = 0, nblk = 0;
+};
+
+static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
+  ws.tiles = (int)((n + RS_TILE - 1) / RS_TILE);
+  ws.ld = (int64_t)ws.tiles * RS_TILE;
+  ws.nblk = ws.tiles;
+  const size_t cells = (size_t)B * ws.ld;
+  CU(cudaMallocAsync((void**)&ws.w, cells * sizeof(float), s));
+  CU(cudaMallocAsync((void**)&ws.anc, cells * sizeof(int32_t), s));
+  CU(cudaMallocAsync((void**)&ws.tilesum, (size_t)B * ws.tiles * sizeof(double), s));
+  CU(cudaMallocAsync((void**)&ws.slots, (size_t)B * ws.tiles * sizeof(TileSlot), s));
+  CU(cudaMallocAsync((void**)&ws.ctrl, sizeof(Ctrl), s));
+  CU(cudaMallocAsync((void**)&ws.stats, (size_t)B * sizeof(ColStats), s));
+  CU(cudaMallocAsync((void**)&ws.parts, (size_t)B * ws.nblk * sizeof(NormPartial), s));
+  CU(cudaMemsetAsync(ws.w, 0, cells * sizeof(float), s));
+  CU(cudaMemsetAsync(ws.slots, 0, (size_t)B * ws.tiles * sizeof(TileSlot), s));
+  CU(cudaMemsetAsync(ws.ctrl, 0, sizeof(Ctrl), s));
+  CU(cudaMemsetAsync(ws.stats, 0, (size_t)B * sizeof(ColStats), s));
+  return SMCB_OK;
+}
+static void op_free(OpWorkspace& ws, cudaStream_t s) {
+  void* ptrs[] = {ws.w, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf};
+  for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
+}
+
+static int op_prepare(OpWorkspace& ws, const float* w_dev, int64_t n, int B, int64_t sn, int64_t sb, bool need_stats, cudaStream_t s) {
+  int rc = op_alloc(ws, n, B, s);
+  if (rc) return rc;
+  op_launch_gather_rows(w_dev, n, B, sn, sb, ws.w, ws.ld, s);
+  if (need_stats) op_launch_colstats(ws.w, n, B, ws.ld, ws.nblk, ws.parts, ws.stats, s);
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_normalize(const float* logw_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, float* out_dev, int64_t osn,
+                              int64_t osb, float* ess_out_dev, void* stream) {
+  if (!logw_dev || n < 1 || B < 1) return fail(SMCB_EINVAL, "bad argument");
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  cudaStream_t s = (cudaStream_t)stream;
+  OpWorkspace ws;
+  int rc = op_prepare(ws, logw_dev, n, B, sn, sb, true, s);
+  if (rc == SMCB_OK) {
+    if (out_dev) op_launch_apply_weights(ws.w, ws.stats, n, B, ws.ld, out_dev, osn, osb, s);
+    if (ess_out_dev) op_launch_copy_ess(ws.stats, ess_out_dev, B, s);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
+  }
+  op_free(ws, s);
+  return rc;
+}
+
+static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized, const float* u_dev,
+                       const double* U_dev, uint64_t seed, int64_t* out_dev, int64_t osn, int64_t osb, int kind, cudaStream_t s) {
+  if (!w_dev || !out_dev || n < 1 || B < 1) return fail(SMCB_EINVAL, "bad argument");
+  if (n >= ((int64_t)1 << 31) - RS_TILE) return fail(SMCB_EINVAL, "too many particles");
+  if (kind == SMCB_MULTINOMIAL && n > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  OpWorkspace ws;
+  int rc = op_prepare(ws, w_dev, n, B, sn, sb, !normalized, s);
+  if (rc == SMCB_OK) {
+    ResampleArgs r;
+    memset(&r, 0, sizeof(r));
+    r.w = ws.w; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
+    r.input_is_w = normalized ? 1 : 0; r.use_rw = 0; r.stats = normalized ? nullptr : ws.stats;
+    r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.slots = ws.slots; r.anc = ws.anc; r.ctrl = ws.ctrl;
+    if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
+    else {
+      cudaError_t e = cudaMallocAsync((void**)&ws.cbuf, (size_t)B * ws.ld * sizeof(float), s);
+      if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
+      r.c_out = ws.cbuf;
+      if (rc == SMCB_OK) rc = op_launch_multinomial(r, U_dev, n, s);
+    }
+    if (rc == SMCB_OK) {
+      op_launch_scatter_i64(ws.anc, n, B, ws.ld, out_dev, osn, osb, s);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
+    }
+  }
+  op_free(ws, s);
+  return rc;
+}
+
+extern "C" int smcb_systematic(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized,
+                               const float* u_dev, uint64_t seed, int64_t* out_dev, int64_t osn, int64_t osb, void* stream) {
+  return op_resample(w_dev, n, B, sn, sb, normalized, u_dev, nullptr, seed, out_dev, osn, osb, SMCB_SYSTEMATIC, (cudaStream_t)stream);
+}
+extern "C" int smcb_multinomial(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized,
+                                const double* U_dev, uint64_t seed, int64_t* out_dev, int64_t osn, int64_t osb, void* stream) {
+  return op_resample(w_dev, n, B, sn, sb, normalized, nullptr, U_dev, seed, out_dev, osn, osb, SMCB_MULTINOMIAL, (cudaStream_t)stream);
+}

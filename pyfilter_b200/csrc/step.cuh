@@ -1,0 +1,569 @@
+// The fused per-time-step kernels of the particle filter (reference filters/particle/{sisr,apf}.py, proposals/{bootstrap,linear}.py).
+//
+//   state_kernel      draws x_0 (or takes the caller's state) and produces the soft-max partials of the log-weights
+//   preweight_kernel  APF look-ahead weights  rw = lw + log p(y_t | .)  when they were not folded into the previous step
+//   step_kernel       ancestor gather -> transition / proposal sample -> observation log-density -> APF correction ->
+//                     128-bit stores of x_t and the log-weight, plus per-block partials for every reduction the step needs
+//                     (normalisers, ESS, log-likelihood increment, filter mean and variance)
+//   finalize_kernel   one block per column folds the partials into ColStats + the moment / likelihood history
+// Layout: state is SoA  x[dim][column][particle]  (pitch ld), weights  lw[column][particle]; one thread owns 4 consecutive
+// particles of one column so every global access except the ancestor gather is a coalesced 128-bit transaction.
+#pragma once
+#include "common.cuh"
+#include "philox.h"
+
+#define ST_NT 256
+#define ST_VEC 4
+
+struct StepArgs {
+  int64_t n, ld;
+  int32_t B, blocks_per_col, iters;  // every block runs `iters` strided chunks of ST_NT*ST_VEC particles
+  const float* P;                    // (B, SMCB_NPARAM)
+  float* xbuf[2];                    // ping-pong state buffers, each (D, B, ld); the live one is xbuf[ctrl->t & 1]
+  float* lw;                         // (B, ld)
+  float* rw;                         // (B, ld)
+  const int32_t* anc;                // (B, ld)
+  int32_t* prev_inds;                // (B, ld) ancestors of the latest move as the API reports them (sisr.py:32 / apf.py:46)
+  ColStats* stats;                   // (B)
+  Partial* partials;                 // (B, blocks_per_col)
+  Ctrl* ctrl;
+  const float* eps_in;               // optional injected N(0,1) draws (D, B, ld)
+  float* eps_out;                    // optional dump of the draws used
+  uint64_t seed;
+  int32_t fold;                      // APF: fold the next look-ahead weight into rw when y_{t+1} is known
+  int32_t store_lw;                  // also store lw_t when folding (API-visible weights)
+  int32_t sample_x0;                 // state_kernel: draw x_0 from the initial distribution
+  float ess_threshold;               // relative threshold (filters/particle/base.py:42)
+  // history (finalize)
+  float* hist_mean; float* hist_var; float* hist_ll;  // (rows, B, D), (rows, B, D), (rows, B)
+  int32_t hist_rows;
+  float* latest_mean; float* latest_var; float* latest_ll; float* ll_total;  // (B, D), (B, D), (B), (B)
+  int32_t fin_mode;
+};
+enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
+
+// ---- soft-max accumulators ---------------------------------------------------------------------------------------------
+template <int K>
+struct SoftAcc {  // running max m and K sums of exp(v - m) * payload
+  float m;
+  float s[K];
+  __device__ __forceinline__ void init() {
+    m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = 0.f;
+  }
+  __device__ __forceinline__ float raise(float nm) {  // make `nm` the reference point; returns exp(old - new)
+    float sc = 1.f;
+    if (nm > m) {
+      sc = (m == -INFINITY) ? 0.f : __expf(m - nm);
+#pragma unroll
+      for (int k = 0; k < K; ++k) s[k] *= sc;
+      m = nm;
+    }
+    return sc;
+  }
+  __device__ __forceinline__ void merge(const SoftAcc& o) {
+    float nm = fmaxf(m, o.m);
+    float sa = (m == -INFINITY) ? 0.f : __expf(m - nm);
+    float sb = (o.m == -INFINITY) ? 0.f : __expf(o.m - nm);
+#pragma unroll
+    for (int k = 0; k < K; ++k) s[k] = s[k] * sa + o.s[k] * sb;
+    m = nm;
+  }
+};
+
+template <int K>
+__device__ __forceinline__ SoftAcc<K> softacc_shfl_xor(const SoftAcc<K>& a, int o) {
+  SoftAcc<K> r;
+  r.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+#pragma unroll
+  for (int k = 0; k < K; ++k) r.s[k] = __shfl_xor_sync(0xffffffffu, a.s[k], o);
+  return r;
+}
+
+// block-wide merge; the result is valid in thread 0.  `scratch` holds (NT/32) records.
+template <int K>
+__device__ __forceinline__ void softacc_block_reduce(SoftAcc<K>& a, SoftAcc<K>* scratch) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) a.merge(softacc_shfl_xor(a, o));
+  __syncthreads();
+  if (lane == 0) scratch[wid] = a;
+  __syncthreads();
+  if (wid == 0) {
+    SoftAcc<K> r;
+    if (lane < ST_NT / 32) r = scratch[lane]; else r.init();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) r.merge(softacc_shfl_xor(r, o));
+    a = r;
+  }
+}
+
+// set 1 over lw: [0] sum e, [1..D] sum e (x - shift), [D+1..2D] sum e (x - shift)^2 ; sum e^2 kept apart (scales with sc^2)
+template <int D>
+struct Moments {
+  SoftAcc<1 + 2 * D> a;
+  SoftAcc<1> q;  // reference point 2*m: sum e^2 = sum exp(2 lw - 2 m)
+  __device__ __forceinline__ void init() { a.init(); q.init(); }
+  __device__ __forceinline__ void add4(const float (&lw)[4], const float (&x)[D][4], const float* shift, const bool (&valid)[4]) {
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (valid[k]) mx = fmaxf(mx, lw[k]);
+    if (mx == -INFINITY) return;
+    a.raise(mx);
+    q.raise(2.f * mx);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (!valid[k]) continue;
+      float e = __expf(lw[k] - a.m);
+      a.s[0] += e;
+      q.s[0] += e * e;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        float c = x[d][k] - shift[d];
+        a.s[1 + d] += e * c;
+        a.s[1 + D + d] += e * c * c;
+      }
+    }
+  }
+};
+
+// ---- proposals -------------------------------------------------------------------------------------------------------------
+// Everything the step needs from one particle: new state, weight increment log p(y|x') (+ proposal correction), and the
+// look-ahead weight of the ancestor that the APF subtracts (apf.py:43) - recomputed from the gathered ancestor state.
+template <int MODEL, int PROP>
+struct Proposal;
+
+template <int MODEL>
+struct Proposal<MODEL, SMCB_PROPOSAL_BOOTSTRAP> {
+  typedef Model<MODEL> M;
+  // proposals/base.py:69-85 + pre_weight_funcs.py:9-11:  log p(y | loc(x))
+  __device__ static __forceinline__ float pre_weight(const float* y, const float* x, const float* P) {
+    float loc[M::D], sc;
+    M::loc_scale(x, P, loc, sc);
+    return M::obs_lp(y, loc, P);
+  }
+  // proposals/bootstrap.py:10-14
+  __device__ static __forceinline__ void sample_and_weight(const float* y, const float* xa, const float* z, const float* P,
+                                                           bool observed, float* xn, float& inc, float& g_anc) {
+    float loc[M::D], sc;
+    M::loc_scale(xa, P, loc, sc);
+#pragma unroll
+    for (int d = 0; d < M::D; ++d) xn[d] = __fadd_rn(loc[d], __fmul_rn(sc, __fmul_rn(z[d], P[P_INC_SCALE])));
+    inc = 0.f; g_anc = 0.f;
+    if (observed) {
+      inc = M::obs_lp(y, xn, P);
+      g_anc = M::obs_lp(y, loc, P);
+    }
+  }
+};
+
+template <int MODEL>
+struct Proposal<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS> {
+  typedef Model<MODEL> M;
+  static_assert(M::LINEAR_OBS && M::D == 1, "LinearGaussianObservations needs y = b + a x + s nu with a scalar state");
+  // proposals/linear.py:57-86: log N(y; b + a x_{t-1}, sqrt(s^2 + a^2 sigma^2))   (centred on the previous state)
+  __device__ static __forceinline__ float pre_weight(const float* y, const float* x, const float* P) {
+    return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_LGO_PRE_INV2VAR], P[P_LGO_PRE_LOGNORM]);
+  }
+  // proposals/linear.py:38-55, proposals/utils.py:219-267, proposals/base.py:45-50
+  __device__ static __forceinline__ void sample_and_weight(const float* y, const float* xa, const float* z, const float* P,
+                                                           bool observed, float* xn, float& inc, float& g_anc) {
+    float m[1], sc;
+    M::loc_scale(xa, P, m, sc);
+    inc = 0.f; g_anc = 0.f;
+    if (!observed) {  // particle/state.py:38-42: missing observations propagate through the dynamics
+      xn[0] = __fadd_rn(m[0], __fmul_rn(sc, __fmul_rn(z[0], P[P_INC_SCALE])));
+      return;
+    }
+    float t1 = __fmul_rn(P[P_LGO_HVI], m[0]);
+    float t3 = __fmul_rn(P[P_OBS_A], __fmul_rn(P[P_LGO_OVI], __fsub_rn(y[0], P[P_OBS_B])));
+    float k = __fmul_rn(P[P_LGO_COV], __fadd_rn(t1, t3));
+    xn[0] = __fadd_rn(__fmul_rn(z[0], P[P_LGO_KSTD]), k);
+    float y_lp = M::obs_lp(y, xn, P);
+    float e = __fmul_rn(__fsub_rn(xn[0], m[0]), P[P_LGO_INV_SIGMA]);
+    float x_lp = smcb_normal_lp(e, 0.f, P[P_LGO_INC_INV2VAR], P[P_LGO_INC_LOGNORM]);
+    float k_lp = smcb_normal_lp(xn[0], k, P[P_LGO_K_INV2VAR], P[P_LGO_K_LOGNORM]);
+    inc = __fsub_rn(__fadd_rn(y_lp, x_lp), k_lp);
+    g_anc = pre_weight(y, xa, P);
+  }
+};
+
+// ---- helpers -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ const float* st_obs(const Ctrl* c, int t, int od) {
+  int k = t - c->y_base;
+  return (c->y && k >= 0 && k < c->y_count) ? c->y + (int64_t)k * od : nullptr;
+}
+template <int OD>
+__device__ __forceinline__ bool st_load_obs(const float* p, float* y) {  // false when missing or all-NaN (filters/base.py:213)
+  if (!p) return false;
+  bool all_nan = true;
+#pragma unroll
+  for (int d = 0; d < OD; ++d) { y[d] = p[d]; all_nan = all_nan && (y[d] != y[d]); }
+  return !all_nan;
+}
+
+template <int D>
+__device__ __forceinline__ void st_noise4(const StepArgs& a, int col, int64_t i0, int t, uint32_t purpose, float (&z)[D][4]) {
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    if (a.eps_in) {
+      const float4 q = *reinterpret_cast<const float4*>(a.eps_in + ((int64_t)d * a.B + col) * a.ld + i0);
+      z[d][0] = q.x; z[d][1] = q.y; z[d][2] = q.z; z[d][3] = q.w;
+    } else {
+      Philox4 r = philox4x32_10((uint32_t)(i0 >> 2), (uint32_t)col, (uint32_t)t, purpose + d, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      smcb_normal4(r, z[d]);
+    }
+    if (a.eps_out)
+      *reinterpret_cast<float4*>(a.eps_out + ((int64_t)d * a.B + col) * a.ld + i0) = make_float4(z[d][0], z[d][1], z[d][2], z[d][3]);
+  }
+}
+
+__device__ __forceinline__ void st_write_partial1(Partial& p, const SoftAcc<3>& a, const SoftAcc<1>& q) {
+  p.m1 = a.m; p.z1 = a.s[0]; p.sx[0] = a.s[1]; p.sxx[0] = a.s[2]; p.sx[1] = p.sx[2] = p.sxx[1] = p.sxx[2] = 0.f;
+  // q holds sum exp(2 lw - q.m) with q.m == 2 a.m up to rounding; express it relative to 2*m1
+  p.zz1 = (q.m == -INFINITY) ? 0.f : q.s[0] * __expf(q.m - 2.f * a.m);
+}
+__device__ __forceinline__ void st_write_partial1(Partial& p, const SoftAcc<7>& a, const SoftAcc<1>& q) {
+  p.m1 = a.m; p.z1 = a.s[0];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) { p.sx[d] = a.s[1 + d]; p.sxx[d] = a.s[4 + d]; }
+  p.zz1 = (q.m == -INFINITY) ? 0.f : q.s[0] * __expf(q.m - 2.f * a.m);
+}
+
+// ---- state kernel: x_0 ~ p_0 (filters/particle/base.py:87-103) or a caller-supplied state; partials of lw --------------------
+template <int MODEL>
+__global__ void __launch_bounds__(ST_NT) state_kernel(StepArgs a) {
+  typedef Model<MODEL> M;
+  constexpr int D = M::D;
+  __shared__ float Ps[SMCB_NPARAM];
+  __shared__ SoftAcc<1 + 2 * D> sA[ST_NT / 32];
+  __shared__ SoftAcc<1> sQ[ST_NT / 32];
+  const int col = blockIdx.y, tid = threadIdx.x;
+  if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
+  __syncthreads();
+  const int t = a.ctrl->t;
+  float* xcur = a.xbuf[t & 1];
+  float shift[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) shift[d] = a.sample_x0 ? Ps[P_X0_LOC + d] : a.stats[col].shift[d];
+  Moments<D> mom; mom.init();
+  for (int it = 0; it < a.iters; ++it) {
+    const int64_t i0 = ((int64_t)(it * a.blocks_per_col + blockIdx.x) * ST_NT + tid) * ST_VEC;
+    if (i0 >= a.n) continue;
+    float x[D][4], lw[4];
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = i0 + k < a.n;
+    if (a.sample_x0) {
+      float z[D][4];
+      st_noise4<D>(a, col, i0, 0, SMCB_RNG_INIT, z);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[d][k] = __fadd_rn(Ps[P_X0_LOC + d], __fmul_rn(Ps[P_X0_SCALE + d], z[d][k]));
+        *reinterpret_cast<float4*>(xcur + ((int64_t)d * a.B + col) * a.ld + i0) = make_float4(x[d][0], x[d][1], x[d][2], x[d][3]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lw[k] = 0.f;
+      *reinterpret_cast<float4*>(a.lw + (int64_t)col * a.ld + i0) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<int4*>(a.prev_inds + (int64_t)col * a.ld + i0) = make_int4((int)i0, (int)i0 + 1, (int)i0 + 2, (int)i0 + 3);
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float4 q = *reinterpret_cast<const float4*>(xcur + ((int64_t)d * a.B + col) * a.ld + i0);
+        x[d][0] = q.x; x[d][1] = q.y; x[d][2] = q.z; x[d][3] = q.w;
+      }
+      float4 q = *reinterpret_cast<const float4*>(a.lw + (int64_t)col * a.ld + i0);
+      lw[0] = smcb_sanitize(q.x); lw[1] = smcb_sanitize(q.y); lw[2] = smcb_sanitize(q.z); lw[3] = smcb_sanitize(q.w);
+      *reinterpret_cast<float4*>(a.lw + (int64_t)col * a.ld + i0) = make_float4(lw[0], lw[1], lw[2], lw[3]);  // utils.py:57 mutates
+    }
+    mom.add4(lw, x, shift, valid);
+  }
+  softacc_block_reduce(mom.a, sA);
+  softacc_block_reduce(mom.q, sQ);
+  if (tid == 0) {
+    Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
+    st_write_partial1(p, mom.a, mom.q);
+    p.m2 = p.m3 = -INFINITY; p.z2 = p.z3 = 0.f;
+  }
+}
+
+// ---- APF look-ahead weights when not folded: rw = lw + log p(y_t | .)  (apf.py:27-29) ----------------------------------------
+template <int MODEL, int PROP>
+__global__ void __launch_bounds__(ST_NT) preweight_kernel(StepArgs a) {
+  typedef Model<MODEL> M;
+  constexpr int D = M::D, OD = M::OD;
+  __shared__ float Ps[SMCB_NPARAM];
+  __shared__ SoftAcc<1> sR[ST_NT / 32];
+  const int col = blockIdx.y, tid = threadIdx.x;
+  if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
+  __syncthreads();
+  const int t = a.ctrl->t;
+  float y[OD];
+  const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+  const float* xcur = a.xbuf[t & 1];
+  SoftAcc<1> r2; r2.init();
+  if (observed) {
+    for (int it = 0; it < a.iters; ++it) {
+      const int64_t i0 = ((int64_t)(it * a.blocks_per_col + blockIdx.x) * ST_NT + tid) * ST_VEC;
+      if (i0 >= a.n) continue;
+      float x[D][4];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float4 q = *reinterpret_cast<const float4*>(xcur + ((int64_t)d * a.B + col) * a.ld + i0);
+        x[d][0] = q.x; x[d][1] = q.y; x[d][2] = q.z; x[d][3] = q.w;
+      }
+      const float4 l = *reinterpret_cast<const float4*>(a.lw + (int64_t)col * a.ld + i0);
+      float lw[4] = {l.x, l.y, l.z, l.w}, rw[4];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float xs[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xs[d] = x[d][k];
+        rw[k] = smcb_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(y, xs, Ps), lw[k]));
+        if (i0 + k < a.n) mx = fmaxf(mx, rw[k]);
+      }
+      *reinterpret_cast<float4*>(a.rw + (int64_t)col * a.ld + i0) = make_float4(rw[0], rw[1], rw[2], rw[3]);
+      if (mx > -INFINITY) {
+        r2.raise(mx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (i0 + k < a.n) r2.s[0] += __expf(rw[k] - r2.m);
+      }
+    }
+  }
+  softacc_block_reduce(r2, sR);
+  if (tid == 0) {
+    Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
+    p.m2 = r2.m; p.z2 = r2.s[0];
+  }
+}
+
+// ---- the fused step ----------------------------------------------------------------------------------------------------------
+template <int MODEL, int PROP, int ALG>
+__global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
+  typedef Model<MODEL> M;
+  constexpr int D = M::D, OD = M::OD;
+  __shared__ float Ps[SMCB_NPARAM];
+  __shared__ SoftAcc<1 + 2 * D> sA[ST_NT / 32];
+  __shared__ SoftAcc<1> sQ[ST_NT / 32];
+  const int col = blockIdx.y, tid = threadIdx.x;
+  if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
+  __syncthreads();
+  const int t = a.ctrl->t;
+  float y[OD], yn[OD];
+  const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+  const bool fold = (ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
+  const ColStats st = a.stats[col];
+  // SISR resamples when the ESS test fired (sisr.py:19-26), the APF on every observed step (apf.py:29-34, filters/base.py:213)
+  const bool resampled = (ALG == SMCB_ALG_APF) ? observed : (st.resample != 0);
+  const float* xprev = a.xbuf[t & 1];
+  float* xnext = a.xbuf[(t + 1) & 1];
+  const float inv_n = 1.0f / (float)a.n;
+  float shift[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) shift[d] = st.shift[d];
+
+  Moments<D> mom; mom.init();
+  SoftAcc<1> r2; r2.init();   // APF: folded resampling weights
+  SoftAcc<1> r3; r3.init();   // SISR: likelihood increment
+
+  for (int it = 0; it < a.iters; ++it) {
+    const int64_t i0 = ((int64_t)(it * a.blocks_per_col + blockIdx.x) * ST_NT + tid) * ST_VEC;
+    if (i0 >= a.n) continue;
+    const int64_t row = (int64_t)col * a.ld + i0;
+    int anc[4] = {(int)i0, (int)i0 + 1, (int)i0 + 2, (int)i0 + 3};
+    bool valid[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid[k] = i0 + k < a.n;
+    if (resampled) {
+      const int4 q = *reinterpret_cast<const int4*>(a.anc + row);
+      anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (!valid[k]) anc[k] = 0;
+      *reinterpret_cast<int4*>(a.prev_inds + row) = q;
+    } else if (ALG == SMCB_ALG_APF) {
+      *reinterpret_cast<int4*>(a.prev_inds + row) = make_int4(anc[0], anc[1], anc[2], anc[3]);  // apf.py:18-23 arange
+    }
+    float lwp[4] = {0.f, 0.f, 0.f, 0.f};
+    if (!resampled) {  // weights carry over (sisr.py:52 without the reset of :34; particle/state.py:42)
+      const float4 q = *reinterpret_cast<const float4*>(a.lw + row);
+      lwp[0] = q.x; lwp[1] = q.y; lwp[2] = q.z; lwp[3] = q.w;
+    }
+    float z[D][4];
+    st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
+
+    float xn[D][4], lwn[4], rwn[4], inc4[4], wprev[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float xa[D], zk[D], xo[D], inc, g_anc;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        xa[d] = __ldg(xprev + ((int64_t)d * a.B + col) * a.ld + anc[k]);
+        zk[d] = z[d][k];
+      }
+      Proposal<MODEL, PROP>::sample_and_weight(y, xa, zk, Ps, observed, xo, inc, g_anc);
+#pragma unroll
+      for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
+      float lw;
+      if (!observed) lw = lwp[k];
+      else if (ALG == SMCB_ALG_APF) lw = __fsub_rn(inc, g_anc);   // apf.py:43
+      else lw = __fadd_rn(inc, lwp[k]);                           // sisr.py:52
+      lwn[k] = smcb_sanitize(lw);
+      inc4[k] = inc;
+      if (ALG == SMCB_ALG_SISR) wprev[k] = resampled ? inv_n : smcb_weight(lwp[k], st.m_lw, st.inv_z_lw);
+      rwn[k] = fold ? smcb_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps), lwn[k])) : lwn[k];
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d)
+      *reinterpret_cast<float4*>(xnext + ((int64_t)d * a.B + col) * a.ld + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
+    if (!fold || a.store_lw) *reinterpret_cast<float4*>(a.lw + row) = make_float4(lwn[0], lwn[1], lwn[2], lwn[3]);
+    if (fold) *reinterpret_cast<float4*>(a.rw + row) = make_float4(rwn[0], rwn[1], rwn[2], rwn[3]);
+
+    mom.add4(lwn, xn, shift, valid);
+    if (fold) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (valid[k]) mx = fmaxf(mx, rwn[k]);
+      if (mx > -INFINITY) {
+        r2.raise(mx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (valid[k]) r2.s[0] += __expf(rwn[k] - r2.m);
+      }
+    }
+    if (ALG == SMCB_ALG_SISR && observed) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (valid[k]) mx = fmaxf(mx, inc4[k]);
+      if (mx > -INFINITY) {
+        r3.raise(mx);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) if (valid[k]) r3.s[0] += wprev[k] * __expf(inc4[k] - r3.m);
+      }
+    }
+  }
+  softacc_block_reduce(mom.a, sA);
+  softacc_block_reduce(mom.q, sQ);
+  softacc_block_reduce(r2, sQ);
+  softacc_block_reduce(r3, sQ);
+  if (tid == 0) {
+    Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
+    st_write_partial1(p, mom.a, mom.q);
+    p.m2 = r2.m; p.z2 = r2.s[0];
+    p.m3 = r3.m; p.z3 = r3.s[0];
+  }
+}
+
+// ---- finalize: one block per column ---------------------------------------------------------------------------------------------
+// FIN_STATE      after state_kernel:      normalisers/ESS/moments of the current weights; history row ctrl->t; no likelihood
+// FIN_PREWEIGHT  after preweight_kernel:  normalisers of rw and the look-ahead term of apf.py:44
+// FIN_STEP       after step_kernel:       everything, history row t+1, running log-likelihood, then t <- t+1
+template <int D, int OD, int ALG>
+__global__ void __launch_bounds__(128) finalize_kernel(StepArgs a) {
+  __shared__ SoftAcc<1 + 2 * D> sA[4];
+  __shared__ SoftAcc<1> sQ[4];
+  const int col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int t = a.ctrl->t;
+  const int mode = a.fin_mode;
+  SoftAcc<1 + 2 * D> A; A.init();
+  SoftAcc<1> Q, R2, R3; Q.init(); R2.init(); R3.init();
+  for (int b = tid; b < a.blocks_per_col; b += 128) {
+    const Partial p = a.partials[(int64_t)col * a.blocks_per_col + b];
+    SoftAcc<1 + 2 * D> o; o.m = p.m1; o.s[0] = p.z1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { o.s[1 + d] = p.sx[d]; o.s[1 + D + d] = p.sxx[d]; }
+    SoftAcc<1> q; q.m = (p.m1 == -INFINITY) ? -INFINITY : 2.f * p.m1; q.s[0] = p.zz1;
+    SoftAcc<1> o2; o2.m = p.m2; o2.s[0] = p.z2;
+    SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
+    A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
+  }
+  // block merge (4 warps)
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { A.merge(softacc_shfl_xor(A, o)); Q.merge(softacc_shfl_xor(Q, o)); }
+  if (lane == 0) { sA[wid] = A; sQ[wid] = Q; }
+  __syncthreads();
+  if (tid == 0) for (int w = 1; w < 4; ++w) { A.merge(sA[w]); Q.merge(sQ[w]); }
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { R2.merge(softacc_shfl_xor(R2, o)); R3.merge(softacc_shfl_xor(R3, o)); }
+  if (lane == 0) { sQ[wid] = R2; }
+  __syncthreads();
+  if (tid == 0) for (int w = 1; w < 4; ++w) R2.merge(sQ[w]);
+  __syncthreads();
+  if (lane == 0) { sQ[wid] = R3; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; ++w) R3.merge(sQ[w]);
+    ColStats st = a.stats[col];
+    const float nf = (float)a.n;
+    if (mode == FIN_PREWEIGHT) {
+      float y[OD];
+      const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      if (observed) {
+        st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
+        st.ll_aux = logf(R2.s[0]) + (R2.m - st.m_lw) - logf(st.z_lw);   // log sum W exp(g), W = softmax(lw)
+      }
+      st.resample = observed ? 1 : 0;
+      st.fold_valid = 1;
+      a.stats[col] = st;
+    } else {
+      float y[OD];
+      const bool observed = (mode == FIN_STEP) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      const float ll_aux_prev = st.ll_aux;
+      st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
+      // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
+      const float zz = (Q.m == -INFINITY) ? 0.f : Q.s[0] * __expf(Q.m - 2.f * A.m);
+      st.ess = (A.s[0] * A.s[0]) / zz;
+      float mean[D], var[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float dm = A.s[1 + d] * st.inv_z_lw;            // E[x - shift]
+        mean[d] = st.shift[d] + dm;
+        var[d] = fmaxf(A.s[1 + D + d] * st.inv_z_lw - dm * dm, 0.f);
+      }
+      float ll = 0.f;
+      if (mode == FIN_STEP && observed) {
+        if (ALG == SMCB_ALG_SISR) ll = R3.m + logf(R3.s[0]);                       // filters/particle/utils.py:16-22
+        else ll = (A.m + logf(A.s[0]) - logf(nf)) + ll_aux_prev;                   // apf.py:44
+      }
+      // next step's resampling decision and (APF) folded normalisers
+      st.fold_valid = 0;
+      if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
+      else {
+        st.resample = 1;
+        float yn[OD];
+        const bool fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
+        if (fold) {
+          st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
+          st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
+          st.fold_valid = 1;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) st.shift[d] = mean[d];
+      a.stats[col] = st;
+      const int rowi = (mode == FIN_STEP) ? t + 1 : t;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        a.latest_mean[col * D + d] = mean[d];
+        a.latest_var[col * D + d] = var[d];
+        if (a.hist_mean && rowi < a.hist_rows) {
+          a.hist_mean[((int64_t)rowi * a.B + col) * D + d] = mean[d];
+          a.hist_var[((int64_t)rowi * a.B + col) * D + d] = var[d];
+        }
+      }
+      a.latest_ll[col] = ll;
+      if (mode == FIN_STEP) a.ll_total[col] += ll;
+      if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
+    }
+    if (mode == FIN_STEP) {
+      __threadfence();
+      const int done = atomicAdd(&a.ctrl->ticket, 1);
+      if (done == (int)gridDim.x - 1) {   // every block has read ctrl->t: safe to advance the clock
+        a.ctrl->ticket = 0;
+        a.ctrl->t = t + 1;
+      }
+    }
+  }
+}

@@ -1,0 +1,143 @@
+"""Python owner of one ``smcb_filter`` handle (C ABI, include/smcb200.h): device buffers, views, the time loop."""
+import ctypes as C
+
+import torch
+
+from ... import _lib
+from ...timeseries import StateSpaceModel, TimeseriesState
+
+
+class Engine:
+    def __init__(self, model: StateSpaceModel, proposal_id: int, algorithm_id: int, resampler_id: int, particles: int,
+                 batch_shape: torch.Size, ess_threshold: float, seed: int, history_rows: int, fold_lookahead: bool = True):
+        _lib.require_cuda()
+        self.lib = _lib.load_library()
+        self.model = model
+        self.batch_shape = torch.Size(batch_shape)
+        self.B = int(self.batch_shape[0]) if len(self.batch_shape) else 1
+        self.N = int(particles)
+        params = model.parameter_matrix(self.B)
+        cfg = _lib.smcb_config()
+        cfg.model, cfg.proposal, cfg.algorithm, cfg.resampler = model.model_id, proposal_id, algorithm_id, resampler_id
+        cfg.particles, cfg.batch = self.N, self.B
+        cfg.n_raw_params, cfg.param_cols = params.shape[0], params.shape[1]
+        cfg.params_host = params.data_ptr() and C.cast(params.data_ptr(), C.POINTER(C.c_float))
+        cfg.ess_threshold = float(ess_threshold)
+        cfg.seed = int(seed) & (2**64 - 1)
+        cfg.history_rows = int(history_rows)
+        cfg.fold_lookahead = int(bool(fold_lookahead))
+        cfg.exact_scan = 1
+        self._params_keepalive = params
+        h = C.c_void_p()
+        _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)))
+        self.handle = h
+        info = self.info()
+        self.ld, self.D, self.OD, self.history_rows = info.ld, info.state_dim, info.obs_dim, info.history_rows
+        self.event_shape = model.hidden.event_shape
+        self.stamp = 0  # bumps on every mutation of the device state; live state objects carry the stamp they were made at
+        self.t = 0
+        self._keep = []
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            try:
+                self.lib.smcb_filter_destroy(h)
+            except Exception:
+                pass
+            self.handle = None
+
+    # ---- raw access
+    def info(self):
+        out = _lib.smcb_info()
+        _lib.check(self.lib.smcb_filter_info(self.handle, C.byref(out)))
+        return out
+
+    def _ptr(self, what: int) -> int:
+        p = C.c_void_p()
+        _lib.check(self.lib.smcb_filter_ptr(self.handle, what, C.byref(p)))
+        return p.value
+
+    def raw(self, what: int, shape, typestr="<f4"):
+        return _lib.as_tensor(self._ptr(what), shape, typestr, self)
+
+    def _squeeze_batch(self, t: torch.Tensor, batch_dim: int):
+        return t.select(batch_dim, 0) if len(self.batch_shape) == 0 else t
+
+    def x_view(self) -> torch.Tensor:
+        """Particles in the reference's layout ``(N, [B], [d])`` - a strided view of the SoA device buffer ``(D, B, ld)``."""
+        v = self.raw(_lib.PTR_X, (self.D, self.B, self.ld))[:, :, : self.N].permute(2, 1, 0)
+        if len(self.event_shape) == 0:
+            v = v[..., 0]
+        return self._squeeze_batch(v, 1)
+
+    def logw_view(self) -> torch.Tensor:
+        return self._squeeze_batch(self.raw(_lib.PTR_LOGW, (self.B, self.ld))[:, : self.N].t(), 1)
+
+    def prev_inds(self) -> torch.Tensor:
+        v = self.raw(_lib.PTR_PREV_INDS, (self.B, self.ld), "<i4")[:, : self.N].t().long()
+        return self._squeeze_batch(v, 1)
+
+    def small(self, what: int, with_dim: bool) -> torch.Tensor:
+        shape = (self.B, self.D) if with_dim else (self.B,)
+        return self._squeeze_batch(self.raw(what, shape).clone(), 0)
+
+    def history(self, rows: int):
+        m = self.raw(_lib.PTR_HIST_MEAN, (self.history_rows, self.B, self.D))[:rows].clone()
+        v = self.raw(_lib.PTR_HIST_VAR, (self.history_rows, self.B, self.D))[:rows].clone()
+        ll = self.raw(_lib.PTR_HIST_LL, (self.history_rows, self.B))[:rows].clone()
+        if len(self.batch_shape) == 0:
+            m, v, ll = m[:, 0], v[:, 0], ll[:, 0]
+        return m, v, ll
+
+    # ---- operations
+    def initialize(self):
+        _lib.check(self.lib.smcb_filter_initialize(self.handle, _lib.current_stream()))
+        self.t = 0
+        self.stamp += 1
+
+    def load_state(self, x: torch.Tensor, w: torch.Tensor, prev_inds: torch.Tensor, t: int):
+        """``init_state=`` / an external state for ``filter``: copy it into the device buffers and refresh the statistics."""
+        self.t = int(t)
+        # the handle picks the live ping-pong buffer from its move counter: set it before fetching the pointer
+        _lib.check(self.lib.smcb_filter_refresh_state(self.handle, self.t, _lib.current_stream()))
+        self.x_view().copy_(x.to("cuda", torch.float32))
+        self.logw_view().copy_(w.to("cuda", torch.float32))
+        pi = self.raw(_lib.PTR_PREV_INDS, (self.B, self.ld), "<i4")[:, : self.N].t()
+        self._squeeze_batch(pi, 1).copy_(prev_inds.to("cuda", torch.int32))
+        _lib.check(self.lib.smcb_filter_refresh_state(self.handle, self.t, _lib.current_stream()))
+        self.stamp += 1
+
+    def set_observations(self, y_dev: torch.Tensor, base_t: int):
+        assert y_dev.is_cuda and y_dev.dtype == torch.float32 and y_dev.is_contiguous()
+        self._keep = [y_dev]
+        count = y_dev.shape[0]
+        _lib.check(self.lib.smcb_filter_set_observations(self.handle, y_dev.data_ptr(), count, base_t, _lib.current_stream()))
+
+    def run(self, steps: int):
+        _lib.check(self.lib.smcb_filter_run(self.handle, steps, _lib.current_stream()))
+        self.t += steps
+        self.stamp += 1
+
+    def set_noise(self, eps=None, u=None, U=None):
+        self._noise_keep = (eps, u, U)
+        _lib.check(self.lib.smcb_filter_set_noise(self.handle, eps.data_ptr() if eps is not None else None,
+                                                  u.data_ptr() if u is not None else None, U.data_ptr() if U is not None else None))
+
+    def dump_noise(self, eps=None, u=None, w=None):
+        self._dump_keep = (eps, u, w)
+        _lib.check(self.lib.smcb_filter_dump_noise(self.handle, eps.data_ptr() if eps is not None else None,
+                                                   u.data_ptr() if u is not None else None, w.data_ptr() if w is not None else None))
+
+    def ess(self):
+        _lib.check(self.lib.smcb_filter_sync_stats(self.handle, _lib.current_stream()))
+        packed = self.raw(_lib.PTR_ESS, (2, self.B)).clone()
+        return self._squeeze_batch(packed[0], 0), self._squeeze_batch(packed[1], 0)
+
+    def make_state(self):
+        from .state import ParticleFilterCorrection
+
+        x = TimeseriesState(torch.tensor(self.t), self.x_view(), self.event_shape)
+        return ParticleFilterCorrection(x, self.logw_view(), self.small(_lib.PTR_LL, False), self.prev_inds,
+                                        self.small(_lib.PTR_MEAN, True), self.small(_lib.PTR_VAR, True), engine=self,
+                                        stamp=self.stamp)

