@@ -72,6 +72,9 @@ typedef struct smcb_info {
   int32_t history_rows;
   int32_t slow_tiles;     /* exact-scan tiles that needed the sequential fallback so far (diagnostic; synchronises) */
   int64_t kernel_launches;/* kernels launched by this handle so far */
+  int64_t lb_windows;     /* diagnostic: 32-tile look-back windows walked so far */
+  int32_t lb_fail;        /* diagnostic: look-backs that had to wait for their direct predecessor */
+  int32_t reserved;
 } smcb_info;
 
 /* library */

@@ -35,6 +35,7 @@ class smcb_info(C.Structure):
     _fields_ = [
         ("particles", C.c_int64), ("ld", C.c_int64), ("batch", C.c_int32), ("state_dim", C.c_int32), ("obs_dim", C.c_int32),
         ("t", C.c_int32), ("history_rows", C.c_int32), ("slow_tiles", C.c_int32), ("kernel_launches", C.c_int64),
+        ("lb_windows", C.c_int64), ("lb_fail", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

@@ -20,12 +20,14 @@ struct ColStats {
 };
 
 // One record per (column, block) of the step / pre-weight / init kernels: soft-max partials.
-struct Partial {
+struct __align__(16) Partial {  // 64 bytes: read back with 128-bit loads
   float m1, z1, zz1;            // over lw:  max, sum e, sum e^2          (e = exp(lw - m1))
   float sx[3], sxx[3];          // sum e (x - shift), sum e (x - shift)^2
   float m2, z2;                 // over rw (APF look-ahead folded)
   float m3, z3;                 // SISR likelihood increment: max inc, sum W_prev exp(inc - m3)   (filters/particle/utils.py:16-22)
+  float pad[3];
 };
+static_assert(sizeof(Partial) == 64, "Partial must stay 64 bytes");
 
 // Device control block: lets one captured CUDA graph serve every time step (no per-step kernel arguments change).
 struct Ctrl {
@@ -36,8 +38,9 @@ struct Ctrl {
   uint32_t epoch;       // bumped once per resampling launch; tags the look-back slots so they never need clearing
   uint32_t tile_counter;
   int32_t slow_tiles;   // diagnostics: tiles that took the sequential fallback of the exact scan
-  int32_t pad;
+  int32_t lb_fail;      // diagnostics: look-backs that fell back to waiting for the direct predecessor
   const float* y;       // (y_count, OD) observations on device
+  int64_t lb_windows;   // diagnostics: 32-tile windows walked by all look-backs
 };
 
 __device__ __forceinline__ float smcb_sanitize(float w) {

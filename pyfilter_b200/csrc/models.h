@@ -92,7 +92,7 @@ template <> struct Model<SMCB_MODEL_SV_AR1> {
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     // Normal(0, exp(x/2)).log_prob(y) = -y^2 / (2 exp(x)) - x/2 - log sqrt(2 pi)
     float hy2 = __fmul_rn(0.5f, __fmul_rn(y[0], y[0]));
-    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, expf(-x[0])), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
+    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, __expf(-x[0])), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
   }
 };
 

@@ -172,8 +172,8 @@ static inline void op_launch_copy_ess(const ColStats* st, float* out, int B, cud
 
 // ---- systematic ------------------------------------------------------------------------------------------------------------------
 static inline void op_launch_systematic(const ResampleArgs& r, cudaStream_t s) {
-  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
-  systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+  normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
 }
 
 // ---- multinomial (resampling.py:55-65 -> ATen multinomial_with_replacement_kernel on CPU) --------------------------------------------
@@ -214,9 +214,9 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
   }
 }
 
-// r.c_out must point at a (B, ld) float scratch buffer owned by the caller; tile_sum_kernel has already been enqueued
+// r.c_out must point at a (B, ld) float scratch buffer owned by the caller; normalize_kernel has already been enqueued
 static inline void op_launch_multinomial_after_tilesum(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
-  systematic_kernel<24, RS_OUT_CUMSUM><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+  systematic_kernel<24, RS_OUT_CUMSUM><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
   MultinomialArgs m;
   m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
   m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc;
@@ -228,7 +228,7 @@ static inline void op_launch_multinomial_after_tilesum(const ResampleArgs& r, co
 }
 static inline int op_launch_multinomial(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
   if (!r.c_out) return SMCB_EINVAL;
-  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
   op_launch_multinomial_after_tilesum(r, U, U_pitch, s);
   return SMCB_OK;
 }

@@ -1,8 +1,10 @@
 // Per-thread phases of the exact tile scan (see exact_scan.h for the arithmetic and DESIGN.md for the kernel structure).
 //
 // A tile is TILE = NT * ITEMS consecutive weights of one column; thread t owns elements [t*ITEMS, (t+1)*ITEMS).
-//   phase A  approximate (fp64, any association) inclusive prefix S'_k -> binade label of every element; an element whose
-//            label differs from its predecessor's is "special" (speculated binade crossing) and opens a new segment.
+//   phase A  approximate (fp64, any association) prefix at every thread boundary -> binade label at the start and end of
+//            each thread.  A thread whose two labels agree is "clean": all its elements are regular in that binade.  In a
+//            "dirty" thread the label of every element is derived; an element whose label differs from its predecessor's is
+//            "special" (speculated binade crossing) and opens a new segment.
 //   phase B  every regular element becomes a transducer in the quantum of its segment; a segmented block scan composes them.
 //   phase C  one thread walks the (few) segments with the EXACT incoming state: special elements are applied with a genuine
 //            IEEE add, segment aggregates with xs_apply; every speculation is verified on the way.
@@ -18,18 +20,19 @@ struct XsSeg {
   int32_t cnt;
 };
 XS_HD XsSeg xs_seg_identity() { XsSeg s; s.t = xs_identity(); s.cnt = 0; return s; }
-// a THEN b
-XS_HD XsSeg xs_seg_combine(const XsSeg& a, const XsSeg& b) {
+// a THEN b; E = binade label at the start of b's range (only used when b has no special, i.e. the open segment continues)
+template <int MB>
+XS_HD XsSeg xs_seg_combine(const XsSeg& a, const XsSeg& b, int E) {
   XsSeg r;
   r.cnt = a.cnt + b.cnt;
-  r.t = b.cnt ? b.t : xs_compose(a.t, b.t);
+  r.t = b.cnt ? b.t : xs_compose<MB>(a.t, b.t, E);
   return r;
 }
 
 // Tile descriptor published for the decoupled look-back (valid when the tile holds at most one special element).
 struct XsDesc {
-  int64_t a_inc0;   // segment 0 aggregate
-  int64_t b_inc0;   // segment 1 aggregate (after the special), if any
+  double a_s;       // segment 0 aggregate
+  double b_s;       // segment 1 aggregate (after the special), if any
   float wc;         // the special element
   int16_t e0;       // speculated label of the incoming state
   int16_t e1;       // speculated label right after the special
@@ -40,57 +43,56 @@ struct XsDesc {
 
 template <int MB>
 XS_HD bool xs_apply_desc(double S, const XsDesc& d, double* out) {
-  XsT a; a.inc0 = d.a_inc0; a.d = d.a_d;
+  XsT a; a.s = d.a_s; a.d = d.a_d;
   double s1;
-  int lab = xs_label(S);
-  if (lab != (int)d.e0) { *out = S; return false; }
-  if (!xs_apply<MB>(S, lab, a, &s1)) { *out = S; return false; }
+  if (!xs_apply<MB>(S, (int)d.e0, a, &s1)) { *out = S; return false; }
   if (!d.has_special) { *out = s1; return true; }
   double s2 = xs_add_special<MB>(s1, d.wc);
   if (xs_label(s2) != (int)d.e1) { *out = S; return false; }
-  XsT b; b.inc0 = d.b_inc0; b.d = d.b_d;
+  XsT b; b.s = d.b_s; b.d = d.b_d;
   return xs_apply<MB>(s2, (int)d.e1, b, out);
 }
 
 // ---- phase A/B, thread-local -------------------------------------------------------------------------------------------
-// In:  w[ITEMS], approximate prefix at thread start (sp_start) and the label of the element before this thread (lab_prev).
-// Out: bit mask of special elements, label after the last element, the thread's segmented-scan contribution, and the
-//      transducer of the regular elements BEFORE the first special (== whole thread when there is none).
+// In:  w[ITEMS], approximate prefix at thread start (sp_start), label of the element before this thread (lab_prev) and the
+//      label after this thread's last element (lab_end = label(sp_start + sum(w)), the value the next thread starts from).
+// Out: bit mask of special elements, the thread's segmented-scan contribution.
 template <int MB, int ITEMS>
-XS_HD void xs_thread_label_and_reduce(const float (&w)[ITEMS], double sp_start, int lab_prev, uint32_t* special_mask,
-                                      XsSeg* contrib, XsT* pre) {
-  double sp = sp_start;
-  int lab = lab_prev;
-  uint32_t mask = 0;
+XS_HD void xs_thread_reduce(const float (&w)[ITEMS], double sp_start, int lab_prev, int lab_end, uint32_t* special_mask,
+                            XsSeg* contrib) {
   XsSeg c = xs_seg_identity();
-  XsT p = xs_identity();
+  uint32_t mask = 0;
+  if (lab_prev == lab_end) {  // clean thread: one binade, no label work
 #pragma unroll
-  for (int j = 0; j < ITEMS; ++j) {
-    sp += (double)w[j];
-    int l = xs_label(sp);
-    if (l != lab) {
-      mask |= 1u << j;
-      if (c.cnt == 0) p = c.t;
-      c.cnt += 1;
-      c.t = xs_identity();
-      lab = l;
-    } else {
-      c.t = xs_compose(c.t, xs_elem<MB>(w[j], lab));
+    for (int j = 0; j < ITEMS; ++j) c.t = xs_compose<MB>(c.t, xs_elem<MB>(w[j], lab_prev), lab_prev);
+  } else {
+    double p = 0.0;
+    int lab = lab_prev;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      p += (double)w[j];
+      int l = (j == ITEMS - 1) ? lab_end : xs_label(sp_start + p);
+      if (l != lab) {
+        mask |= 1u << j;
+        c.cnt += 1;
+        c.t = xs_identity();
+        lab = l;
+      } else {
+        c.t = xs_compose<MB>(c.t, xs_elem<MB>(w[j], lab), lab);
+      }
     }
   }
-  if (c.cnt == 0) p = c.t;
   *special_mask = mask;
   *contrib = c;
-  *pre = p;
 }
 
-// Labels only (to learn the label at the end of each thread before phase B can start).
+// label after element j of a dirty thread (same expression as in xs_thread_reduce)
 template <int ITEMS>
-XS_HD int xs_thread_end_label(const float (&w)[ITEMS], double sp_start) {
-  double sp = sp_start;
-#pragma unroll
-  for (int j = 0; j < ITEMS; ++j) sp += (double)w[j];
-  return xs_label(sp);
+XS_HD int xs_elem_label(const float (&w)[ITEMS], double sp_start, int lab_end, int j) {
+  if (j == ITEMS - 1) return lab_end;
+  double p = 0.0;
+  for (int k = 0; k <= j; ++k) p += (double)w[k];
+  return xs_label(sp_start + p);
 }
 
 // ---- phase C: walk the segments of one tile with the exact incoming state (one thread) ---------------------------------
@@ -122,6 +124,7 @@ XS_HD void xs_thread_finalize(const float (&w)[ITEMS], uint32_t special_mask, in
   XsT T = t_open;
   double b = base[s];
   int par = xs_parity<MB>(b);
+  double q = (E == XS_E_ZERO) ? 0.0 : xs_pow2(E - (MB - 1));
 #pragma unroll
   for (int j = 0; j < ITEMS; ++j) {
     double S;
@@ -130,11 +133,12 @@ XS_HD void xs_thread_finalize(const float (&w)[ITEMS], uint32_t special_mask, in
       b = base[s];
       par = xs_parity<MB>(b);
       E = seg_e[s];
+      q = xs_pow2(E - (MB - 1));
       T = xs_identity();
       S = b;
     } else {
-      T = xs_compose(T, xs_elem<MB>(w[j], E));
-      S = (E == XS_E_ZERO) ? b : b + (double)xs_inc(T, par) * xs_pow2(E - (MB - 1));
+      T = xs_compose<MB>(T, xs_elem<MB>(w[j], E), E);
+      S = xs_dadd(b, (T.d && par) ? xs_dadd(T.s, (double)T.d * q) : T.s);
     }
     c[j] = (float)S;
   }

@@ -99,6 +99,7 @@ struct smcb_filter {
   ColStats* stats = nullptr;
   Partial* partials = nullptr;
   Ctrl* ctrl = nullptr;
+  int32_t* col_ticket = nullptr;
   double* tilesum = nullptr;
   TileSlot* slots = nullptr;
   float *hist_mean = nullptr, *hist_var = nullptr, *hist_ll = nullptr;
@@ -106,6 +107,8 @@ struct smcb_filter {
   float* y_own = nullptr;
   int y_own_cap = 0;
   float* cbuf = nullptr;  // multinomial: sequential float32 prefix sums (B, ld)
+  float* wn = nullptr;    // normalised weights of the current resampling pass (B, ld)
+  long long* dbg = nullptr;  // SMCB_DEBUG_TIMELINE=1: per-tile timeline of the scan kernel
   const float *eps_in = nullptr, *u_in = nullptr;
   const double* U_in = nullptr;
   float *eps_out = nullptr, *u_out = nullptr, *w_out = nullptr;
@@ -139,7 +142,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->slots, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
-                  f->ll_total, f->ess_packed, f->y_own, f->cbuf};
+                  f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -169,7 +172,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   {
     const int64_t chunk = ST_NT * ST_VEC;
     const int64_t nchunks = (f->n + chunk - 1) / chunk;
-    int64_t cap = (148 * 8) / f->B;
+    int64_t cap = (148 * 4) / f->B;  // one resident wave of step-kernel blocks (4 per SM)
     if (cap < 1) cap = 1;
     f->iters = (int)((nchunks + cap - 1) / cap);
     f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);
@@ -184,11 +187,13 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->xbuf[1], cells * f->D));
   A_(dalloc(&f->lw, cells));
   A_(dalloc(&f->rw, cells));
+  A_(dalloc(&f->wn, cells));
   A_(dalloc(&f->anc, cells));
   A_(dalloc(&f->prev_inds, cells));
   A_(dalloc(&f->stats, (size_t)f->B));
   A_(dalloc(&f->partials, (size_t)f->B * f->blocks_per_col));
   A_(dalloc(&f->ctrl, (size_t)1));
+  A_(dalloc(&f->col_ticket, (size_t)f->B));
   A_(dalloc(&f->tilesum, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->slots, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
@@ -200,6 +205,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)f->B * f->tiles_per_col * 8));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -222,7 +228,7 @@ extern "C" int smcb_filter_info(smcb_filter* f, smcb_info* o) {
   o->t = f->t_host; o->history_rows = f->cfg.history_rows; o->kernel_launches = f->launches;
   Ctrl c;
   CU(cudaMemcpy(&c, f->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
-  o->slow_tiles = c.slow_tiles;
+  o->slow_tiles = c.slow_tiles; o->lb_fail = c.lb_fail; o->lb_windows = c.lb_windows; o->reserved = 0;
   return SMCB_OK;
 }
 
@@ -232,7 +238,7 @@ static StepArgs make_args(smcb_filter* f) {
   memset(&a, 0, sizeof(a));
   a.n = f->n; a.ld = f->ld; a.B = f->B; a.blocks_per_col = f->blocks_per_col; a.iters = f->iters;
   a.P = f->P_dev; a.xbuf[0] = f->xbuf[0]; a.xbuf[1] = f->xbuf[1]; a.lw = f->lw; a.rw = f->rw;
-  a.anc = f->anc; a.prev_inds = f->prev_inds; a.stats = f->stats; a.partials = f->partials; a.ctrl = f->ctrl;
+  a.anc = f->anc; a.prev_inds = f->prev_inds; a.stats = f->stats; a.partials = f->partials; a.ctrl = f->ctrl; a.col_ticket = f->col_ticket;
   a.eps_in = f->eps_in; a.eps_out = f->eps_out; a.seed = f->cfg.seed;
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
@@ -288,11 +294,11 @@ static void launch_finalize(smcb_filter* f, StepArgs a, int mode, cudaStream_t s
   a.fin_mode = mode;
   const bool apf = f->cfg.algorithm == SMCB_APF;
   if (f->D == 1) {
-    if (apf) finalize_kernel<1, 1, SMCB_ALG_APF><<<f->B, 128, 0, s>>>(a);
-    else finalize_kernel<1, 1, SMCB_ALG_SISR><<<f->B, 128, 0, s>>>(a);
+    if (apf) finalize_kernel<1, 1, SMCB_ALG_APF><<<f->B, ST_NT, 0, s>>>(a);
+    else finalize_kernel<1, 1, SMCB_ALG_SISR><<<f->B, ST_NT, 0, s>>>(a);
   } else {
-    if (apf) finalize_kernel<3, 2, SMCB_ALG_APF><<<f->B, 128, 0, s>>>(a);
-    else finalize_kernel<3, 2, SMCB_ALG_SISR><<<f->B, 128, 0, s>>>(a);
+    if (apf) finalize_kernel<3, 2, SMCB_ALG_APF><<<f->B, ST_NT, 0, s>>>(a);
+    else finalize_kernel<3, 2, SMCB_ALG_SISR><<<f->B, ST_NT, 0, s>>>(a);
   }
   f->launches++;
 }
@@ -359,15 +365,18 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   ResampleArgs r;
   memset(&r, 0, sizeof(r));
   r.w = apf ? f->rw : f->lw;
+  r.wn = f->wn;
   r.n = f->n; r.ld = f->ld; r.B = f->B; r.tiles_per_col = f->tiles_per_col;
   r.input_is_w = 0; r.use_rw = apf ? 1 : 0; r.stats = f->stats;
   r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed;
   r.tilesum = f->tilesum; r.slots = f->slots; r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
-  tile_sum_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  r.approx = f->cfg.exact_scan ? 0 : 1;
+  r.dbg = f->dbg;
+  normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
   if (f->cfg.resampler == SMCB_SYSTEMATIC) {
-    systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_NT, sizeof(RsSmem), s>>>(r);
+    systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
     f->launches++;
   } else {
     r.c_out = f->cbuf;
@@ -375,9 +384,8 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
     f->launches += 2;
   }
   if (ev) cudaEventRecord(ev[3], s);
-  launch_step(f, a, s);
+  launch_step(f, a, s);  // the block that completes a column also folds its partials (finalize_column, FIN_STEP)
   if (ev) cudaEventRecord(ev[4], s);
-  launch_finalize(f, a, FIN_STEP, s);
   if (ev) cudaEventRecord(ev[5], s);
   f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
   f->t_host = t + 1;
@@ -470,6 +478,7 @@ extern "C" int smcb_filter_ptr(smcb_filter* f, int32_t what, void** p) {
     case SMCB_PTR_HIST_VAR: *p = f->hist_var; break;
     case SMCB_PTR_HIST_LL: *p = f->hist_ll; break;
     case SMCB_PTR_ESS: *p = f->ess_packed; break;
+    case 20: *p = f->dbg; break;  /* diagnostics */
     default: return fail(SMCB_EINVAL, "unknown pointer id");
   }
   return SMCB_OK;
@@ -489,7 +498,7 @@ extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
 
 // ---- stand-alone operators ---------------------------------------------------------------------------------------------------------
 struct OpWorkspace {
-  float* w = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; TileSlot* slots = nullptr; Ctrl* ctrl = nullptr;
+  float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; TileSlot* slots = nullptr; Ctrl* ctrl = nullptr;
   ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
   int64_t ld = 0; int tiles = 0, nblk = 0;
 };
@@ -500,6 +509,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   ws.nblk = ws.tiles;
   const size_t cells = (size_t)B * ws.ld;
   CU(cudaMallocAsync((void**)&ws.w, cells * sizeof(float), s));
+  CU(cudaMallocAsync((void**)&ws.wn, cells * sizeof(float), s));
   CU(cudaMallocAsync((void**)&ws.anc, cells * sizeof(int32_t), s));
   CU(cudaMallocAsync((void**)&ws.tilesum, (size_t)B * ws.tiles * sizeof(double), s));
   CU(cudaMallocAsync((void**)&ws.slots, (size_t)B * ws.tiles * sizeof(TileSlot), s));
@@ -513,7 +523,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   return SMCB_OK;
 }
 static void op_free(OpWorkspace& ws, cudaStream_t s) {
-  void* ptrs[] = {ws.w, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf};
+  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf};
   for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
 }
 
@@ -554,7 +564,7 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
   if (rc == SMCB_OK) {
     ResampleArgs r;
     memset(&r, 0, sizeof(r));
-    r.w = ws.w; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
+    r.w = ws.w; r.wn = normalized ? ws.w : ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
     r.input_is_w = normalized ? 1 : 0; r.use_rw = 0; r.stats = normalized ? nullptr : ws.stats;
     r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.slots = ws.slots; r.anc = ws.anc; r.ctrl = ws.ctrl;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);

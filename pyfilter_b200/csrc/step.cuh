@@ -27,6 +27,7 @@ struct StepArgs {
   ColStats* stats;                   // (B)
   Partial* partials;                 // (B, blocks_per_col)
   Ctrl* ctrl;
+  int32_t* col_ticket;               // (B) last-block-done counters of the fused finalize
   const float* eps_in;               // optional injected N(0,1) draws (D, B, ld)
   float* eps_out;                    // optional dump of the draws used
   uint64_t seed;
@@ -82,20 +83,38 @@ __device__ __forceinline__ SoftAcc<K> softacc_shfl_xor(const SoftAcc<K>& a, int 
 }
 
 // block-wide merge; the result is valid in thread 0.  `scratch` holds (NT/32) records.
+// Two phases so that only ONE exp per thread is spent: block max of the reference points, rescale, plain sums.
 template <int K>
 __device__ __forceinline__ void softacc_block_reduce(SoftAcc<K>& a, SoftAcc<K>* scratch) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float mb = a.m;
 #pragma unroll
-  for (int o = 16; o; o >>= 1) a.merge(softacc_shfl_xor(a, o));
+  for (int o = 16; o; o >>= 1) mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
   __syncthreads();
-  if (lane == 0) scratch[wid] = a;
+  if (lane == 0) scratch[wid].m = mb;
   __syncthreads();
-  if (wid == 0) {
-    SoftAcc<K> r;
-    if (lane < ST_NT / 32) r = scratch[lane]; else r.init();
 #pragma unroll
-    for (int o = 16; o; o >>= 1) r.merge(softacc_shfl_xor(r, o));
-    a = r;
+  for (int w = 0; w < ST_NT / 32; ++w) mb = fmaxf(mb, scratch[w].m);
+  const float sc = (a.m == -INFINITY) ? 0.f : __expf(a.m - mb);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    float v = a.s[k] * sc;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    a.s[k] = v;
+  }
+  a.m = mb;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) scratch[wid].s[k] = a.s[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < ST_NT / 32; ++w) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) a.s[k] += scratch[w].s[k];
+    }
   }
 }
 
@@ -340,14 +359,134 @@ __global__ void __launch_bounds__(ST_NT) preweight_kernel(StepArgs a) {
   }
 }
 
+// ---- finalize: folds the per-block partials of one column ------------------------------------------------------------------------
+// FIN_STATE      after state_kernel:      normalisers/ESS/moments of the current weights; history row ctrl->t; no likelihood
+// FIN_PREWEIGHT  after preweight_kernel:  normalisers of rw and the look-ahead term of apf.py:44
+// FIN_STEP       after step_kernel:       everything, history row t+1, running log-likelihood, then t <- t+1
+// Runs either as its own kernel (one block per column) or as the tail of the step kernel in the block that finishes a column last.
+template <int D>
+struct FinSmem {
+  SoftAcc<1 + 2 * D> A[ST_NT / 32];
+  SoftAcc<1> Q[ST_NT / 32];
+};
+
+template <int D, int OD, int ALG>
+__device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int mode, int t, FinSmem<D>& fs) {
+  const int tid = threadIdx.x;
+  SoftAcc<1 + 2 * D> A; A.init();
+  SoftAcc<1> Q, R2, R3; Q.init(); R2.init(); R3.init();
+  for (int b = tid; b < a.blocks_per_col; b += ST_NT) {
+    const Partial* pp = a.partials + (int64_t)col * a.blocks_per_col + b;
+    Partial p;
+    {  // L2 loads: the records were written by other blocks of a kernel that may still be running
+      const float4* q = reinterpret_cast<const float4*>(pp);
+      float4 v0 = __ldcg(q), v1 = __ldcg(q + 1), v2 = __ldcg(q + 2);
+      float v3 = __ldcg(reinterpret_cast<const float*>(pp) + 12);
+      p.m1 = v0.x; p.z1 = v0.y; p.zz1 = v0.z; p.sx[0] = v0.w; p.sx[1] = v1.x; p.sx[2] = v1.y; p.sxx[0] = v1.z; p.sxx[1] = v1.w;
+      p.sxx[2] = v2.x; p.m2 = v2.y; p.z2 = v2.z; p.m3 = v2.w; p.z3 = v3;
+    }
+    SoftAcc<1 + 2 * D> o; o.m = p.m1; o.s[0] = p.z1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { o.s[1 + d] = p.sx[d]; o.s[1 + D + d] = p.sxx[d]; }
+    SoftAcc<1> q; q.m = (p.m1 == -INFINITY) ? -INFINITY : 2.f * p.m1; q.s[0] = p.zz1;
+    SoftAcc<1> o2; o2.m = p.m2; o2.s[0] = p.z2;
+    SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
+    A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
+  }
+  softacc_block_reduce(A, fs.A);
+  softacc_block_reduce(Q, fs.Q);
+  softacc_block_reduce(R2, fs.Q);
+  softacc_block_reduce(R3, fs.Q);
+  if (tid == 0) {
+    ColStats st = a.stats[col];
+    const float nf = (float)a.n;
+    if (mode == FIN_PREWEIGHT) {
+      float y[OD];
+      const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      if (observed) {
+        st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
+        st.ll_aux = logf(R2.s[0]) + (R2.m - st.m_lw) - logf(st.z_lw);   // log sum W exp(g), W = softmax(lw)
+      }
+      st.resample = observed ? 1 : 0;
+      st.fold_valid = 1;
+      a.stats[col] = st;
+    } else {
+      float y[OD];
+      const bool observed = (mode == FIN_STEP) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      const float ll_aux_prev = st.ll_aux;
+      st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
+      // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
+      const float zz = (Q.m == -INFINITY) ? 0.f : Q.s[0] * __expf(Q.m - 2.f * A.m);
+      st.ess = (A.s[0] * A.s[0]) / zz;
+      float mean[D], var[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float dm = A.s[1 + d] * st.inv_z_lw;            // E[x - shift]
+        mean[d] = st.shift[d] + dm;
+        var[d] = fmaxf(A.s[1 + D + d] * st.inv_z_lw - dm * dm, 0.f);
+      }
+      float ll = 0.f;
+      if (mode == FIN_STEP && observed) {
+        if (ALG == SMCB_ALG_SISR) ll = R3.m + logf(R3.s[0]);                       // filters/particle/utils.py:16-22
+        else ll = (A.m + logf(A.s[0]) - logf(nf)) + ll_aux_prev;                   // apf.py:44
+      }
+      // next step's resampling decision and (APF) folded normalisers
+      st.fold_valid = 0;
+      if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
+      else {
+        st.resample = 0;  // set by the pre-weight pass unless the look-ahead was folded below
+        float yn[OD];
+        const bool fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
+        if (fold) {
+          st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
+          st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
+          st.fold_valid = 1;
+          st.resample = 1;
+        }
+      }
+#pragma unroll
+      for (int d = 0; d < D; ++d) st.shift[d] = mean[d];
+      a.stats[col] = st;
+      const int rowi = (mode == FIN_STEP) ? t + 1 : t;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        a.latest_mean[col * D + d] = mean[d];
+        a.latest_var[col * D + d] = var[d];
+        if (a.hist_mean && rowi < a.hist_rows) {
+          a.hist_mean[((int64_t)rowi * a.B + col) * D + d] = mean[d];
+          a.hist_var[((int64_t)rowi * a.B + col) * D + d] = var[d];
+        }
+      }
+      a.latest_ll[col] = ll;
+      if (mode == FIN_STEP) a.ll_total[col] += ll;
+      if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
+    }
+    if (mode == FIN_STEP) {
+      __threadfence();
+      const int done = atomicAdd(&a.ctrl->ticket, 1);
+      if (done == a.B - 1) {   // every column is finalized, hence every block has read ctrl->t: safe to advance the clock
+        a.ctrl->ticket = 0;
+        a.ctrl->t = t + 1;
+      }
+    }
+  }
+}
+
+template <int D, int OD, int ALG>
+__global__ void __launch_bounds__(ST_NT) finalize_kernel(StepArgs a) {
+  __shared__ FinSmem<D> fs;
+  finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, a.ctrl->t, fs);
+}
+
 // ---- the fused step ----------------------------------------------------------------------------------------------------------
 template <int MODEL, int PROP, int ALG>
 __global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
   typedef Model<MODEL> M;
   constexpr int D = M::D, OD = M::OD;
   __shared__ float Ps[SMCB_NPARAM];
-  __shared__ SoftAcc<1 + 2 * D> sA[ST_NT / 32];
-  __shared__ SoftAcc<1> sQ[ST_NT / 32];
+  __shared__ FinSmem<D> fin_smem;
+  SoftAcc<1 + 2 * D>* sA = fin_smem.A;
+  SoftAcc<1>* sQ = fin_smem.Q;
   const int col = blockIdx.y, tid = threadIdx.x;
   if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
   __syncthreads();
@@ -447,123 +586,21 @@ __global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
   softacc_block_reduce(mom.q, sQ);
   softacc_block_reduce(r2, sQ);
   softacc_block_reduce(r3, sQ);
+  __shared__ int is_last;
   if (tid == 0) {
     Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
     st_write_partial1(p, mom.a, mom.q);
     p.m2 = r2.m; p.z2 = r2.s[0];
     p.m3 = r3.m; p.z3 = r3.s[0];
+    __threadfence();
+    is_last = (atomicAdd(&a.col_ticket[col], 1) == a.blocks_per_col - 1);
+  }
+  __syncthreads();
+  if (is_last) {  // this block completed the column: fold the partials here instead of launching another kernel
+    if (tid == 0) a.col_ticket[col] = 0;
+    __threadfence();
+    FinSmem<D>& fs = *reinterpret_cast<FinSmem<D>*>(sA);
+    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, fs);
   }
 }
 
-// ---- finalize: one block per column ---------------------------------------------------------------------------------------------
-// FIN_STATE      after state_kernel:      normalisers/ESS/moments of the current weights; history row ctrl->t; no likelihood
-// FIN_PREWEIGHT  after preweight_kernel:  normalisers of rw and the look-ahead term of apf.py:44
-// FIN_STEP       after step_kernel:       everything, history row t+1, running log-likelihood, then t <- t+1
-template <int D, int OD, int ALG>
-__global__ void __launch_bounds__(128) finalize_kernel(StepArgs a) {
-  __shared__ SoftAcc<1 + 2 * D> sA[4];
-  __shared__ SoftAcc<1> sQ[4];
-  const int col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int t = a.ctrl->t;
-  const int mode = a.fin_mode;
-  SoftAcc<1 + 2 * D> A; A.init();
-  SoftAcc<1> Q, R2, R3; Q.init(); R2.init(); R3.init();
-  for (int b = tid; b < a.blocks_per_col; b += 128) {
-    const Partial p = a.partials[(int64_t)col * a.blocks_per_col + b];
-    SoftAcc<1 + 2 * D> o; o.m = p.m1; o.s[0] = p.z1;
-#pragma unroll
-    for (int d = 0; d < D; ++d) { o.s[1 + d] = p.sx[d]; o.s[1 + D + d] = p.sxx[d]; }
-    SoftAcc<1> q; q.m = (p.m1 == -INFINITY) ? -INFINITY : 2.f * p.m1; q.s[0] = p.zz1;
-    SoftAcc<1> o2; o2.m = p.m2; o2.s[0] = p.z2;
-    SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
-    A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
-  }
-  // block merge (4 warps)
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { A.merge(softacc_shfl_xor(A, o)); Q.merge(softacc_shfl_xor(Q, o)); }
-  if (lane == 0) { sA[wid] = A; sQ[wid] = Q; }
-  __syncthreads();
-  if (tid == 0) for (int w = 1; w < 4; ++w) { A.merge(sA[w]); Q.merge(sQ[w]); }
-  __syncthreads();
-#pragma unroll
-  for (int o = 16; o; o >>= 1) { R2.merge(softacc_shfl_xor(R2, o)); R3.merge(softacc_shfl_xor(R3, o)); }
-  if (lane == 0) { sQ[wid] = R2; }
-  __syncthreads();
-  if (tid == 0) for (int w = 1; w < 4; ++w) R2.merge(sQ[w]);
-  __syncthreads();
-  if (lane == 0) { sQ[wid] = R3; }
-  __syncthreads();
-  if (tid == 0) {
-    for (int w = 1; w < 4; ++w) R3.merge(sQ[w]);
-    ColStats st = a.stats[col];
-    const float nf = (float)a.n;
-    if (mode == FIN_PREWEIGHT) {
-      float y[OD];
-      const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
-      if (observed) {
-        st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
-        st.ll_aux = logf(R2.s[0]) + (R2.m - st.m_lw) - logf(st.z_lw);   // log sum W exp(g), W = softmax(lw)
-      }
-      st.resample = observed ? 1 : 0;
-      st.fold_valid = 1;
-      a.stats[col] = st;
-    } else {
-      float y[OD];
-      const bool observed = (mode == FIN_STEP) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
-      const float ll_aux_prev = st.ll_aux;
-      st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
-      // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
-      const float zz = (Q.m == -INFINITY) ? 0.f : Q.s[0] * __expf(Q.m - 2.f * A.m);
-      st.ess = (A.s[0] * A.s[0]) / zz;
-      float mean[D], var[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const float dm = A.s[1 + d] * st.inv_z_lw;            // E[x - shift]
-        mean[d] = st.shift[d] + dm;
-        var[d] = fmaxf(A.s[1 + D + d] * st.inv_z_lw - dm * dm, 0.f);
-      }
-      float ll = 0.f;
-      if (mode == FIN_STEP && observed) {
-        if (ALG == SMCB_ALG_SISR) ll = R3.m + logf(R3.s[0]);                       // filters/particle/utils.py:16-22
-        else ll = (A.m + logf(A.s[0]) - logf(nf)) + ll_aux_prev;                   // apf.py:44
-      }
-      // next step's resampling decision and (APF) folded normalisers
-      st.fold_valid = 0;
-      if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
-      else {
-        st.resample = 1;
-        float yn[OD];
-        const bool fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
-        if (fold) {
-          st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
-          st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
-          st.fold_valid = 1;
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) st.shift[d] = mean[d];
-      a.stats[col] = st;
-      const int rowi = (mode == FIN_STEP) ? t + 1 : t;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        a.latest_mean[col * D + d] = mean[d];
-        a.latest_var[col * D + d] = var[d];
-        if (a.hist_mean && rowi < a.hist_rows) {
-          a.hist_mean[((int64_t)rowi * a.B + col) * D + d] = mean[d];
-          a.hist_var[((int64_t)rowi * a.B + col) * D + d] = var[d];
-        }
-      }
-      a.latest_ll[col] = ll;
-      if (mode == FIN_STEP) a.ll_total[col] += ll;
-      if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
-    }
-    if (mode == FIN_STEP) {
-      __threadfence();
-      const int done = atomicAdd(&a.ctrl->ticket, 1);
-      if (done == (int)gridDim.x - 1) {   // every block has read ctrl->t: safe to advance the clock
-        a.ctrl->ticket = 0;
-        a.ctrl->t = t + 1;
-      }
-    }
-  }
-}

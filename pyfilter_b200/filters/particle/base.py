@@ -40,6 +40,7 @@ class ParticleFilter:
         self._seed = seed
         self._fold = fold_lookahead
         self._engine: Engine = None
+        self._exact_scan = True
 
     # ---- reference surface
     @property
@@ -100,7 +101,7 @@ class ParticleFilter:
             seed = self._seed if self._seed is not None else int(torch.randint(0, 2**62, (1,)).item())
             n = int(self._base_particles[0])
             e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS[self._resampler], n,
-                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold)
+                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_scan)
             self._engine = e
         return e
 
