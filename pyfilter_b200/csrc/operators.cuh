@@ -173,6 +173,7 @@ static inline void op_launch_copy_ess(const ColStats* st, float* out, int B, cud
 // ---- systematic ------------------------------------------------------------------------------------------------------------------
 static inline void op_launch_systematic(const ResampleArgs& r, cudaStream_t s) {
   normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  systematic_benign_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
   systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
 }
 

@@ -47,12 +47,25 @@ struct ResampleArgs {
   long long* dbg;          // optional per-tile timeline (8 x int64 globaltimer stamps per tile), diagnostics only
   int32_t approx;          // 1: skip the exact chaining (incoming state := fp64 approximate prefix); NOT bit-exact, diagnostics only
   Ctrl* ctrl;
+  uint32_t* tilemin;       // (B, tiles_per_col) smallest non-zero weight of every tile (float bits; 0 when a weight is negative)
+  int32_t* ncounter;       // (B) last-block-done tickets of normalize_kernel (self resetting)
+  int32_t* verdict;        // (B) bit 0: the column is "benign" - its sequential fp64 prefix sum never rounds (benign kernel)
+  float* u_col;            // (B) the systematic offset of every column for this launch (injected or Philox)
 };
 enum { RS_OUT_ANCESTORS = 0, RS_OUT_CUMSUM = 1 };
 
-// ---- pre-pass: normalised weights (written once, zero beyond n) and their fp64 tile sums -------------------------------------
+// ---- pre-pass: normalised weights (written once, zero beyond n), their fp64 tile sums and the column verdict ---------------------
+// A column is BENIGN when every non-zero weight is a multiple of 2^-52 (w >= 2^-29) and the weights sum to less than 2: then
+// every partial sum is a multiple of 2^-52 below 2, i.e. exactly representable, so the reference's sequential fp64 prefix sum
+// never rounds and equals the exact real prefix sum in ANY association.  Such columns need no binade labels, no transducers
+// and no chaining across tiles (systematic_benign_kernel); all others take the general exact scan (systematic_kernel).
+struct OpMinU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; } };
+#define RS_BENIGN_MIN_BITS 0x31000000u  // 2^-29
+
 __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   __shared__ double scratch[33];
+  __shared__ uint32_t uscratch[33];
+  __shared__ int is_last;
   const int col = blockIdx.y, tile = blockIdx.x;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // arm the scan kernel that follows in stream order
     a.ctrl->tile_counter = 0;
@@ -68,6 +81,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
   }
   double s = 0.0;
+  uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
   for (int v = 0; v < RS_ITEMS / 4; ++v) {  // striped float4: fully coalesced
     const int e = (v * RS_NT + threadIdx.x) * 4;
@@ -78,12 +92,47 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
       if (!a.input_is_w) x[k] = smcb_weight(smcb_sanitize(x[k]), m, iz);
       if (g0 + e + k >= a.n) x[k] = 0.f;
       s += (double)x[k];
+      const uint32_t b = __float_as_uint(x[k]);
+      const uint32_t kk = (b == 0u) ? 0xFFFFFFFFu : ((b >> 31) ? 0u : b);
+      key = min(key, kk);
     }
     if (!a.input_is_w || a.wn != a.w) *reinterpret_cast<float4*>(a.wn + off + e) = make_float4(x[0], x[1], x[2], x[3]);
     if (a.w_out) *reinterpret_cast<float4*>(a.w_out + off + e) = make_float4(x[0], x[1], x[2], x[3]);
   }
   s = block_allreduce<RS_NT>(s, 0.0, OpSumD(), scratch);
-  if (threadIdx.x == 0) a.tilesum[(int64_t)col * a.tiles_per_col + tile] = s;
+  key = block_allreduce<RS_NT>(key, 0xFFFFFFFFu, OpMinU(), uscratch);
+  if (threadIdx.x == 0) {
+    a.tilesum[(int64_t)col * a.tiles_per_col + tile] = s;
+    a.tilemin[(int64_t)col * a.tiles_per_col + tile] = key;
+    __threadfence();
+    is_last = (atomicAdd(&a.ncounter[col], 1) == a.tiles_per_col - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  // ---- the block that completes a column settles its systematic offset and the verdict
+  __threadfence();
+  double tot = 0.0;
+  uint32_t mk = 0xFFFFFFFFu;
+  for (int q = threadIdx.x; q < a.tiles_per_col; q += RS_NT) {
+    tot += __ldcg(a.tilesum + (int64_t)col * a.tiles_per_col + q);
+    mk = min(mk, __ldcg(a.tilemin + (int64_t)col * a.tiles_per_col + q));
+  }
+  tot = block_allreduce<RS_NT>(tot, 0.0, OpSumD(), scratch);
+  mk = block_allreduce<RS_NT>(mk, 0xFFFFFFFFu, OpMinU(), uscratch);
+  if (threadIdx.x == 0) {
+    float u;  // one uniform per column (resampling.py:41)
+    if (a.u_in) u = a.u_in[col];
+    else {
+      Philox4 r = philox4x32_10((uint32_t)col, 0u, (uint32_t)a.ctrl->t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      u = smcb_u01(r.x);
+    }
+    a.u_col[col] = u;
+    if (a.u_out) a.u_out[col] = u;
+    const bool u_ok = (u == 0.f) || (u >= 5.5e-20f && u < 1.0f);
+    const bool benign = !a.approx && mk >= RS_BENIGN_MIN_BITS && tot < 1.5 && a.n <= (1 << 23) && u_ok;
+    a.verdict[col] = benign ? 1 : 0;
+    a.ncounter[col] = 0;
+  }
 }
 
 // ---- block scans (the RS_NT compute threads synchronise on named barrier 1; the look-back warp is not involved) ------------
@@ -426,6 +475,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) systematic_kernel(ResampleArgs 
   const int col = id / a.tiles_per_col, tile = id % a.tiles_per_col;
   if (col >= a.B) return;
   if (a.stats && !a.stats[col].resample) return;
+  if (MB == 53 && OUT == RS_OUT_ANCESTORS && (a.verdict[col] & 1)) return;  // systematic_benign_kernel owns this column
   const uint32_t epoch = a.ctrl->epoch;
   TileSlot* slots = a.slots + (int64_t)col * a.tiles_per_col;
 
@@ -479,13 +529,7 @@ __global__ void __launch_bounds__(RS_THREADS, 3) systematic_kernel(ResampleArgs 
   // ================================ compute warps ================================
   const int32_t n = (int32_t)a.n;
   const float nf = (float)a.n;
-  float u;  // systematic offset of this column (one uniform per column, resampling.py:41)
-  if (a.u_in) u = a.u_in[col];
-  else {
-    Philox4 r = philox4x32_10((uint32_t)col, 0u, (uint32_t)a.ctrl->t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
-    u = smcb_u01(r.x);
-  }
-  if (a.u_out && tile == 0 && tid == 0) a.u_out[col] = u;
+  const float u = a.u_col[col];  // systematic offset of this column, settled by normalize_kernel
 
   if (tid == 0) RS_STAMP(0);
   // ---- this thread's 16 consecutive normalised weights (zero beyond n, written by normalize_kernel)
@@ -698,4 +742,161 @@ __global__ void __launch_bounds__(RS_THREADS, 3) systematic_kernel(ResampleArgs 
     for (int i = tid; i < clen; i += RS_NT) anc[n_in + i] = tile_base + max(sm.stage[i], sm.pre[i >> kshift]);
   }
   if (tid == 0) RS_STAMP(4);
+}
+
+// ---- benign columns: no rounding anywhere, hence no labels, no transducers, no chaining -----------------------------------------
+// One CTA per tile, no dependency between CTAs: the exact state before the tile is the (exact) sum of the preceding tile sums.
+// Expansion as in systematic_kernel: particle j owns the output slots [count(c_{j-1}), count(c_j)).  Every particle with
+// offspring marks its first slot in a shared-memory window; a "last mark at or before me" scan (ancestors are sorted, so this is
+// a running maximum) turns the marks into ancestors, which leave as coalesced 128-bit stores.
+#define FB_ROWS 5                              // int4 rows per warp and window
+#define FB_WIN (RS_NT / 32 * FB_ROWS * 32 * 4) // 5120 output slots per window
+struct FbSmem {
+  int32_t stage[FB_WIN];
+  double dscratch[33];
+  int32_t wtot[RS_NT / 32];
+  int32_t carry, n_out;
+};
+
+// counts of this thread's particles, marking the first slot of every particle with offspring inside the window [wb, wb + FB_WIN)
+__device__ __forceinline__ int32_t fb_mark_pass(const float (&w)[RS_ITEMS], double base, int32_t lo, int32_t gbase, int32_t wb, bool first,
+                                                float u, int32_t n, double nd, double nfd, FbSmem& sm) {
+  double run = base;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    run += (double)w[j];
+    int32_t hi = xs_count_fast((float)run, u, n, nd, nfd);
+    hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
+    const int32_t r = lo - wb;
+    if (hi > lo && (uint32_t)r < (uint32_t)FB_WIN) sm.stage[r] = gbase + j;
+    if (!first && hi > lo && r < 0 && hi > wb) sm.carry = gbase + j;  // its slots began in an earlier window (one such particle at most)
+    lo = hi;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(RS_NT, 4) systematic_benign_kernel(ResampleArgs a) {
+  __shared__ __align__(16) FbSmem sm;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tile = blockIdx.x, col = blockIdx.y;
+  if (a.stats && !a.stats[col].resample) return;
+  if (!(a.verdict[col] & 1)) return;
+  const int32_t n = (int32_t)a.n;
+  const double nd = (double)n, nfd = (double)(float)a.n;
+  const float u = a.u_col[col];
+
+  float w[RS_ITEMS];
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + tid * RS_ITEMS);
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+      const float4 q = __ldg(src + v);
+      w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+  }
+  // clear the first window while the loads are in flight
+#pragma unroll
+  for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+  if (tid == 0) sm.carry = -1;
+  // exact state before the tile and before this thread (all additions are exact in a benign column)
+  double S_in;
+  {
+    const double* ts = a.tilesum + (int64_t)col * a.tiles_per_col;
+    double part = 0.0;
+    for (int q = tid; q < tile; q += RS_NT) part += ts[q];
+    S_in = block_allreduce<RS_NT>(part, 0.0, OpSumD(), sm.dscratch);
+  }
+  double tsum = 0.0;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
+  double base;
+  {  // exclusive block scan of the thread sums
+    double inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) sm.dscratch[wid] = inc;
+    __syncthreads();
+    double off = 0.0;
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; ++k) off += (k < wid) ? sm.dscratch[k] : 0.0;
+    base = S_in + (off + (inc - tsum));
+  }
+  // slots owned by the tile start at n_in = #probes at or below the cumulative weight before the tile
+  const int32_t gbase = tile * RS_TILE + tid * RS_ITEMS;  // global index of this thread's first particle
+  const int32_t n_in = (tile == 0) ? 0 : ((tile * RS_TILE - 1 >= n - 1) ? n : xs_count_fast((float)S_in, u, n, nd, nfd));
+  int32_t lo_thread = n_in;
+  if (tid) lo_thread = (gbase - 1 >= n - 1) ? n : xs_count_fast((float)base, u, n, nd, nfd);
+  const int32_t wb0 = n_in & ~3;
+  {
+    const int32_t last = fb_mark_pass(w, base, lo_thread, gbase, wb0, true, u, n, nd, nfd, sm);
+    if (tid == RS_NT - 1) sm.n_out = last;
+  }
+  __syncthreads();
+  const int32_t n_out = sm.n_out;
+
+  int32_t* anc = a.anc + (int64_t)col * a.ld;
+  int32_t carry = -1;
+  for (int32_t wb = wb0; wb < n_out; wb += FB_WIN) {
+    if (wb != wb0) {  // rare: more than one window of offspring
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+      if (tid == 0) sm.carry = -1;
+      __syncthreads();
+      fb_mark_pass(w, base, lo_thread, gbase, wb, false, u, n, nd, nfd, sm);
+      __syncthreads();
+      carry = max(carry, sm.carry);
+    }
+    const int32_t wlen = min(FB_WIN, n_out - wb);
+    // last mark at or before every slot; warp `wid` owns FB_ROWS rows of 32 int4, row k = int4 [(wid*FB_ROWS + k)*32, +32)
+    int4 m[FB_ROWS];
+    int32_t cin[FB_ROWS];
+    int32_t wrun = -1;  // last mark seen by this warp so far
+#pragma unroll
+    for (int k = 0; k < FB_ROWS; ++k) {
+      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+      m[k] = *reinterpret_cast<const int4*>(&sm.stage[i4 * 4]);
+      const int32_t v = max(max(m[k].x, m[k].y), max(m[k].z, m[k].w));
+      const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
+      const uint32_t before = bal & ((1u << lane) - 1u);
+      const int32_t vb = __shfl_sync(0xffffffffu, v, before ? 31 - __clz(before) : 0);
+      cin[k] = before ? vb : wrun;
+      const int32_t vl = __shfl_sync(0xffffffffu, v, bal ? 31 - __clz(bal) : 0);
+      if (bal) wrun = vl;
+    }
+    if (lane == 0) sm.wtot[wid] = wrun;
+    __syncthreads();
+    int32_t cw = carry;  // last mark before this warp's rows
+    int32_t call = carry;
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; ++k) {
+      const int32_t t = sm.wtot[k];
+      if (k < wid) cw = max(cw, t);
+      call = max(call, t);
+    }
+    carry = call;
+#pragma unroll
+    for (int k = 0; k < FB_ROWS; ++k) {
+      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+      const int32_t s0 = wb + i4 * 4;
+      if (i4 * 4 < wlen) {
+        int4 o;
+        o.x = max(max(cw, cin[k]), m[k].x);
+        o.y = max(o.x, m[k].y);
+        o.z = max(o.y, m[k].z);
+        o.w = max(o.z, m[k].w);
+        if (s0 >= n_in && s0 + 4 <= n_out) *reinterpret_cast<int4*>(anc + s0) = o;
+        else {
+          if (s0 >= n_in && s0 < n_out) anc[s0] = o.x;
+          if (s0 + 1 >= n_in && s0 + 1 < n_out) anc[s0 + 1] = o.y;
+          if (s0 + 2 >= n_in && s0 + 2 < n_out) anc[s0 + 2] = o.z;
+          if (s0 + 3 >= n_in && s0 + 3 < n_out) anc[s0 + 3] = o.w;
+        }
+      }
+    }
+  }
 }

@@ -102,6 +102,9 @@ struct smcb_filter {
   int32_t* col_ticket = nullptr;
   double* tilesum = nullptr;
   TileSlot* slots = nullptr;
+  uint32_t* tilemin = nullptr;
+  int32_t *ncounter = nullptr, *verdict = nullptr;
+  float* u_col = nullptr;
   float *hist_mean = nullptr, *hist_var = nullptr, *hist_ll = nullptr;
   float *latest_mean = nullptr, *latest_var = nullptr, *latest_ll = nullptr, *ll_total = nullptr, *ess_packed = nullptr;
   float* y_own = nullptr;
@@ -142,7 +145,8 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->slots, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
-                  f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg};
+                  f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict,
+                  f->u_col};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -196,6 +200,10 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->col_ticket, (size_t)f->B));
   A_(dalloc(&f->tilesum, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->slots, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->tilemin, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->ncounter, (size_t)f->B));
+  A_(dalloc(&f->verdict, (size_t)f->B));
+  A_(dalloc(&f->u_col, (size_t)f->B));
   A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_var, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_ll, (size_t)rows * f->B));
@@ -372,12 +380,15 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.tilesum = f->tilesum; r.slots = f->slots; r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
   r.approx = f->cfg.exact_scan ? 0 : 1;
   r.dbg = f->dbg;
+  r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.verdict = f->verdict; r.u_col = f->u_col;
   normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
   if (f->cfg.resampler == SMCB_SYSTEMATIC) {
+    // every column is served by exactly one of the two kernels (verdict of normalize_kernel, decided on the device)
+    systematic_benign_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
     systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
-    f->launches++;
+    f->launches += 2;
   } else {
     r.c_out = f->cbuf;
     op_launch_multinomial_after_tilesum(r, f->U_in, f->ld, s);
@@ -479,6 +490,7 @@ extern "C" int smcb_filter_ptr(smcb_filter* f, int32_t what, void** p) {
     case SMCB_PTR_HIST_LL: *p = f->hist_ll; break;
     case SMCB_PTR_ESS: *p = f->ess_packed; break;
     case 20: *p = f->dbg; break;  /* diagnostics */
+    case 21: *p = f->verdict; break;
     default: return fail(SMCB_EINVAL, "unknown pointer id");
   }
   return SMCB_OK;
@@ -500,6 +512,7 @@ extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
 struct OpWorkspace {
   float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; TileSlot* slots = nullptr; Ctrl* ctrl = nullptr;
   ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
+  uint32_t* tilemin = nullptr; int32_t* ncounter = nullptr; int32_t* verdict = nullptr; float* u_col = nullptr;
   int64_t ld = 0; int tiles = 0, nblk = 0;
 };
 
@@ -516,6 +529,12 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   CU(cudaMallocAsync((void**)&ws.ctrl, sizeof(Ctrl), s));
   CU(cudaMallocAsync((void**)&ws.stats, (size_t)B * sizeof(ColStats), s));
   CU(cudaMallocAsync((void**)&ws.parts, (size_t)B * ws.nblk * sizeof(NormPartial), s));
+  CU(cudaMallocAsync((void**)&ws.tilemin, (size_t)B * ws.tiles * sizeof(uint32_t), s));
+  CU(cudaMallocAsync((void**)&ws.ncounter, (size_t)B * sizeof(int32_t), s));
+  CU(cudaMallocAsync((void**)&ws.verdict, (size_t)B * sizeof(int32_t), s));
+  CU(cudaMallocAsync((void**)&ws.u_col, (size_t)B * sizeof(float), s));
+  CU(cudaMemsetAsync(ws.ncounter, 0, (size_t)B * sizeof(int32_t), s));
+  CU(cudaMemsetAsync(ws.verdict, 0, (size_t)B * sizeof(int32_t), s));
   CU(cudaMemsetAsync(ws.w, 0, cells * sizeof(float), s));
   CU(cudaMemsetAsync(ws.slots, 0, (size_t)B * ws.tiles * sizeof(TileSlot), s));
   CU(cudaMemsetAsync(ws.ctrl, 0, sizeof(Ctrl), s));
@@ -523,7 +542,8 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   return SMCB_OK;
 }
 static void op_free(OpWorkspace& ws, cudaStream_t s) {
-  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf};
+  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
+                  ws.u_col};
   for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
 }
 
@@ -567,6 +587,7 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
     r.w = ws.w; r.wn = normalized ? ws.w : ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
     r.input_is_w = normalized ? 1 : 0; r.use_rw = 0; r.stats = normalized ? nullptr : ws.stats;
     r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.slots = ws.slots; r.anc = ws.anc; r.ctrl = ws.ctrl;
+    r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
     else {
       cudaError_t e = cudaMallocAsync((void**)&ws.cbuf, (size_t)B * ws.ld * sizeof(float), s);
