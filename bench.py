@@ -203,9 +203,9 @@ def run_b200(args):
     prof = (C.c_float * 5)()
     _lib.check(lib.smcb_filter_profile(e.handle, P, prof, stream.cuda_stream))
     e.t += P
-    names = ["apf_preweight", "normalize_kernel", "systematic_kernel", "step_kernel", "finalize_kernel"]
+    names = ["apf_preweight", "normalize_kernel", "describe_kernel", "expand_kernel", "step_kernel"]
     per = {n_: prof[i] / P for i, n_ in enumerate(names)}
-    alg_bytes = {"normalize_kernel": 4.0 * N, "systematic_kernel": 8.0 * N, "step_kernel": 16.0 * N, "finalize_kernel": 0.0,
+    alg_bytes = {"normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N, "expand_kernel": 8.0 * N, "step_kernel": 16.0 * N,
                  "apf_preweight": 12.0 * N}
     dom = max(per, key=per.get)
     peak, peak_src = load_peaks()

@@ -103,8 +103,8 @@ int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, int32_t cou
 int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream);
 
 /* measurement aid: runs `steps` moves like smcb_filter_run with CUDA events around every kernel group and returns the summed
- * device time in milliseconds: out_ms_host[0..4] = {APF pre-weight (+finalize), tile sums, scan + ancestors, fused step,
- * finalize}.  Synchronises the stream. */
+ * device time in milliseconds: out_ms_host[0..4] = {APF pre-weight (+finalize), normalize, describe (+chain), expand, fused
+ * step}.  Synchronises the stream. */
 int smcb_filter_profile(smcb_filter* f, int32_t steps, float* out_ms_host, void* stream);
 
 /* BaseFilter.batch_filter (filters/base.py:140-158) end to end on HOST buffers: initialises, copies y (T, obs_dim) to the

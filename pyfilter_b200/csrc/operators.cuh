@@ -172,9 +172,10 @@ static inline void op_launch_copy_ess(const ColStats* st, float* out, int B, cud
 
 // ---- systematic ------------------------------------------------------------------------------------------------------------------
 static inline void op_launch_systematic(const ResampleArgs& r, cudaStream_t s) {
-  normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
-  systematic_benign_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
-  systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
+  const dim3 g(r.tiles_per_col, r.B);
+  normalize_kernel<<<g, RS_NT, 0, s>>>(r);
+  describe_kernel<53><<<g, RS_NT, 0, s>>>(r);
+  expand_kernel<53, RS_OUT_ANCESTORS><<<g, RS_NT, 0, s>>>(r);
 }
 
 // ---- multinomial (resampling.py:55-65 -> ATen multinomial_with_replacement_kernel on CPU) --------------------------------------------
@@ -216,8 +217,10 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
 }
 
 // r.c_out must point at a (B, ld) float scratch buffer owned by the caller; normalize_kernel has already been enqueued
-static inline void op_launch_multinomial_after_tilesum(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
-  systematic_kernel<24, RS_OUT_CUMSUM><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
+static inline void op_launch_multinomial_after_normalize(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
+  const dim3 g(r.tiles_per_col, r.B);
+  describe_kernel<24><<<g, RS_NT, 0, s>>>(r);
+  expand_kernel<24, RS_OUT_CUMSUM><<<g, RS_NT, 0, s>>>(r);
   MultinomialArgs m;
   m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
   m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc;
@@ -230,6 +233,6 @@ static inline void op_launch_multinomial_after_tilesum(const ResampleArgs& r, co
 static inline int op_launch_multinomial(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
   if (!r.c_out) return SMCB_EINVAL;
   normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
-  op_launch_multinomial_after_tilesum(r, U, U_pitch, s);
+  op_launch_multinomial_after_normalize(r, U, U_pitch, s);
   return SMCB_OK;
 }

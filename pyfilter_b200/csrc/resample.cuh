@@ -1,10 +1,12 @@
 // Systematic resampling on the device, bit-exact against the reference's CPU path
 //     probs = (arange(n) + u) / n ; cumsum = W.cumsum(-1) ; cumsum[-1] = 1 ; searchsorted(cumsum, probs)     (resampling.py:44-50)
 //
-//   tile_sum_kernel   fp64 sum of every tile of normalised weights (approximate prefix -> binade labels)
-//   systematic_kernel one pass per tile: exact transducer scan (scan_tile.h) chained across tiles by a decoupled look-back on
-//                     exact states, then the ancestors are produced by EXPANSION: particle j owns the probes
-//                     [count(c_{j-1}), count(c_j)), staged through shared memory and written with coalesced stores.
+//   normalize_kernel   normalised weights, their fp64 tile sums and exclusive tile prefix, the column verdict (benign or not)
+//   describe_kernel    general columns only: every tile's transducer descriptor (scan_tile.h); the block that completes a column
+//                      chains the descriptors into the EXACT state before every tile
+//   expand_kernel      exact cumulative weights of the tile, then the ancestors by EXPANSION: particle j owns the output slots
+//                      [count(c_{j-1}), count(c_j)); marks in shared memory, a "last mark" scan, coalesced 128-bit stores
+// No kernel waits on another CTA: the dependencies between tiles are carried by the kernel boundaries and the small tails.
 // Layout: one column (independent filter) is a contiguous row of `ld` floats; tiles never straddle columns.
 #pragma once
 #include "common.cuh"
@@ -15,15 +17,16 @@
 #define RS_ITEMS 16
 #define RS_TILE (RS_NT * RS_ITEMS)
 #define RS_MAXSEG 192
-#define RS_LBSTACK 64
-#define RS_BIGLIST 32
-#define RS_BIG 96
 
-struct __align__(16) TileSlot {
-  XsDesc desc;       // 32 B
-  double incl;       // exact state after the tile
-  uint32_t status;   // (epoch << 2) | {0 none, 1 descriptor, 2 inclusive, 3 opaque}
-  uint32_t pad;
+// has_special of a published XsDesc: 0 / 1 as in scan_tile.h, or
+#define RS_KIND_TABLE 2   // more than one special element: the segment table sits in global memory (e1 = number of specials)
+#define RS_KIND_RAW 3     // too many segments: the chain walks the raw weights
+#define RS_KIND_ABS 4     // the state after the tile is a_s whatever came before (tile 0 resolves itself: it starts from 0)
+
+struct SegTable {
+  XsT agg[RS_MAXSEG];
+  float wc[RS_MAXSEG];
+  int32_t e[RS_MAXSEG];
 };
 
 struct ResampleArgs {
@@ -39,38 +42,63 @@ struct ResampleArgs {
   const float* u_in;       // optional injected offsets (B)
   float* u_out;            // optional dump of the offsets used (B)
   uint64_t seed;
-  double* tilesum;         // (B, tiles_per_col)
-  TileSlot* slots;         // (B, tiles_per_col)
+  double* tilesum;         // (B, tiles_per_col) fp64 sum of every tile
+  double* prefix;          // (B, tiles_per_col) exclusive prefix of the tile sums (exact in a benign column)
+  double* sin;             // (B, tiles_per_col) general columns: exact state before every tile (describe_kernel's chain)
+  int32_t* tileflag;       // (B, tiles_per_col) bit 0: the tile's speculation failed, expand it sequentially
+  XsDesc* desc;            // (B, tiles_per_col)
+  SegTable* tables;        // (B, tiles_per_col)
   int32_t* anc;            // (B, ld) ancestors out
   float* w_out;            // optional dump of the normalised weights used (B, ld)
   float* c_out;            // OUT_CUMSUM: the emulated sequential prefix sums (B, ld)
-  long long* dbg;          // optional per-tile timeline (8 x int64 globaltimer stamps per tile), diagnostics only
-  int32_t approx;          // 1: skip the exact chaining (incoming state := fp64 approximate prefix); NOT bit-exact, diagnostics only
   Ctrl* ctrl;
   uint32_t* tilemin;       // (B, tiles_per_col) smallest non-zero weight of every tile (float bits; 0 when a weight is negative)
   int32_t* ncounter;       // (B) last-block-done tickets of normalize_kernel (self resetting)
-  int32_t* verdict;        // (B) bit 0: the column is "benign" - its sequential fp64 prefix sum never rounds (benign kernel)
+  int32_t* dcounter;       // (B) last-block-done tickets of describe_kernel (self resetting)
+  int32_t* verdict;        // (B) bit 0: the column is "benign" - its sequential fp64 prefix sum never rounds; bit 1: n and u allow
+                           //     the lean probe count
   float* u_col;            // (B) the systematic offset of every column for this launch (injected or Philox)
+  long long* dbg;          // optional diagnostics (SMCB_DEBUG_TIMELINE): globaltimer stamps / counters of describe_kernel's chain
 };
+__device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { RS_OUT_ANCESTORS = 0, RS_OUT_CUMSUM = 1 };
 
 // ---- pre-pass: normalised weights (written once, zero beyond n), their fp64 tile sums and the column verdict ---------------------
 // A column is BENIGN when every non-zero weight is a multiple of 2^-52 (w >= 2^-29) and the weights sum to less than 2: then
 // every partial sum is a multiple of 2^-52 below 2, i.e. exactly representable, so the reference's sequential fp64 prefix sum
 // never rounds and equals the exact real prefix sum in ANY association.  Such columns need no binade labels, no transducers
-// and no chaining across tiles (systematic_benign_kernel); all others take the general exact scan (systematic_kernel).
+// and no chaining: the exact state before a tile is the plain sum of the preceding tile sums.
 struct OpMinU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a < b ? a : b; } };
 #define RS_BENIGN_MIN_BITS 0x31000000u  // 2^-29
+
+// exclusive block scan of one double per thread (blockDim.x == RS_NT); *total = sum over the block
+__device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch /*>=8*/, double* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  __syncthreads();
+  if (lane == 31) scratch[wid] = inc;
+  __syncthreads();
+  double off = 0.0, tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < RS_NT / 32; ++k) {
+    const double s = scratch[k];
+    off += (k < wid) ? s : 0.0;
+    tot += s;
+  }
+  *total = tot;
+  return off + (inc - v);
+}
 
 __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   __shared__ double scratch[33];
   __shared__ uint32_t uscratch[33];
   __shared__ int is_last;
   const int col = blockIdx.y, tile = blockIdx.x;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {  // arm the scan kernel that follows in stream order
-    a.ctrl->tile_counter = 0;
-    a.ctrl->epoch += 1;
-  }
   if (a.stats && !a.stats[col].resample) return;
   const int64_t off = (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
   const int64_t g0 = (int64_t)tile * RS_TILE;
@@ -109,15 +137,24 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   }
   __syncthreads();
   if (!is_last) return;
-  // ---- the block that completes a column settles its systematic offset and the verdict
+  // ---- the block that completes a column: exclusive prefix of the tile sums, systematic offset, verdict
   __threadfence();
-  double tot = 0.0;
+  const int T = a.tiles_per_col;
+  const int per = (T + RS_NT - 1) / RS_NT;
+  const int q0 = min(T, (int)threadIdx.x * per), q1 = min(T, q0 + per);
+  const double* ts = a.tilesum + (int64_t)col * T;
+  double part = 0.0;
   uint32_t mk = 0xFFFFFFFFu;
-  for (int q = threadIdx.x; q < a.tiles_per_col; q += RS_NT) {
-    tot += __ldcg(a.tilesum + (int64_t)col * a.tiles_per_col + q);
-    mk = min(mk, __ldcg(a.tilemin + (int64_t)col * a.tiles_per_col + q));
+  for (int q = q0; q < q1; ++q) {
+    part += __ldcg(ts + q);
+    mk = min(mk, __ldcg(a.tilemin + (int64_t)col * T + q));
   }
-  tot = block_allreduce<RS_NT>(tot, 0.0, OpSumD(), scratch);
+  double tot;
+  double run = rs_block_excl_scan_d(part, scratch, &tot);
+  for (int q = q0; q < q1; ++q) {
+    a.prefix[(int64_t)col * T + q] = run;
+    run += __ldcg(ts + q);
+  }
   mk = block_allreduce<RS_NT>(mk, 0xFFFFFFFFu, OpMinU(), uscratch);
   if (threadIdx.x == 0) {
     float u;  // one uniform per column (resampling.py:41)
@@ -129,64 +166,15 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     a.u_col[col] = u;
     if (a.u_out) a.u_out[col] = u;
     const bool u_ok = (u == 0.f) || (u >= 5.5e-20f && u < 1.0f);
-    const bool benign = !a.approx && mk >= RS_BENIGN_MIN_BITS && tot < 1.5 && a.n <= (1 << 23) && u_ok;
-    a.verdict[col] = benign ? 1 : 0;
+    const bool fast_ok = a.n <= (1 << 23) && u_ok;  // xs_count_fast applies (exact_scan.h)
+    const bool benign = fast_ok && mk >= RS_BENIGN_MIN_BITS && tot < 1.5;
+    a.verdict[col] = (benign ? 1 : 0) | (fast_ok ? 2 : 0);
     a.ncounter[col] = 0;
   }
 }
 
-// ---- block scans (the RS_NT compute threads synchronise on named barrier 1; the look-back warp is not involved) ------------
+// ---- block-level pieces of the exact tile scan ------------------------------------------------------------------------------------
 __device__ __forceinline__ void rs_cbar() { asm volatile("bar.sync 1, %0;" ::"n"(RS_NT) : "memory"); }
-
-__device__ __forceinline__ double rs_block_sum(double v, double* scratch /*>=33*/) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  rs_cbar();
-  if (lane == 0) scratch[wid] = v;
-  rs_cbar();
-  double r = 0.0;
-#pragma unroll
-  for (int k = 0; k < RS_NT / 32; ++k) r += scratch[k];
-  return r;
-}
-
-__device__ __forceinline__ double rs_block_excl_scan(double v, double* scratch /*>=33*/) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  double inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    double t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  rs_cbar();
-  if (lane == 31) scratch[wid] = inc;
-  rs_cbar();
-  double off = 0.0;
-#pragma unroll
-  for (int k = 0; k < RS_NT / 32; ++k) off += (k < wid) ? scratch[k] : 0.0;
-  return off + (inc - v);
-}
-
-// exclusive max-scan of one int per thread
-__device__ __forceinline__ int rs_block_excl_maxscan(int v, int* scratch /*>=8*/) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc = max(inc, t);
-  }
-  int excl = __shfl_up_sync(0xffffffffu, inc, 1);
-  if (lane == 0) excl = 0;
-  rs_cbar();
-  if (lane == 31) scratch[wid] = inc;
-  rs_cbar();
-  int off = 0;
-#pragma unroll
-  for (int k = 0; k < RS_NT / 32; ++k) off = max(off, (k < wid) ? scratch[k] : 0);
-  return max(off, excl);
-}
 
 __device__ __forceinline__ XsSeg rs_shfl_up(const XsSeg& s, int o) {
   XsSeg r;
@@ -224,7 +212,6 @@ __device__ __forceinline__ XsSeg rs_block_excl_scan_seg(const XsSeg& v, int lab,
   return xs_seg_combine<MB>(mine, excl, lab);
 }
 
-// ---- decoupled look-back on exact states (warp 0) ---------------------------------------------------------------------------
 __device__ __forceinline__ XsDesc rs_shfl_desc(const XsDesc& d, int src) {
   XsDesc r;
   r.a_s = __shfl_sync(0xffffffffu, d.a_s, src);
@@ -243,10 +230,11 @@ __device__ __forceinline__ XsDesc rs_shfl_desc(const XsDesc& d, int src) {
   return r;
 }
 
-__device__ __forceinline__ XsDesc rs_read_desc(const TileSlot* s) {
+// descriptors are written by other CTAs of the same launch: read them through L2
+__device__ __forceinline__ XsDesc rs_read_desc(const XsDesc* p) {
   XsDesc d;
-  const double2 q0 = __ldcg(reinterpret_cast<const double2*>(&s->desc));
-  const int4 q1 = __ldcg(reinterpret_cast<const int4*>(&s->desc) + 1);
+  const double2 q0 = __ldcg(reinterpret_cast<const double2*>(p));
+  const int4 q1 = __ldcg(reinterpret_cast<const int4*>(p) + 1);
   d.a_s = q0.x; d.b_s = q0.y;
   d.wc = __int_as_float(q1.x);
   d.e0 = (int16_t)(q1.y & 0xffff);
@@ -258,155 +246,18 @@ __device__ __forceinline__ XsDesc rs_read_desc(const TileSlot* s) {
   return d;
 }
 
-__device__ __forceinline__ uint32_t rs_wait_state(const TileSlot* s, uint32_t epoch, uint32_t want_mask) {
-  // spin until the slot carries this launch's epoch and a state whose bit is set in want_mask
-  for (;;) {
-    uint32_t st = ld_acquire_u32(&s->status);
-    if ((st >> 2) == epoch && ((want_mask >> (st & 3u)) & 1u)) return st & 3u;
-    __nanosleep(20);
-  }
-}
-
-__device__ __forceinline__ XsT rs_shfl_down_t(const XsT& t, int o) {
-  XsT r;
-  r.s = __shfl_down_sync(0xffffffffu, t.s, o);
-  r.d = __shfl_down_sync(0xffffffffu, t.d, o);
-  return r;
-}
-
-// Exact incoming state of `tile`: walk back over the predecessors' descriptors (32 per round) until a tile with a published
-// inclusive state is found, composing descriptors on the way.  Runs of descriptors without a special element in one binade
-// compose associatively (xs_compose), so a whole window folds in five shuffle steps; descriptors with a special element are
-// kept individually.  The collected entries are then applied forward to the exact state, each application verifying the
-// speculation behind it; on any failure the tile simply waits for its direct predecessor's inclusive state.
-template <int MB>
-__device__ double rs_lookback(const TileSlot* slots, int tile, uint32_t epoch, XsDesc* stack /*RS_LBSTACK*/, Ctrl* ctrl) {
-  const int lane = threadIdx.x & 31;
-  int win_base = tile - 1, top = 0;
-  bool have_run = false, overflow = false;
-  XsT run = xs_identity();
-  int runE = 0;
-  double S = 0.0;
-  auto flush_run = [&]() {
-    if (!have_run) return;
-    if (top < RS_LBSTACK) {
-      XsDesc e;
-      e.a_s = run.s; e.a_d = (int8_t)run.d; e.e0 = (int16_t)runE; e.has_special = 0;
-      e.b_s = 0.0; e.b_d = 0; e.wc = 0.f; e.e1 = 0; e.pad = 0;
-      if (lane == 0) stack[top] = e;
-      ++top;
-    } else overflow = true;
-    have_run = false;
-  };
-  auto add_plain = [&](const XsT& T, int E) {  // T is EARLIER in the sequence than the current run
-    if (have_run && runE == E) run = xs_compose<MB>(T, run, E);
-    else { flush_run(); run = T; runE = E; have_run = true; }
-  };
-  for (;;) {
-    const int idx = win_base - lane;
-    uint32_t st = 4u;  // 4 = before the first tile
-    if (idx >= 0) st = rs_wait_state(slots + idx, epoch, 0xEu);
-    unsigned m2 = __ballot_sync(0xffffffffu, st == 2u), m3 = __ballot_sync(0xffffffffu, st == 3u);
-    int l2 = m2 ? __ffs(m2) - 1 : 32, l3 = m3 ? __ffs(m3) - 1 : 32;
-    if (l3 < l2) {  // an opaque tile sits in front of the nearest inclusive state: wait for it to finish
-      if (lane == l3) st = rs_wait_state(slots + idx, epoch, 0x4u);
-      __syncwarp();
-      l2 = l3;
-    }
-    const int nd = l2;  // lanes [0, nd) hold descriptors
-    XsDesc d = {};
-    double incl = 0.0;
-    if (lane < nd) d = rs_read_desc(slots + idx);
-    if (lane == l2) incl = __ldcg(&slots[idx].incl);
-    if (nd > 0) {
-      const int e_first = __shfl_sync(0xffffffffu, (int)d.e0, 0);
-      const bool simple = lane >= nd || (!d.has_special && (int)d.e0 == e_first);
-      if (__all_sync(0xffffffffu, simple)) {
-        XsT T;
-        T.s = lane < nd ? d.a_s : 0.0;
-        T.d = lane < nd ? (int)d.a_d : 0;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          XsT up = rs_shfl_down_t(T, o);  // lane + o is a farther = earlier tile
-          if (lane + o < 32) T = xs_compose<MB>(up, T, e_first);
-        }
-        XsT T0;
-        T0.s = __shfl_sync(0xffffffffu, T.s, 0);
-        T0.d = __shfl_sync(0xffffffffu, T.d, 0);
-        add_plain(T0, e_first);
-      } else {
-        for (int l = 0; l < nd; ++l) {
-          XsDesc dl = rs_shfl_desc(d, l);
-          if (!dl.has_special) {
-            XsT T; T.s = dl.a_s; T.d = dl.a_d;
-            add_plain(T, (int)dl.e0);
-          } else {
-            flush_run();
-            if (top < RS_LBSTACK) { if (lane == 0) stack[top] = dl; ++top; } else overflow = true;
-          }
-        }
-      }
-    }
-    if (l2 < 32) { S = __shfl_sync(0xffffffffu, incl, l2); break; }
-    win_base -= 32;
-  }
-  flush_run();
-  __syncwarp();
-  bool ok = !overflow;
-  for (int k = top - 1; k >= 0 && ok; --k) {
-    const XsDesc e = stack[k];
-    double S2;
-    ok = xs_apply_desc<MB>(S, e, &S2);
-    S = S2;
-  }
-  if (lane == 0) atomicAdd((unsigned long long*)&ctrl->lb_windows, (unsigned long long)((tile - 1 - win_base) / 32 + 1));
-  if (!ok) {  // some speculation on the way does not hold for the true state: take the predecessor's own result
-    if (lane == 0) atomicAdd(&ctrl->lb_fail, 1);
-    const TileSlot* q = slots + (tile - 1);
-    rs_wait_state(q, epoch, 0x4u);
-    S = __ldcg(&q->incl);
-  }
-  return S;
-}
-
-// ---- the scan + expansion kernel ----------------------------------------------------------------------------------------------
-// Block = RS_NT compute threads (8 warps, 16 consecutive weights each) + ONE look-back warp.  The compute warps never wait for
-// the exact incoming state of the tile: they run the whole expansion SPECULATIVELY from the approximate prefix (accurate to
-// ~1e-13 relative, so the float32-rounded cumulative weights almost always come out identical), while the look-back warp
-// chains the exact state across tiles.  When the exact state arrives every thread re-derives its exact cumulative weights
-// (a handful of double additions) and compares bit for bit; only a tile where some value differs repeats the expansion.
-#define RS_STAGE (2 * RS_TILE)
-#define RS_THREADS (RS_NT + 32)
-struct RsSmem {
-  union {
-    int32_t stage[RS_STAGE];     // local index + 1 of the particle owning each output slot (0 = not yet known)
-    float c_slow[RS_TILE];       // cumulative weights from the sequential fallback
-  };
-  XsDesc stack[RS_LBSTACK];
+struct RsTileSmem {
+  double dscratch[33];
+  XsSeg sscratch[8];
+  int lscratch[8];
+  int lab_end[RS_NT];
   XsT seg_agg[RS_MAXSEG];
   double base[RS_MAXSEG];
   float seg_wc[RS_MAXSEG];
   int seg_e[RS_MAXSEG];
-  double dscratch[33];
-  XsSeg sscratch[8];
-  int lscratch[8];
-  int iscratch[8];
-  int lab_end[RS_NT];
-  int pre[RS_NT];
-  int tile_id, ok, X, e0, table_ok, carry, n_out;
-  double S_in, S_out, sp0;
+  int X, e0, table_ok, ok, is_last;
+  double S_out;
 };
-
-__device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define RS_STAMP(k) do { if (a.dbg && (threadIdx.x & 31) == 0) a.dbg[((int64_t)col * a.tiles_per_col + tile) * 8 + (k)] = rs_now(); } while (0)
-__device__ __forceinline__ void rs_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(RS_THREADS) : "memory"); }
-__device__ __forceinline__ void rs_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(RS_THREADS) : "memory"); }
-__device__ __forceinline__ int rs_cbar_or(int pred) {
-  int r;
-  asm volatile("{\n .reg .pred p, q;\n setp.ne.s32 p, %1, 0;\n bar.red.or.pred q, 1, %2, p;\n selp.s32 %0, 1, 0, q;\n}\n"
-               : "=r"(r) : "r"(pred), "n"(RS_NT) : "memory");
-  return r;
-}
 
 // rare paths, kept out of line so that the hot loops stay small (instruction-cache footprint)
 template <int MB>
@@ -416,12 +267,14 @@ __device__ __noinline__ void rs_thread_reduce_slow(const float (&w)[RS_ITEMS], d
 }
 template <int MB>
 __device__ __noinline__ void rs_thread_finalize_slow(const float (&w)[RS_ITEMS], uint32_t mask, int lab_prev, int s_base, XsT t_open,
-                                                     const double* base, const int* seg_e, float (&c)[RS_ITEMS]) {
-  xs_thread_finalize<MB, RS_ITEMS>(w, mask, lab_prev, s_base, t_open, base, seg_e, c);
+                                                     const double* base, const int* seg_e, float* c /*RS_ITEMS, shared memory*/) {
+  float cl[RS_ITEMS];
+  xs_thread_finalize<MB, RS_ITEMS>(w, mask, lab_prev, s_base, t_open, base, seg_e, cl);
+  for (int j = 0; j < RS_ITEMS; ++j) c[j] = cl[j];
 }
 template <int MB>
 __device__ __noinline__ void rs_fill_table(const float (&w)[RS_ITEMS], uint32_t mask, double sp_thread, int lab_prev, int lab_end,
-                                           XsSeg excl, RsSmem& sm) {
+                                           XsSeg excl, RsTileSmem& sm) {
   int s = excl.cnt;
   XsT T = excl.t;
   int E = lab_prev;
@@ -438,101 +291,314 @@ __device__ __noinline__ void rs_fill_table(const float (&w)[RS_ITEMS], uint32_t 
     }
   }
 }
-__device__ __noinline__ int32_t rs_count_slow(float c, float u, int32_t n, float nf) { return xs_count_le_t<int32_t>(c, u, n, nf); }
 
-// #{ i in [0,n) : fl32(fl32(i + u) / nf) <= c }  (exact_scan.h explains the midpoint argument).  Branch-free for n < 2^24:
-// with v = t - u, the probes i <= floor(v) - 1 always qualify and i >= floor(v) + 2 never do (fl32(i + u) is off by at most
-// half an ulp <= 0.5), so two float compares at floor(v) and floor(v) + 1 settle the count.
-__device__ __forceinline__ int32_t rs_count(float c, float u, int32_t n, float nf) {
-  const uint32_t cb = __float_as_uint(c);
-  const double t = (0.5 * ((double)c + (double)__uint_as_float(cb + 1u))) * (double)nf;
-  float tf = __double2float_rd(t);                       // largest float <= t
-  if ((cb & 1u) && (double)tf == t) tf = __uint_as_float(__float_as_uint(tf) - 1u);  // tie rounds away from c: need s < t
-  if (n >= (1 << 24) || !(c == c) || !(tf > 0.f)) return rs_count_slow(c, u, n, nf);
-  int i = __double2int_rd(t - (double)u);
-  i = min(i, n - 1);                                     // i >= -1 because t > 0 and u < 1
-  const bool ok0 = (i < 0) || (__fadd_rn((float)i, u) <= tf);
-  const bool ok1 = (i + 1 < n) && (__fadd_rn((float)(i + 1), u) <= tf);
-  return i + (ok0 ? 1 : 0) + ((ok0 && ok1) ? 1 : 0);
-}
-
-// RN_q(w) for an even incoming state in binade E (M = 2^E)
+// RN_q(w) for an even incoming state in binade E (M = 2^E; M = 0: the element is added unrounded)
 template <int MB>
 __device__ __forceinline__ double rs_round_q(float w, double M) {
   return (MB == 53) ? __dadd_rn(__dadd_rn(M, (double)w), -M) : (double)__fadd_rn(__fadd_rn((float)M, w), -(float)M);
 }
 
-template <int MB, int OUT>
-__global__ void __launch_bounds__(RS_THREADS, 3) systematic_kernel(ResampleArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  RsSmem& sm = *reinterpret_cast<RsSmem*>(smem_raw);
+// Phases A and B of scan_tile.h for one tile plus the block scan of the contributions.  Identical inputs give identical results
+// in describe_kernel and expand_kernel (same code, no atomics), which is what lets the two kernels share the speculation.
+template <int MB>
+struct RsScan {
+  double sp_thread;  // approximate state before this thread
+  double M;          // 2^lab_prev (0 in the zero state)
+  int lab_prev, lab_end;
+  bool simple;       // one binade, no tie: the thread's contribution is the plain exact sum of RN_q(w_j)
+  bool tile_simple;  // every thread of the tile is simple
+  uint32_t mask;     // special elements (non-simple threads)
+  XsSeg excl, total; // exclusive prefix of the contributions / whole tile
+};
+
+template <int MB>
+__device__ __forceinline__ void rs_tile_scan(const float (&w)[RS_ITEMS], double sp0, RsTileSmem& sm, RsScan<MB>& r) {
   const int tid = threadIdx.x;
-
-  // dynamic tile id: tiles start in id order, so every predecessor a tile waits on is running or finished
-  if (tid == 0) sm.tile_id = (int)atomicAdd(&a.ctrl->tile_counter, 1u);
-  __syncthreads();
-  const int id = sm.tile_id;
-  const int col = id / a.tiles_per_col, tile = id % a.tiles_per_col;
-  if (col >= a.B) return;
-  if (a.stats && !a.stats[col].resample) return;
-  if (MB == 53 && OUT == RS_OUT_ANCESTORS && (a.verdict[col] & 1)) return;  // systematic_benign_kernel owns this column
-  const uint32_t epoch = a.ctrl->epoch;
-  TileSlot* slots = a.slots + (int64_t)col * a.tiles_per_col;
-
-  if (tid >= RS_NT) {
-    // ================================ look-back warp ================================
-    rs_bar_sync(2);  // the compute warps have written the segment table
-    RS_STAMP(5);
-    const int lane = tid - RS_NT;
-    const int X = sm.X, e0 = sm.e0;
-    const bool table_ok = sm.table_ok != 0;
-    if (lane == 0 && tile > 0) {  // publish what successors can use before our own incoming state is known
-      TileSlot* me = slots + tile;
-      if (table_ok && X <= 1) {
-        XsDesc d;
-        d.a_s = sm.seg_agg[0].s; d.a_d = (int8_t)sm.seg_agg[0].d;
-        d.e0 = (int16_t)e0; d.has_special = (int8_t)X; d.pad = 0;
-        d.b_s = 0.0; d.b_d = 0; d.wc = 0.f; d.e1 = 0;
-        if (X) { d.wc = sm.seg_wc[1]; d.e1 = (int16_t)sm.seg_e[1]; d.b_s = sm.seg_agg[1].s; d.b_d = (int8_t)sm.seg_agg[1].d; }
-        me->desc = d;
-        st_release_u32(&me->status, (epoch << 2) | 1u);
-      } else {
-        st_release_u32(&me->status, (epoch << 2) | 3u);
-      }
-    }
-    double S_in = 0.0;
-    if (a.approx) S_in = sm.sp0;
-    else if (tile > 0) S_in = rs_lookback<MB>(slots, tile, epoch, sm.stack, a.ctrl);
-    if (lane == 0) {
-      double S_out = S_in;
-      bool ok = table_ok && xs_walk_segments<MB>(S_in, e0, X, sm.seg_agg, sm.seg_wc, sm.seg_e, sm.base, &S_out);
-      if (!ok) {  // speculation failed verification (or too many segments): genuine sequential adds over the tile
-        const float* wrow = a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
-        double S = S_in;
-        for (int k = 0; k < RS_TILE; ++k) S = xs_add_special<MB>(S, __ldg(wrow + k));
-        S_out = S;
-        atomicAdd(&a.ctrl->slow_tiles, 1);
-      }
-      sm.S_in = S_in;
-      sm.S_out = S_out;
-      sm.ok = ok ? 1 : 0;
-      slots[tile].incl = S_out;
-      st_release_u32(&slots[tile].status, (epoch << 2) | 2u);
-    }
-    RS_STAMP(6);
-    __syncwarp();
-    __threadfence_block();
-    rs_bar_arrive(3);
-    return;
+  double tsum = 0.0;
+  uint32_t key = 0xFFFFFFFFu;  // smallest non-zero weight of the thread (bits - 1; zeros wrap to the top)
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    tsum += (double)w[j];
+    key = min(key, __float_as_uint(w[j]) - 1u);
   }
+  double tot_approx;
+  r.sp_thread = sp0 + rs_block_excl_scan_d(tsum, sm.dscratch, &tot_approx);
+  const int e0 = xs_label(sp0);
+  r.lab_end = xs_label(r.sp_thread + tsum);
+  sm.lab_end[tid] = r.lab_end;
+  __syncthreads();
+  r.lab_prev = tid ? sm.lab_end[tid - 1] : e0;
+  r.M = (r.lab_prev == XS_E_ZERO) ? 0.0 : xs_pow2(r.lab_prev);
+  r.mask = 0;
+  XsSeg contrib = xs_seg_identity();
+  r.simple = (r.lab_prev == r.lab_end);
+  if (r.simple && r.lab_prev != XS_E_ZERO) {
+    // coarse thread: every non-zero weight is a multiple of the quantum 2^(E-(MB-1)), nothing rounds and tsum is exact
+    const int ef = r.lab_prev - (MB == 53 ? 29 : 0) + 127;
+    const bool coarse = (key == 0xFFFFFFFFu) || ef <= 0 || (ef < 255 && key + 1u >= ((uint32_t)ef << 23));
+    if (coarse) contrib.t.s = tsum;
+    else {
+      const double hq = xs_pow2(r.lab_prev - MB);
+      double acc = 0.0;
+      bool tie = false;
+#pragma unroll
+      for (int j = 0; j < RS_ITEMS; ++j) {
+        const double q = rs_round_q<MB>(w[j], r.M);
+        tie |= (fabs(__dadd_rn((double)w[j], -q)) == hq);
+        acc = __dadd_rn(acc, q);
+      }
+      contrib.t.s = acc;
+      r.simple = !tie;
+    }
+  }
+  if (!r.simple) rs_thread_reduce_slow<MB>(w, r.sp_thread, r.lab_prev, r.lab_end, &r.mask, &contrib);
+  r.tile_simple = !__syncthreads_or(r.simple ? 0 : 1);
+  int X = 0;
+  bool table_ok = true;
+  if (r.tile_simple) {
+    double tot;
+    r.excl.t.s = rs_block_excl_scan_d(contrib.t.s, sm.dscratch, &tot);  // exact: multiples of the quantum below 2^(E+1)
+    r.excl.t.d = 0; r.excl.cnt = 0;
+    r.total.t.s = tot; r.total.t.d = 0; r.total.cnt = 0;
+  } else {
+    r.excl = rs_block_excl_scan_seg<MB>(contrib, r.lab_prev, sm.sscratch, sm.lscratch, &r.total);
+    X = r.total.cnt;
+    table_ok = X < RS_MAXSEG;
+    if (table_ok && r.mask) rs_fill_table<MB>(w, r.mask, r.sp_thread, r.lab_prev, r.lab_end, r.excl, sm);
+  }
+  if (tid == 0) {
+    if (table_ok) sm.seg_agg[X] = r.total.t;
+    sm.X = X; sm.e0 = e0; sm.table_ok = table_ok ? 1 : 0;
+  }
+  __syncthreads();
+}
 
-  // ================================ compute warps ================================
-  const int32_t n = (int32_t)a.n;
-  const float nf = (float)a.n;
-  const float u = a.u_col[col];  // systematic offset of this column, settled by normalize_kernel
+// the reference operation itself over one whole tile, by one warp (fallback when a speculation fails): S <- fl_MB(S + w_k);
+// c (optional, shared memory) receives fl32 of every state
+template <int MB>
+__device__ __noinline__ double rs_warp_raw_walk(const float* wrow, double S, float* c) {
+  const int lane = threadIdx.x & 31;
+  for (int k0 = 0; k0 < RS_TILE; k0 += 32) {
+    const float v = __ldg(wrow + k0 + lane);
+    float cl = 0.f;
+    for (int i = 0; i < 32; ++i) {
+      S = xs_add_special<MB>(S, __shfl_sync(0xffffffffu, v, i));
+      if (i == lane) cl = (float)S;
+    }
+    if (c) c[k0 + lane] = cl;
+  }
+  return S;
+}
 
-  if (tid == 0) RS_STAMP(0);
-  // ---- this thread's 16 consecutive normalised weights (zero beyond n, written by normalize_kernel)
+// ---- describe_kernel: one descriptor per tile; the last block of a column chains them -----------------------------------------------
+// Chain semantics: S = 0; for every tile in order: sin[tile] = S; S = descriptor(S), every application verifying the speculation
+// behind the descriptor (scan_tile.h).  Rounds of RS_NT tiles, three phases per round:
+//   P1 (all warps)  descriptors -> integer transducers (scan_tile.h, XiT); each warp runs a segmented scan over its 32 tiles, a
+//                   segment being a maximal run of descriptors without special element in one binade (any other descriptor is a
+//                   segment of its own), and lists its segments;
+//   P2 (warp 0)     walks the segments in order: a handful of integer instructions per run, one genuine IEEE addition per special
+//                   element; a descriptor that does not verify is replaced by the reference operation over the raw tile and the
+//                   tile is flagged so that expand_kernel takes the same sequential route;
+//   P3 (all warps)  state before every tile = state at its segment start advanced by the tile's exclusive transducer.
+struct ChainSmem {
+  XiT ta[RS_NT];             // the tile's own transducer (first one when it has a special element)
+  XiT tb[RS_NT];             // second transducer of a descriptor with one special element; .k = bits of the state for RS_KIND_ABS
+  XiT ex[RS_NT];             // exclusive transducer of the tile inside its segment
+  float wc[RS_NT];
+  int16_t e0[RS_NT], e1[RS_NT];
+  int8_t kind[RS_NT];        // has_special of the descriptor; -1: the conversion to integer form failed
+  uint8_t seg_of[RS_NT];     // local segment index of the tile inside its warp
+  XiT seg_t[RS_NT];          // per (warp, local segment): aggregate transducer of a run
+  int16_t seg_tile[RS_NT];   // tile (index inside the round) of a single-descriptor segment, -1 for a run
+  uint64_t seg_start[RS_NT]; // P2 -> P3: bit pattern of the state at the start of the segment
+  int8_t seg_flag[RS_NT];    // 1: the single tile of the segment failed verification; 2: P2 wrote the tiles of the run itself
+  int nseg[RS_NT / 32];
+  uint64_t S;                // state carried from round to round
+};
+
+// one descriptor that is not part of a run (executed by a whole warp, uniformly); returns false when it does not verify
+template <int MB>
+__device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, int tile, int t, const ChainSmem& cs, uint64_t S,
+                                                uint64_t* out) {
+  const int lane = threadIdx.x & 31;
+  const int kind = cs.kind[t];
+  *out = S;
+  if (kind == 0) return xi_apply<MB>(S, (int)cs.e0[t], cs.ta[t], out);
+  if (kind == 1) {
+    uint64_t s1;
+    if (!xi_apply<MB>(S, (int)cs.e0[t], cs.ta[t], &s1)) return false;
+    const double s2 = xs_add_special<MB>(xs_u2d(s1), cs.wc[t]);
+    if (xs_label(s2) != (int)cs.e1[t]) return false;
+    return xi_apply<MB>(xs_d2u(s2), (int)cs.e1[t], cs.tb[t], out);
+  }
+  if (kind == RS_KIND_ABS) { *out = (uint64_t)cs.tb[t].k; return true; }
+  if (kind == RS_KIND_TABLE) {  // walk the tile's segments; 32 table entries are fetched per round trip
+    const SegTable* tb = a.tables + (int64_t)col * a.tiles_per_col + tile;
+    const int X = (int)cs.e1[t];
+    double S2 = xs_u2d(S);
+    bool ok = true;
+    for (int r0 = 0; r0 <= X && ok; r0 += 32) {
+      const int sl = min(r0 + lane, X);
+      const double gs = __ldcg(&tb->agg[sl].s);
+      const int gd = __ldcg(&tb->agg[sl].d);
+      const float gw = __ldcg(&tb->wc[sl]);
+      const int ge = __ldcg(&tb->e[sl]);
+      const int m = min(32, X + 1 - r0);
+      for (int i = 0; i < m && ok; ++i) {
+        XsT ts;
+        ts.s = __shfl_sync(0xffffffffu, gs, i);
+        ts.d = __shfl_sync(0xffffffffu, gd, i);
+        const float wc = __shfl_sync(0xffffffffu, gw, i);
+        int es = __shfl_sync(0xffffffffu, ge, i);
+        if (r0 + i == 0) es = (int)cs.e0[t];
+        else { S2 = xs_add_special<MB>(S2, wc); ok = (xs_label(S2) == es); }
+        if (ok) ok = xs_apply<MB>(S2, es, ts, &S2);
+      }
+    }
+    *out = xs_d2u(S2);
+    return ok;
+  }
+  return false;  // RS_KIND_RAW, failed conversion
+}
+
+template <int MB>
+__device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int T = a.tiles_per_col;
+  const XsDesc* desc = a.desc + (int64_t)col * T;
+  double* sin = a.sin + (int64_t)col * T;
+  int32_t* flag = a.tileflag + (int64_t)col * T;
+  const float* wcol = a.wn + (int64_t)col * a.ld;
+  if (tid == 0) cs.S = 0;
+  XsDesc dn = {};
+  if (tid < T) dn = rs_read_desc(desc + tid);
+  for (int base = 0; base < T; base += RS_NT) {
+    const int tile = base + tid;
+    const bool live = tile < T;
+    const XsDesc d = dn;
+    if (tile + RS_NT < T) dn = rs_read_desc(desc + tile + RS_NT);  // in flight while this round is processed
+    // ---- P1
+    XiT ta = xi_identity(), tb = xi_identity();
+    int kind = live ? (int)d.has_special : 0;
+    const int e0 = live ? (int)d.e0 : XS_E_ZERO;
+    if (live && kind <= 1) {
+      bool ok = xi_from<MB>(d.a_s, d.a_d, e0, &ta);
+      if (kind == 1) ok = ok && xi_from<MB>(d.b_s, d.b_d, (int)d.e1, &tb);
+      if (!ok) kind = -1;
+    }
+    if (kind == RS_KIND_ABS) tb.k = (int64_t)xs_d2u(d.a_s);
+    const bool plain = live && kind == 0;
+    const int e_left = __shfl_up_sync(0xffffffffu, e0, 1);
+    const int plain_left = __shfl_up_sync(0xffffffffu, plain ? 1 : 0, 1);
+    const bool head = (lane == 0) || !plain || !plain_left || e_left != e0;
+    XiT inc = plain ? ta : xi_identity();
+    bool hacc = head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {  // segmented inclusive scan (Kogge-Stone with head flags)
+      XiT t;
+      t.k = __shfl_up_sync(0xffffffffu, inc.k, o);
+      t.d = __shfl_up_sync(0xffffffffu, inc.d, o);
+      const int th = __shfl_up_sync(0xffffffffu, hacc ? 1 : 0, o);
+      if (lane >= o && !hacc) { inc = xi_compose<MB>(t, inc); hacc = th != 0; }
+    }
+    XiT ex;
+    ex.k = __shfl_up_sync(0xffffffffu, inc.k, 1);
+    ex.d = __shfl_up_sync(0xffffffffu, inc.d, 1);
+    if (head) ex = xi_identity();
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const int seg = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+    const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);  // last tile of its segment
+    cs.ta[tid] = ta; cs.tb[tid] = tb; cs.ex[tid] = ex; cs.wc[tid] = d.wc; cs.e0[tid] = (int16_t)e0; cs.e1[tid] = d.e1;
+    cs.kind[tid] = (int8_t)kind; cs.seg_of[tid] = (uint8_t)seg;
+    if (tail) { cs.seg_t[wid * 32 + seg] = inc; cs.seg_tile[wid * 32 + seg] = plain ? (int16_t)-1 : (int16_t)tid; }
+    if (lane == 0) cs.nseg[wid] = __popc(heads);
+    __syncthreads();
+    if (a.dbg && tid == 0 && base == 0) a.dbg[4] = rs_now();
+    // ---- P2: warp 0 walks the segments; their records are fetched 32 at a time so that only the state itself is a serial chain
+    if (wid == 0) {
+      uint64_t S = cs.S;
+      const int nw = min(RS_NT / 32, (T - base + 31) / 32);
+      int total = 0;
+      for (int w = 0; w < nw; ++w) total += cs.nseg[w];
+      for (int f0 = 0; f0 < total; f0 += 32) {
+        // flat segment f0 + lane -> (warp, local index)
+        int f = f0 + lane, w = 0;
+        while (w < nw - 1 && f >= cs.nseg[w]) { f -= cs.nseg[w]; ++w; }
+        const bool have = f0 + lane < total;
+        const int si_l = have ? w * 32 + f : 0;
+        const int st_l = have ? (int)cs.seg_tile[si_l] : -1;
+        int t0_l = w * 32;  // first tile of a run
+        if (have && st_l < 0) while (cs.seg_of[t0_l] != f) ++t0_l;
+        const XiT t_l = cs.seg_t[si_l];
+        const int e_l = (st_l < 0) ? (int)cs.e0[t0_l] : 0;
+        const int m = min(32, total - f0);
+        for (int i = 0; i < m; ++i) {
+          const int si = __shfl_sync(0xffffffffu, si_l, i);
+          const int st = __shfl_sync(0xffffffffu, st_l, i);
+          const int t0 = __shfl_sync(0xffffffffu, t0_l, i);
+          XiT t;
+          t.k = __shfl_sync(0xffffffffu, t_l.k, i);
+          t.d = __shfl_sync(0xffffffffu, t_l.d, i);
+          const int E = __shfl_sync(0xffffffffu, e_l, i);
+          if (st >= 0 && base + st >= T) break;  // padding behind the last tile
+          uint64_t S2 = S;
+          int fl = 0;
+          if (st < 0) {  // a run of plain descriptors in one binade
+            if (!xi_apply<MB>(S, E, t, &S2)) {  // some speculation inside the run is wrong: tile by tile
+              fl = 2;
+              S2 = S;
+              const int wq = t0 >> 5, jq = cs.seg_of[t0];
+              for (int q = t0; q < wq * 32 + 32 && cs.seg_of[q] == jq && base + q < T; ++q) {
+                uint64_t S3;
+                int tf = 0;
+                if (!xi_apply<MB>(S2, (int)cs.e0[q], cs.ta[q], &S3)) {
+                  S3 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + q) * RS_TILE, xs_u2d(S2), nullptr));
+                  tf = 1;
+                  if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
+                }
+                if (lane == 0) { sin[base + q] = xs_u2d(S2); flag[base + q] = tf; }
+                S2 = S3;
+              }
+            }
+          } else if (!rs_chain_single<MB>(a, col, base + st, st, cs, S, &S2)) {
+            S2 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + st) * RS_TILE, xs_u2d(S), nullptr));
+            fl = 1;
+            if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
+          }
+          if (lane == 0) { cs.seg_start[si] = S; cs.seg_flag[si] = (int8_t)fl; }
+          S = S2;
+        }
+      }
+      if (lane == 0) cs.S = S;
+    }
+    __syncthreads();
+    if (a.dbg && tid == 0 && base == 0) a.dbg[5] = rs_now();
+    // ---- P3
+    if (live) {
+      const int si = wid * 32 + seg;
+      const int fl = cs.seg_flag[si];
+      if (fl != 2) {
+        uint64_t sb;
+        xi_apply<MB>(cs.seg_start[si], e0, ex, &sb);
+        sin[tile] = xs_u2d(sb);
+        flag[tile] = fl;
+      }
+    }
+    __syncthreads();  // the round's tables are reused
+    if (a.dbg && tid == 0 && base == 0) a.dbg[6] = rs_now();
+  }
+}
+
+template <int MB>
+__global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
+  __shared__ __align__(16) RsTileSmem sm;
+  __shared__ __align__(16) ChainSmem cs;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x, col = blockIdx.y;
+  if (a.stats && !a.stats[col].resample) return;
+  if (MB == 53 && (a.verdict[col] & 1)) return;  // benign column: nothing to chain
+  const int T = a.tiles_per_col;
+  if (a.dbg && tid == 0) atomicMin((unsigned long long*)&a.dbg[0], (unsigned long long)rs_now());
   float w[RS_ITEMS];
   {
     const float4* src = reinterpret_cast<const float4*>(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + tid * RS_ITEMS);
@@ -542,248 +608,102 @@ __global__ void __launch_bounds__(RS_THREADS, 3) systematic_kernel(ResampleArgs 
       w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
     }
   }
-
-  // ---- phase A: approximate prefix -> labels at the thread boundaries
-  double sp0;
-  {
-    const double* ts = a.tilesum + (int64_t)col * a.tiles_per_col;
-    double part = 0.0;
-    for (int q = tid; q < tile; q += RS_NT) part += ts[q];
-    sp0 = rs_block_sum(part, sm.dscratch);
+  RsScan<MB> r;
+  rs_tile_scan<MB>(w, a.prefix[(int64_t)col * T + tile], sm, r);
+  const int X = sm.X;
+  const bool table_ok = sm.table_ok != 0;
+  if (table_ok && X > 1) {  // the segment table goes to global memory for the chain
+    SegTable* tb = a.tables + (int64_t)col * T + tile;
+    for (int s = tid; s <= X; s += RS_NT) { tb->agg[s] = sm.seg_agg[s]; tb->wc[s] = sm.seg_wc[s]; tb->e[s] = sm.seg_e[s]; }
   }
-  double tsum = 0.0;
-#pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
-  const double sp_thread = sp0 + rs_block_excl_scan(tsum, sm.dscratch);
-  const int e0 = xs_label(sp0);
-  const int lab_end = xs_label(sp_thread + tsum);
-  sm.lab_end[tid] = lab_end;
-  rs_cbar();
-  const int lab_prev = tid ? sm.lab_end[tid - 1] : e0;
-
-  // ---- phase B: per-thread transducer.  Hot path: a clean thread without ties is a plain sum of RN_q(w_j).
-  uint32_t mask = 0;
-  XsSeg contrib = xs_seg_identity();
-  bool simple = (lab_prev == lab_end);
-  const double M = (lab_prev == XS_E_ZERO) ? 0.0 : xs_pow2(lab_prev);
-  if (simple && lab_prev != XS_E_ZERO) {
-    const double hq = xs_pow2(lab_prev - MB);
-    double acc = 0.0;
-    bool tie = false;
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j) {
-      const double r = rs_round_q<MB>(w[j], M);
-      tie |= (fabs(__dadd_rn((double)w[j], -r)) == hq);
-      acc = __dadd_rn(acc, r);
-    }
-    contrib.t.s = acc;
-    simple = !tie;
-  }
-  if (!simple) rs_thread_reduce_slow<MB>(w, sp_thread, lab_prev, lab_end, &mask, &contrib);
-  XsSeg total;
-  const XsSeg excl = rs_block_excl_scan_seg<MB>(contrib, lab_prev, sm.sscratch, sm.lscratch, &total);
-  const int X = total.cnt;
-  const bool table_ok = X < RS_MAXSEG;
-  if (table_ok && mask) rs_fill_table<MB>(w, mask, sp_thread, lab_prev, lab_end, excl, sm);
   if (tid == 0) {
-    if (table_ok) sm.seg_agg[X] = total.t;
-    sm.X = X; sm.e0 = e0; sm.table_ok = table_ok ? 1 : 0; sm.sp0 = sp0;
+    XsDesc d;
+    d.a_s = 0.0; d.b_s = 0.0; d.wc = 0.f; d.e0 = (int16_t)sm.e0; d.e1 = 0; d.a_d = 0; d.b_d = 0; d.pad = 0;
+    double S_abs;
+    if (!table_ok) d.has_special = RS_KIND_RAW;
+    else if (tile == 0 && X > 0 && xs_walk_segments<MB>(0.0, sm.e0, X, sm.seg_agg, sm.seg_wc, sm.seg_e, sm.base, &S_abs)) {
+      d.has_special = RS_KIND_ABS; d.a_s = S_abs;
+    }
+    else if (X > 1) { d.has_special = RS_KIND_TABLE; d.e1 = (int16_t)X; }
+    else {
+      d.a_s = sm.seg_agg[0].s; d.a_d = (int8_t)sm.seg_agg[0].d; d.has_special = (int8_t)X;
+      if (X) { d.wc = sm.seg_wc[1]; d.e1 = (int16_t)sm.seg_e[1]; d.b_s = sm.seg_agg[1].s; d.b_d = (int8_t)sm.seg_agg[1].d; }
+    }
+    a.desc[(int64_t)col * T + tile] = d;
   }
-  __threadfence_block();
-  if (tid == 0) RS_STAMP(1);
-  rs_bar_arrive(2);  // hand the table to the look-back warp and carry on
-
-  // ---- phase D + expansion: first speculatively from the approximate prefix, then (rarely) again from the exact state
-  const int64_t g0 = (int64_t)tile * RS_TILE + tid * RS_ITEMS;
-  const int lidx0 = tid * RS_ITEMS;  // local index of this thread's first particle
-  int32_t* anc = a.anc + (int64_t)col * a.ld;
-  float c[RS_ITEMS];
-  float c_prev = 0.f;      // float32 cumulative weight just before this thread's first particle
-  int32_t n_in = 0;
-  bool staged = false;     // the ancestors of the whole tile are sitting in sm.stage / sm.pre
-  bool have_exact = false;
-  double S_in = 0.0;
-  for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1) {
-      if (tid == 0) RS_STAMP(2);
-      rs_bar_sync(3);
-      if (tid == 0) RS_STAMP(3);  // exact incoming state, segment bases and the verdict of the segment walk are in shared memory
-      have_exact = true;
-      S_in = sm.S_in;
-    }
-    // ---- cumulative weights of this thread
-    bool mismatch = false;
-    if (have_exact && !sm.ok) {
-      // sequential fallback: one compute thread redoes the genuine adds and leaves the results in shared memory
-      rs_cbar();
-      if (tid == 0) {
-        const float* wrow = a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
-        double S = S_in;
-        for (int k = 0; k < RS_TILE; ++k) { S = xs_add_special<MB>(S, __ldg(wrow + k)); sm.c_slow[k] = (float)S; }
-      }
-      rs_cbar();
-      mismatch = true;
-      c_prev = tid ? sm.c_slow[lidx0 - 1] : (float)S_in;
-      for (int k = 0; k < RS_ITEMS; ++k) c[k] = sm.c_slow[lidx0 + k];
-      rs_cbar();
-    } else if (simple) {
-      double S0;
-      if (have_exact) {
-        const double b = sm.base[excl.cnt];
-        S0 = b;
-        if (lab_prev != XS_E_ZERO) {
-          double inc = excl.t.s;
-          if (excl.t.d && xs_parity<MB>(b)) inc = __dadd_rn(inc, (double)excl.t.d * xs_pow2(lab_prev - (MB - 1)));
-          S0 = __dadd_rn(b, inc);
-        }
-      } else {
-        S0 = sp_thread;
-      }
-      const float cp = (float)S0;
-      mismatch |= have_exact && (__float_as_uint(cp) != __float_as_uint(c_prev));
-      c_prev = cp;
-      double acc = 0.0;
-#pragma unroll
-      for (int j = 0; j < RS_ITEMS; ++j) {
-        if (lab_prev != XS_E_ZERO) acc = __dadd_rn(acc, rs_round_q<MB>(w[j], M));
-        const float cj = (float)__dadd_rn(S0, acc);
-        mismatch |= have_exact && (__float_as_uint(cj) != __float_as_uint(c[j]));
-        c[j] = cj;
-      }
-    } else if (have_exact) {
-      rs_thread_finalize_slow<MB>(w, mask, lab_prev, excl.cnt, excl.t, sm.base, sm.seg_e, c);
-      int sb = excl.cnt;
-      double b = sm.base[sb];
-      double S0 = b;
-      if (lab_prev != XS_E_ZERO) xs_apply<MB>(b, lab_prev, excl.t, &S0);
-      c_prev = (float)S0;
-      mismatch = true;
-    } else {
-      mismatch = true;  // threads with ties or specials do not speculate
-#pragma unroll
-      for (int j = 0; j < RS_ITEMS; ++j) c[j] = 0.f;
-    }
-    if (pass == 0) {
-      if (rs_cbar_or(mismatch)) continue;        // somebody cannot speculate: wait for the exact state
-    } else {
-      if (tile == 0 && tid == 0) mismatch |= false;
-      const int redo = rs_cbar_or(mismatch || !staged);
-      if (!redo) break;                          // the speculative expansion was exact: its staged ancestors stand
-    }
-
-    if (OUT == RS_OUT_CUMSUM) {  // torch.multinomial's prefix sums: the search over them happens in multinomial_draw_kernel
-      if (!have_exact) continue;
-      float* dst = a.c_out + (int64_t)col * a.ld + g0;
-#pragma unroll
-      for (int v = 0; v < RS_ITEMS / 4; ++v)
-        reinterpret_cast<float4*>(dst)[v] = make_float4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
-      return;
-    }
-
-    // ---- expansion: particle j owns the probes [count(c_{j-1}), count(c_j))
-    int32_t cnt[RS_ITEMS];
-#pragma unroll
-    for (int j = 0; j < RS_ITEMS; ++j)
-      cnt[j] = (g0 + j >= n - 1) ? n : rs_count(c[j], u, n, nf);  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
-    const int32_t lo_thread = (tile == 0 && tid == 0) ? 0 : ((g0 - 1 >= n - 1) ? n : rs_count(c_prev, u, n, nf));
-    if (tid == 0) n_in = lo_thread;
-    if (tid == RS_NT - 1) sm.n_out = cnt[RS_ITEMS - 1];
-    if (tid == 0) { sm.carry = 0; sm.pre[0] = lo_thread; }
-    rs_cbar();
-    n_in = sm.pre[0];
-    const int32_t n_out = sm.n_out;
-    const int32_t len = n_out - n_in;
-    if (!have_exact && (len > RS_STAGE || len < 0)) { staged = false; continue; }  // too long to hold speculatively
-    rs_cbar();
-    for (int32_t chunk = n_in; chunk < n_out; chunk += RS_STAGE) {
-      const int32_t clen = min(RS_STAGE, n_out - chunk);
-      const int kshift = clen > RS_TILE ? 5 : 4;  // slots per thread in the max-scan: 32 or 16
-      // (a) clear, (b) every particle with offspring marks the first of its slots, (c) max-scan spreads the marks
-      for (int i = tid * 4; i < clen; i += RS_NT * 4) *reinterpret_cast<int4*>(&sm.stage[i]) = make_int4(0, 0, 0, 0);
-      rs_cbar();
-      {
-        int32_t lo = lo_thread;
-#pragma unroll
-        for (int j = 0; j < RS_ITEMS; ++j) {
-          const int32_t hi = cnt[j];
-          if (hi > lo) {
-            if (lo >= chunk) { if (lo < chunk + clen) sm.stage[lo - chunk] = lidx0 + j + 1; }
-            else if (hi > chunk) sm.carry = lidx0 + j + 1;  // its slots began in an earlier chunk (one such particle at most)
-          }
-          lo = hi;
-        }
-      }
-      rs_cbar();
-      int run = 0;
-      {
-        const int i0 = tid << kshift, i1 = min(i0 + (1 << kshift), clen);
-        for (int i = i0; i < i1; ++i) { run = max(run, sm.stage[i]); sm.stage[i] = run; }
-      }
-      const int pre = max(rs_block_excl_maxscan(run, sm.iscratch), sm.carry);
-      sm.pre[tid] = pre;
-      rs_cbar();
-      if (have_exact) {
-        const int32_t tile_base = tile * RS_TILE - 1;
-        for (int i = tid; i < clen; i += RS_NT) anc[chunk + i] = tile_base + max(sm.stage[i], sm.pre[i >> kshift]);
-        rs_cbar();
-        if (tid == 0) sm.carry = max(sm.stage[clen - 1], sm.pre[(clen - 1) >> kshift]);
-        rs_cbar();
-      }
-    }
-    if (have_exact) { if (tid == 0) RS_STAMP(7); return; }
-    staged = true;
+  __threadfence();  // table and descriptor stores of every thread precede the ticket
+  __syncthreads();
+  if (tid == 0) {
+    sm.is_last = (atomicAdd(&a.dcounter[col], 1) == T - 1);
   }
-  // ---- the speculative expansion was verified: write its staged ancestors
-  {
-    const int32_t n_out = sm.n_out;
-    const int32_t clen = n_out - n_in;
-    const int kshift = clen > RS_TILE ? 5 : 4;
-    const int32_t tile_base = tile * RS_TILE - 1;
-    for (int i = tid; i < clen; i += RS_NT) anc[n_in + i] = tile_base + max(sm.stage[i], sm.pre[i >> kshift]);
-  }
-  if (tid == 0) RS_STAMP(4);
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  if (a.dbg && tid == 0) a.dbg[1] = rs_now();
+  rs_chain<MB>(a, col, cs);
+  if (tid == 0) a.dcounter[col] = 0;
+  if (a.dbg && tid == 0) a.dbg[2] = rs_now();
 }
 
-// ---- benign columns: no rounding anywhere, hence no labels, no transducers, no chaining -----------------------------------------
-// One CTA per tile, no dependency between CTAs: the exact state before the tile is the (exact) sum of the preceding tile sums.
-// Expansion as in systematic_kernel: particle j owns the output slots [count(c_{j-1}), count(c_j)).  Every particle with
-// offspring marks its first slot in a shared-memory window; a "last mark at or before me" scan (ancestors are sorted, so this is
-// a running maximum) turns the marks into ancestors, which leave as coalesced 128-bit stores.
+// ---- probes at or below a cumulative weight ------------------------------------------------------------------------------------------
+__device__ __noinline__ int32_t rs_count_slow(float c, float u, int32_t n, float nf) { return xs_count_le_t<int32_t>(c, u, n, nf); }
+
+// general form: any n < 2^31, any c, any u
+__device__ __forceinline__ int32_t rs_count_any(float c, float u, int32_t n, float nf, double nd, double nfd, bool fast_ok) {
+  const uint32_t cb = __float_as_uint(c);
+  if (fast_ok && (cb == 0u || (cb >= 0x00800000u && cb < 0x7F800000u))) return xs_count_fast(c, u, n, nd, nfd);
+  return rs_count_slow(c, u, n, nf);
+}
+
+// ---- expand_kernel -------------------------------------------------------------------------------------------------------------------
 #define FB_ROWS 5                              // int4 rows per warp and window
 #define FB_WIN (RS_NT / 32 * FB_ROWS * 32 * 4) // 5120 output slots per window
-struct FbSmem {
-  int32_t stage[FB_WIN];
-  double dscratch[33];
+struct ExpandSmem {
+  int32_t stage[FB_WIN];      // global index of the particle whose FIRST offspring sits in this slot, -1 elsewhere
+  float c_tile[RS_TILE];      // cumulative weights of the tile (general tiles only)
+  RsTileSmem core;
   int32_t wtot[RS_NT / 32];
   int32_t carry, n_out;
 };
 
-// counts of this thread's particles, marking the first slot of every particle with offspring inside the window [wb, wb + FB_WIN)
-__device__ __forceinline__ int32_t fb_mark_pass(const float (&w)[RS_ITEMS], double base, int32_t lo, int32_t gbase, int32_t wb, bool first,
-                                                float u, int32_t n, double nd, double nfd, FbSmem& sm) {
-  double run = base;
+// Counts of this thread's particles; every particle with offspring marks its first slot inside the window [wb, wb + FB_WIN).
+// FAST: cumulative weights on the fly, c_j = fl32(S0 + sum_{i<=j} RN_q(w_i)); otherwise they are read from shared memory.
+template <int MB, bool FAST, bool BENIGN>
+__device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[RS_ITEMS], double S0, double M, const float* c_thread, int32_t lo,
+                                                int32_t gbase, int32_t wb, bool first, float u, int32_t n, float nf, double nd,
+                                                double nfd, bool fast_ok, ExpandSmem& sm) {
+  double run = S0;
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
-    run += (double)w[j];
-    int32_t hi = xs_count_fast((float)run, u, n, nd, nfd);
+    float c;
+    if (FAST) {
+      run = __dadd_rn(run, BENIGN ? (double)w[j] : rs_round_q<MB>(w[j], M));
+      c = (float)run;
+    } else c = c_thread[j];
+    int32_t hi = BENIGN ? xs_count_fast(c, u, n, nd, nfd) : rs_count_any(c, u, n, nf, nd, nfd, fast_ok);
     hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
     const int32_t r = lo - wb;
     if (hi > lo && (uint32_t)r < (uint32_t)FB_WIN) sm.stage[r] = gbase + j;
     if (!first && hi > lo && r < 0 && hi > wb) sm.carry = gbase + j;  // its slots began in an earlier window (one such particle at most)
-    lo = hi;
+    lo = max(lo, hi);
   }
   return lo;
 }
 
-__global__ void __launch_bounds__(RS_NT, 4) systematic_benign_kernel(ResampleArgs a) {
-  __shared__ __align__(16) FbSmem sm;
+template <int MB, int OUT>
+__global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
+  __shared__ __align__(16) ExpandSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile = blockIdx.x, col = blockIdx.y;
   if (a.stats && !a.stats[col].resample) return;
-  if (!(a.verdict[col] & 1)) return;
+  const int T = a.tiles_per_col;
+  const int vd = (OUT == RS_OUT_ANCESTORS) ? a.verdict[col] : 0;
+  const bool benign = (MB == 53) && (vd & 1);
+  const bool fast_ok = (vd & 2) != 0;
   const int32_t n = (int32_t)a.n;
-  const double nd = (double)n, nfd = (double)(float)a.n;
-  const float u = a.u_col[col];
+  const float nf = (float)a.n;
+  const double nd = (double)n, nfd = (double)nf;
+  const float u = (OUT == RS_OUT_ANCESTORS) ? a.u_col[col] : 0.f;
 
   float w[RS_ITEMS];
   {
@@ -794,45 +714,93 @@ __global__ void __launch_bounds__(RS_NT, 4) systematic_benign_kernel(ResampleArg
       w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
     }
   }
-  // clear the first window while the loads are in flight
+  if (OUT == RS_OUT_ANCESTORS) {  // clear the first window while the loads are in flight
 #pragma unroll
-  for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-  if (tid == 0) sm.carry = -1;
-  // exact state before the tile and before this thread (all additions are exact in a benign column)
-  double S_in;
-  {
-    const double* ts = a.tilesum + (int64_t)col * a.tiles_per_col;
-    double part = 0.0;
-    for (int q = tid; q < tile; q += RS_NT) part += ts[q];
-    S_in = block_allreduce<RS_NT>(part, 0.0, OpSumD(), sm.dscratch);
+    for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+    if (tid == 0) sm.carry = -1;
   }
-  double tsum = 0.0;
+  const double sp0 = a.prefix[(int64_t)col * T + tile];
+
+  // ---- exact state before the tile (S_in) and before this thread (S0)
+  double S_in, S0, M = 0.0;
+  bool fast = true;  // block-uniform: cumulative weights on the fly from (S0, M); else through sm.c_tile
+  if (benign) {
+    double tsum = 0.0, tot;
 #pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
-  double base;
-  {  // exclusive block scan of the thread sums
-    double inc = tsum;
+    for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
+    S_in = sp0;
+    S0 = S_in + rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);  // exact
+  } else {
+    S_in = a.sin[(int64_t)col * T + tile];
+    bool slow = (a.tileflag[(int64_t)col * T + tile] & 1) != 0;
+    RsScan<MB> r;
+    S0 = S_in;
+    if (!slow) {
+      rs_tile_scan<MB>(w, sp0, sm.core, r);
+      M = r.M;
+      if (r.tile_simple) S0 = __dadd_rn(S_in, r.excl.t.s);  // exact; the chain verified binade and range
+      else {
+        fast = false;
+        if (tid == 0) {
+          double S_out;
+          sm.core.ok = (sm.core.table_ok && xs_walk_segments<MB>(S_in, sm.core.e0, sm.core.X, sm.core.seg_agg, sm.core.seg_wc,
+                                                                 sm.core.seg_e, sm.core.base, &S_out)) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!sm.core.ok) slow = true;  // cannot happen after a verified chain; stay safe
+        else if (r.simple) {
+          const double b = sm.core.base[r.excl.cnt];
+          double Ss = b;
+          if (r.lab_prev != XS_E_ZERO) xs_apply<MB>(b, r.lab_prev, r.excl.t, &Ss);
+          double acc = Ss;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
+          for (int j = 0; j < RS_ITEMS; ++j) {
+            acc = __dadd_rn(acc, rs_round_q<MB>(w[j], r.M));
+            sm.c_tile[tid * RS_ITEMS + j] = (float)acc;
+          }
+        } else rs_thread_finalize_slow<MB>(w, r.mask, r.lab_prev, r.excl.cnt, r.excl.t, sm.core.base, sm.core.seg_e,
+                                           &sm.c_tile[tid * RS_ITEMS]);
+      }
     }
-    __syncthreads();
-    if (lane == 31) sm.dscratch[wid] = inc;
-    __syncthreads();
-    double off = 0.0;
-#pragma unroll
-    for (int k = 0; k < RS_NT / 32; ++k) off += (k < wid) ? sm.dscratch[k] : 0.0;
-    base = S_in + (off + (inc - tsum));
+    if (slow) {  // the reference operation itself, sequentially
+      fast = false;
+      __syncthreads();
+      if (tid < 32) rs_warp_raw_walk<MB>(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE, S_in, sm.c_tile);
+    }
+    if (!fast) __syncthreads();
   }
-  // slots owned by the tile start at n_in = #probes at or below the cumulative weight before the tile
+
   const int32_t gbase = tile * RS_TILE + tid * RS_ITEMS;  // global index of this thread's first particle
-  const int32_t n_in = (tile == 0) ? 0 : ((tile * RS_TILE - 1 >= n - 1) ? n : xs_count_fast((float)S_in, u, n, nd, nfd));
+  if (OUT == RS_OUT_CUMSUM) {  // torch.multinomial's prefix sums: the search over them happens in multinomial_draw_kernel
+    float c[RS_ITEMS];
+    double run = S0;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) {
+      if (fast) { run = __dadd_rn(run, rs_round_q<MB>(w[j], M)); c[j] = (float)run; }
+      else c[j] = sm.c_tile[tid * RS_ITEMS + j];
+    }
+    float* dst = a.c_out + (int64_t)col * a.ld + gbase;
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v)
+      reinterpret_cast<float4*>(dst)[v] = make_float4(c[4 * v], c[4 * v + 1], c[4 * v + 2], c[4 * v + 3]);
+    return;
+  }
+
+  // ---- expansion: the tile owns the output slots [n_in, n_out)
+  const float c_in = (float)S_in;  // cumulative weight just before the tile
+  const float c_prev = fast ? (float)S0 : (tid ? sm.c_tile[tid * RS_ITEMS - 1] : c_in);
+  const float* c_thread = &sm.c_tile[tid * RS_ITEMS];
+  const int32_t n_in = (tile == 0) ? 0 : ((tile * RS_TILE - 1 >= n - 1) ? n : rs_count_any(c_in, u, n, nf, nd, nfd, fast_ok));
   int32_t lo_thread = n_in;
-  if (tid) lo_thread = (gbase - 1 >= n - 1) ? n : xs_count_fast((float)base, u, n, nd, nfd);
+  if (tid) lo_thread = max(n_in, (gbase - 1 >= n - 1) ? n : rs_count_any(c_prev, u, n, nf, nd, nfd, fast_ok));
   const int32_t wb0 = n_in & ~3;
+  auto mark = [&](int32_t wb, bool first) -> int32_t {
+    if (benign) return rs_mark_pass<MB, true, true>(w, S0, 0.0, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, sm);
+    if (fast) return rs_mark_pass<MB, true, false>(w, S0, M, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, fast_ok, sm);
+    return rs_mark_pass<MB, false, false>(w, S0, M, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, fast_ok, sm);
+  };
   {
-    const int32_t last = fb_mark_pass(w, base, lo_thread, gbase, wb0, true, u, n, nd, nfd, sm);
+    const int32_t last = mark(wb0, true);
     if (tid == RS_NT - 1) sm.n_out = last;
   }
   __syncthreads();
@@ -847,7 +815,7 @@ __global__ void __launch_bounds__(RS_NT, 4) systematic_benign_kernel(ResampleArg
       for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
       if (tid == 0) sm.carry = -1;
       __syncthreads();
-      fb_mark_pass(w, base, lo_thread, gbase, wb, false, u, n, nd, nfd, sm);
+      mark(wb, false);
       __syncthreads();
       carry = max(carry, sm.carry);
     }

@@ -143,3 +143,55 @@ XS_HD void xs_thread_finalize(const float (&w)[ITEMS], uint32_t special_mask, in
     c[j] = (float)S;
   }
 }
+
+// ---- integer form of the transducers (used by the chain of describe_kernel) ---------------------------------------------
+// Inside one binade the bit pattern of the state is an integer counter: adding one quantum 2^(E-(MB-1)) adds
+// XI_UNIT = 1 << (53 - MB) to the pattern.  A transducer becomes (k, d): k pattern units for an even state, k + d*XI_UNIT for an
+// odd one.  Applying and composing are then a handful of integer instructions with no floating-point latency chain.
+struct XiT {
+  int64_t k;
+  int32_t d;
+};
+XS_HD XiT xi_identity() { XiT t; t.k = 0; t.d = 0; return t; }
+
+// (s, d) in binade E -> integer form; false when s is not an increment that can stay inside the binade
+template <int MB>
+XS_HD bool xi_from(double s, int d, int E, XiT* out) {
+  out->k = 0; out->d = 0;
+  if (E == XS_E_ZERO) return s == 0.0 && d == 0;
+  const double M = xs_pow2(E);
+  if (!(s >= 0.0 && s < M)) return false;
+  out->k = (int64_t)(xs_d2u(xs_dadd(M, s)) - xs_d2u(M));
+  out->d = d;
+  return true;
+}
+
+// a THEN b, both in the same binade
+template <int MB>
+XS_HD XiT xi_compose(const XiT& a, const XiT& b) {
+  constexpr int SH = 53 - MB;
+  const int64_t U = (int64_t)1 << SH;
+  XiT r;
+  const int64_t a1 = a.k + (int64_t)a.d * U;
+  const int p0 = (int)((a.k >> SH) & 1);        // parity of the state after a, incoming even
+  const int p1 = (int)((a1 >> SH) & 1) ^ 1;     // ... incoming odd
+  const int64_t r0 = a.k + b.k + (p0 ? (int64_t)b.d * U : 0);
+  const int64_t r1 = a1 + b.k + (p1 ? (int64_t)b.d * U : 0);
+  r.k = r0;
+  r.d = r1 > r0 ? 1 : (r1 < r0 ? -1 : 0);
+  return r;
+}
+
+// bit pattern of a state in binade E (or 0 with E == XS_E_ZERO) advanced by a transducer; false when it would leave the binade
+template <int MB>
+XS_HD bool xi_apply(uint64_t bits, int E, const XiT& t, uint64_t* out) {
+  constexpr int SH = 53 - MB;
+  *out = bits;
+  if (E == XS_E_ZERO) return bits == 0 && t.k == 0 && t.d == 0;
+  if ((int)(bits >> 52) != E + 1023) return false;
+  const int64_t inc = t.k + ((t.d && ((bits >> SH) & 1)) ? (int64_t)t.d * ((int64_t)1 << SH) : 0);
+  if (inc < 0) return false;
+  const uint64_t nb = bits + (uint64_t)inc;
+  *out = nb;
+  return (nb >> 52) == (bits >> 52);
+}

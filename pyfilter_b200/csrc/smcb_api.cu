@@ -100,10 +100,12 @@ struct smcb_filter {
   Partial* partials = nullptr;
   Ctrl* ctrl = nullptr;
   int32_t* col_ticket = nullptr;
-  double* tilesum = nullptr;
-  TileSlot* slots = nullptr;
+  double *tilesum = nullptr, *prefix = nullptr, *sin = nullptr;
+  int32_t* tileflag = nullptr;
+  XsDesc* desc = nullptr;
+  SegTable* tables = nullptr;
   uint32_t* tilemin = nullptr;
-  int32_t *ncounter = nullptr, *verdict = nullptr;
+  int32_t *ncounter = nullptr, *dcounter = nullptr, *verdict = nullptr;
   float* u_col = nullptr;
   float *hist_mean = nullptr, *hist_var = nullptr, *hist_ll = nullptr;
   float *latest_mean = nullptr, *latest_var = nullptr, *latest_ll = nullptr, *ll_total = nullptr, *ess_packed = nullptr;
@@ -144,7 +146,7 @@ static int upload_params(smcb_filter* f, const float* params_host, int n_raw, in
 extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
-                  f->tilesum, f->slots, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
+                  f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict,
                   f->u_col};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -199,7 +201,12 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ctrl, (size_t)1));
   A_(dalloc(&f->col_ticket, (size_t)f->B));
   A_(dalloc(&f->tilesum, (size_t)f->B * f->tiles_per_col));
-  A_(dalloc(&f->slots, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->prefix, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->sin, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->tileflag, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->desc, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->tables, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->dcounter, (size_t)f->B));
   A_(dalloc(&f->tilemin, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->ncounter, (size_t)f->B));
   A_(dalloc(&f->verdict, (size_t)f->B));
@@ -213,7 +220,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
-  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)f->B * f->tiles_per_col * 8));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)16));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -236,7 +243,7 @@ extern "C" int smcb_filter_info(smcb_filter* f, smcb_info* o) {
   o->t = f->t_host; o->history_rows = f->cfg.history_rows; o->kernel_launches = f->launches;
   Ctrl c;
   CU(cudaMemcpy(&c, f->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost));
-  o->slow_tiles = c.slow_tiles; o->lb_fail = c.lb_fail; o->lb_windows = c.lb_windows; o->reserved = 0;
+  o->slow_tiles = c.slow_tiles; o->lb_fail = 0; o->lb_windows = 0; o->reserved = 0;
   return SMCB_OK;
 }
 
@@ -377,26 +384,27 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.n = f->n; r.ld = f->ld; r.B = f->B; r.tiles_per_col = f->tiles_per_col;
   r.input_is_w = 0; r.use_rw = apf ? 1 : 0; r.stats = f->stats;
   r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed;
-  r.tilesum = f->tilesum; r.slots = f->slots; r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
-  r.approx = f->cfg.exact_scan ? 0 : 1;
+  r.tilesum = f->tilesum; r.prefix = f->prefix; r.sin = f->sin; r.tileflag = f->tileflag; r.desc = f->desc; r.tables = f->tables;
+  r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
+  r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.dcounter = f->dcounter; r.verdict = f->verdict; r.u_col = f->u_col;
   r.dbg = f->dbg;
-  r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.verdict = f->verdict; r.u_col = f->u_col;
-  normalize_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
+  const dim3 rgrid(r.tiles_per_col, r.B);
+  normalize_kernel<<<rgrid, RS_NT, 0, s>>>(r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
   if (f->cfg.resampler == SMCB_SYSTEMATIC) {
-    // every column is served by exactly one of the two kernels (verdict of normalize_kernel, decided on the device)
-    systematic_benign_kernel<<<dim3(r.tiles_per_col, r.B), RS_NT, 0, s>>>(r);
-    systematic_kernel<53, RS_OUT_ANCESTORS><<<r.tiles_per_col * r.B, RS_THREADS, sizeof(RsSmem), s>>>(r);
+    describe_kernel<53><<<rgrid, RS_NT, 0, s>>>(r);  // returns at once for benign columns (verdict decided on the device)
+    if (ev) cudaEventRecord(ev[3], s);
+    expand_kernel<53, RS_OUT_ANCESTORS><<<rgrid, RS_NT, 0, s>>>(r);
     f->launches += 2;
   } else {
     r.c_out = f->cbuf;
-    op_launch_multinomial_after_tilesum(r, f->U_in, f->ld, s);
-    f->launches += 2;
+    if (ev) cudaEventRecord(ev[3], s);
+    op_launch_multinomial_after_normalize(r, f->U_in, f->ld, s);
+    f->launches += 3;
   }
-  if (ev) cudaEventRecord(ev[3], s);
-  launch_step(f, a, s);  // the block that completes a column also folds its partials (finalize_column, FIN_STEP)
   if (ev) cudaEventRecord(ev[4], s);
+  launch_step(f, a, s);  // the block that completes a column also folds its partials (finalize_column, FIN_STEP)
   if (ev) cudaEventRecord(ev[5], s);
   f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
   f->t_host = t + 1;
@@ -510,7 +518,8 @@ extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
 
 // ---- stand-alone operators ---------------------------------------------------------------------------------------------------------
 struct OpWorkspace {
-  float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; TileSlot* slots = nullptr; Ctrl* ctrl = nullptr;
+  float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; Ctrl* ctrl = nullptr;
+  double *prefix = nullptr, *sin = nullptr; int32_t *tileflag = nullptr, *dcounter = nullptr; XsDesc* desc = nullptr; SegTable* tables = nullptr;
   ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
   uint32_t* tilemin = nullptr; int32_t* ncounter = nullptr; int32_t* verdict = nullptr; float* u_col = nullptr;
   int64_t ld = 0; int tiles = 0, nblk = 0;
@@ -525,7 +534,13 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   CU(cudaMallocAsync((void**)&ws.wn, cells * sizeof(float), s));
   CU(cudaMallocAsync((void**)&ws.anc, cells * sizeof(int32_t), s));
   CU(cudaMallocAsync((void**)&ws.tilesum, (size_t)B * ws.tiles * sizeof(double), s));
-  CU(cudaMallocAsync((void**)&ws.slots, (size_t)B * ws.tiles * sizeof(TileSlot), s));
+  CU(cudaMallocAsync((void**)&ws.prefix, (size_t)B * ws.tiles * sizeof(double), s));
+  CU(cudaMallocAsync((void**)&ws.sin, (size_t)B * ws.tiles * sizeof(double), s));
+  CU(cudaMallocAsync((void**)&ws.tileflag, (size_t)B * ws.tiles * sizeof(int32_t), s));
+  CU(cudaMallocAsync((void**)&ws.desc, (size_t)B * ws.tiles * sizeof(XsDesc), s));
+  CU(cudaMallocAsync((void**)&ws.tables, (size_t)B * ws.tiles * sizeof(SegTable), s));
+  CU(cudaMallocAsync((void**)&ws.dcounter, (size_t)B * sizeof(int32_t), s));
+  CU(cudaMemsetAsync(ws.dcounter, 0, (size_t)B * sizeof(int32_t), s));
   CU(cudaMallocAsync((void**)&ws.ctrl, sizeof(Ctrl), s));
   CU(cudaMallocAsync((void**)&ws.stats, (size_t)B * sizeof(ColStats), s));
   CU(cudaMallocAsync((void**)&ws.parts, (size_t)B * ws.nblk * sizeof(NormPartial), s));
@@ -536,13 +551,12 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   CU(cudaMemsetAsync(ws.ncounter, 0, (size_t)B * sizeof(int32_t), s));
   CU(cudaMemsetAsync(ws.verdict, 0, (size_t)B * sizeof(int32_t), s));
   CU(cudaMemsetAsync(ws.w, 0, cells * sizeof(float), s));
-  CU(cudaMemsetAsync(ws.slots, 0, (size_t)B * ws.tiles * sizeof(TileSlot), s));
   CU(cudaMemsetAsync(ws.ctrl, 0, sizeof(Ctrl), s));
   CU(cudaMemsetAsync(ws.stats, 0, (size_t)B * sizeof(ColStats), s));
   return SMCB_OK;
 }
 static void op_free(OpWorkspace& ws, cudaStream_t s) {
-  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.slots, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
+  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.prefix, ws.sin, ws.tileflag, ws.desc, ws.tables, ws.dcounter, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
                   ws.u_col};
   for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
 }
@@ -586,7 +600,8 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
     memset(&r, 0, sizeof(r));
     r.w = ws.w; r.wn = normalized ? ws.w : ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
     r.input_is_w = normalized ? 1 : 0; r.use_rw = 0; r.stats = normalized ? nullptr : ws.stats;
-    r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.slots = ws.slots; r.anc = ws.anc; r.ctrl = ws.ctrl;
+    r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.anc = ws.anc; r.ctrl = ws.ctrl;
+    r.prefix = ws.prefix; r.sin = ws.sin; r.tileflag = ws.tileflag; r.desc = ws.desc; r.tables = ws.tables; r.dcounter = ws.dcounter;
     r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
     else {

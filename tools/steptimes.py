@@ -21,7 +21,8 @@ for t in range(T):
     rows.append((v, [prof[i] * 1e3 for i in range(5)]))
 import statistics as st
 for tag, sel in (("benign", 1), ("general", 0)):
-    r = [x[1] for x in rows if x[0] == sel]
+    r = [x[1] for x in rows if (x[0] & 1) == sel]
     if r:
-        print(f"{tag:8s} moves {len(r):4d}  normalize {st.mean(a[1] for a in r):7.1f} us  resample {st.mean(a[2] for a in r):7.1f} us (min {min(a[2] for a in r):.1f} max {max(a[2] for a in r):.1f})  step {st.mean(a[3] for a in r):7.1f} us")
+        print(f"{tag:8s} moves {len(r):4d}  normalize {st.mean(a[1] for a in r):6.1f}  describe {st.mean(a[2] for a in r):6.1f} (max {max(a[2] for a in r):.1f})  "
+              f"expand {st.mean(a[3] for a in r):6.1f} (max {max(a[3] for a in r):.1f})  step {st.mean(a[4] for a in r):6.1f} us")
 print("all      moves %4d  total %.1f us/move" % (len(rows), st.mean(sum(a[1]) for a in rows)))
