@@ -190,9 +190,10 @@ def run_b200(args):
     launches = e.info().kernel_launches - l0
     if dist:
         # the one collective of the theta-sharded loop: marginal log-likelihoods of all replicas (outside the kernels' data path)
+        from pyfilter_b200.sharding import gather_loglikelihood
+
         ll = e.raw(_lib.PTR_LL_TOTAL, (e.B,)).clone()
-        gathered = [torch.zeros_like(ll) for _ in range(world)]
-        dist.all_gather(gathered, ll)
+        gather_loglikelihood(ll, world * e.B)
         tmax = torch.tensor([ms], device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         ms = float(tmax)

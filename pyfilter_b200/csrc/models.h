@@ -92,7 +92,9 @@ template <> struct Model<SMCB_MODEL_SV_AR1> {
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     // Normal(0, exp(x/2)).log_prob(y) = -y^2 / (2 exp(x)) - x/2 - log sqrt(2 pi)
     float hy2 = __fmul_rn(0.5f, __fmul_rn(y[0], y[0]));
-    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, __expf(-x[0])), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
+    float e;  // exp(-x) through the SFU: ex2.approx.ftz(-x log2 e), 2 ulp
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(-x[0], 1.4426950408889634f)));
+    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, e), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
   }
 };
 

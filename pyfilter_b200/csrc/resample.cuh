@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   __shared__ int is_last;
   const int col = blockIdx.y, tile = blockIdx.x;
   if (a.stats && !a.stats[col].resample) return;
+  if (a.dbg && threadIdx.x == 0) atomicMin((unsigned long long*)&a.dbg[8], (unsigned long long)rs_now());
   const int64_t off = (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
   const int64_t g0 = (int64_t)tile * RS_TILE;
   float m = 0.f, iz = 1.f;
@@ -108,6 +109,10 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     m = a.use_rw ? st.m_rw : st.m_lw;
     iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
   }
+  // what the tail of the last block needs, fetched now (a dependent global round trip in the serial tail costs ~1 us)
+  int t_now = 0;
+  float u_inj = 0.f;
+  if (threadIdx.x == 0) { t_now = a.ctrl->t; if (a.u_in) u_inj = a.u_in[col]; }
   double s = 0.0;
   uint32_t key = 0xFFFFFFFFu;
 #pragma unroll
@@ -139,6 +144,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   if (!is_last) return;
   // ---- the block that completes a column: exclusive prefix of the tile sums, systematic offset, verdict
   __threadfence();
+  if (a.dbg && threadIdx.x == 0) a.dbg[9] = rs_now();
   const int T = a.tiles_per_col;
   const int per = (T + RS_NT - 1) / RS_NT;
   const int q0 = min(T, (int)threadIdx.x * per), q1 = min(T, q0 + per);
@@ -158,9 +164,9 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   mk = block_allreduce<RS_NT>(mk, 0xFFFFFFFFu, OpMinU(), uscratch);
   if (threadIdx.x == 0) {
     float u;  // one uniform per column (resampling.py:41)
-    if (a.u_in) u = a.u_in[col];
+    if (a.u_in) u = u_inj;
     else {
-      Philox4 r = philox4x32_10((uint32_t)col, 0u, (uint32_t)a.ctrl->t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      Philox4 r = philox4x32_10((uint32_t)col, 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       u = smcb_u01(r.x);
     }
     a.u_col[col] = u;
@@ -170,6 +176,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     const bool benign = fast_ok && mk >= RS_BENIGN_MIN_BITS && tot < 1.5;
     a.verdict[col] = (benign ? 1 : 0) | (fast_ok ? 2 : 0);
     a.ncounter[col] = 0;
+    if (a.dbg) a.dbg[10] = rs_now();
   }
 }
 

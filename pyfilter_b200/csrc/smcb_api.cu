@@ -162,7 +162,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
   if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
   if (cfg->resampler != SMCB_SYSTEMATIC && cfg->resampler != SMCB_MULTINOMIAL) return fail(SMCB_EUNSUPPORTED, "unknown resampler");
-  if (cfg->particles < 1 || cfg->particles >= ((int64_t)1 << 31) - RS_TILE) return fail(SMCB_EINVAL, "particles out of range");
+  if (cfg->particles < 1 || cfg->particles >= ((int64_t)1 << 31) - (1 << 21)) return fail(SMCB_EINVAL, "particles out of range");
   if (cfg->resampler == SMCB_MULTINOMIAL && cfg->particles > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");  // torch.multinomial's limit
   if (cfg->batch < 1) return fail(SMCB_EINVAL, "batch must be >= 1");
   if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
@@ -257,6 +257,7 @@ static StepArgs make_args(smcb_filter* f) {
   a.eps_in = f->eps_in; a.eps_out = f->eps_out; a.seed = f->cfg.seed;
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
+  a.dbg = f->dbg;
   a.latest_mean = f->latest_mean; a.latest_var = f->latest_var; a.latest_ll = f->latest_ll; a.ll_total = f->ll_total;
   return a;
 }

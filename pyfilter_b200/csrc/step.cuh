@@ -40,7 +40,9 @@ struct StepArgs {
   int32_t hist_rows;
   float* latest_mean; float* latest_var; float* latest_ll; float* ll_total;  // (B, D), (B, D), (B), (B)
   int32_t fin_mode;
+  long long* dbg;                    // optional diagnostics (SMCB_DEBUG_TIMELINE)
 };
+__device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
 
 // ---- soft-max accumulators ---------------------------------------------------------------------------------------------
@@ -370,8 +372,25 @@ struct FinSmem {
   SoftAcc<1> Q[ST_NT / 32];
 };
 
+// what the finalizing thread needs besides the partials, loaded BEFORE the serial tail (every dependent global round trip
+// of the tail costs about a microsecond)
+struct FinPre {
+  ColStats st;
+  bool observed;   // y_t is present
+  bool fold;       // y_{t+1} is present and the look-ahead is folded
+};
+template <int OD>
+__device__ __forceinline__ FinPre fin_preload(const StepArgs& a, int col, int mode, int t) {
+  FinPre p;
+  p.st = a.stats[col];
+  float y[OD];
+  p.observed = (mode != FIN_STATE) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+  p.fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), y);
+  return p;
+}
+
 template <int D, int OD, int ALG>
-__device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int mode, int t, FinSmem<D>& fs) {
+__device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int mode, int t, FinSmem<D>& fs, const FinPre& pre) {
   const int tid = threadIdx.x;
   SoftAcc<1 + 2 * D> A; A.init();
   SoftAcc<1> Q, R2, R3; Q.init(); R2.init(); R3.init();
@@ -398,11 +417,10 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
   softacc_block_reduce(R2, fs.Q);
   softacc_block_reduce(R3, fs.Q);
   if (tid == 0) {
-    ColStats st = a.stats[col];
+    ColStats st = pre.st;
     const float nf = (float)a.n;
     if (mode == FIN_PREWEIGHT) {
-      float y[OD];
-      const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      const bool observed = pre.observed;
       if (observed) {
         st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
         st.ll_aux = logf(R2.s[0]) + (R2.m - st.m_lw) - logf(st.z_lw);   // log sum W exp(g), W = softmax(lw)
@@ -411,8 +429,7 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       st.fold_valid = 1;
       a.stats[col] = st;
     } else {
-      float y[OD];
-      const bool observed = (mode == FIN_STEP) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
+      const bool observed = (mode == FIN_STEP) && pre.observed;
       const float ll_aux_prev = st.ll_aux;
       st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
       // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
@@ -435,8 +452,7 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
       else {
         st.resample = 0;  // set by the pre-weight pass unless the look-ahead was folded below
-        float yn[OD];
-        const bool fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
+        const bool fold = pre.fold;
         if (fold) {
           st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
           st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
@@ -462,9 +478,8 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
     }
     if (mode == FIN_STEP) {
-      __threadfence();
-      const int done = atomicAdd(&a.ctrl->ticket, 1);
-      if (done == a.B - 1) {   // every column is finalized, hence every block has read ctrl->t: safe to advance the clock
+      if (a.B == 1) a.ctrl->t = t + 1;
+      else if (atomicAdd(&a.ctrl->ticket, 1) == a.B - 1) {  // every column is finalized, hence every block has read ctrl->t
         a.ctrl->ticket = 0;
         a.ctrl->t = t + 1;
       }
@@ -475,19 +490,87 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
 template <int D, int OD, int ALG>
 __global__ void __launch_bounds__(ST_NT) finalize_kernel(StepArgs a) {
   __shared__ FinSmem<D> fs;
-  finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, a.ctrl->t, fs);
+  const int t = a.ctrl->t;
+  const FinPre pre = fin_preload<OD>(a, blockIdx.x, a.fin_mode, t);
+  finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, t, fs, pre);
 }
 
 // ---- the fused step ----------------------------------------------------------------------------------------------------------
+#define SMCB_L2E 1.4426950408889634f
+__device__ __forceinline__ float st_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// nan_to_num of utils.py:57 for values that only feed the accumulators and the stored log-weights
+__device__ __forceinline__ float st_sanitize(float w) { return (w != w || w == INFINITY) ? -INFINITY : fmaxf(w, -SMCB_FLT_MAX); }
+
+// running soft-max sums of one thread: reference point m, sum e, sum e^2, sum e (x - shift), sum e (x - shift)^2, e = exp(lw - m)
+template <int D>
+struct StepAcc {
+  float m, s0, q, sx[D], sxx[D];
+  __device__ __forceinline__ void init() {
+    m = -INFINITY; s0 = 0.f; q = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { sx[d] = 0.f; sxx[d] = 0.f; }
+  }
+  __device__ __forceinline__ void add4(const float (&lw)[4], const float (&x)[D][4], const float (&shift)[D]) {
+    const float mx = fmaxf(fmaxf(lw[0], lw[1]), fmaxf(lw[2], lw[3]));
+    if (mx == -INFINITY) return;
+    if (mx > m) {  // rare after the first few groups
+      const float sc = (m == -INFINITY) ? 0.f : st_ex2((m - mx) * SMCB_L2E);
+      s0 *= sc; q *= sc * sc;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { sx[d] *= sc; sxx[d] *= sc; }
+      m = mx;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = st_ex2((lw[k] - m) * SMCB_L2E);
+      s0 += e;
+      q = fmaf(e, e, q);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const float c = x[d][k] - shift[d];
+        const float ec = e * c;
+        sx[d] += ec;
+        sxx[d] = fmaf(ec, c, sxx[d]);
+      }
+    }
+  }
+  __device__ __forceinline__ void to_softacc(SoftAcc<1 + 2 * D>& A, SoftAcc<1>& Q) const {
+    A.m = m; A.s[0] = s0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) { A.s[1 + d] = sx[d]; A.s[1 + D + d] = sxx[d]; }
+    Q.m = (m == -INFINITY) ? -INFINITY : 2.f * m;
+    Q.s[0] = q;
+  }
+};
+// sum of w * exp(v - m) with a running reference point (w = 1: plain soft-max sum)
+struct StepAcc1 {
+  float m, z;
+  __device__ __forceinline__ void init() { m = -INFINITY; z = 0.f; }
+  __device__ __forceinline__ void add4(const float (&v)[4], const float (&w)[4]) {
+    const float mx = fmaxf(fmaxf(v[0], v[1]), fmaxf(v[2], v[3]));
+    if (mx == -INFINITY) return;
+    if (mx > m) { z *= (m == -INFINITY) ? 0.f : st_ex2((m - mx) * SMCB_L2E); m = mx; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) z = fmaf(w[k], st_ex2((v[k] - m) * SMCB_L2E), z);
+  }
+  __device__ __forceinline__ void to_softacc(SoftAcc<1>& R) const { R.m = m; R.s[0] = z; }
+};
+
 template <int MODEL, int PROP, int ALG>
-__global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   typedef Model<MODEL> M;
   constexpr int D = M::D, OD = M::OD;
   __shared__ float Ps[SMCB_NPARAM];
   __shared__ FinSmem<D> fin_smem;
+  __shared__ FinPre fin_pre;
   SoftAcc<1 + 2 * D>* sA = fin_smem.A;
   SoftAcc<1>* sQ = fin_smem.Q;
   const int col = blockIdx.y, tid = threadIdx.x;
+  if (a.dbg && tid == 0) atomicMin((unsigned long long*)&a.dbg[11], (unsigned long long)st_now());
   if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
   __syncthreads();
   const int t = a.ctrl->t;
@@ -495,40 +578,63 @@ __global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
   const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
   const bool fold = (ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
   const ColStats st = a.stats[col];
+  if (tid == 0) { fin_pre.st = st; fin_pre.observed = observed; fin_pre.fold = fold; }  // for the finalizing block's tail
+  if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[14] = st_now();
   // SISR resamples when the ESS test fired (sisr.py:19-26), the APF on every observed step (apf.py:29-34, filters/base.py:213)
   const bool resampled = (ALG == SMCB_ALG_APF) ? observed : (st.resample != 0);
-  const float* xprev = a.xbuf[t & 1];
-  float* xnext = a.xbuf[(t + 1) & 1];
+  const int32_t n = (int32_t)a.n;
   const float inv_n = 1.0f / (float)a.n;
+  const float one4[4] = {1.f, 1.f, 1.f, 1.f};
   float shift[D];
+  const float* xprev[D];
+  float* xnext[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) shift[d] = st.shift[d];
+  for (int d = 0; d < D; ++d) {
+    shift[d] = st.shift[d];
+    xprev[d] = a.xbuf[t & 1] + ((int64_t)d * a.B + col) * a.ld;
+    xnext[d] = a.xbuf[(t + 1) & 1] + ((int64_t)d * a.B + col) * a.ld;
+  }
+  const int32_t* ancrow = a.anc + (int64_t)col * a.ld;
+  int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
+  float* lwrow = a.lw + (int64_t)col * a.ld;
+  float* rwrow = a.rw + (int64_t)col * a.ld;
 
-  Moments<D> mom; mom.init();
-  SoftAcc<1> r2; r2.init();   // APF: folded resampling weights
-  SoftAcc<1> r3; r3.init();   // SISR: likelihood increment
+  StepAcc<D> mom; mom.init();
+  StepAcc1 r2; r2.init();   // APF: folded resampling weights
+  StepAcc1 r3; r3.init();   // SISR: likelihood increment
 
-  for (int it = 0; it < a.iters; ++it) {
-    const int64_t i0 = ((int64_t)(it * a.blocks_per_col + blockIdx.x) * ST_NT + tid) * ST_VEC;
-    if (i0 >= a.n) continue;
-    const int64_t row = (int64_t)col * a.ld + i0;
-    int anc[4] = {(int)i0, (int)i0 + 1, (int)i0 + 2, (int)i0 + 3};
-    bool valid[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) valid[k] = i0 + k < a.n;
+  const int32_t stride = a.blocks_per_col * (ST_NT * ST_VEC);
+  int32_t i0 = (blockIdx.x * ST_NT + tid) * ST_VEC;
+  int4 ancq = make_int4(i0, i0 + 1, i0 + 2, i0 + 3);
+  if (resampled && i0 < n) ancq = *reinterpret_cast<const int4*>(ancrow + i0);
+  for (int it = 0; it < a.iters; ++it, i0 += stride) {
+    if (i0 >= n) break;
+    const bool full = i0 + 4 <= n;
+    int anc[4] = {ancq.x, ancq.y, ancq.z, ancq.w};
+    {  // fetch the next group's ancestors while this one is processed
+      const int32_t inext = i0 + stride;
+      ancq = make_int4(inext, inext + 1, inext + 2, inext + 3);
+      if (resampled && it + 1 < a.iters && inext < n) ancq = *reinterpret_cast<const int4*>(ancrow + inext);
+    }
     if (resampled) {
-      const int4 q = *reinterpret_cast<const int4*>(a.anc + row);
-      anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
+      *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+      if (!full) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (!valid[k]) anc[k] = 0;
-      *reinterpret_cast<int4*>(a.prev_inds + row) = q;
+        for (int k = 0; k < 4; ++k) if (i0 + k >= n) anc[k] = 0;
+      }
     } else if (ALG == SMCB_ALG_APF) {
-      *reinterpret_cast<int4*>(a.prev_inds + row) = make_int4(anc[0], anc[1], anc[2], anc[3]);  // apf.py:18-23 arange
+      *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);  // apf.py:18-23 arange
     }
     float lwp[4] = {0.f, 0.f, 0.f, 0.f};
     if (!resampled) {  // weights carry over (sisr.py:52 without the reset of :34; particle/state.py:42)
-      const float4 q = *reinterpret_cast<const float4*>(a.lw + row);
+      const float4 q = *reinterpret_cast<const float4*>(lwrow + i0);
       lwp[0] = q.x; lwp[1] = q.y; lwp[2] = q.z; lwp[3] = q.w;
+    }
+    float xa[D][4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) xa[d][k] = __ldg(xprev[d] + anc[k]);
     }
     float z[D][4];
     st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
@@ -536,62 +642,48 @@ __global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
     float xn[D][4], lwn[4], rwn[4], inc4[4], wprev[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      float xa[D], zk[D], xo[D], inc, g_anc;
+      float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
-        xa[d] = __ldg(xprev + ((int64_t)d * a.B + col) * a.ld + anc[k]);
-        zk[d] = z[d][k];
-      }
-      Proposal<MODEL, PROP>::sample_and_weight(y, xa, zk, Ps, observed, xo, inc, g_anc);
+      for (int d = 0; d < D; ++d) { xk[d] = xa[d][k]; zk[d] = z[d][k]; }
+      Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
       for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
       float lw;
       if (!observed) lw = lwp[k];
       else if (ALG == SMCB_ALG_APF) lw = __fsub_rn(inc, g_anc);   // apf.py:43
       else lw = __fadd_rn(inc, lwp[k]);                           // sisr.py:52
-      lwn[k] = smcb_sanitize(lw);
+      lwn[k] = st_sanitize(lw);
       inc4[k] = inc;
       if (ALG == SMCB_ALG_SISR) wprev[k] = resampled ? inv_n : smcb_weight(lwp[k], st.m_lw, st.inv_z_lw);
-      rwn[k] = fold ? smcb_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps), lwn[k])) : lwn[k];
+      rwn[k] = fold ? st_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps), lwn[k])) : lwn[k];
     }
 #pragma unroll
-    for (int d = 0; d < D; ++d)
-      *reinterpret_cast<float4*>(xnext + ((int64_t)d * a.B + col) * a.ld + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
-    if (!fold || a.store_lw) *reinterpret_cast<float4*>(a.lw + row) = make_float4(lwn[0], lwn[1], lwn[2], lwn[3]);
-    if (fold) *reinterpret_cast<float4*>(a.rw + row) = make_float4(rwn[0], rwn[1], rwn[2], rwn[3]);
+    for (int d = 0; d < D; ++d) *reinterpret_cast<float4*>(xnext[d] + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
+    if (!fold || a.store_lw) *reinterpret_cast<float4*>(lwrow + i0) = make_float4(lwn[0], lwn[1], lwn[2], lwn[3]);
+    if (fold) *reinterpret_cast<float4*>(rwrow + i0) = make_float4(rwn[0], rwn[1], rwn[2], rwn[3]);
 
-    mom.add4(lwn, xn, shift, valid);
-    if (fold) {
-      float mx = -INFINITY;
+    if (!full) {  // the tail of the column: padding contributes nothing
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (valid[k]) mx = fmaxf(mx, rwn[k]);
-      if (mx > -INFINITY) {
-        r2.raise(mx);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (valid[k]) r2.s[0] += __expf(rwn[k] - r2.m);
-      }
+      for (int k = 0; k < 4; ++k) if (i0 + k >= n) { lwn[k] = -INFINITY; rwn[k] = -INFINITY; inc4[k] = -INFINITY; }
     }
-    if (ALG == SMCB_ALG_SISR && observed) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) if (valid[k]) mx = fmaxf(mx, inc4[k]);
-      if (mx > -INFINITY) {
-        r3.raise(mx);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (valid[k]) r3.s[0] += wprev[k] * __expf(inc4[k] - r3.m);
-      }
-    }
+    mom.add4(lwn, xn, shift);
+    if (fold) r2.add4(rwn, one4);
+    if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
   }
-  softacc_block_reduce(mom.a, sA);
-  softacc_block_reduce(mom.q, sQ);
-  softacc_block_reduce(r2, sQ);
-  softacc_block_reduce(r3, sQ);
+  if (a.dbg && tid == 0) atomicMax((unsigned long long*)&a.dbg[15], (unsigned long long)st_now());
+  SoftAcc<1 + 2 * D> A;
+  SoftAcc<1> Q, R2, R3;
+  mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
+  softacc_block_reduce(A, sA);
+  softacc_block_reduce(Q, sQ);
+  softacc_block_reduce(R2, sQ);
+  softacc_block_reduce(R3, sQ);
   __shared__ int is_last;
   if (tid == 0) {
     Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
-    st_write_partial1(p, mom.a, mom.q);
-    p.m2 = r2.m; p.z2 = r2.s[0];
-    p.m3 = r3.m; p.z3 = r3.s[0];
+    st_write_partial1(p, A, Q);
+    p.m2 = R2.m; p.z2 = R2.s[0];
+    p.m3 = R3.m; p.z3 = R3.s[0];
     __threadfence();
     is_last = (atomicAdd(&a.col_ticket[col], 1) == a.blocks_per_col - 1);
   }
@@ -599,8 +691,9 @@ __global__ void __launch_bounds__(ST_NT) step_kernel(StepArgs a) {
   if (is_last) {  // this block completed the column: fold the partials here instead of launching another kernel
     if (tid == 0) a.col_ticket[col] = 0;
     __threadfence();
+    if (a.dbg && tid == 0) a.dbg[12] = st_now();
     FinSmem<D>& fs = *reinterpret_cast<FinSmem<D>*>(sA);
-    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, fs);
+    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, fs, fin_pre);
+    if (a.dbg && tid == 0) a.dbg[13] = st_now();
   }
 }
-

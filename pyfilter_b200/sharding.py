@@ -1,0 +1,42 @@
+"""Column sharding of a batch of independent filters across GPUs.
+
+The batch dimension of ``set_batch_shape`` (reference filters/base.py:93-119; the theta-particles of SMC2 / NESS,
+inference/sequential/base.py:31-34) is embarrassingly parallel: every rank owns a contiguous block of columns and runs the
+single-GPU kernels unchanged.  The only exchange is the vector of marginal log-likelihoods every rank needs for the theta-level
+ESS test (inference/sequential/state.py:43-44, smc2.py:59-62): one all-gather of ``(B_local,)`` floats per step.
+"""
+from typing import Tuple
+
+import torch
+
+
+def column_shard(batch: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block ``[lo, hi)`` of the ``batch`` columns owned by ``rank`` (sizes differ by at most one)."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    base, rem = divmod(batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def gather_loglikelihood(ll_local: torch.Tensor, batch: int, group=None) -> torch.Tensor:
+    """All-gathers the per-column log-likelihoods of every rank into the full ``(batch,)`` vector, in column order."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = [column_shard(batch, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    lo, hi = sizes[rank]
+    if ll_local.numel() != hi - lo:
+        raise ValueError("local vector does not match this rank's shard")
+    padded = torch.zeros(width, dtype=ll_local.dtype, device=ll_local.device)
+    padded[: hi - lo] = ll_local
+    out = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(out, padded, group=group)
+    return torch.cat([o[: h - l] for o, (l, h) in zip(out, sizes)])
+
+
+def theta_ess(ll_total: torch.Tensor) -> torch.Tensor:
+    """ESS of the theta-particles from their accumulated log-likelihoods (reference utils.py:8-20 on the theta weights)."""
+    w = torch.softmax(ll_total - ll_total.max(), dim=0)
+    return 1.0 / (w * w).sum()

@@ -147,8 +147,71 @@ static bool check_counts(const std::vector<float>& w, float u, std::mt19937_64&)
   return true;
 }
 
+// xs_count_fast against xs_count_le (itself checked against lower_bound over the probes in check_counts)
+static bool check_count_fast(std::mt19937_64& rng) {
+  int ns[] = {1, 2, 3, 7, 300, 1000, 4097, 1000003, 4000000, (1 << 22), (1 << 23) - 1, (1 << 23)};
+  for (int n : ns) {
+    float nf = (float)n; double nfd = (double)nf;
+    for (int rep = 0; rep < 200000; ++rep) {
+      float u = (float)(rng() >> 40) * 5.9604644775390625e-08f;
+      if (rep % 17 == 0) u = 0.f;
+      float c;
+      int mode = rep % 5;
+      if (mode == 0) c = (float)((rng() >> 11) * 1.1102230246251565e-16);
+      else if (mode == 1) { long i = rng() % (unsigned long)n; c = xs_probe(i, u, nf); int d = (int)(rng() % 5) - 2; c = xs_u2f(xs_f2u(c) + d); if (!(c >= 0)) c = 0; }
+      else if (mode == 2) c = (float)((rng() >> 11) * 1.1102230246251565e-16) * 1e-3f;
+      else if (mode == 3) c = 1.0f - (float)(rng() % 64) * 5.96e-8f;
+      else c = (rng() % 3 == 0) ? 0.f : (float)((rng() >> 11) * 1.1102230246251565e-16) * 1.0001f;
+      if (c != 0.f && c < 1.2e-38f) continue;
+      int a = (int)xs_count_le(c, u, (int64_t)n, nf), b = xs_count_fast(c, u, n, (double)n, nfd);
+      if (a != b) { fprintf(stderr, "count_fast mismatch n=%d c=%.9g u=%.9g ref=%d fast=%d\n", n, c, u, a, b); return false; }
+    }
+  }
+  return true;
+}
+
+// integer transducers (XiT) against the double ones: sequential and composed application, validity included
+template <int MB>
+static bool check_integer_transducers(std::mt19937_64& rng) {
+  std::uniform_real_distribution<double> un(0, 1);
+  for (int rep = 0; rep < 200000; ++rep) {
+    int E = -1 - (int)(rng() % 30);
+    double q = xs_pow2(E - (MB - 1));
+    double S = xs_pow2(E) + floor(un(rng) * 0.98 * (xs_pow2(E) / q)) * q;
+    int ng = 1 + rng() % 6;
+    std::vector<XsT> ts; std::vector<XiT> ti; bool conv_ok = true;
+    for (int g = 0; g < ng; ++g) {
+      XsT T = xs_identity();
+      int ne = 1 + rng() % 20;
+      for (int j = 0; j < ne; ++j) {
+        int ew = E - MB - 4 + (int)(rng() % 12);
+        if (rng() % 40 == 0) ew = E - 3;  // large element: may leave the binade
+        float w = (float)ldexp(1.0 + floor(un(rng) * 16) / 16.0, ew);
+        if (rng() % 7 == 0) w = (float)ldexp(1.0, E - MB);  // half a quantum: tie
+        T = xs_compose<MB>(T, xs_elem<MB>(w, E), E);
+      }
+      ts.push_back(T);
+      XiT I; conv_ok = conv_ok && xi_from<MB>(T.s, T.d, E, &I); ti.push_back(I);
+    }
+    if (!conv_ok) continue;
+    double Sd = S; uint64_t Sb = xs_d2u(S); bool okd = true, oki = true;
+    for (int g = 0; g < ng && okd; ++g) okd = xs_apply<MB>(Sd, E, ts[g], &Sd);
+    for (int g = 0; g < ng && oki; ++g) oki = xi_apply<MB>(Sb, E, ti[g], &Sb);
+    XsT Tc = xs_identity(); XiT Ic = xi_identity();
+    for (int g = 0; g < ng; ++g) { Tc = xs_compose<MB>(Tc, ts[g], E); Ic = xi_compose<MB>(Ic, ti[g]); }
+    double Sc; uint64_t Sbc;
+    bool okc_d = xs_apply<MB>(S, E, Tc, &Sc), okc_i = xi_apply<MB>(xs_d2u(S), E, Ic, &Sbc);
+    if (okd != oki || okc_d != okc_i) { fprintf(stderr, "XiT validity mismatch MB=%d\n", MB); return false; }
+    if (okd && (xs_d2u(Sd) != Sb)) { fprintf(stderr, "XiT state mismatch MB=%d\n", MB); return false; }
+    if (okc_d && (xs_d2u(Sc) != Sbc)) { fprintf(stderr, "XiT composed state mismatch MB=%d\n", MB); return false; }
+  }
+  return true;
+}
+
 int main(int argc, char** argv) {
   std::mt19937_64 rng(12345);
+  if (!check_count_fast(rng)) return 1;
+  if (!check_integer_transducers<53>(rng) || !check_integer_transducers<24>(rng)) return 1;
   size_t big = argc > 1 ? (size_t)atol(argv[1]) : (size_t)1 << 20;
   Stats st;
   bool ok = true;

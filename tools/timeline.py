@@ -14,9 +14,11 @@ e = f._get_engine(T + 40)
 e.initialize(); e.set_observations(y.reshape(-1, 1).cuda(), 0); e.run(20); torch.cuda.synchronize()
 dbg = e.raw(20, (16,), "<i8")
 for t in range(T):
-    dbg.zero_(); dbg[0] = 2**62
+    dbg.zero_(); dbg[0] = 2**62; dbg[8] = 2**62; dbg[11] = 2**62
     e.run(1); torch.cuda.synchronize()
     v = int(e.raw(21, (1,), "<i4")[0])
     d = dbg.cpu().tolist()
+    if t < 6:
+        print(f"move {t}: normalize main {(d[9]-d[8])/1e3:5.1f} tail {(d[10]-d[9])/1e3:5.1f} | step prologue {(d[14]-d[11])/1e3:5.1f} loop-end(max) {(d[15]-d[11])/1e3:5.1f} ticket {(d[12]-d[11])/1e3:5.1f} finalize {(d[13]-d[12])/1e3:5.1f} us")
     if not (v & 1):
         print(f"move {t}: main {(d[1]-d[0])/1e3:6.1f} us  chain {(d[2]-d[1])/1e3:6.1f} us  slow tiles so far {e.info().slow_tiles}  P1 {(d[4]-d[1])/1e3:5.1f} P2 {(d[5]-d[4])/1e3:5.1f} P3 {(d[6]-d[5])/1e3:5.1f} (first round)")
