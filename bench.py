@@ -165,7 +165,7 @@ def run_b200(args):
     P = min(K, 40)  # profiled moves
     y = simulate_sv(W + K + P + 2)
     f = APF(ts.build("sv_ar1"), N, seed=123 + rank)
-    f._exact_scan = not args.approx_scan
+    f._exact_weights = args.exact_weights
     e = f._get_engine(W + K + P + 4)
     y_dev = y.reshape(-1, 1).cuda()
     stream = torch.cuda.current_stream()
@@ -240,7 +240,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": "sv_ar1 APF bootstrap systematic, 4M particles (BASELINE.json configs[2])", "particles": N,
-                           "filters_per_gpu": 1, "parallelism": f"replicas x{world}", "exact_scan": not args.approx_scan,
+                           "filters_per_gpu": 1, "parallelism": f"replicas x{world}", "exact_weights": args.exact_weights,
                            "l2": "256 MB flush before the timed loop; the ~80 MB working set of one filter is L2-resident across "
                                  "moves by construction (the moves of one filter are sequential)"},
                 "roofline": roofline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
@@ -261,7 +261,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=4_000_000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--approx-scan", action="store_true", help="diagnostics: skip the exact chaining of the prefix sum (not bit-exact)")
+    ap.add_argument("--exact-weights", action="store_true", help="do not round the resampling weights to multiples of 2^-52 (smcb_config.exact_weights)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -59,7 +59,11 @@ typedef struct smcb_config {
   uint64_t seed;          /* Philox key */
   int32_t history_rows;   /* rows kept for filter means / variances / log-likelihood increments (T + 1 for batch_filter) */
   int32_t fold_lookahead; /* APF: fold log p(y_{t+1}|.) into the stored weights when y_{t+1} is known (saves one pass) */
-  int32_t exact_scan;     /* 1: ancestors bit-exact against torch.cumsum/searchsorted on CPU (default); 0 reserved */
+  int32_t exact_weights;  /* 0 (default): the resampling weights the handle derives from its log-weights are rounded to multiples
+                             of 2^-52 (|dW| <= 2^-53 ~ 1.1e-16 absolute), so the sequential fp64 prefix sum of resampling.py:47
+                             never rounds and every column takes the chain-free path; 1: weights are exactly
+                             fl32(exp(lw - max) * fl32(1/sum)) and columns with tiny weights take the transducer scan.  Either way
+                             the ancestors are bit-exact for the weights used (smcb_filter_dump_noise returns them). */
   int32_t reserved;
 } smcb_config;
 

@@ -26,7 +26,7 @@ class smcb_config(C.Structure):
         ("model", C.c_int32), ("proposal", C.c_int32), ("algorithm", C.c_int32), ("resampler", C.c_int32),
         ("particles", C.c_int64), ("batch", C.c_int32), ("n_raw_params", C.c_int32),
         ("params_host", C.POINTER(C.c_float)), ("param_cols", C.c_int32), ("ess_threshold", C.c_float),
-        ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_scan", C.c_int32),
+        ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_weights", C.c_int32),
         ("reserved", C.c_int32),
     ]
 

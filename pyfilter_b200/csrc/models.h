@@ -90,11 +90,11 @@ template <> struct Model<SMCB_MODEL_SV_AR1> {
     scale = P[2];
   }
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
-    // Normal(0, exp(x/2)).log_prob(y) = -y^2 / (2 exp(x)) - x/2 - log sqrt(2 pi)
-    float hy2 = __fmul_rn(0.5f, __fmul_rn(y[0], y[0]));
-    float e;  // exp(-x) through the SFU: ex2.approx.ftz(-x log2 e), 2 ulp
+    // Normal(0, exp(x/2)).log_prob(y) = -y^2 / (2 exp(x)) - x/2 - log sqrt(2 pi); exp(-x) through the SFU (ex2.approx.ftz, 2 ulp)
+    const float hy2 = __fmul_rn(0.5f, __fmul_rn(y[0], y[0]));
+    float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(-x[0], 1.4426950408889634f)));
-    return __fsub_rn(__fsub_rn(-__fmul_rn(hy2, e), __fmul_rn(0.5f, x[0])), SMCB_LOG_SQRT_2PI);
+    return fmaf(-hy2, e, fmaf(-0.5f, x[0], -SMCB_LOG_SQRT_2PI));  // explicit fma: the same bits at every call site
   }
 };
 

@@ -59,6 +59,8 @@ struct ResampleArgs {
                            //     the lean probe count
   float* u_col;            // (B) the systematic offset of every column for this launch (injected or Philox)
   long long* dbg;          // optional diagnostics (SMCB_DEBUG_TIMELINE): globaltimer stamps / counters of describe_kernel's chain
+  int32_t quantize;        // 1: round the weights derived from log-weights to multiples of 2^-52 (every column becomes benign)
+  int32_t force_benign;    // 1: the host skipped describe_kernel (quantised weights, n <= 2^23, Philox offsets): benign by construction
 };
 __device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { RS_OUT_ANCESTORS = 0, RS_OUT_CUMSUM = 1 };
@@ -99,32 +101,43 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   __shared__ uint32_t uscratch[33];
   __shared__ int is_last;
   const int col = blockIdx.y, tile = blockIdx.x;
-  if (a.stats && !a.stats[col].resample) return;
-  if (a.dbg && threadIdx.x == 0) atomicMin((unsigned long long*)&a.dbg[8], (unsigned long long)rs_now());
   const int64_t off = (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
   const int64_t g0 = (int64_t)tile * RS_TILE;
-  float m = 0.f, iz = 1.f;
-  if (!a.input_is_w) {
-    const ColStats& st = a.stats[col];
-    m = a.use_rw ? st.m_rw : st.m_lw;
-    iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
-  }
+  // every independent global load first (striped float4: fully coalesced)
+  float4 q4[RS_ITEMS / 4];
+#pragma unroll
+  for (int v = 0; v < RS_ITEMS / 4; ++v) q4[v] = __ldg(reinterpret_cast<const float4*>(a.w + off + (v * RS_NT + threadIdx.x) * 4));
+  ColStats st;
+  st.resample = 1; st.m_lw = 0.f; st.inv_z_lw = 1.f; st.m_rw = 0.f; st.inv_z_rw = 1.f;
+  if (a.stats) st = a.stats[col];
   // what the tail of the last block needs, fetched now (a dependent global round trip in the serial tail costs ~1 us)
   int t_now = 0;
   float u_inj = 0.f;
   if (threadIdx.x == 0) { t_now = a.ctrl->t; if (a.u_in) u_inj = a.u_in[col]; }
+  if (!st.resample) return;
+  if (a.dbg && threadIdx.x == 0) atomicMin((unsigned long long*)&a.dbg[8], (unsigned long long)rs_now());
+  float m = 0.f, iz = 1.f;
+  if (!a.input_is_w) {
+    m = a.use_rw ? st.m_rw : st.m_lw;
+    iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
+  }
   double s = 0.0;
   uint32_t key = 0xFFFFFFFFu;
+  const bool quant = a.quantize && !a.input_is_w && m == m && iz == iz && iz < 1e30f;  // finite normalisers only
 #pragma unroll
-  for (int v = 0; v < RS_ITEMS / 4; ++v) {  // striped float4: fully coalesced
+  for (int v = 0; v < RS_ITEMS / 4; ++v) {
     const int e = (v * RS_NT + threadIdx.x) * 4;
-    float4 q = __ldg(reinterpret_cast<const float4*>(a.w + off + e));
-    float x[4] = {q.x, q.y, q.z, q.w};
+    float x[4] = {q4[v].x, q4[v].y, q4[v].z, q4[v].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       if (!a.input_is_w) x[k] = smcb_weight(smcb_sanitize(x[k]), m, iz);
       if (g0 + e + k >= a.n) x[k] = 0.f;
-      s += (double)x[k];
+      double xd = (double)x[k];
+      if (quant) {  // RN to a multiple of 2^-52: exact in float32 (at most 23 significant bits below 2^-29), |dW| <= 2^-53
+        xd = __dadd_rn(__dadd_rn(1.0, xd), -1.0);
+        x[k] = (float)xd;
+      }
+      s += xd;
       const uint32_t b = __float_as_uint(x[k]);
       const uint32_t kk = (b == 0u) ? 0xFFFFFFFFu : ((b >> 31) ? 0u : b);
       key = min(key, kk);
@@ -173,7 +186,9 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     if (a.u_out) a.u_out[col] = u;
     const bool u_ok = (u == 0.f) || (u >= 5.5e-20f && u < 1.0f);
     const bool fast_ok = a.n <= (1 << 23) && u_ok;  // xs_count_fast applies (exact_scan.h)
-    const bool benign = fast_ok && mk >= RS_BENIGN_MIN_BITS && tot < 1.5;
+    // quantised weights are multiples of 2^-52 by construction (the smallest-weight proxy does not apply to them)
+    const bool quant = a.quantize && !a.input_is_w;
+    const bool benign = fast_ok && tot < 1.5 && (quant ? (mk != 0u) : (mk >= RS_BENIGN_MIN_BITS));
     a.verdict[col] = (benign ? 1 : 0) | (fast_ok ? 2 : 0);
     a.ncounter[col] = 0;
     if (a.dbg) a.dbg[10] = rs_now();
@@ -397,6 +412,24 @@ __device__ __noinline__ double rs_warp_raw_walk(const float* wrow, double S, flo
   return S;
 }
 
+// Tile 0 is where the running sum climbs through a dozen binades, i.e. where all the special elements of a typical column sit.
+// But while the sum is small its quantum is tiny: if every non-zero weight of tile 0 is a multiple of the quantum of the highest
+// binade the tile can reach (one binade of margin), nothing in the tile rounds and - the tile starting from 0 - its states are the
+// exact real prefix sums in any association, like a benign column.  Both kernels evaluate this same predicate from the tile sum
+// and the smallest weight normalize_kernel recorded.
+template <int MB>
+__device__ __forceinline__ bool rs_tile0_exact(const ResampleArgs& a, int col, double* tile_sum) {
+  if (MB != 53) return false;
+  const double ts = a.tilesum[(int64_t)col * a.tiles_per_col];
+  const uint32_t key = a.tilemin[(int64_t)col * a.tiles_per_col];
+  *tile_sum = ts;
+  if (!(ts >= 0.0 && ts < 2.0)) return false;
+  if (key == 0xFFFFFFFFu) return true;  // all zero
+  if (key == 0u) return false;          // a negative weight
+  const int ef = xs_label(ts) + 1 - 29 + 127;
+  return ef <= 0 || (ef < 255 && key >= ((uint32_t)ef << 23));
+}
+
 // ---- describe_kernel: one descriptor per tile; the last block of a column chains them -----------------------------------------------
 // Chain semantics: S = 0; for every tile in order: sin[tile] = S; S = descriptor(S), every application verifying the speculation
 // behind the descriptor (scan_tile.h).  Rounds of RS_NT tiles, three phases per round:
@@ -579,7 +612,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
       if (lane == 0) cs.S = S;
     }
     __syncthreads();
-    if (a.dbg && tid == 0 && base == 0) a.dbg[5] = rs_now();
+
     // ---- P3
     if (live) {
       const int si = wid * 32 + seg;
@@ -592,7 +625,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
       }
     }
     __syncthreads();  // the round's tables are reused
-    if (a.dbg && tid == 0 && base == 0) a.dbg[6] = rs_now();
+
   }
 }
 
@@ -602,10 +635,8 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
   __shared__ __align__(16) ChainSmem cs;
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, col = blockIdx.y;
-  if (a.stats && !a.stats[col].resample) return;
-  if (MB == 53 && (a.verdict[col] & 1)) return;  // benign column: nothing to chain
   const int T = a.tiles_per_col;
-  if (a.dbg && tid == 0) atomicMin((unsigned long long*)&a.dbg[0], (unsigned long long)rs_now());
+  // every independent global load is issued before the first dependent use: a short-lived block cannot afford serialised round trips
   float w[RS_ITEMS];
   {
     const float4* src = reinterpret_cast<const float4*>(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + tid * RS_ITEMS);
@@ -615,10 +646,24 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
       w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
     }
   }
+  const double sp0 = a.prefix[(int64_t)col * T + tile];
+  const int resample = a.stats ? a.stats[col].resample : 1;
+  const int vd = a.verdict[col];
+  if (!resample) return;
+  if (MB == 53 && (vd & 1)) return;  // benign column: nothing to chain
+  long long t_start = 0;
+  if (a.dbg && tid == 0) {
+    t_start = rs_now();
+    atomicMin((unsigned long long*)&a.dbg[0], (unsigned long long)t_start);
+    atomicMax((unsigned long long*)&a.dbg[7], (unsigned long long)t_start);
+  }
+  double ts0 = 0.0;
+  const bool exact0 = (tile == 0) && rs_tile0_exact<MB>(a, col, &ts0);  // block-uniform
   RsScan<MB> r;
-  rs_tile_scan<MB>(w, a.prefix[(int64_t)col * T + tile], sm, r);
-  const int X = sm.X;
-  const bool table_ok = sm.table_ok != 0;
+  if (!exact0) rs_tile_scan<MB>(w, sp0, sm, r);
+  if (a.dbg && tid == 0) atomicAdd((unsigned long long*)&a.dbg[3], (unsigned long long)(rs_now() - t_start));
+  const int X = exact0 ? 0 : sm.X;
+  const bool table_ok = exact0 ? true : (sm.table_ok != 0);
   if (table_ok && X > 1) {  // the segment table goes to global memory for the chain
     SegTable* tb = a.tables + (int64_t)col * T + tile;
     for (int s = tid; s <= X; s += RS_NT) { tb->agg[s] = sm.seg_agg[s]; tb->wc[s] = sm.seg_wc[s]; tb->e[s] = sm.seg_e[s]; }
@@ -627,7 +672,8 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
     XsDesc d;
     d.a_s = 0.0; d.b_s = 0.0; d.wc = 0.f; d.e0 = (int16_t)sm.e0; d.e1 = 0; d.a_d = 0; d.b_d = 0; d.pad = 0;
     double S_abs;
-    if (!table_ok) d.has_special = RS_KIND_RAW;
+    if (exact0) { d.has_special = RS_KIND_ABS; d.a_s = ts0; }
+    else if (!table_ok) d.has_special = RS_KIND_RAW;
     else if (tile == 0 && X > 0 && xs_walk_segments<MB>(0.0, sm.e0, X, sm.seg_agg, sm.seg_wc, sm.seg_e, sm.base, &S_abs)) {
       d.has_special = RS_KIND_ABS; d.a_s = S_abs;
     }
@@ -638,10 +684,15 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
     }
     a.desc[(int64_t)col * T + tile] = d;
   }
-  __threadfence();  // table and descriptor stores of every thread precede the ticket
+  if (tid == 0 || (table_ok && X > 1)) __threadfence();  // table and descriptor stores precede the ticket
   __syncthreads();
   if (tid == 0) {
     sm.is_last = (atomicAdd(&a.dcounter[col], 1) == T - 1);
+    if (a.dbg) {
+      const long long dt = rs_now() - t_start;
+      atomicAdd((unsigned long long*)&a.dbg[2], (unsigned long long)dt);
+      atomicMax((unsigned long long*)&a.dbg[5], ((unsigned long long)dt << 20) | (unsigned long long)tile);
+    }
   }
   __syncthreads();
   if (!sm.is_last) return;
@@ -649,7 +700,7 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
   if (a.dbg && tid == 0) a.dbg[1] = rs_now();
   rs_chain<MB>(a, col, cs);
   if (tid == 0) a.dcounter[col] = 0;
-  if (a.dbg && tid == 0) a.dbg[2] = rs_now();
+  if (a.dbg && tid == 0) a.dbg[6] = rs_now();
 }
 
 // ---- probes at or below a cumulative weight ------------------------------------------------------------------------------------------
@@ -702,16 +753,8 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
   __shared__ __align__(16) ExpandSmem sm;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile = blockIdx.x, col = blockIdx.y;
-  if (a.stats && !a.stats[col].resample) return;
   const int T = a.tiles_per_col;
-  const int vd = (OUT == RS_OUT_ANCESTORS) ? a.verdict[col] : 0;
-  const bool benign = (MB == 53) && (vd & 1);
-  const bool fast_ok = (vd & 2) != 0;
-  const int32_t n = (int32_t)a.n;
-  const float nf = (float)a.n;
-  const double nd = (double)n, nfd = (double)nf;
-  const float u = (OUT == RS_OUT_ANCESTORS) ? a.u_col[col] : 0.f;
-
+  // every independent global load is issued before the first dependent use
   float w[RS_ITEMS];
   {
     const float4* src = reinterpret_cast<const float4*>(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + tid * RS_ITEMS);
@@ -721,12 +764,23 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
       w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
     }
   }
+  const double sp0 = a.prefix[(int64_t)col * T + tile];
+  const double sin_t = a.sin[(int64_t)col * T + tile];
+  const int flag_t = a.tileflag[(int64_t)col * T + tile];
+  const int resample = a.stats ? a.stats[col].resample : 1;
+  const int vd = (OUT == RS_OUT_ANCESTORS) ? a.verdict[col] : 0;
+  const float u = (OUT == RS_OUT_ANCESTORS) ? a.u_col[col] : 0.f;
   if (OUT == RS_OUT_ANCESTORS) {  // clear the first window while the loads are in flight
 #pragma unroll
     for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
     if (tid == 0) sm.carry = -1;
   }
-  const double sp0 = a.prefix[(int64_t)col * T + tile];
+  if (!resample) return;
+  const bool benign = (MB == 53) && ((vd & 1) || a.force_benign);
+  const bool fast_ok = (vd & 2) != 0;
+  const int32_t n = (int32_t)a.n;
+  const float nf = (float)a.n;
+  const double nd = (double)n, nfd = (double)nf;
 
   // ---- exact state before the tile (S_in) and before this thread (S0)
   double S_in, S0, M = 0.0;
@@ -737,9 +791,15 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
     for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
     S_in = sp0;
     S0 = S_in + rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);  // exact
+  } else if (tile == 0 && rs_tile0_exact<MB>(a, col, &S_in)) {  // nothing rounds in the first tile: exact sums in any order
+    double tsum = 0.0, tot;
+#pragma unroll
+    for (int j = 0; j < RS_ITEMS; ++j) tsum += (double)w[j];
+    S_in = 0.0;
+    S0 = rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);
   } else {
-    S_in = a.sin[(int64_t)col * T + tile];
-    bool slow = (a.tileflag[(int64_t)col * T + tile] & 1) != 0;
+    S_in = sin_t;
+    bool slow = (flag_t & 1) != 0;
     RsScan<MB> r;
     S0 = S_in;
     if (!slow) {

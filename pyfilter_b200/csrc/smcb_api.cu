@@ -389,15 +389,21 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
   r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.dcounter = f->dcounter; r.verdict = f->verdict; r.u_col = f->u_col;
   r.dbg = f->dbg;
+  r.quantize = f->cfg.exact_weights ? 0 : 1;
   const dim3 rgrid(r.tiles_per_col, r.B);
   normalize_kernel<<<rgrid, RS_NT, 0, s>>>(r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
   if (f->cfg.resampler == SMCB_SYSTEMATIC) {
-    describe_kernel<53><<<rgrid, RS_NT, 0, s>>>(r);  // returns at once for benign columns (verdict decided on the device)
+    // quantised weights of at most 2^23 particles with Philox offsets are benign by construction: nothing to describe or chain
+    r.force_benign = (r.quantize && f->n <= (1 << 23) && !f->u_in) ? 1 : 0;
+    if (!r.force_benign) {
+      describe_kernel<53><<<rgrid, RS_NT, 0, s>>>(r);  // returns at once for benign columns (verdict decided on the device)
+      f->launches++;
+    }
     if (ev) cudaEventRecord(ev[3], s);
     expand_kernel<53, RS_OUT_ANCESTORS><<<rgrid, RS_NT, 0, s>>>(r);
-    f->launches += 2;
+    f->launches++;
   } else {
     r.c_out = f->cbuf;
     if (ev) cudaEventRecord(ev[3], s);

@@ -120,6 +120,63 @@ __device__ __forceinline__ void softacc_block_reduce(SoftAcc<K>& a, SoftAcc<K>* 
   }
 }
 
+// the four accumulators of the step in one pass (three barriers instead of twelve); results valid in thread 0
+template <int K>
+struct Fin4Scratch {
+  float m[4][ST_NT / 32];
+  float a[K][ST_NT / 32];
+  float q[ST_NT / 32], r2[ST_NT / 32], r3[ST_NT / 32];
+};
+template <int K>
+__device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>& Q, SoftAcc<1>& R2, SoftAcc<1>& R3, Fin4Scratch<K>& sc) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  float mb[4] = {A.m, Q.m, R2.m, R3.m};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mb[i] = fmaxf(mb[i], __shfl_xor_sync(0xffffffffu, mb[i], o));
+  }
+  __syncthreads();
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sc.m[i][wid] = mb[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int w = 0; w < ST_NT / 32; ++w) mb[i] = fmaxf(mb[i], sc.m[i][w]);
+  }
+  const float sA = (A.m == -INFINITY) ? 0.f : __expf(A.m - mb[0]);
+  const float sQ = (Q.m == -INFINITY) ? 0.f : __expf(Q.m - mb[1]);
+  const float s2 = (R2.m == -INFINITY) ? 0.f : __expf(R2.m - mb[2]);
+  const float s3 = (R3.m == -INFINITY) ? 0.f : __expf(R3.m - mb[3]);
+  float va[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) va[k] = warp_sum(A.s[k] * sA);
+  const float vq = warp_sum(Q.s[0] * sQ), v2 = warp_sum(R2.s[0] * s2), v3 = warp_sum(R3.s[0] * s3);
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) sc.a[k][wid] = va[k];
+    sc.q[wid] = vq; sc.r2[wid] = v2; sc.r3[wid] = v3;
+  }
+  __syncthreads();
+  A.m = mb[0]; Q.m = mb[1]; R2.m = mb[2]; R3.m = mb[3];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < ST_NT / 32; ++w) t += sc.a[k][w];
+      A.s[k] = t;
+    }
+    float tq = 0.f, t2 = 0.f, t3 = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_NT / 32; ++w) { tq += sc.q[w]; t2 += sc.r2[w]; t3 += sc.r3[w]; }
+    Q.s[0] = tq; R2.s[0] = t2; R3.s[0] = t3;
+  }
+}
+
 // set 1 over lw: [0] sum e, [1..D] sum e (x - shift), [D+1..2D] sum e (x - shift)^2 ; sum e^2 kept apart (scales with sc^2)
 template <int D>
 struct Moments {
@@ -370,6 +427,7 @@ template <int D>
 struct FinSmem {
   SoftAcc<1 + 2 * D> A[ST_NT / 32];
   SoftAcc<1> Q[ST_NT / 32];
+  Fin4Scratch<1 + 2 * D> f4;
 };
 
 // what the finalizing thread needs besides the partials, loaded BEFORE the serial tail (every dependent global round trip
@@ -412,10 +470,7 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
     SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
     A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
   }
-  softacc_block_reduce(A, fs.A);
-  softacc_block_reduce(Q, fs.Q);
-  softacc_block_reduce(R2, fs.Q);
-  softacc_block_reduce(R3, fs.Q);
+  softacc4_block_reduce(A, Q, R2, R3, fs.f4);
   if (tid == 0) {
     ColStats st = pre.st;
     const float nf = (float)a.n;
@@ -674,10 +729,7 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   SoftAcc<1 + 2 * D> A;
   SoftAcc<1> Q, R2, R3;
   mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
-  softacc_block_reduce(A, sA);
-  softacc_block_reduce(Q, sQ);
-  softacc_block_reduce(R2, sQ);
-  softacc_block_reduce(R3, sQ);
+  softacc4_block_reduce(A, Q, R2, R3, fin_smem.f4);
   __shared__ int is_last;
   if (tid == 0) {
     Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
@@ -692,8 +744,7 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
     if (tid == 0) a.col_ticket[col] = 0;
     __threadfence();
     if (a.dbg && tid == 0) a.dbg[12] = st_now();
-    FinSmem<D>& fs = *reinterpret_cast<FinSmem<D>*>(sA);
-    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, fs, fin_pre);
+    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, fin_smem, fin_pre);
     if (a.dbg && tid == 0) a.dbg[13] = st_now();
   }
 }

@@ -19,7 +19,8 @@ class ParticleFilter:
 
     def __init__(self, model, particles: int, resampling: Callable = _resampling.systematic, proposal: Union[str, Proposal] = None,
                  ess_threshold=0.9, record_states=False, record_moments=True, nan_strategy: str = "skip",
-                 record_intermediary_states: bool = False, seed: int = None, fold_lookahead: bool = True):
+                 record_intermediary_states: bool = False, seed: int = None, fold_lookahead: bool = True,
+                 exact_weights: bool = False):
         if not (isinstance(model, StateSpaceModel) or callable(model)):
             raise ValueError("`model` must be a `StateSpaceModel` or a callable that returns one!")
         builder = callable(model) and not isinstance(model, StateSpaceModel)
@@ -40,7 +41,7 @@ class ParticleFilter:
         self._seed = seed
         self._fold = fold_lookahead
         self._engine: Engine = None
-        self._exact_scan = True
+        self._exact_weights = bool(exact_weights)  # see include/smcb200.h: smcb_config.exact_weights
 
     # ---- reference surface
     @property
@@ -79,7 +80,7 @@ class ParticleFilter:
         res = type(self)(model=self._model_builder, particles=self._base_particles[0], resampling=self._resampler,
                          proposal=self._proposal.copy(), ess_threshold=self._resample_threshold,  # sic: base.py:165 (Appendix A-12)
                          record_states=self.record_states, record_moments=self.record_moments, nan_strategy=self._nan_strategy,
-                         record_intermediary_states=self._record_intermediary, seed=self._seed, fold_lookahead=self._fold)
+                         record_intermediary_states=self._record_intermediary, seed=self._seed, fold_lookahead=self._fold, exact_weights=self._exact_weights)
         res._model = self._model
         res.set_batch_shape(self.batch_shape)
         return res
@@ -101,7 +102,7 @@ class ParticleFilter:
             seed = self._seed if self._seed is not None else int(torch.randint(0, 2**62, (1,)).item())
             n = int(self._base_particles[0])
             e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS[self._resampler], n,
-                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_scan)
+                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_weights)
             self._engine = e
         return e
 

@@ -10,7 +10,7 @@ from ...timeseries import StateSpaceModel, TimeseriesState
 class Engine:
     def __init__(self, model: StateSpaceModel, proposal_id: int, algorithm_id: int, resampler_id: int, particles: int,
                  batch_shape: torch.Size, ess_threshold: float, seed: int, history_rows: int, fold_lookahead: bool = True,
-                 exact_scan: bool = True):
+                 exact_weights: bool = False):
         _lib.require_cuda()
         self.lib = _lib.load_library()
         self.model = model
@@ -27,7 +27,7 @@ class Engine:
         cfg.seed = int(seed) & (2**64 - 1)
         cfg.history_rows = int(history_rows)
         cfg.fold_lookahead = int(bool(fold_lookahead))
-        cfg.exact_scan = int(bool(exact_scan))
+        cfg.exact_weights = int(bool(exact_weights))
         self._params_keepalive = params
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)))

@@ -163,11 +163,14 @@ def _noise_buffers(e, z, u, U):
     return eps.cuda(), ub.cuda(), (Ub.cuda() if Ub is not None else None)
 
 
+@pytest.mark.parametrize("exact_weights", [False, True])
 @pytest.mark.parametrize("tag", filter_cases())
-def test_teacher_forced_steps_vs_reference_golden(pf, tag):
+def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights):
+    """exact_weights=False (default): the handle rounds its resampling weights to multiples of 2^-52 (|dW| <= 1.1e-16) and every
+    column takes the chain-free path; True: unrounded weights, columns with tiny weights take the transducer scan."""
     g = load_filter_case(tag)
     N, B, T = g["N"], g["B"], g["T"]
-    f = _make_filter(pf, g, N, B)
+    f = _make_filter(pf, g, N, B, exact_weights=exact_weights)
     e = f._get_engine(2)
     lgo = g["proposal"] == "linear_gaussian"
     wdump = torch.zeros(e.B, e.ld, device="cuda")

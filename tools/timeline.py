@@ -21,4 +21,5 @@ for t in range(T):
     if t < 6:
         print(f"move {t}: normalize main {(d[9]-d[8])/1e3:5.1f} tail {(d[10]-d[9])/1e3:5.1f} | step prologue {(d[14]-d[11])/1e3:5.1f} loop-end(max) {(d[15]-d[11])/1e3:5.1f} ticket {(d[12]-d[11])/1e3:5.1f} finalize {(d[13]-d[12])/1e3:5.1f} us")
     if not (v & 1):
-        print(f"move {t}: main {(d[1]-d[0])/1e3:6.1f} us  chain {(d[2]-d[1])/1e3:6.1f} us  slow tiles so far {e.info().slow_tiles}  P1 {(d[4]-d[1])/1e3:5.1f} P2 {(d[5]-d[4])/1e3:5.1f} P3 {(d[6]-d[5])/1e3:5.1f} (first round)")
+        nt = (N + 4095) // 4096
+        print(f"move {t}: describe first block start -> chain start {(d[1]-d[0])/1e3:6.1f} us; last block started at {(d[7]-d[0])/1e3:5.1f}; mean block: scan {d[3]/nt/1e3:5.2f} us, total {d[2]/nt/1e3:5.2f} us; chain {(d[6]-d[1])/1e3:6.1f} us; slowest block {(d[5]>>20)/1e3:5.1f} us (tile {d[5] & 0xfffff})")
