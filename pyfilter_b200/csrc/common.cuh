@@ -43,6 +43,12 @@ struct Ctrl {
   int64_t lb_windows;   // diagnostics: 32-tile windows walked by all look-backs
 };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream drains; pdl_wait() blocks until the predecessor has completed and its writes are visible
+// (a no-op for ordinary launches), pdl_trigger() lets the successor's blocks be scheduled once every block has called it or exited.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ float smcb_sanitize(float w) {
   // utils.py:57 nan_to_num_(nan=-inf, posinf=-inf) with neginf left at its default (lowest finite float)
   if (w != w || w == INFINITY) return -INFINITY;

@@ -103,6 +103,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   const int col = blockIdx.y, tile = blockIdx.x;
   const int64_t off = (int64_t)col * a.ld + (int64_t)tile * RS_TILE;
   const int64_t g0 = (int64_t)tile * RS_TILE;
+  pdl_wait();
   // every independent global load first (striped float4: fully coalesced)
   float4 q4[RS_ITEMS / 4];
 #pragma unroll
@@ -147,6 +148,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   }
   s = block_allreduce<RS_NT>(s, 0.0, OpSumD(), scratch);
   key = block_allreduce<RS_NT>(key, 0xFFFFFFFFu, OpMinU(), uscratch);
+  pdl_trigger();  // the successor may be scheduled while the last block runs the serial tail
   if (threadIdx.x == 0) {
     a.tilesum[(int64_t)col * a.tiles_per_col + tile] = s;
     a.tilemin[(int64_t)col * a.tiles_per_col + tile] = key;
@@ -636,6 +638,7 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
   const int tid = threadIdx.x;
   const int tile = blockIdx.x, col = blockIdx.y;
   const int T = a.tiles_per_col;
+  pdl_wait();
   // every independent global load is issued before the first dependent use: a short-lived block cannot afford serialised round trips
   float w[RS_ITEMS];
   {
@@ -754,6 +757,7 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int tile = blockIdx.x, col = blockIdx.y;
   const int T = a.tiles_per_col;
+  pdl_wait();
   // every independent global load is issued before the first dependent use
   float w[RS_ITEMS];
   {

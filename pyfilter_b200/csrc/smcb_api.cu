@@ -22,6 +22,24 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
                   std::string(#call) + ": " + cudaGetErrorString(e_));                                      \
   } while (0)
 
+// Launch with programmatic stream serialisation (common.cuh: pdl_wait / pdl_trigger); SMCB_NO_PDL=1 falls back to plain launches.
+static bool use_pdl() {
+  static int v = -1;
+  if (v < 0) v = getenv("SMCB_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+template <typename K, typename A>
+static void launch_pdl(K kernel, dim3 grid, dim3 block, cudaStream_t s, const A& args) {
+  if (!use_pdl()) { kernel<<<grid, block, 0, s>>>(args); return; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, args);
+}
+
 extern "C" int smcb_version(void) { return SMCB_VERSION; }
 extern "C" const char* smcb_last_error(void) { return g_err.c_str(); }
 extern "C" int smcb_device_count(void) {
@@ -272,8 +290,8 @@ static StepArgs make_args(smcb_filter* f) {
 
 template <int MODEL, int PROP>
 static void launch_step_alg(int alg, dim3 g, cudaStream_t s, const StepArgs& a) {
-  if (alg == SMCB_SISR) step_kernel<MODEL, PROP, SMCB_ALG_SISR><<<g, ST_NT, 0, s>>>(a);
-  else step_kernel<MODEL, PROP, SMCB_ALG_APF><<<g, ST_NT, 0, s>>>(a);
+  if (alg == SMCB_SISR) launch_pdl(step_kernel<MODEL, PROP, SMCB_ALG_SISR>, g, dim3(ST_NT), s, a);
+  else launch_pdl(step_kernel<MODEL, PROP, SMCB_ALG_APF>, g, dim3(ST_NT), s, a);
 }
 
 static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
@@ -391,18 +409,18 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.dbg = f->dbg;
   r.quantize = f->cfg.exact_weights ? 0 : 1;
   const dim3 rgrid(r.tiles_per_col, r.B);
-  normalize_kernel<<<rgrid, RS_NT, 0, s>>>(r);
+  launch_pdl(normalize_kernel, rgrid, dim3(RS_NT), s, r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
   if (f->cfg.resampler == SMCB_SYSTEMATIC) {
     // quantised weights of at most 2^23 particles with Philox offsets are benign by construction: nothing to describe or chain
     r.force_benign = (r.quantize && f->n <= (1 << 23) && !f->u_in) ? 1 : 0;
     if (!r.force_benign) {
-      describe_kernel<53><<<rgrid, RS_NT, 0, s>>>(r);  // returns at once for benign columns (verdict decided on the device)
+      launch_pdl(describe_kernel<53>, rgrid, dim3(RS_NT), s, r);  // returns at once for benign columns (verdict decided on the device)
       f->launches++;
     }
     if (ev) cudaEventRecord(ev[3], s);
-    expand_kernel<53, RS_OUT_ANCESTORS><<<rgrid, RS_NT, 0, s>>>(r);
+    launch_pdl(expand_kernel<53, RS_OUT_ANCESTORS>, rgrid, dim3(RS_NT), s, r);
     f->launches++;
   } else {
     r.c_out = f->cbuf;

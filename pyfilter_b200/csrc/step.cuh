@@ -452,23 +452,35 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
   const int tid = threadIdx.x;
   SoftAcc<1 + 2 * D> A; A.init();
   SoftAcc<1> Q, R2, R3; Q.init(); R2.init(); R3.init();
-  for (int b = tid; b < a.blocks_per_col; b += ST_NT) {
-    const Partial* pp = a.partials + (int64_t)col * a.blocks_per_col + b;
-    Partial p;
-    {  // L2 loads: the records were written by other blocks of a kernel that may still be running
-      const float4* q = reinterpret_cast<const float4*>(pp);
-      float4 v0 = __ldcg(q), v1 = __ldcg(q + 1), v2 = __ldcg(q + 2);
-      float v3 = __ldcg(reinterpret_cast<const float*>(pp) + 12);
-      p.m1 = v0.x; p.z1 = v0.y; p.zz1 = v0.z; p.sx[0] = v0.w; p.sx[1] = v1.x; p.sx[2] = v1.y; p.sxx[0] = v1.z; p.sxx[1] = v1.w;
-      p.sxx[2] = v2.x; p.m2 = v2.y; p.z2 = v2.z; p.m3 = v2.w; p.z3 = v3;
-    }
-    SoftAcc<1 + 2 * D> o; o.m = p.m1; o.s[0] = p.z1;
+  for (int b0 = tid; b0 < a.blocks_per_col; b0 += 4 * ST_NT) {
+    // up to four records per thread, all loads in flight before the first merge (one L2 round trip instead of one per record)
+    float4 v0[4], v1[4], v2[4];
+    float v3[4];
 #pragma unroll
-    for (int d = 0; d < D; ++d) { o.s[1 + d] = p.sx[d]; o.s[1 + D + d] = p.sxx[d]; }
-    SoftAcc<1> q; q.m = (p.m1 == -INFINITY) ? -INFINITY : 2.f * p.m1; q.s[0] = p.zz1;
-    SoftAcc<1> o2; o2.m = p.m2; o2.s[0] = p.z2;
-    SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
-    A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
+    for (int r = 0; r < 4; ++r) {
+      const int b = b0 + r * ST_NT;
+      if (b < a.blocks_per_col) {  // L2 loads: the records were written by other blocks of a kernel that may still be running
+        const Partial* pp = a.partials + (int64_t)col * a.blocks_per_col + b;
+        const float4* q = reinterpret_cast<const float4*>(pp);
+        v0[r] = __ldcg(q); v1[r] = __ldcg(q + 1); v2[r] = __ldcg(q + 2);
+        v3[r] = __ldcg(reinterpret_cast<const float*>(pp) + 12);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int b = b0 + r * ST_NT;
+      if (b >= a.blocks_per_col) break;
+      Partial p;
+      p.m1 = v0[r].x; p.z1 = v0[r].y; p.zz1 = v0[r].z; p.sx[0] = v0[r].w; p.sx[1] = v1[r].x; p.sx[2] = v1[r].y; p.sxx[0] = v1[r].z;
+      p.sxx[1] = v1[r].w; p.sxx[2] = v2[r].x; p.m2 = v2[r].y; p.z2 = v2[r].z; p.m3 = v2[r].w; p.z3 = v3[r];
+      SoftAcc<1 + 2 * D> o; o.m = p.m1; o.s[0] = p.z1;
+#pragma unroll
+      for (int d = 0; d < D; ++d) { o.s[1 + d] = p.sx[d]; o.s[1 + D + d] = p.sxx[d]; }
+      SoftAcc<1> q; q.m = (p.m1 == -INFINITY) ? -INFINITY : 2.f * p.m1; q.s[0] = p.zz1;
+      SoftAcc<1> o2; o2.m = p.m2; o2.s[0] = p.z2;
+      SoftAcc<1> o3; o3.m = p.m3; o3.s[0] = p.z3;
+      A.merge(o); Q.merge(q); R2.merge(o2); R3.merge(o3);
+    }
   }
   softacc4_block_reduce(A, Q, R2, R3, fs.f4);
   if (tid == 0) {
@@ -625,8 +637,9 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   SoftAcc<1 + 2 * D>* sA = fin_smem.A;
   SoftAcc<1>* sQ = fin_smem.Q;
   const int col = blockIdx.y, tid = threadIdx.x;
+  if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];  // parameters do not depend on the predecessor kernel
+  pdl_wait();
   if (a.dbg && tid == 0) atomicMin((unsigned long long*)&a.dbg[11], (unsigned long long)st_now());
-  if (tid < SMCB_NPARAM) Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
   __syncthreads();
   const int t = a.ctrl->t;
   float y[OD], yn[OD];
@@ -730,6 +743,7 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   SoftAcc<1> Q, R2, R3;
   mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
   softacc4_block_reduce(A, Q, R2, R3, fin_smem.f4);
+  pdl_trigger();  // the successor may be scheduled while the last block folds the partials
   __shared__ int is_last;
   if (tid == 0) {
     Partial& p = a.partials[(int64_t)col * a.blocks_per_col + blockIdx.x];
