@@ -60,6 +60,7 @@ struct ResampleArgs {
   float* u_col;            // (B) the systematic offset of every column for this launch (injected or Philox)
   long long* dbg;          // optional diagnostics (SMCB_DEBUG_TIMELINE): globaltimer stamps / counters of describe_kernel's chain
   int32_t quantize;        // 1: round the weights derived from log-weights to multiples of 2^-52 (every column becomes benign)
+  int32_t presanitized;    // 1: the log-weights were stored by the step / state kernels, nan_to_num (utils.py:57) already applied
   int32_t force_benign;    // 1: the host skipped describe_kernel (quantised weights, n <= 2^23, Philox offsets): benign by construction
 };
 __device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -125,23 +126,27 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
   double s = 0.0;
   uint32_t key = 0xFFFFFFFFu;
   const bool quant = a.quantize && !a.input_is_w && m == m && iz == iz && iz < 1e30f;  // finite normalisers only
+  const bool inner = g0 + RS_TILE <= a.n;            // no padding in this tile
+  const bool raw = !a.input_is_w && !a.presanitized;  // apply nan_to_num here
 #pragma unroll
   for (int v = 0; v < RS_ITEMS / 4; ++v) {
     const int e = (v * RS_NT + threadIdx.x) * 4;
     float x[4] = {q4[v].x, q4[v].y, q4[v].z, q4[v].w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      if (!a.input_is_w) x[k] = smcb_weight(smcb_sanitize(x[k]), m, iz);
-      if (g0 + e + k >= a.n) x[k] = 0.f;
+      if (raw) x[k] = smcb_sanitize(x[k]);
+      if (!a.input_is_w) x[k] = smcb_weight(x[k], m, iz);
+      if (!inner && g0 + e + k >= a.n) x[k] = 0.f;
       double xd = (double)x[k];
       if (quant) {  // RN to a multiple of 2^-52: exact in float32 (at most 23 significant bits below 2^-29), |dW| <= 2^-53
         xd = __dadd_rn(__dadd_rn(1.0, xd), -1.0);
         x[k] = (float)xd;
+      } else {      // the verdict needs the smallest non-zero weight (quantised weights are multiples of 2^-52 by construction)
+        const uint32_t b = __float_as_uint(x[k]);
+        const uint32_t kk = (b == 0u) ? 0xFFFFFFFFu : ((b >> 31) ? 0u : b);
+        key = min(key, kk);
       }
       s += xd;
-      const uint32_t b = __float_as_uint(x[k]);
-      const uint32_t kk = (b == 0u) ? 0xFFFFFFFFu : ((b >> 31) ? 0u : b);
-      key = min(key, kk);
     }
     if (!a.input_is_w || a.wn != a.w) *reinterpret_cast<float4*>(a.wn + off + e) = make_float4(x[0], x[1], x[2], x[3]);
     if (a.w_out) *reinterpret_cast<float4*>(a.w_out + off + e) = make_float4(x[0], x[1], x[2], x[3]);
@@ -189,8 +194,8 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     const bool u_ok = (u == 0.f) || (u >= 5.5e-20f && u < 1.0f);
     const bool fast_ok = a.n <= (1 << 23) && u_ok;  // xs_count_fast applies (exact_scan.h)
     // quantised weights are multiples of 2^-52 by construction (the smallest-weight proxy does not apply to them)
-    const bool quant = a.quantize && !a.input_is_w;
-    const bool benign = fast_ok && tot < 1.5 && (quant ? (mk != 0u) : (mk >= RS_BENIGN_MIN_BITS));
+    const bool quant = a.quantize && !a.input_is_w;  // weights exp(.) * c >= 0, multiples of 2^-52 (NaN normalisers give tot = NaN)
+    const bool benign = fast_ok && tot < 1.5 && (quant || mk >= RS_BENIGN_MIN_BITS);
     a.verdict[col] = (benign ? 1 : 0) | (fast_ok ? 2 : 0);
     a.ncounter[col] = 0;
     if (a.dbg) a.dbg[10] = rs_now();

@@ -408,6 +408,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.dcounter = f->dcounter; r.verdict = f->verdict; r.u_col = f->u_col;
   r.dbg = f->dbg;
   r.quantize = f->cfg.exact_weights ? 0 : 1;
+  r.presanitized = 1;  // lw / rw were stored by the step, state and pre-weight kernels
   const dim3 rgrid(r.tiles_per_col, r.B);
   launch_pdl(normalize_kernel, rgrid, dim3(RS_NT), s, r);
   f->launches++;

@@ -707,7 +707,7 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
     float z[D][4];
     st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
 
-    float xn[D][4], lwn[4], rwn[4], inc4[4], wprev[4];
+    float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float xk[D], zk[D], xo[D], inc, g_anc;
@@ -720,10 +720,26 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
       if (!observed) lw = lwp[k];
       else if (ALG == SMCB_ALG_APF) lw = __fsub_rn(inc, g_anc);   // apf.py:43
       else lw = __fadd_rn(inc, lwp[k]);                           // sisr.py:52
-      lwn[k] = st_sanitize(lw);
+      lwn[k] = lw;
       inc4[k] = inc;
       if (ALG == SMCB_ALG_SISR) wprev[k] = resampled ? inv_n : smcb_weight(lwp[k], st.m_lw, st.inv_z_lw);
-      rwn[k] = fold ? st_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps), lwn[k])) : lwn[k];
+      gnx[k] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
+    }
+    {  // nan_to_num (utils.py:57) only when something in the group is not finite: a sum of four finite floats can overflow at worst
+      const float chk = fabsf(lwn[0]) + fabsf(lwn[1]) + fabsf(lwn[2]) + fabsf(lwn[3]);
+      if (!(chk < INFINITY)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lwn[k] = st_sanitize(lwn[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rwn[k] = __fadd_rn(gnx[k], lwn[k]);
+      if (fold) {
+        const float chk2 = fabsf(rwn[0]) + fabsf(rwn[1]) + fabsf(rwn[2]) + fabsf(rwn[3]);
+        if (!(chk2 < INFINITY)) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) rwn[k] = st_sanitize(rwn[k]);
+        }
+      }
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) *reinterpret_cast<float4*>(xnext[d] + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
