@@ -48,39 +48,51 @@ def load_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks and throttle reasons WHILE the timed region runs: NVML polled from a thread every millisecond (the timed
+    region is tens of milliseconds, too short for `nvidia-smi -lms`); falls back to one nvidia-smi query per sample."""
+
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.mask, self.max_mhz, self.stop_flag, self.thread, self.h = index, [], 0, None, False, None, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        while not self.stop_flag:
+            try:
+                if self.nv:
+                    self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                    time.sleep(0.001)
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    a, b = [float(v) for v in out.strip().split(",")[:2]]
+                    self.sm.append(a); self.max_mhz = b
+            except Exception:
+                time.sleep(0.005)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
-        sm, mx, reasons = [], 0, set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(2)
+        sm = sorted(self.sm)
+        reasons = sorted(k for k, bit in self.REASONS.items() if self.mask & bit)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(sm)}
 
 
 def cpu_baseline(particles, budget_s=20.0):
@@ -213,8 +225,15 @@ def run_b200(args):
     achieved = alg_bytes[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0
     step_ms = sum(per.values())
     whole = 24.0 * N / (ms / K * 1e-3) / 1e9
+    traffic = None  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if int(tj["particles"]) == N:
+            traffic = tj["bytes_per_launch"].get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": per,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": per,
                 "whole_step": {"algorithmic_bytes_per_particle": 24, "achieved": whole, "frac": whole / peak,
                                "ms_per_step_profiled": step_ms}}
 
@@ -256,7 +275,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=2000)  # T of BASELINE.json configs[2]
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--particles", type=int, default=4_000_000)
