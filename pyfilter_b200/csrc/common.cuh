@@ -56,10 +56,18 @@ __device__ __forceinline__ float smcb_sanitize(float w) {
   return w;
 }
 
-// normalised weight exactly as every kernel of this library evaluates it (must be ONE function: the tile-sum pre-pass and the
-// scan kernel have to see identical bits).  Differs from the reference's exp(v)/sum by at most a few ulp (tolerance 1e-6).
+// normalised weight exactly as every kernel of this library evaluates it (must be ONE function: every kernel has to see identical
+// bits).  exp(v) = 2^t (1 + r ln 2) with t = fl(v log2 e) and r the exact residual of that product plus the low part of log2 e: one
+// SFU ex2 (2 ulp) and five FMA-pipe instructions, ~3e-7 relative for any v <= 0 (tolerance of the parity tests: 3e-6).
 __device__ __forceinline__ float smcb_weight(float lw, float m, float inv_z) {
-  return __fmul_rn(expf(__fsub_rn(lw, m)), inv_z);
+  const float v = fmaxf(__fsub_rn(lw, m), -200.f);                         // exp(-200) = 0 in float32; keeps -inf out of the residual
+  const float t = __fmul_rn(v, 1.4426950216293335f);                       // log2(e), high part
+  float r = fmaf(v, 1.4426950216293335f, -t);                              // exact residual of the product
+  r = fmaf(v, 1.9259629911766e-8f, r);                                     // + v * low part of log2(e)
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  e = fmaf(e, __fmul_rn(r, 0.6931471805599453f), e);
+  return __fmul_rn(e, inv_z);
 }
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {

@@ -23,6 +23,11 @@
 #define RS_KIND_RAW 3     // too many segments: the chain walks the raw weights
 #define RS_KIND_ABS 4     // the state after the tile is a_s whatever came before (tile 0 resolves itself: it starts from 0)
 
+struct __align__(16) FusedSlot {  // written and read with one 128-bit access: the tag says the sum belongs to this launch
+  double sum;
+  unsigned long long tag;
+};
+
 struct SegTable {
   XsT agg[RS_MAXSEG];
   float wc[RS_MAXSEG];
@@ -60,6 +65,7 @@ struct ResampleArgs {
   float* u_col;            // (B) the systematic offset of every column for this launch (injected or Philox)
   long long* dbg;          // optional diagnostics (SMCB_DEBUG_TIMELINE): globaltimer stamps / counters of describe_kernel's chain
   int32_t quantize;        // 1: round the weights derived from log-weights to multiples of 2^-52 (every column becomes benign)
+  struct FusedSlot* fslots; // (B, tiles_per_col) resample_fused_kernel: tile sums tagged with the launch epoch
   int32_t presanitized;    // 1: the log-weights were stored by the step / state kernels, nan_to_num (utils.py:57) already applied
   int32_t force_benign;    // 1: the host skipped describe_kernel (quantised weights, n <= 2^23, Philox offsets): benign by construction
 };
@@ -756,6 +762,81 @@ __device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[RS_ITEMS], doub
   return lo;
 }
 
+// ---- ancestors of one tile from the marks: the tile owns the output slots [n_in, n_out) ----------------------------------------------
+// `mark(wb, first)` runs the mark pass for the window starting at slot wb and returns the thread's last count.
+template <typename Mark>
+__device__ __forceinline__ void rs_emit_ancestors(ExpandSmem& sm, Mark mark, int32_t n_in, int32_t* anc) {
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int32_t wb0 = n_in & ~3;
+  {
+    const int32_t last = mark(wb0, true);
+    if (tid == RS_NT - 1) sm.n_out = last;
+  }
+  __syncthreads();
+  const int32_t n_out = sm.n_out;
+
+  int32_t carry = -1;
+  for (int32_t wb = wb0; wb < n_out; wb += FB_WIN) {
+    if (wb != wb0) {  // rare: more than one window of offspring
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+      if (tid == 0) sm.carry = -1;
+      __syncthreads();
+      mark(wb, false);
+      __syncthreads();
+      carry = max(carry, sm.carry);
+    }
+    const int32_t wlen = min(FB_WIN, n_out - wb);
+    // last mark at or before every slot; warp `wid` owns FB_ROWS rows of 32 int4, row k = int4 [(wid*FB_ROWS + k)*32, +32)
+    int4 m[FB_ROWS];
+    int32_t cin[FB_ROWS];
+    int32_t wrun = -1;  // last mark seen by this warp so far
+#pragma unroll
+    for (int k = 0; k < FB_ROWS; ++k) {
+      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+      m[k] = *reinterpret_cast<const int4*>(&sm.stage[i4 * 4]);
+      const int32_t v = max(max(m[k].x, m[k].y), max(m[k].z, m[k].w));
+      const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
+      const uint32_t before = bal & ((1u << lane) - 1u);
+      const int32_t vb = __shfl_sync(0xffffffffu, v, before ? 31 - __clz(before) : 0);
+      cin[k] = before ? vb : wrun;
+      const int32_t vl = __shfl_sync(0xffffffffu, v, bal ? 31 - __clz(bal) : 0);
+      if (bal) wrun = vl;
+    }
+    if (lane == 0) sm.wtot[wid] = wrun;
+    __syncthreads();
+    int32_t cw = carry;  // last mark before this warp's rows
+    int32_t call = carry;
+#pragma unroll
+    for (int k = 0; k < RS_NT / 32; ++k) {
+      const int32_t t = sm.wtot[k];
+      if (k < wid) cw = max(cw, t);
+      call = max(call, t);
+    }
+    carry = call;
+#pragma unroll
+    for (int k = 0; k < FB_ROWS; ++k) {
+      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+      const int32_t s0 = wb + i4 * 4;
+      if (i4 * 4 < wlen) {
+        int4 o;
+        o.x = max(max(cw, cin[k]), m[k].x);
+        o.y = max(o.x, m[k].y);
+        o.z = max(o.y, m[k].z);
+        o.w = max(o.z, m[k].w);
+        if (s0 >= n_in && s0 + 4 <= n_out) *reinterpret_cast<int4*>(anc + s0) = o;
+        else {
+          if (s0 >= n_in && s0 < n_out) anc[s0] = o.x;
+          if (s0 + 1 >= n_in && s0 + 1 < n_out) anc[s0 + 1] = o.y;
+          if (s0 + 2 >= n_in && s0 + 2 < n_out) anc[s0 + 2] = o.z;
+          if (s0 + 3 >= n_in && s0 + 3 < n_out) anc[s0 + 3] = o.w;
+        }
+      }
+    }
+  }
+}
+
 template <int MB, int OUT>
 __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
   __shared__ __align__(16) ExpandSmem sm;
@@ -869,78 +950,99 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
   const int32_t n_in = (tile == 0) ? 0 : ((tile * RS_TILE - 1 >= n - 1) ? n : rs_count_any(c_in, u, n, nf, nd, nfd, fast_ok));
   int32_t lo_thread = n_in;
   if (tid) lo_thread = max(n_in, (gbase - 1 >= n - 1) ? n : rs_count_any(c_prev, u, n, nf, nd, nfd, fast_ok));
-  const int32_t wb0 = n_in & ~3;
   auto mark = [&](int32_t wb, bool first) -> int32_t {
     if (benign) return rs_mark_pass<MB, true, true>(w, S0, 0.0, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, sm);
     if (fast) return rs_mark_pass<MB, true, false>(w, S0, M, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, fast_ok, sm);
     return rs_mark_pass<MB, false, false>(w, S0, M, c_thread, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, fast_ok, sm);
   };
-  {
-    const int32_t last = mark(wb0, true);
-    if (tid == RS_NT - 1) sm.n_out = last;
-  }
-  __syncthreads();
-  const int32_t n_out = sm.n_out;
-
-  int32_t* anc = a.anc + (int64_t)col * a.ld;
-  int32_t carry = -1;
-  for (int32_t wb = wb0; wb < n_out; wb += FB_WIN) {
-    if (wb != wb0) {  // rare: more than one window of offspring
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-      if (tid == 0) sm.carry = -1;
-      __syncthreads();
-      mark(wb, false);
-      __syncthreads();
-      carry = max(carry, sm.carry);
-    }
-    const int32_t wlen = min(FB_WIN, n_out - wb);
-    // last mark at or before every slot; warp `wid` owns FB_ROWS rows of 32 int4, row k = int4 [(wid*FB_ROWS + k)*32, +32)
-    int4 m[FB_ROWS];
-    int32_t cin[FB_ROWS];
-    int32_t wrun = -1;  // last mark seen by this warp so far
-#pragma unroll
-    for (int k = 0; k < FB_ROWS; ++k) {
-      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
-      m[k] = *reinterpret_cast<const int4*>(&sm.stage[i4 * 4]);
-      const int32_t v = max(max(m[k].x, m[k].y), max(m[k].z, m[k].w));
-      const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
-      const uint32_t before = bal & ((1u << lane) - 1u);
-      const int32_t vb = __shfl_sync(0xffffffffu, v, before ? 31 - __clz(before) : 0);
-      cin[k] = before ? vb : wrun;
-      const int32_t vl = __shfl_sync(0xffffffffu, v, bal ? 31 - __clz(bal) : 0);
-      if (bal) wrun = vl;
-    }
-    if (lane == 0) sm.wtot[wid] = wrun;
-    __syncthreads();
-    int32_t cw = carry;  // last mark before this warp's rows
-    int32_t call = carry;
-#pragma unroll
-    for (int k = 0; k < RS_NT / 32; ++k) {
-      const int32_t t = sm.wtot[k];
-      if (k < wid) cw = max(cw, t);
-      call = max(call, t);
-    }
-    carry = call;
-#pragma unroll
-    for (int k = 0; k < FB_ROWS; ++k) {
-      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
-      const int32_t s0 = wb + i4 * 4;
-      if (i4 * 4 < wlen) {
-        int4 o;
-        o.x = max(max(cw, cin[k]), m[k].x);
-        o.y = max(o.x, m[k].y);
-        o.z = max(o.y, m[k].z);
-        o.w = max(o.z, m[k].w);
-        if (s0 >= n_in && s0 + 4 <= n_out) *reinterpret_cast<int4*>(anc + s0) = o;
-        else {
-          if (s0 >= n_in && s0 < n_out) anc[s0] = o.x;
-          if (s0 + 1 >= n_in && s0 + 1 < n_out) anc[s0 + 1] = o.y;
-          if (s0 + 2 >= n_in && s0 + 2 < n_out) anc[s0 + 2] = o.z;
-          if (s0 + 3 >= n_in && s0 + 3 < n_out) anc[s0 + 3] = o.w;
-        }
-      }
-    }
-  }
+  rs_emit_ancestors(sm, mark, n_in, a.anc + (int64_t)col * a.ld);
 }
+
+// ---- resample_fused_kernel: normalise + prefix + expand in ONE pass (weights rounded to multiples of 2^-52) ---------------------
+// With rounding-free weights the state before a tile is the plain sum of the preceding tile sums, in any order.  So one kernel can do
+// everything: weights from the log-weights (registers only - they are never written), tile sum published with the launch epoch as
+// tag, then ALL threads of the CTA poll the preceding tiles' slots in parallel (one 128-bit load per predecessor and round trip; tile
+// ids are handed out in start order, so every predecessor is running or finished and nobody can wait on a tile that has not started),
+// sum them exactly, and expand as expand_kernel does.  No normalised weights in memory, no serial tail, one launch per resampling.
+__global__ void __launch_bounds__(RS_NT, 4) resample_fused_kernel(ResampleArgs a) {
+  __shared__ __align__(16) ExpandSmem sm;
+  __shared__ int s_id;
+  const int tid = threadIdx.x;
+  pdl_wait();
+  if (tid == 0) s_id = (int)atomicAdd(&a.ctrl->tile_counter, 1u);
+#pragma unroll
+  for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+  if (tid == 0) sm.carry = -1;
+  __syncthreads();
+  const int T = a.tiles_per_col;
+  const int col = s_id / T, tile = s_id % T;
+  if (col >= a.B) return;
+  // independent loads first
+  float w[RS_ITEMS];
+  {
+    const float4* src = reinterpret_cast<const float4*>(a.w + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + tid * RS_ITEMS);
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+      const float4 q = __ldg(src + v);
+      w[4 * v] = q.x; w[4 * v + 1] = q.y; w[4 * v + 2] = q.z; w[4 * v + 3] = q.w;
+    }
+  }
+  const ColStats st = a.stats[col];
+  const unsigned long long epoch = a.ctrl->epoch;
+  const int t_now = a.ctrl->t;
+  if (!st.resample) return;
+  const float m = a.use_rw ? st.m_rw : st.m_lw, iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
+  const int32_t n = (int32_t)a.n;
+  const double nd = (double)n, nfd = (double)(float)a.n;
+  const int32_t gbase = tile * RS_TILE + tid * RS_ITEMS;
+  // weights, rounded to multiples of 2^-52 (exactly what normalize_kernel computes with `quantize`)
+  double tsum = 0.0;
+#pragma unroll
+  for (int j = 0; j < RS_ITEMS; ++j) {
+    float x = smcb_weight(w[j], m, iz);
+    if (gbase + j >= n) x = 0.f;
+    const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);
+    w[j] = (float)xd;
+    tsum += xd;
+  }
+  if (a.w_out) {
+    float* dst = a.w_out + (int64_t)col * a.ld + gbase;
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v)
+      reinterpret_cast<float4*>(dst)[v] = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+  }
+  double tot;
+  const double ex = rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);
+  FusedSlot* slots = a.fslots + (int64_t)col * T;
+  if (tid == 0) {  // publish: one 128-bit store carries the sum and its tag
+    double2 v;
+    v.x = tot; v.y = __longlong_as_double((long long)epoch);
+    __stcg(reinterpret_cast<double2*>(slots + tile), v);
+  }
+  // exact sum of the preceding tiles: every thread polls its share of the predecessors
+  double part = 0.0;
+  for (int q = tile - 1 - tid; q >= 0; q -= RS_NT) {
+    double2 v;
+    for (;;) {
+      v = __ldcg(reinterpret_cast<const double2*>(slots + q));
+      if ((unsigned long long)__double_as_longlong(v.y) == epoch) break;
+      __nanosleep(64);
+    }
+    part += v.x;
+  }
+  const double S_in = block_allreduce<RS_NT>(part, 0.0, OpSumD(), sm.core.dscratch);
+  const double S0 = S_in + ex;
+  // one uniform per column (resampling.py:41)
+  const Philox4 r4 = philox4x32_10((uint32_t)col, 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const float u = smcb_u01(r4.x);
+  if (a.u_out && tile == 0 && tid == 0) a.u_out[col] = u;
+  const float nf = (float)a.n;
+  const int32_t n_in = (tile == 0) ? 0 : xs_count_fast((float)S_in, u, n, nd, nfd);
+  int32_t lo_thread = n_in;
+  if (tid) lo_thread = max(n_in, (gbase - 1 >= n - 1) ? n : xs_count_fast((float)S0, u, n, nd, nfd));
+  auto mark = [&](int32_t wb, bool first) -> int32_t {
+    return rs_mark_pass<53, true, true>(w, S0, 0.0, nullptr, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, sm);
+  };
+  rs_emit_ancestors(sm, mark, n_in, a.anc + (int64_t)col * a.ld);
+}
+

@@ -124,6 +124,7 @@ struct smcb_filter {
   SegTable* tables = nullptr;
   uint32_t* tilemin = nullptr;
   int32_t *ncounter = nullptr, *dcounter = nullptr, *verdict = nullptr;
+  FusedSlot* fslots = nullptr;
   float* u_col = nullptr;
   float *hist_mean = nullptr, *hist_var = nullptr, *hist_ll = nullptr;
   float *latest_mean = nullptr, *latest_var = nullptr, *latest_ll = nullptr, *ll_total = nullptr, *ess_packed = nullptr;
@@ -165,7 +166,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
-                  f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict,
+                  f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
                   f->u_col};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
@@ -225,6 +226,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->desc, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->tables, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->dcounter, (size_t)f->B));
+  A_(dalloc(&f->fslots, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->tilemin, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->ncounter, (size_t)f->B));
   A_(dalloc(&f->verdict, (size_t)f->B));
@@ -410,6 +412,19 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.quantize = f->cfg.exact_weights ? 0 : 1;
   r.presanitized = 1;  // lw / rw were stored by the step, state and pre-weight kernels
   const dim3 rgrid(r.tiles_per_col, r.B);
+  // rounding-free weights of at most 2^23 particles with Philox offsets and no dump of the weights' prefix: one fused kernel
+  static const bool no_fused = getenv("SMCB_NO_FUSED") != nullptr;
+  if (f->cfg.resampler == SMCB_SYSTEMATIC && r.quantize && f->n <= (1 << 23) && !f->u_in && !no_fused) {
+    r.fslots = f->fslots;
+    launch_pdl(resample_fused_kernel, dim3(r.tiles_per_col * r.B), dim3(RS_NT), s, r);
+    f->launches++;
+    if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); cudaEventRecord(ev[4], s); }
+    launch_step(f, a, s);
+    if (ev) cudaEventRecord(ev[5], s);
+    f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
+    f->t_host = t + 1;
+    return SMCB_OK;
+  }
   launch_pdl(normalize_kernel, rgrid, dim3(RS_NT), s, r);
   f->launches++;
   if (ev) cudaEventRecord(ev[2], s);
