@@ -191,28 +191,59 @@ struct MultinomialArgs {
   uint64_t seed;
   const Ctrl* ctrl;
   int32_t* anc;            // (B, ld)
+  int32_t stride;          // coarse table: last element of every `stride` cumulative weights (power of two)
+  int32_t ncoarse;
 };
 
+// Draw i picks the first k with (double) fl32(c_k / c_{n-1}) >= U_i.  The predicate is monotone in c_k, so it is turned into a
+// threshold on c_k itself once per draw - no division inside the search: with Uc = U rounded up to float32 and Up its predecessor,
+// fl32(c / total) >= Uc  <=>  c >= mid(Up, Uc) * total (exact in fp64: 25 x 24 bits), strictly when the tie rounds to the odd Up.
+// Two-level search: a coarse table of every `stride`-th cumulative weight in shared memory, then one chunk in global memory.
 __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a) {
+  extern __shared__ float coarse[];
+  pdl_wait();
   const int col = blockIdx.y;
   if (a.stats && !a.stats[col].resample) return;
   const float* c = a.c + (int64_t)col * a.ld;
-  const float total = c[a.n - 1];
+  const int64_t n = a.n;
+  for (int i = threadIdx.x; i < a.ncoarse; i += blockDim.x) {
+    const int64_t k = min((int64_t)(i + 1) * a.stride, n) - 1;
+    coarse[i] = __ldg(c + k);
+  }
+  const double total = (double)__ldg(c + n - 1);
   const int t = a.ctrl->t;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (int64_t)gridDim.x * blockDim.x) {
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     double U;
     if (a.U) U = a.U[(int64_t)col * a.U_pitch + i];
     else {
       Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)col, (uint32_t)t, SMCB_RNG_MULTINOMIAL, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       U = smcb_u01_double(r.x, r.y);
     }
-    int64_t lo = 0, hi = a.n;
-    while (hi - lo > 0) {
-      const int64_t mid = lo + (hi - lo) / 2;
-      const float cn = __fdiv_rn(__ldg(c + mid), total);
-      if ((double)cn < U) lo = mid + 1; else hi = mid;
+    const float Uc = __double2float_ru(U);
+    float cthr = 0.f;  // U <= 0: every cumulative weight qualifies
+    if (Uc > 0.f) {
+      const uint32_t ub = __float_as_uint(Uc);
+      const double mid = 0.5 * ((double)__uint_as_float(ub - 1u) + (double)Uc);
+      double thr = mid * total;
+      if (ub & 1u) thr = __longlong_as_double(__double_as_longlong(thr) + 1);  // a tie rounds to the even neighbour Up: need c/total > mid
+      cthr = __double2float_ru(thr);
     }
-    a.anc[(int64_t)col * a.ld + i] = (int32_t)(lo < a.n ? lo : a.n - 1);
+    int lo = 0, hi = a.ncoarse;  // first chunk whose last element reaches the threshold
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (coarse[mid] < cthr) lo = mid + 1; else hi = mid;
+    }
+    int64_t ans = n - 1;
+    if (lo < a.ncoarse) {
+      int64_t k0 = (int64_t)lo * a.stride, k1 = min(k0 + a.stride, n) - 1;
+      while (k0 < k1) {
+        const int64_t m = (k0 + k1) >> 1;
+        if (__ldg(c + m) < cthr) k0 = m + 1; else k1 = m;
+      }
+      ans = k0;
+    }
+    a.anc[(int64_t)col * a.ld + i] = (int32_t)ans;
   }
 }
 
@@ -224,11 +255,14 @@ static inline void op_launch_multinomial_after_normalize(const ResampleArgs& r, 
   MultinomialArgs m;
   m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
   m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc;
+  int stride = 256;  // every block gathers the coarse table itself (one sector per entry): keep it to ~1k entries
+  while ((r.n + stride - 1) / stride > 1024) stride *= 2;
+  m.stride = stride; m.ncoarse = (int)((r.n + stride - 1) / stride);
   int bx = (int)((r.n + 255) / 256);
-  const int cap = (148 * 8 + r.B - 1) / r.B;
+  const int cap = (148 * 6 + r.B - 1) / r.B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
-  multinomial_draw_kernel<<<dim3(bx, r.B), 256, 0, s>>>(m);
+  multinomial_draw_kernel<<<dim3(bx, r.B), 256, (size_t)m.ncoarse * sizeof(float), s>>>(m);
 }
 static inline int op_launch_multinomial(const ResampleArgs& r, const double* U, int64_t U_pitch, cudaStream_t s) {
   if (!r.c_out) return SMCB_EINVAL;
