@@ -216,10 +216,14 @@ def run_b200(args):
     prof = (C.c_float * 5)()
     _lib.check(lib.smcb_filter_profile(e.handle, P, prof, stream.cuda_stream))
     e.t += P
-    names = ["apf_preweight", "normalize_kernel", "describe_kernel", "expand_kernel", "step_kernel"]
+    fused = (not args.exact_weights) and N <= (1 << 23) and not os.environ.get("SMCB_NO_FUSED")  # run_one's own condition
+    names = ["apf_preweight", "resample_fused_kernel" if fused else "normalize_kernel", "describe_kernel", "expand_kernel", "step_kernel"]
     per = {n_: prof[i] / P for i, n_ in enumerate(names)}
-    alg_bytes = {"normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N, "expand_kernel": 8.0 * N, "step_kernel": 16.0 * N,
-                 "apf_preweight": 12.0 * N}
+    if fused:  # the two slots only hold the bracketing events' own overhead
+        per.pop("describe_kernel"); per.pop("expand_kernel")
+    # algorithmic bytes per launch: resampling = load log-weight 4 + store ancestor 4; step = ancestor 4 + gather 4 + x 4 + log-weight 4
+    alg_bytes = {"resample_fused_kernel": 8.0 * N, "normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N, "expand_kernel": 8.0 * N,
+                 "step_kernel": 16.0 * N, "apf_preweight": 12.0 * N}
     dom = max(per, key=per.get)
     peak, peak_src = load_peaks()
     achieved = alg_bytes[dom] / (per[dom] * 1e-3) / 1e9 if per[dom] > 0 else 0.0

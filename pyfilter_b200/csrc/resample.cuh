@@ -753,7 +753,7 @@ __device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[RS_ITEMS], doub
       c = (float)run;
     } else c = c_thread[j];
     int32_t hi = BENIGN ? xs_count_fast(c, u, n, nd, nfd) : rs_count_any(c, u, n, nf, nd, nfd, fast_ok);
-    hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
+    if (gbase + RS_ITEMS >= n) hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
     const int32_t r = lo - wb;
     if (hi > lo && (uint32_t)r < (uint32_t)FB_WIN) sm.stage[r] = gbase + j;
     if (!first && hi > lo && r < 0 && hi > wb) sm.carry = gbase + j;  // its slots began in an earlier window (one such particle at most)
@@ -997,10 +997,11 @@ __global__ void __launch_bounds__(RS_NT, 4) resample_fused_kernel(ResampleArgs a
   const int32_t gbase = tile * RS_TILE + tid * RS_ITEMS;
   // weights, rounded to multiples of 2^-52 (exactly what normalize_kernel computes with `quantize`)
   double tsum = 0.0;
+  const bool inner = gbase + RS_ITEMS <= n;  // no padding among this thread's particles
 #pragma unroll
   for (int j = 0; j < RS_ITEMS; ++j) {
     float x = smcb_weight(w[j], m, iz);
-    if (gbase + j >= n) x = 0.f;
+    if (!inner && gbase + j >= n) x = 0.f;
     const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);
     w[j] = (float)xd;
     tsum += xd;
