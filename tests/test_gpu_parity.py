@@ -405,3 +405,58 @@ def test_full_size_config5_shard_vs_oracle(pf):
     assert int(clean.sum()) >= 4  # ~2 ulp-induced flips per column on average: roughly e^-2 of the columns are clean
     assert torch.allclose(st.get_loglikelihood().cpu()[clean], ref["ll"][clean], rtol=2e-5, atol=2e-4)
     assert torch.allclose(st.get_mean().cpu().reshape(-1)[clean], ref["mean"].reshape(-1)[clean], rtol=1e-4, atol=2e-4)
+
+
+def test_fused_resampling_batched_exact(pf):
+    """Default path (one fused resampling kernel, Philox offsets, weights rounded to multiples of 2^-52) on a ragged batch:
+    131 columns x 5000 particles (two tiles per column, the second one mostly padding), SISR so that only some columns resample in a
+    move.  Ancestors of every resampling column are bit-exact against the oracle's CPU systematic for the dumped weights and offsets;
+    the other columns keep their ancestors."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import SISR
+
+    N, B = 5000, 131
+    torch.manual_seed(3)
+    _, y = O.build_model("lg_ar1").simulate(12)
+    gen = torch.Generator().manual_seed(4)
+    f = SISR(ts.build("lg_ar1", sigma=0.05 + 0.2 * torch.rand(B, generator=gen)), N, seed=17, ess_threshold=0.5)
+    f.set_batch_shape(torch.Size([B]))
+    e = f._get_engine(16)
+    e.initialize()
+    e.set_observations(y.float().reshape(-1, 1).cuda().contiguous(), 0)
+    wdump = torch.zeros(e.B, e.ld, device="cuda")
+    udump = torch.zeros(e.B, device="cuda")
+    e.dump_noise(None, udump, wdump)
+    seen_resampled = seen_kept = 0
+    for t in range(10):
+        before = e.prev_inds().clone()
+        _, flags = e.ess()          # resample decision taken for the coming move
+        torch.cuda.synchronize()
+        flags = flags.cpu() > 0
+        wdump.zero_()
+        e.run(1)
+        torch.cuda.synchronize()
+        anc = e.prev_inds().cpu()
+        for b in range(B):
+            if flags[b]:
+                W = wdump[b, :N].cpu()
+                exp = O.systematic(W.clone().unsqueeze(1), normalized=True, u=udump[b].cpu().reshape(1, 1))[:, 0]
+                assert torch.equal(anc[:, b], exp), (t, b)
+                seen_resampled += 1
+            else:
+                assert torch.equal(anc[:, b], before[:, b].cpu()), (t, b)
+                seen_kept += 1
+    assert seen_resampled > 0 and seen_kept > 0
+
+
+@pytest.mark.parametrize("n,b", [(1, 1), (2, 3), (300, 128), (4096, 5), (4097, 5)])
+def test_systematic_small_and_wide(pf, n, b):
+    gen = torch.Generator().manual_seed(n * 31 + b)
+    W = O.normalize(torch.randn(n, b, generator=gen) * 1.5)
+    u = torch.rand(b, 1, generator=gen)
+    got = pf.resampling.systematic(W.cuda(), normalized=True, u=u.cuda()).cpu()
+    assert torch.equal(got, O.systematic(W.clone(), normalized=True, u=u))
+    lw = torch.randn(n, b, generator=gen) * 3
+    got = pf.resampling.systematic(lw.clone().cuda(), u=u.cuda()).cpu()
+    Wd = pf.utils.normalize(lw.clone().cuda()).cpu()
+    assert torch.equal(got, O.systematic(Wd.clone(), normalized=True, u=u))
