@@ -190,15 +190,21 @@ XS_HD I xs_count_le_t(float c, float u, I n, float nf) {
 }
 XS_HD int64_t xs_count_le(float c, float u, int64_t n, float nf) { return xs_count_le_t<int64_t>(c, u, n, nf); }
 
-// Lean variant for the kernels' hot path (no type conversions, 4 double-precision operations).  Requirements: n <= 2^23,
+// Lean variant for the kernels' hot path (two float->double conversions, 4 double-precision operations, no division).  Requirements: n <= 2^23,
 // c == 0 or a normal float, u == 0 or u >= 2^-64.  With t = (c + ulp(c)/2) * n exact in double and tt = t, or the double just
 // below t when the midpoint tie rounds away from c, probe i qualifies iff fl32(i + u) <= tt.  For K = floor(tt): every
 // i <= K - 1 has i + u < K <= tt, hence fl32(i + u) <= K <= tt (rounding is monotone, K is a float); every i >= K + 1 has
 // fl32(i + u) >= K + 1 > tt.  Only probe K itself has to be evaluated.
 XS_HD int32_t xs_count_fast(float c, float u, int32_t n, double nd /* (double)n */, double nfd /* (double)(float)n */) {
   const uint32_t cb = xs_f2u(c);
+#if defined(__CUDA_ARCH__)
+  // (double)c + half an ulp of c: the conversion leaves the low 29 mantissa bits clear, bit 28 is half a float32 ulp
+  const double cd = (double)c;
+  const double t = __hiloint2double(__double2hiint(cd), __double2loint(cd) | 0x10000000) * nfd;  // exact: 25 x 24 bits
+#else
   const uint64_t mb = ((uint64_t)((cb >> 3) + 0x38000000u) << 32) | (uint64_t)((cb << 29) | 0x10000000u);
-  const double t = xs_u2d(mb) * nfd;                                   // exact: 25 x 24 bits
+  const double t = xs_u2d(mb) * nfd;
+#endif
   const double tt = xs_u2d(xs_d2u(t) - (uint64_t)(cb & 1u));           // t > 0
   const double tc = (tt < nd) ? tt : nd;                               // also catches NaN / inf
 #if defined(__CUDA_ARCH__)
@@ -207,9 +213,13 @@ XS_HD int32_t xs_count_fast(float c, float u, int32_t n, double nd /* (double)n 
   const int32_t K = (int32_t)floor(tc);
 #endif
   const float Kf = xs_fadd(xs_u2f(0x4B000000u | (uint32_t)K), -8388608.0f);   // exact for K <= 2^23
+#if defined(__CUDA_ARCH__)
+  const double sd = (double)xs_fadd(Kf, u);
+#else
   const uint32_t sb = xs_f2u(xs_fadd(Kf, u));
   const uint32_t shi = sb ? (sb >> 3) + 0x38000000u : 0u;
   const double sd = xs_u2d(((uint64_t)shi << 32) | (uint64_t)(sb << 29));
+#endif
   const int32_t r = K + (sd <= tt ? 1 : 0);
   return r < n ? r : n;
 }
