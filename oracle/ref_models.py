@@ -9,7 +9,7 @@ import math
 import torch
 
 
-def build_reference_model(name: str, params: dict):
+def build_reference_model(name: str, params: dict, observe_every_step: int = 1):
     from pyro.distributions import Normal  # stand-in
     from stochproc import timeseries as ts  # stand-in
 
@@ -33,7 +33,8 @@ def build_reference_model(name: str, params: dict):
             f, (t(params["gamma"]), t(params["sigma"])), Normal(loc=0.0, scale=math.sqrt(dt)), dt=dt,
             initial_kernel=initial_kernel,
         )
-        return ts.LinearStateSpaceModel(hidden, (t(params["a"]), t(params["b"]), t(params["s"])), torch.Size([]))
+        return ts.LinearStateSpaceModel(hidden, (t(params["a"]), t(params["b"]), t(params["s"])), torch.Size([]),
+                                        observe_every_step=observe_every_step)
 
     if name == "sv_ar1":
         def mean_scale(x, mu, phi, sigma_v):

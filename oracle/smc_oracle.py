@@ -523,7 +523,7 @@ STEPS = {"sisr": sisr_step, "apf": apf_step}
 # ----------------------------------------------------------------------------------------------------------------------
 def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, particles: int,
                  batch_shape: Tuple[int, ...] = (), resampler: str = "systematic", ess_threshold: float = 0.9,
-                 x0: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+                 x0: Optional[torch.Tensor] = None, observe_every_step: int = 1) -> Dict[str, torch.Tensor]:
     """``BaseFilter.batch_filter`` for SISR/APF using torch's global CPU generator in the reference's draw order
     (Appendix A-15: ``u`` - only when something resamples - then the transition noise)."""
     shape = (particles,) + tuple(batch_shape)
@@ -536,7 +536,17 @@ def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, p
     mean, var = filter_mean_and_variance(x, normalize(lw.clone()), model.state_dim)
     means, variances = [mean], [var]
     nb = int(np.prod(batch_shape)) if batch_shape else 1
+    # filters/base.py:204-210: before an observation is used, the filter propagates (predict + propagate, no weighting, no
+    # likelihood, nothing recorded) until the time index of the state is a multiple of `observe_every_step`
+    time_index = 0
+    moves = []
     for y_t in y:
+        while time_index % observe_every_step != 0:
+            moves.append((torch.full_like(torch.as_tensor(y_t), float("nan")), False))
+            time_index += 1
+        moves.append((y_t, True))
+        time_index += 1
+    for y_t, recorded in moves:
         # which columns draw resampling randomness (reference order: u first, then the transition noise)
         if algorithm == "sisr":
             mask = (get_ess(normalize(lw.clone()), True) < ess_threshold * n).reshape(-1)  # sisr.py:16-19
@@ -559,6 +569,8 @@ def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, p
         else:
             out = apf_step(model, proposal, x, lw, inds, y_t, z, u, resampler, U)
         x, lw, inds = out["x"], out["lw"], out["prev_inds"]
+        if not recorded:
+            continue
         ll_total = ll_total + out["ll"]
         means.append(out["mean"])
         variances.append(out["var"])

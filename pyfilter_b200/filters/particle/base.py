@@ -119,50 +119,85 @@ class ParticleFilter:
     def initialize_with_result(self, state=None) -> FilterResult:
         return FilterResult(state or self.initialize(), self.record_states, self.record_moments)
 
+    def _expand_observations(self, y: torch.Tensor, t0: int):
+        """``observe_every_step`` (filters/base.py:204-210): before an observation is used the filter makes propagate-only moves
+        until the time index is a multiple of ``observe_every_step``.  On the device a propagate-only move is a move whose
+        observation is NaN (filters/base.py:213-214 takes the same route), so the observations are interleaved with NaN rows.
+        Returns the expanded ``(moves, obs_dim)`` tensor and the (0-based) move index of every real observation."""
+        k = int(getattr(self._model, "observe_every_step", 1))
+        T = int(y.shape[0])
+        y2 = y.to(dtype=torch.float32).reshape(T, -1)
+        if k == 1:
+            return y2, list(range(T))
+        rows, observed, t = [], [], int(t0)
+        nan_row = torch.full((1, y2.shape[1]), float("nan"))
+        for i in range(T):
+            while t % k != 0:
+                rows.append(nan_row)
+                t += 1
+            observed.append(len(rows))
+            rows.append(y2[i: i + 1].cpu())
+            t += 1
+        return torch.cat(rows, 0), observed
+
     def batch_filter(self, y, bar=True, init_state=None) -> FilterResult:
         """``BaseFilter.batch_filter`` (filters/base.py:140-158): the whole time loop stays on the device."""
         y = torch.as_tensor(y)
         T = int(y.shape[0])
-        e = self._get_engine(T + 1)
+        k = int(getattr(self._model, "observe_every_step", 1))
+        t_start = 0 if init_state is None else int(init_state.timeseries_state.time_index)
+        e = self._get_engine(t_start + T * k + 1)
         if init_state is None:
             e.initialize()
             init_state = e.make_state()
         else:
             self._adopt(e, init_state)
         result = FilterResult(init_state, self.record_states, self.record_moments)
-        y_dev = y.to(device="cuda", dtype=torch.float32).reshape(T, -1).contiguous()
         t0 = e.t
+        y_moves, observed = self._expand_observations(y, t0)
+        M = int(y_moves.shape[0])  # moves, propagate-only ones included
+        if t0 + M + 1 > e.history_rows:
+            raise ValueError("the moment history of the handle is too short for this call; create the filter anew")
+        y_dev = y_moves.to(device="cuda", dtype=torch.float32).contiguous()
         e.set_observations(y_dev, t0)
         keep_all = not (self.record_states is False)
-        if keep_all:  # every intermediate state is wanted: one move at a time
-            for _ in range(T):
+        if keep_all:  # every recorded state is wanted: one move at a time
+            obs = set(observed)
+            for mv in range(M):
                 e.run(1)
-                result.append(e.make_state())
+                if mv in obs or self._record_intermediary:
+                    result.append(e.make_state())
             return result
         if bar:
             from tqdm import tqdm
 
-            chunk = max(1, T // 20)
-            for start in tqdm(range(0, T, chunk), desc=type(self).__name__):
-                e.run(min(chunk, T - start))
+            chunk = max(1, M // 20)
+            for start in tqdm(range(0, M, chunk), desc=type(self).__name__):
+                e.run(min(chunk, M - start))
         else:
-            e.run(T)
-        hist_rows = min(e.history_rows, t0 + T + 1)
-        means, variances, ll = e.history(hist_rows)
-        lo = t0 + 1
-        if lo + T <= hist_rows:
-            result.extend_moments(means[lo: lo + T], variances[lo: lo + T])
-            result._loglikelihood = result._loglikelihood + ll[lo: lo + T].sum(0)
+            e.run(M)
+        means, variances, ll = e.history(t0 + M + 1)
+        rows = torch.as_tensor([t0 + 1 + mv for mv in observed], device=means.device)  # history row of a move = its index + 1
+        result.extend_moments(means[rows], variances[rows])
+        result._loglikelihood = result._loglikelihood + ll[rows].sum(0)
         result._states.append(e.make_state())
         return result
 
     def filter(self, y, correction: ParticleFilterCorrection, result: FilterResult = None) -> ParticleFilterCorrection:
-        """``BaseFilter.filter`` (filters/base.py:188-221): one move."""
+        """``BaseFilter.filter`` (filters/base.py:188-221): one observation - the propagate-only moves ``observe_every_step`` asks
+        for, then the observed move."""
         e = self._get_engine(2)
         self._adopt(e, correction)
-        y_dev = torch.as_tensor(y).to(device="cuda", dtype=torch.float32).reshape(1, -1).contiguous()
-        e.set_observations(y_dev, e.t)
-        e.run(1)
+        y_moves, _ = self._expand_observations(torch.as_tensor(y).reshape(1, -1), e.t)
+        M = int(y_moves.shape[0])
+        e.set_observations(y_moves.to(device="cuda", dtype=torch.float32).contiguous(), e.t)
+        if result is not None and self._record_intermediary and M > 1:
+            for _ in range(M - 1):
+                e.run(1)
+                result.append(e.make_state())
+            e.run(1)
+        else:
+            e.run(M)
         state = e.make_state()
         if result is not None:
             result.append(state)

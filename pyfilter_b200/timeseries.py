@@ -157,10 +157,10 @@ class StateSpaceModel:
         self.model_id = model_id
         self.parameters = tuple(_t(p) for p in obs_parameters)
         self.event_shape = torch.Size(event_shape)
-        self.observe_every_step = observe_every_step
+        self.observe_every_step = int(observe_every_step)  # filters/base.py:204-210: propagate-only moves between observations
         self.is_linear_gaussian = linear
-        if observe_every_step != 1:
-            raise NotImplementedError("observe_every_step > 1 is listed under 'next' (SURVEY.md 8(f) f3)")
+        if self.observe_every_step < 1:
+            raise ValueError("observe_every_step must be >= 1")
 
     @property
     def n_dim(self) -> int:
@@ -250,17 +250,19 @@ class StochasticVolatilityModel(StateSpaceModel):
 
 
 def build(name: str, **params) -> StateSpaceModel:
-    """Factory keyed by the zoo names used in tests/golden and bench.py."""
+    """Factory keyed by the zoo names used in tests/golden and bench.py (``observe_every_step=k`` is passed through)."""
+    every = int(params.pop("observe_every_step", 1))
     if name == "lg_ar1":
         p = dict(alpha=0.0, beta=0.99, sigma=0.05, a=1.0, b=0.0, s=0.15); p.update(params)
-        return LinearStateSpaceModel(AR(p["alpha"], p["beta"], p["sigma"]), (p["a"], p["b"], p["s"]))
+        return LinearStateSpaceModel(AR(p["alpha"], p["beta"], p["sigma"]), (p["a"], p["b"], p["s"]), observe_every_step=every)
     if name == "sine_em":
         p = dict(gamma=0.0, sigma=1.0, dt=0.1, a=1.0, b=0.0, s=0.1); p.update(params)
-        return LinearStateSpaceModel(SineDiffusion(p["gamma"], p["sigma"], p["dt"]), (p["a"], p["b"], p["s"]))
+        return LinearStateSpaceModel(SineDiffusion(p["gamma"], p["sigma"], p["dt"]), (p["a"], p["b"], p["s"]), observe_every_step=every)
     if name == "sv_ar1":
         p = dict(mu=-1.0, phi=0.97, sigma_v=0.2); p.update(params)
-        return StochasticVolatilityModel(StochasticVolatilityAR(p["mu"], p["phi"], p["sigma_v"]))
+        return StochasticVolatilityModel(StochasticVolatilityAR(p["mu"], p["phi"], p["sigma_v"]), observe_every_step=every)
     if name == "lorenz63_em":
         p = dict(s=10.0, r=28.0, b=8.0 / 3.0, sigma=1.0, dt=0.01, obs_a=0.8, obs_s=math.sqrt(0.1)); p.update(params)
-        return LinearStateSpaceModel(Lorenz63(p["s"], p["r"], p["b"], p["sigma"], p["dt"]), (p["obs_a"], p["obs_s"]), torch.Size([2]))
+        return LinearStateSpaceModel(Lorenz63(p["s"], p["r"], p["b"], p["sigma"], p["dt"]), (p["obs_a"], p["obs_s"]), torch.Size([2]),
+                                     observe_every_step=every)
     raise NotImplementedError(f"'{name}' is not in the compiled model zoo")

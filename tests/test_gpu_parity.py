@@ -460,3 +460,40 @@ def test_systematic_small_and_wide(pf, n, b):
     got = pf.resampling.systematic(lw.clone().cuda(), u=u.cuda()).cpu()
     Wd = pf.utils.normalize(lw.clone().cuda()).cpu()
     assert torch.equal(got, O.systematic(Wd.clone(), normalized=True, u=u))
+
+
+@pytest.mark.parametrize("alg", ["sisr", "apf"])
+def test_observe_every_step(pf, alg):
+    """``observe_every_step = 3`` (filters/base.py:204-210): two propagate-only moves before every observation but the first.
+    The result has one moment row per OBSERVATION, the time index counts every move, and the run agrees statistically with the
+    oracle's restatement (itself bit-for-bit equal to the reference: tests/test_oracle_pinned.py)."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR
+
+    torch.manual_seed(21)
+    mo = O.build_model("sine_em")
+    _, y = mo.simulate(30)
+    N, k = 20_000, 3
+    cls = {"sisr": SISR, "apf": APF}[alg]
+    f = cls(ts.build("sine_em", observe_every_step=k), N, seed=5)
+    res = f.batch_filter(y, bar=False)
+    assert res.filter_means.shape[0] == 31
+    assert int(res.latest_state.timeseries_state.time_index) == 1 + 29 * k
+    lls = []
+    for seed in range(3):
+        torch.manual_seed(200 + seed)
+        lls.append(float(O.batch_filter(mo, alg, "bootstrap", y, N, observe_every_step=k)["loglikelihood"]))
+    ref = O.batch_filter(mo, alg, "bootstrap", y, N, observe_every_step=k)
+    spread = max(np.std(lls), 1e-3 * abs(np.mean(lls)), 0.05)
+    assert abs(float(res.loglikelihood) - np.mean(lls)) < 6 * spread, (float(res.loglikelihood), lls)
+    d = (res.filter_means.cpu() - ref["filter_means"]).abs()
+    scale = ref["filter_means"].abs().mean() + ref["filter_means"].std()
+    assert float(d.mean()) < 0.05 * float(scale)
+    # move by move through filter(): same counters, same result
+    f2 = cls(ts.build("sine_em", observe_every_step=k), N, seed=5, fold_lookahead=False)
+    st = f2.initialize()
+    r2 = f2.initialize_with_result(st)
+    for yt in y:
+        st = f2.filter(yt, st, result=r2)
+    assert torch.allclose(res.filter_means, r2.filter_means, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(res.loglikelihood, r2.loglikelihood, rtol=1e-4, atol=1e-3)

@@ -109,11 +109,12 @@ def test_kalman_agreement_config1():
 
 
 @pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
-@pytest.mark.parametrize("alg,proposal,resampler,bshape", [
-    ("sisr", "bootstrap", "systematic", ()), ("sisr", "linear_gaussian", "multinomial", (3,)),
-    ("apf", "bootstrap", "systematic", (3,)), ("apf", "linear_gaussian", "systematic", ()),
+@pytest.mark.parametrize("alg,proposal,resampler,bshape,every", [
+    ("sisr", "bootstrap", "systematic", (), 1), ("sisr", "linear_gaussian", "multinomial", (3,), 1),
+    ("apf", "bootstrap", "systematic", (3,), 1), ("apf", "linear_gaussian", "systematic", (), 1),
+    ("sisr", "bootstrap", "systematic", (3,), 3), ("apf", "bootstrap", "systematic", (), 4),
 ])
-def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape):
+def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape, every):
     from oracle.ref_loader import load_reference
     from oracle.ref_models import build_reference_model
 
@@ -124,7 +125,7 @@ def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape):
     torch.manual_seed(5)
     m = O.build_model("sine_em")
     _, y = m.simulate(40)
-    ssm = build_reference_model("sine_em", O.DEFAULT_PARAMS["sine_em"])
+    ssm = build_reference_model("sine_em", O.DEFAULT_PARAMS["sine_em"], observe_every_step=every)
     cls = {"sisr": SISR, "apf": APF}[alg]
     prop = {"bootstrap": pr.Bootstrap, "linear_gaussian": pr.LinearGaussianObservations}[proposal]()
     f = cls(ssm, 300, proposal=prop, resampling=getattr(RR, resampler))
@@ -132,7 +133,7 @@ def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape):
     torch.manual_seed(11)
     r = f.batch_filter(y, bar=False)
     torch.manual_seed(11)
-    o = O.batch_filter(m, alg, proposal, y, 300, bshape, resampler)
+    o = O.batch_filter(m, alg, proposal, y, 300, bshape, resampler, observe_every_step=every)
     assert torch.equal(r.loglikelihood, o["loglikelihood"])
     assert torch.equal(r.filter_means, o["filter_means"])
     assert torch.equal(r.filter_variance, o["filter_variance"])
