@@ -13,6 +13,7 @@
  *   - a handle is not thread-safe; distinct handles are independent;
  *   - device layout: one column per independent filter (the reference's batch dimension, filters/base.py:93-119); a column is
  *     a contiguous row of `ld` elements (ld = particles rounded up to 4096); states are SoA x[dim][column][particle];
+ *   - kernels of one move are chained with programmatic dependent launch (SMCB_NO_PDL=1 in the environment disables it);
  *   - there is NO CPU fallback: without a CUDA device every compute entry point returns SMCB_ENODEVICE.
  */
 #ifndef SMCB200_H
@@ -76,8 +77,8 @@ typedef struct smcb_info {
   int32_t history_rows;
   int32_t slow_tiles;     /* exact-scan tiles that needed the sequential fallback so far (diagnostic; synchronises) */
   int64_t kernel_launches;/* kernels launched by this handle so far */
-  int64_t lb_windows;     /* diagnostic: 32-tile look-back windows walked so far */
-  int32_t lb_fail;        /* diagnostic: look-backs that had to wait for their direct predecessor */
+  int64_t lb_windows;     /* reserved (0) */
+  int32_t lb_fail;        /* reserved (0) */
   int32_t reserved;
 } smcb_info;
 

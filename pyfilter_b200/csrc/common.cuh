@@ -35,12 +35,12 @@ struct Ctrl {
   int32_t y_base;       // time index of y[0]
   int32_t y_count;      // observations available at y
   int32_t ticket;       // last-block-done counter of the finalize kernel
-  uint32_t epoch;       // bumped once per resampling launch; tags the look-back slots so they never need clearing
+  uint32_t epoch;       // bumped once per move; tags the slots of resample_fused_kernel so they never need clearing
   uint32_t tile_counter;
   int32_t slow_tiles;   // diagnostics: tiles that took the sequential fallback of the exact scan
-  int32_t lb_fail;      // diagnostics: look-backs that fell back to waiting for the direct predecessor
+  int32_t lb_fail;      // reserved
   const float* y;       // (y_count, OD) observations on device
-  int64_t lb_windows;   // diagnostics: 32-tile windows walked by all look-backs
+  int64_t lb_windows;   // reserved
 };
 
 // Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start

@@ -1,6 +1,7 @@
 """Diagnostics (SMCB_DEBUG_TIMELINE=1): where describe_kernel spends its time on general (non-benign) moves."""
 import os, sys
 os.environ["SMCB_DEBUG_TIMELINE"] = "1"
+os.environ["SMCB_NO_FUSED"] = "1"   # the stamps live in the three-kernel pipeline (normalize / describe / expand) and the step kernel
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import bench
