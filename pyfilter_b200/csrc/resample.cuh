@@ -21,6 +21,7 @@
 // has_special of a published XsDesc: 0 / 1 as in scan_tile.h, or
 #define RS_KIND_TABLE 2   // more than one special element: the segment table sits in global memory (e1 = number of specials)
 #define RS_KIND_RAW 3     // too many segments: the chain walks the raw weights
+#define RS_KIND_NONE 5    // no (alternative) descriptor
 #define RS_KIND_ABS 4     // the state after the tile is a_s whatever came before (tile 0 resolves itself: it starts from 0)
 
 struct __align__(16) FusedSlot {  // written and read with one 128-bit access: the tag says the sum belongs to this launch
@@ -52,6 +53,7 @@ struct ResampleArgs {
   double* sin;             // (B, tiles_per_col) general columns: exact state before every tile (describe_kernel's chain)
   int32_t* tileflag;       // (B, tiles_per_col) bit 0: the tile's speculation failed, expand it sequentially
   XsDesc* desc;            // (B, tiles_per_col)
+  XsDesc* desc2;           // (B, tiles_per_col) alternative descriptor of tiles next to a binade crossing (has_special = RS_KIND_NONE: absent)
   SegTable* tables;        // (B, tiles_per_col)
   int32_t* anc;            // (B, ld) ancestors out
   float* w_out;            // optional dump of the normalised weights used (B, ld)
@@ -291,7 +293,7 @@ struct RsTileSmem {
   float seg_wc[RS_MAXSEG];
   int seg_e[RS_MAXSEG];
   int X, e0, table_ok, ok, is_last;
-  double S_out;
+  double S_out, sp_end;
 };
 
 // rare paths, kept out of line so that the hot loops stay small (instruction-cache footprint)
@@ -347,7 +349,7 @@ struct RsScan {
 };
 
 template <int MB>
-__device__ __forceinline__ void rs_tile_scan(const float (&w)[RS_ITEMS], double sp0, RsTileSmem& sm, RsScan<MB>& r) {
+__device__ __forceinline__ void rs_tile_scan(const float (&w)[RS_ITEMS], double sp0, RsTileSmem& sm, RsScan<MB>& r, double bias = 1.0) {
   const int tid = threadIdx.x;
   double tsum = 0.0;
   uint32_t key = 0xFFFFFFFFu;  // smallest non-zero weight of the thread (bits - 1; zeros wrap to the top)
@@ -356,11 +358,14 @@ __device__ __forceinline__ void rs_tile_scan(const float (&w)[RS_ITEMS], double 
     tsum += (double)w[j];
     key = min(key, __float_as_uint(w[j]) - 1u);
   }
+  // `bias` scales the predictor only (speculation): the float32-accumulated sum of torch.multinomial drifts below the fp64 prefix
   double tot_approx;
-  r.sp_thread = sp0 + rs_block_excl_scan_d(tsum, sm.dscratch, &tot_approx);
-  const int e0 = xs_label(sp0);
-  r.lab_end = xs_label(r.sp_thread + tsum);
+  const double sp_raw = sp0 + rs_block_excl_scan_d(tsum, sm.dscratch, &tot_approx);
+  r.sp_thread = sp_raw * bias;
+  const int e0 = xs_label(sp0 * bias);
+  r.lab_end = xs_label((sp_raw + tsum) * bias);
   sm.lab_end[tid] = r.lab_end;
+  if (tid == RS_NT - 1) sm.sp_end = sp_raw + tsum;
   __syncthreads();
   r.lab_prev = tid ? sm.lab_end[tid - 1] : e0;
   r.M = (r.lab_prev == XS_E_ZERO) ? 0.0 : xs_pow2(r.lab_prev);
@@ -409,20 +414,26 @@ __device__ __forceinline__ void rs_tile_scan(const float (&w)[RS_ITEMS], double 
 }
 
 // the reference operation itself over one whole tile, by one warp (fallback when a speculation fails): S <- fl_MB(S + w_k);
-// c (optional, shared memory) receives fl32 of every state
+// c (optional, shared memory) receives fl32 of every state.  The loads run one chunk ahead and the state stays in its own type, so
+// the serial chain is one addition per element.
 template <int MB>
 __device__ __noinline__ double rs_warp_raw_walk(const float* wrow, double S, float* c) {
   const int lane = threadIdx.x & 31;
+  float vn = __ldg(wrow + lane);
+  float Sf = (float)S;  // MB == 24: the state is a float32
   for (int k0 = 0; k0 < RS_TILE; k0 += 32) {
-    const float v = __ldg(wrow + k0 + lane);
+    const float v = vn;
+    if (k0 + 32 < RS_TILE) vn = __ldg(wrow + k0 + 32 + lane);
     float cl = 0.f;
+#pragma unroll
     for (int i = 0; i < 32; ++i) {
-      S = xs_add_special<MB>(S, __shfl_sync(0xffffffffu, v, i));
-      if (i == lane) cl = (float)S;
+      const float x = __shfl_sync(0xffffffffu, v, i);
+      if (MB == 24) { Sf = __fadd_rn(Sf, x); if (i == lane) cl = Sf; }
+      else { S = __dadd_rn(S, (double)x); if (i == lane) cl = (float)S; }
     }
     if (c) c[k0 + lane] = cl;
   }
-  return S;
+  return MB == 24 ? (double)Sf : S;
 }
 
 // Tile 0 is where the running sum climbs through a dozen binades, i.e. where all the special elements of a typical column sit.
@@ -453,13 +464,17 @@ __device__ __forceinline__ bool rs_tile0_exact(const ResampleArgs& a, int col, d
 //                   element; a descriptor that does not verify is replaced by the reference operation over the raw tile and the
 //                   tile is flagged so that expand_kernel takes the same sequential route;
 //   P3 (all warps)  state before every tile = state at its segment start advanced by the tile's exclusive transducer.
+struct ChainEnt {            // one descriptor in integer form
+  XiT ta;                    // the tile's transducer (first one when it has a special element)
+  XiT tb;                    // second transducer of a descriptor with one special element; .k = bits of the state for RS_KIND_ABS
+  float wc;
+  int16_t e0, e1;
+  int8_t kind;               // has_special of the descriptor; -1: the conversion to integer form failed
+};
 struct ChainSmem {
-  XiT ta[RS_NT];             // the tile's own transducer (first one when it has a special element)
-  XiT tb[RS_NT];             // second transducer of a descriptor with one special element; .k = bits of the state for RS_KIND_ABS
+  ChainEnt prim[RS_NT];      // the descriptor speculated from the fp64 prefix
+  ChainEnt alt[RS_NT];       // the one speculated from the biased prefix (tiles next to a binade crossing), kind RS_KIND_NONE if absent
   XiT ex[RS_NT];             // exclusive transducer of the tile inside its segment
-  float wc[RS_NT];
-  int16_t e0[RS_NT], e1[RS_NT];
-  int8_t kind[RS_NT];        // has_special of the descriptor; -1: the conversion to integer form failed
   uint8_t seg_of[RS_NT];     // local segment index of the tile inside its warp
   XiT seg_t[RS_NT];          // per (warp, local segment): aggregate transducer of a run
   int16_t seg_tile[RS_NT];   // tile (index inside the round) of a single-descriptor segment, -1 for a run
@@ -469,25 +484,40 @@ struct ChainSmem {
   uint64_t S;                // state carried from round to round
 };
 
+template <int MB>
+__device__ __forceinline__ ChainEnt rs_chain_convert(const XsDesc& d, bool live) {
+  ChainEnt c;
+  c.ta = xi_identity(); c.tb = xi_identity(); c.wc = d.wc; c.e1 = d.e1;
+  int kind = live ? (int)d.has_special : 0;
+  const int e0 = live ? (int)d.e0 : XS_E_ZERO;
+  if (live && kind <= 1) {
+    bool ok = xi_from<MB>(d.a_s, d.a_d, e0, &c.ta);
+    if (kind == 1) ok = ok && xi_from<MB>(d.b_s, d.b_d, (int)d.e1, &c.tb);
+    if (!ok) kind = -1;
+  }
+  if (kind == RS_KIND_ABS) c.tb.k = (int64_t)xs_d2u(d.a_s);
+  c.e0 = (int16_t)e0; c.kind = (int8_t)kind;
+  return c;
+}
+
 // one descriptor that is not part of a run (executed by a whole warp, uniformly); returns false when it does not verify
 template <int MB>
-__device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, int tile, int t, const ChainSmem& cs, uint64_t S,
-                                                uint64_t* out) {
+__device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, int tile, const ChainEnt& c, uint64_t S, uint64_t* out) {
   const int lane = threadIdx.x & 31;
-  const int kind = cs.kind[t];
+  const int kind = c.kind;
   *out = S;
-  if (kind == 0) return xi_apply<MB>(S, (int)cs.e0[t], cs.ta[t], out);
+  if (kind == 0) return xi_apply<MB>(S, (int)c.e0, c.ta, out);
   if (kind == 1) {
     uint64_t s1;
-    if (!xi_apply<MB>(S, (int)cs.e0[t], cs.ta[t], &s1)) return false;
-    const double s2 = xs_add_special<MB>(xs_u2d(s1), cs.wc[t]);
-    if (xs_label(s2) != (int)cs.e1[t]) return false;
-    return xi_apply<MB>(xs_d2u(s2), (int)cs.e1[t], cs.tb[t], out);
+    if (!xi_apply<MB>(S, (int)c.e0, c.ta, &s1)) return false;
+    const double s2 = xs_add_special<MB>(xs_u2d(s1), c.wc);
+    if (xs_label(s2) != (int)c.e1) return false;
+    return xi_apply<MB>(xs_d2u(s2), (int)c.e1, c.tb, out);
   }
-  if (kind == RS_KIND_ABS) { *out = (uint64_t)cs.tb[t].k; return true; }
+  if (kind == RS_KIND_ABS) { *out = (uint64_t)c.tb.k; return true; }
   if (kind == RS_KIND_TABLE) {  // walk the tile's segments; 32 table entries are fetched per round trip
     const SegTable* tb = a.tables + (int64_t)col * a.tiles_per_col + tile;
-    const int X = (int)cs.e1[t];
+    const int X = (int)c.e1;
     double S2 = xs_u2d(S);
     bool ok = true;
     for (int r0 = 0; r0 <= X && ok; r0 += 32) {
@@ -503,7 +533,7 @@ __device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, 
         ts.d = __shfl_sync(0xffffffffu, gd, i);
         const float wc = __shfl_sync(0xffffffffu, gw, i);
         int es = __shfl_sync(0xffffffffu, ge, i);
-        if (r0 + i == 0) es = (int)cs.e0[t];
+        if (r0 + i == 0) es = (int)c.e0;
         else { S2 = xs_add_special<MB>(S2, wc); ok = (xs_label(S2) == es); }
         if (ok) ok = xs_apply<MB>(S2, es, ts, &S2);
       }
@@ -511,7 +541,21 @@ __device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, 
     *out = xs_d2u(S2);
     return ok;
   }
-  return false;  // RS_KIND_RAW, failed conversion
+  return false;  // RS_KIND_RAW, RS_KIND_NONE, failed conversion
+}
+
+// diagnostics: why did a descriptor not verify (SMCB_DEBUG_TIMELINE)
+template <int MB>
+__device__ __noinline__ void rs_chain_why(const ResampleArgs& a, const ChainEnt& p, const ChainEnt& q, uint64_t S) {
+  if (!a.dbg || (threadIdx.x & 31)) return;
+  int why = 0;                                        // 0: other
+  if (p.kind < 0) why = 1;                            // conversion failed
+  else if (p.kind >= 2) why = 2;                      // table / raw
+  else if ((int)(S >> 52) - 1023 < (int)p.e0) why = 3;  // state still below the speculated binade
+  else if ((int)(S >> 52) - 1023 > (int)p.e0) why = 4;  // state already above
+  else why = 5;                                       // right binade at the start, leaves it inside (or second part fails)
+  atomicAdd((unsigned long long*)&a.dbg[16 + why], 1ull);
+  atomicAdd((unsigned long long*)&a.dbg[24 + (q.kind == RS_KIND_NONE ? 0 : 1)], 1ull);
 }
 
 template <int MB>
@@ -523,23 +567,20 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
   int32_t* flag = a.tileflag + (int64_t)col * T;
   const float* wcol = a.wn + (int64_t)col * a.ld;
   if (tid == 0) cs.S = 0;
-  XsDesc dn = {};
-  if (tid < T) dn = rs_read_desc(desc + tid);
+  const XsDesc* desc2 = a.desc2 + (int64_t)col * T;
+  XsDesc dn = {}, dn2 = {};
+  if (tid < T) { dn = rs_read_desc(desc + tid); dn2 = rs_read_desc(desc2 + tid); }
   for (int base = 0; base < T; base += RS_NT) {
     const int tile = base + tid;
     const bool live = tile < T;
-    const XsDesc d = dn;
-    if (tile + RS_NT < T) dn = rs_read_desc(desc + tile + RS_NT);  // in flight while this round is processed
+    const XsDesc d = dn, d2 = dn2;
+    if (tile + RS_NT < T) { dn = rs_read_desc(desc + tile + RS_NT); dn2 = rs_read_desc(desc2 + tile + RS_NT); }  // in flight while this round runs
     // ---- P1
-    XiT ta = xi_identity(), tb = xi_identity();
-    int kind = live ? (int)d.has_special : 0;
-    const int e0 = live ? (int)d.e0 : XS_E_ZERO;
-    if (live && kind <= 1) {
-      bool ok = xi_from<MB>(d.a_s, d.a_d, e0, &ta);
-      if (kind == 1) ok = ok && xi_from<MB>(d.b_s, d.b_d, (int)d.e1, &tb);
-      if (!ok) kind = -1;
-    }
-    if (kind == RS_KIND_ABS) tb.k = (int64_t)xs_d2u(d.a_s);
+    const ChainEnt pe = rs_chain_convert<MB>(d, live);
+    ChainEnt ae = rs_chain_convert<MB>(d2, live);
+    if (!live || d2.has_special > 1) ae.kind = RS_KIND_NONE;
+    const XiT ta = pe.ta;
+    const int kind = pe.kind, e0 = pe.e0;
     const bool plain = live && kind == 0;
     const int e_left = __shfl_up_sync(0xffffffffu, e0, 1);
     const int plain_left = __shfl_up_sync(0xffffffffu, plain ? 1 : 0, 1);
@@ -561,8 +602,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
     const uint32_t heads = __ballot_sync(0xffffffffu, head);
     const int seg = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
     const bool tail = (lane == 31) || ((heads >> (lane + 1)) & 1u);  // last tile of its segment
-    cs.ta[tid] = ta; cs.tb[tid] = tb; cs.ex[tid] = ex; cs.wc[tid] = d.wc; cs.e0[tid] = (int16_t)e0; cs.e1[tid] = d.e1;
-    cs.kind[tid] = (int8_t)kind; cs.seg_of[tid] = (uint8_t)seg;
+    cs.prim[tid] = pe; cs.alt[tid] = ae; cs.ex[tid] = ex; cs.seg_of[tid] = (uint8_t)seg;
     if (tail) { cs.seg_t[wid * 32 + seg] = inc; cs.seg_tile[wid * 32 + seg] = plain ? (int16_t)-1 : (int16_t)tid; }
     if (lane == 0) cs.nseg[wid] = __popc(heads);
     __syncthreads();
@@ -583,7 +623,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
         int t0_l = w * 32;  // first tile of a run
         if (have && st_l < 0) while (cs.seg_of[t0_l] != f) ++t0_l;
         const XiT t_l = cs.seg_t[si_l];
-        const int e_l = (st_l < 0) ? (int)cs.e0[t0_l] : 0;
+        const int e_l = (st_l < 0) ? (int)cs.prim[t0_l].e0 : 0;
         const int m = min(32, total - f0);
         for (int i = 0; i < m; ++i) {
           const int si = __shfl_sync(0xffffffffu, si_l, i);
@@ -604,7 +644,9 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
               for (int q = t0; q < wq * 32 + 32 && cs.seg_of[q] == jq && base + q < T; ++q) {
                 uint64_t S3;
                 int tf = 0;
-                if (!xi_apply<MB>(S2, (int)cs.e0[q], cs.ta[q], &S3)) {
+                if (!xi_apply<MB>(S2, (int)cs.prim[q].e0, cs.prim[q].ta, &S3) &&
+                    !rs_chain_single<MB>(a, col, base + q, cs.alt[q], S2, &S3)) {  // neither speculation holds: the reference operation
+                  rs_chain_why<MB>(a, cs.prim[q], cs.alt[q], S2);
                   S3 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + q) * RS_TILE, xs_u2d(S2), nullptr));
                   tf = 1;
                   if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
@@ -613,7 +655,9 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
                 S2 = S3;
               }
             }
-          } else if (!rs_chain_single<MB>(a, col, base + st, st, cs, S, &S2)) {
+          } else if (!rs_chain_single<MB>(a, col, base + st, cs.prim[st], S, &S2) &&
+                     !rs_chain_single<MB>(a, col, base + st, cs.alt[st], S, &S2)) {
+            rs_chain_why<MB>(a, cs.prim[st], cs.alt[st], S);
             S2 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + st) * RS_TILE, xs_u2d(S), nullptr));
             fl = 1;
             if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
@@ -697,6 +741,39 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
       if (X) { d.wc = sm.seg_wc[1]; d.e1 = (int16_t)sm.seg_e[1]; d.b_s = sm.seg_agg[1].s; d.b_d = (int8_t)sm.seg_agg[1].d; }
     }
     a.desc[(int64_t)col * T + tile] = d;
+  }
+  // A tile next to a binade crossing gets a second descriptor, speculated from a predictor biased downwards: the sequential sum
+  // lags the fp64 prefix (by up to ~1 % for the float32 accumulation of torch.multinomial), so around a crossing the true state may
+  // still be in the lower binade when the predictor already is in the upper one.  The chain tries both before the sequential walk.
+  {
+    constexpr double kBias = (MB == 24) ? 0.98 : (1.0 - 1e-9);
+    __shared__ int need_alt;
+    if (tid == 0) {
+      const double spe = sm.sp_end;
+      need_alt = (!exact0 && tile > 0 && (xs_label(sp0 * kBias) != xs_label(sp0) || xs_label(spe * kBias) != xs_label(spe))) ? 1 : 0;
+      if (!need_alt) {
+        XsDesc d;
+        memset(&d, 0, sizeof(d));
+        d.has_special = RS_KIND_NONE;
+        a.desc2[(int64_t)col * T + tile] = d;
+      }
+    }
+    __syncthreads();
+    if (need_alt) {
+      RsScan<MB> r2;
+      rs_tile_scan<MB>(w, sp0, sm, r2, kBias);
+      if (tid == 0) {
+        XsDesc d;
+        d.a_s = 0.0; d.b_s = 0.0; d.wc = 0.f; d.e0 = (int16_t)sm.e0; d.e1 = 0; d.a_d = 0; d.b_d = 0; d.pad = 0;
+        const int X2 = sm.X;
+        if (!sm.table_ok || X2 > 1) d.has_special = RS_KIND_NONE;
+        else {
+          d.a_s = sm.seg_agg[0].s; d.a_d = (int8_t)sm.seg_agg[0].d; d.has_special = (int8_t)X2;
+          if (X2) { d.wc = sm.seg_wc[1]; d.e1 = (int16_t)sm.seg_e[1]; d.b_s = sm.seg_agg[1].s; d.b_d = (int8_t)sm.seg_agg[1].d; }
+        }
+        a.desc2[(int64_t)col * T + tile] = d;
+      }
+    }
   }
   if (tid == 0 || (table_ok && X > 1)) __threadfence();  // table and descriptor stores precede the ticket
   __syncthreads();
@@ -856,7 +933,6 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
   }
   const double sp0 = a.prefix[(int64_t)col * T + tile];
   const double sin_t = a.sin[(int64_t)col * T + tile];
-  const int flag_t = a.tileflag[(int64_t)col * T + tile];
   const int resample = a.stats ? a.stats[col].resample : 1;
   const int vd = (OUT == RS_OUT_ANCESTORS) ? a.verdict[col] : 0;
   const float u = (OUT == RS_OUT_ANCESTORS) ? a.u_col[col] : 0.f;
@@ -888,15 +964,21 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
     S_in = 0.0;
     S0 = rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);
   } else {
+    // the exact state before the tile is the predictor here (better than the fp64 prefix the descriptors were speculated from),
+    // so the speculation is verified again: by the apply below for a simple tile, by the segment walk otherwise
     S_in = sin_t;
-    bool slow = (flag_t & 1) != 0;
+    bool slow = false;
     RsScan<MB> r;
     S0 = S_in;
-    if (!slow) {
-      rs_tile_scan<MB>(w, sp0, sm.core, r);
+    {
+      rs_tile_scan<MB>(w, S_in, sm.core, r);
       M = r.M;
-      if (r.tile_simple) S0 = __dadd_rn(S_in, r.excl.t.s);  // exact; the chain verified binade and range
-      else {
+      if (r.tile_simple) {
+        if (tid == 0) { double o; sm.core.ok = xs_apply<MB>(S_in, sm.core.e0, r.total.t, &o) ? 1 : 0; }
+        __syncthreads();
+        if (!sm.core.ok) slow = true;
+        else S0 = __dadd_rn(S_in, r.excl.t.s);  // exact: multiples of the quantum inside one binade
+      } else {
         fast = false;
         if (tid == 0) {
           double S_out;

@@ -120,7 +120,7 @@ struct smcb_filter {
   int32_t* col_ticket = nullptr;
   double *tilesum = nullptr, *prefix = nullptr, *sin = nullptr;
   int32_t* tileflag = nullptr;
-  XsDesc* desc = nullptr;
+  XsDesc *desc = nullptr, *desc2 = nullptr;
   SegTable* tables = nullptr;
   uint32_t* tilemin = nullptr;
   int32_t *ncounter = nullptr, *dcounter = nullptr, *verdict = nullptr;
@@ -165,7 +165,7 @@ static int upload_params(smcb_filter* f, const float* params_host, int n_raw, in
 extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
-                  f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
+                  f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
                   f->u_col};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -224,6 +224,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->sin, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->tileflag, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->desc, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->desc2, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->tables, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->dcounter, (size_t)f->B));
   A_(dalloc(&f->fslots, (size_t)f->B * f->tiles_per_col));
@@ -240,7 +241,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
-  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)16));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -405,7 +406,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   r.n = f->n; r.ld = f->ld; r.B = f->B; r.tiles_per_col = f->tiles_per_col;
   r.input_is_w = 0; r.use_rw = apf ? 1 : 0; r.stats = f->stats;
   r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed;
-  r.tilesum = f->tilesum; r.prefix = f->prefix; r.sin = f->sin; r.tileflag = f->tileflag; r.desc = f->desc; r.tables = f->tables;
+  r.tilesum = f->tilesum; r.prefix = f->prefix; r.sin = f->sin; r.tileflag = f->tileflag; r.desc = f->desc; r.desc2 = f->desc2; r.tables = f->tables;
   r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
   r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.dcounter = f->dcounter; r.verdict = f->verdict; r.u_col = f->u_col;
   r.dbg = f->dbg;
@@ -560,7 +561,7 @@ extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
 // ---- stand-alone operators ---------------------------------------------------------------------------------------------------------
 struct OpWorkspace {
   float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; Ctrl* ctrl = nullptr;
-  double *prefix = nullptr, *sin = nullptr; int32_t *tileflag = nullptr, *dcounter = nullptr; XsDesc* desc = nullptr; SegTable* tables = nullptr;
+  double *prefix = nullptr, *sin = nullptr; int32_t *tileflag = nullptr, *dcounter = nullptr; XsDesc *desc = nullptr, *desc2 = nullptr; SegTable* tables = nullptr;
   ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
   uint32_t* tilemin = nullptr; int32_t* ncounter = nullptr; int32_t* verdict = nullptr; float* u_col = nullptr;
   int64_t ld = 0; int tiles = 0, nblk = 0;
@@ -579,6 +580,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   CU(cudaMallocAsync((void**)&ws.sin, (size_t)B * ws.tiles * sizeof(double), s));
   CU(cudaMallocAsync((void**)&ws.tileflag, (size_t)B * ws.tiles * sizeof(int32_t), s));
   CU(cudaMallocAsync((void**)&ws.desc, (size_t)B * ws.tiles * sizeof(XsDesc), s));
+  CU(cudaMallocAsync((void**)&ws.desc2, (size_t)B * ws.tiles * sizeof(XsDesc), s));
   CU(cudaMallocAsync((void**)&ws.tables, (size_t)B * ws.tiles * sizeof(SegTable), s));
   CU(cudaMallocAsync((void**)&ws.dcounter, (size_t)B * sizeof(int32_t), s));
   CU(cudaMemsetAsync(ws.dcounter, 0, (size_t)B * sizeof(int32_t), s));
@@ -597,7 +599,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
   return SMCB_OK;
 }
 static void op_free(OpWorkspace& ws, cudaStream_t s) {
-  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.prefix, ws.sin, ws.tileflag, ws.desc, ws.tables, ws.dcounter, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
+  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.prefix, ws.sin, ws.tileflag, ws.desc, ws.desc2, ws.tables, ws.dcounter, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
                   ws.u_col};
   for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
 }
@@ -642,7 +644,7 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
     r.w = ws.w; r.wn = normalized ? ws.w : ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
     r.input_is_w = normalized ? 1 : 0; r.use_rw = 0; r.stats = normalized ? nullptr : ws.stats;
     r.u_in = u_dev; r.seed = seed; r.tilesum = ws.tilesum; r.anc = ws.anc; r.ctrl = ws.ctrl;
-    r.prefix = ws.prefix; r.sin = ws.sin; r.tileflag = ws.tileflag; r.desc = ws.desc; r.tables = ws.tables; r.dcounter = ws.dcounter;
+    r.prefix = ws.prefix; r.sin = ws.sin; r.tileflag = ws.tileflag; r.desc = ws.desc; r.desc2 = ws.desc2; r.tables = ws.tables; r.dcounter = ws.dcounter;
     r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
     else {
