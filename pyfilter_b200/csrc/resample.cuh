@@ -481,7 +481,6 @@ struct ChainSmem {
   uint64_t seg_start[RS_NT]; // P2 -> P3: bit pattern of the state at the start of the segment
   int8_t seg_flag[RS_NT];    // 1: the single tile of the segment failed verification; 2: P2 wrote the tiles of the run itself
   int nseg[RS_NT / 32];
-  uint64_t S;                // state carried from round to round
 };
 
 template <int MB>
@@ -566,7 +565,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
   double* sin = a.sin + (int64_t)col * T;
   int32_t* flag = a.tileflag + (int64_t)col * T;
   const float* wcol = a.wn + (int64_t)col * a.ld;
-  if (tid == 0) cs.S = 0;
+  uint64_t S_carry = 0;  // state carried from round to round (identical in every lane of warp 0, the only warp that uses it)
   const XsDesc* desc2 = a.desc2 + (int64_t)col * T;
   XsDesc dn = {}, dn2 = {};
   if (tid < T) { dn = rs_read_desc(desc + tid); dn2 = rs_read_desc(desc2 + tid); }
@@ -609,7 +608,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
     if (a.dbg && tid == 0 && base == 0) a.dbg[4] = rs_now();
     // ---- P2: warp 0 walks the segments; their records are fetched 32 at a time so that only the state itself is a serial chain
     if (wid == 0) {
-      uint64_t S = cs.S;
+      uint64_t S = S_carry;
       const int nw = min(RS_NT / 32, (T - base + 31) / 32);
       int total = 0;
       for (int w = 0; w < nw; ++w) total += cs.nseg[w];
@@ -666,7 +665,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
           S = S2;
         }
       }
-      if (lane == 0) cs.S = S;
+      S_carry = S;
     }
     __syncthreads();
 

@@ -30,14 +30,19 @@ static bool use_pdl() {
 }
 template <typename K, typename A>
 static void launch_pdl(K kernel, dim3 grid, dim3 block, cudaStream_t s, const A& args) {
-  if (!use_pdl()) { kernel<<<grid, block, 0, s>>>(args); return; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, kernel, args);
+  static bool pdl_ok = true;  // cleared when the driver refuses the attribute: plain launches from then on
+  if (use_pdl() && pdl_ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, args) == cudaSuccess) return;
+    cudaGetLastError();
+    pdl_ok = false;
+  }
+  kernel<<<grid, block, 0, s>>>(args);
 }
 
 extern "C" int smcb_version(void) { return SMCB_VERSION; }
