@@ -55,6 +55,7 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.sm, self.mask, self.max_mhz, self.stop_flag, self.thread, self.h = index, [], 0, None, False, None, None
+        self.errors = 0
         try:
             import pynvml
 
@@ -69,18 +70,28 @@ class ClockSampler:
 
     def _poll(self):
         while not self.stop_flag:
-            try:
-                if self.nv:
+            if self.nv:
+                try:
                     self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                except Exception:
+                    self.errors += 1
+                try:
                     self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-                    time.sleep(0.001)
-                else:
+                except Exception:
+                    try:
+                        self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    except Exception:
+                        self.errors += 1
+                time.sleep(0.001)
+            else:
+                try:
                     out = subprocess.run(["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
                                           "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                     a, b = [float(v) for v in out.strip().split(",")[:2]]
                     self.sm.append(a); self.max_mhz = b
-            except Exception:
-                time.sleep(0.005)
+                except Exception:
+                    self.errors += 1
+                    time.sleep(0.005)
 
     def start(self):
         self.thread = threading.Thread(target=self._poll, daemon=True)
