@@ -497,3 +497,30 @@ def test_observe_every_step(pf, alg):
         st = f2.filter(yt, st, result=r2)
     assert torch.allclose(res.filter_means, r2.filter_means, rtol=1e-4, atol=1e-5)
     assert torch.allclose(res.loglikelihood, r2.loglikelihood, rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("n", [(1 << 23), (1 << 23) + 5000])
+def test_filter_at_the_lean_count_limit(pf, n):
+    """2^23 particles is the last size served by the fused kernel / lean probe count (exact_scan.h: K <= 2^23); above it the filter
+    takes the three-kernel pipeline with the general count.  One free-running APF move each, ancestors bit-exact against the oracle's
+    CPU systematic for the dumped weights and offset."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF
+
+    torch.manual_seed(8)
+    _, y = O.build_model("sv_ar1").simulate(4)
+    f = APF(ts.build("sv_ar1"), n, seed=31)
+    e = f._get_engine(6)
+    e.initialize()
+    e.set_observations(y.float().reshape(-1, 1).cuda().contiguous(), 0)
+    e.run(2)
+    wdump = torch.zeros(e.B, e.ld, device="cuda")
+    udump = torch.zeros(e.B, device="cuda")
+    e.dump_noise(None, udump, wdump)
+    e.run(1)
+    torch.cuda.synchronize()
+    anc = e.prev_inds().cpu()
+    W = wdump[0, :n].cpu()
+    expect = O.systematic(W.clone().unsqueeze(1), normalized=True, u=udump.cpu().reshape(1, 1))[:, 0]
+    assert torch.equal(anc, expect)
+    assert e.info().slow_tiles == 0
