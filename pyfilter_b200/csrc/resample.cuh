@@ -22,6 +22,7 @@
 #define RS_KIND_TABLE 2   // more than one special element: the segment table sits in global memory (e1 = number of specials)
 #define RS_KIND_RAW 3     // too many segments: the chain walks the raw weights
 #define RS_KIND_NONE 5    // no (alternative) descriptor
+#define RS_KIND_CROSS 6   // crossing descriptor: per-thread sums under both binades in the tile's table slot (a_s, b_s = the two totals)
 #define RS_KIND_ABS 4     // the state after the tile is a_s whatever came before (tile 0 resolves itself: it starts from 0)
 
 struct __align__(16) FusedSlot {  // written and read with one 128-bit access: the tag says the sum belongs to this launch
@@ -495,6 +496,7 @@ __device__ __forceinline__ ChainEnt rs_chain_convert(const XsDesc& d, bool live)
     if (!ok) kind = -1;
   }
   if (kind == RS_KIND_ABS) c.tb.k = (int64_t)xs_d2u(d.a_s);
+  if (kind == RS_KIND_CROSS) { c.ta.k = (int64_t)xs_d2u(d.a_s); c.tb.k = (int64_t)xs_d2u(d.b_s); }
   c.e0 = (int16_t)e0; c.kind = (int8_t)kind;
   return c;
 }
@@ -540,6 +542,39 @@ __device__ __forceinline__ bool rs_chain_single(const ResampleArgs& a, int col, 
     *out = xs_d2u(S2);
     return ok;
   }
+  if (kind == RS_KIND_CROSS) {
+    const int eA = (int)c.e0;
+    const double Sd = xs_u2d(S);
+    const double totA = xs_u2d((uint64_t)c.ta.k), totB = xs_u2d((uint64_t)c.tb.k);
+    const int E = xs_label(Sd);
+    XsT t; t.d = 0;
+    double o;
+    if (E == eA + 1) { t.s = totB; const bool ok = xs_apply<MB>(Sd, eA + 1, t, &o); *out = xs_d2u(o); return ok; }
+    if (E != eA) return false;
+    const double* cr = reinterpret_cast<const double*>(a.tables + (int64_t)col * a.tiles_per_col + tile);
+    const double lim = __dadd_rn(xs_pow2(eA + 1), -Sd);  // exact: the sum leaves the lower binade once the increment reaches this
+    int first = 8;  // this lane looks at the threads [8 lane, 8 lane + 8)
+    double pa[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) pa[k] = __ldcg(cr + lane * 8 + k);
+#pragma unroll
+    for (int k = 7; k >= 0; --k) if (pa[k] >= lim) first = k;
+    const uint32_t hit = __ballot_sync(0xffffffffu, first < 8);
+    if (!hit) { t.s = totA; const bool ok = xs_apply<MB>(Sd, eA, t, &o); *out = xs_d2u(o); return ok; }
+    const int hl = __ffs(hit) - 1;
+    const int j = hl * 8 + __shfl_sync(0xffffffffu, first, hl);  // the thread whose particles take the sum across the boundary
+    const double before = j ? __ldcg(cr + j - 1) : 0.0;
+    const double upto = __ldcg(cr + RS_NT + j);
+    double S2 = __dadd_rn(Sd, before);  // exact, still in the lower binade
+    const float wv = (lane < RS_ITEMS) ? __ldg(a.wn + (int64_t)col * a.ld + (int64_t)tile * RS_TILE + j * RS_ITEMS + lane) : 0.f;
+#pragma unroll
+    for (int k = 0; k < RS_ITEMS; ++k) S2 = xs_add_special<MB>(S2, __shfl_sync(0xffffffffu, wv, k));
+    if (xs_label(S2) != eA + 1) return false;
+    t.s = __dadd_rn(totB, -upto);  // exact: both are sums of multiples of the upper quantum
+    const bool ok = xs_apply<MB>(S2, eA + 1, t, &o);
+    *out = xs_d2u(o);
+    return ok;
+  }
   return false;  // RS_KIND_RAW, RS_KIND_NONE, failed conversion
 }
 
@@ -566,6 +601,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
   int32_t* flag = a.tileflag + (int64_t)col * T;
   const float* wcol = a.wn + (int64_t)col * a.ld;
   uint64_t S_carry = 0;  // state carried from round to round (identical in every lane of warp 0, the only warp that uses it)
+  long long t_raw = 0, t_p2 = 0, n_raw = 0, n_single = 0, n_run = 0;  // diagnostics (SMCB_DEBUG_TIMELINE)
   const XsDesc* desc2 = a.desc2 + (int64_t)col * T;
   XsDesc dn = {}, dn2 = {};
   if (tid < T) { dn = rs_read_desc(desc + tid); dn2 = rs_read_desc(desc2 + tid); }
@@ -577,10 +613,12 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
     // ---- P1
     const ChainEnt pe = rs_chain_convert<MB>(d, live);
     ChainEnt ae = rs_chain_convert<MB>(d2, live);
-    if (!live || d2.has_special > 1) ae.kind = RS_KIND_NONE;
+    if (!live || d2.has_special != RS_KIND_CROSS) ae.kind = RS_KIND_NONE;
     const XiT ta = pe.ta;
     const int kind = pe.kind, e0 = pe.e0;
-    const bool plain = live && kind == 0;
+    // a tile with an alternative descriptor sits next to a binade crossing: keep it out of the runs, so that a misplaced crossing
+    // costs one descriptor (tried both ways) instead of the whole run around it
+    const bool plain = live && kind == 0 && ae.kind == RS_KIND_NONE;
     const int e_left = __shfl_up_sync(0xffffffffu, e0, 1);
     const int plain_left = __shfl_up_sync(0xffffffffu, plain ? 1 : 0, 1);
     const bool head = (lane == 0) || !plain || !plain_left || e_left != e0;
@@ -608,6 +646,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
     if (a.dbg && tid == 0 && base == 0) a.dbg[4] = rs_now();
     // ---- P2: warp 0 walks the segments; their records are fetched 32 at a time so that only the state itself is a serial chain
     if (wid == 0) {
+      const long long t_p2_0 = a.dbg ? rs_now() : 0;
       uint64_t S = S_carry;
       const int nw = min(RS_NT / 32, (T - base + 31) / 32);
       int total = 0;
@@ -635,6 +674,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
           if (st >= 0 && base + st >= T) break;  // padding behind the last tile
           uint64_t S2 = S;
           int fl = 0;
+          if (a.dbg) { if (st < 0) n_run++; else n_single++; }
           if (st < 0) {  // a run of plain descriptors in one binade
             if (!xi_apply<MB>(S, E, t, &S2)) {  // some speculation inside the run is wrong: tile by tile
               fl = 2;
@@ -646,7 +686,9 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
                 if (!xi_apply<MB>(S2, (int)cs.prim[q].e0, cs.prim[q].ta, &S3) &&
                     !rs_chain_single<MB>(a, col, base + q, cs.alt[q], S2, &S3)) {  // neither speculation holds: the reference operation
                   rs_chain_why<MB>(a, cs.prim[q], cs.alt[q], S2);
+                  const long long t0r = a.dbg ? rs_now() : 0;
                   S3 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + q) * RS_TILE, xs_u2d(S2), nullptr));
+                  if (a.dbg) { t_raw += rs_now() - t0r; n_raw++; }
                   tf = 1;
                   if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
                 }
@@ -657,7 +699,9 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
           } else if (!rs_chain_single<MB>(a, col, base + st, cs.prim[st], S, &S2) &&
                      !rs_chain_single<MB>(a, col, base + st, cs.alt[st], S, &S2)) {
             rs_chain_why<MB>(a, cs.prim[st], cs.alt[st], S);
+            const long long t0r = a.dbg ? rs_now() : 0;
             S2 = xs_d2u(rs_warp_raw_walk<MB>(wcol + (int64_t)(base + st) * RS_TILE, xs_u2d(S), nullptr));
+            if (a.dbg) { t_raw += rs_now() - t0r; n_raw++; }
             fl = 1;
             if (lane == 0) atomicAdd(&a.ctrl->slow_tiles, 1);
           }
@@ -666,6 +710,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
         }
       }
       S_carry = S;
+      if (a.dbg) t_p2 += rs_now() - t_p2_0;
     }
     __syncthreads();
 
@@ -683,6 +728,7 @@ __device__ void rs_chain(const ResampleArgs& a, int col, ChainSmem& cs) {
     __syncthreads();  // the round's tables are reused
 
   }
+  if (a.dbg && tid == 0) { a.dbg[26] = t_raw; a.dbg[27] = t_p2; a.dbg[28] = n_raw; a.dbg[29] = n_single; a.dbg[30] = n_run; }
 }
 
 template <int MB>
@@ -741,38 +787,50 @@ __global__ void __launch_bounds__(RS_NT, 4) describe_kernel(ResampleArgs a) {
     }
     a.desc[(int64_t)col * T + tile] = d;
   }
-  // A tile next to a binade crossing gets a second descriptor, speculated from a predictor biased downwards: the sequential sum
-  // lags the fp64 prefix (by up to ~1 % for the float32 accumulation of torch.multinomial), so around a crossing the true state may
-  // still be in the lower binade when the predictor already is in the upper one.  The chain tries both before the sequential walk.
+  // A tile next to a binade crossing also gets a CROSSING descriptor.  The sequential sum lags the fp64 prefix (by up to ~1 % for the
+  // float32 accumulation of torch.multinomial), so WHICH element crosses cannot be predicted - but only one thread of the tile contains
+  // it.  With eA the lower of the two binades: per thread the sum of RN_q(w) under "all in eA" and under "all in eA + 1", and their
+  // inclusive scans over the threads (2 x 256 doubles, kept in the tile's table slot).  The chain then finds the crossing thread from
+  // the EXACT state with one comparison per thread, walks that thread's 16 weights with genuine additions and adds the upper-binade
+  // sums of the threads behind it (rs_chain_single, RS_KIND_CROSS).
   {
     constexpr double kBias = (MB == 24) ? 0.98 : (1.0 - 1e-9);
     __shared__ int need_alt;
     if (tid == 0) {
       const double spe = sm.sp_end;
-      need_alt = (!exact0 && tile > 0 && (xs_label(sp0 * kBias) != xs_label(sp0) || xs_label(spe * kBias) != xs_label(spe))) ? 1 : 0;
-      if (!need_alt) {
-        XsDesc d;
-        memset(&d, 0, sizeof(d));
-        d.has_special = RS_KIND_NONE;
-        a.desc2[(int64_t)col * T + tile] = d;
-      }
+      const int eA = xs_label(sp0 * kBias);
+      need_alt = (!exact0 && tile > 0 && table_ok && X <= 1 && eA != XS_E_ZERO && xs_label(spe) <= eA + 1 &&
+                  (eA != xs_label(sp0) || xs_label(spe * kBias) != xs_label(spe))) ? 1 : 0;
     }
     __syncthreads();
+    XsDesc d2;
+    memset(&d2, 0, sizeof(d2));
+    d2.has_special = RS_KIND_NONE;
     if (need_alt) {
-      RsScan<MB> r2;
-      rs_tile_scan<MB>(w, sp0, sm, r2, kBias);
-      if (tid == 0) {
-        XsDesc d;
-        d.a_s = 0.0; d.b_s = 0.0; d.wc = 0.f; d.e0 = (int16_t)sm.e0; d.e1 = 0; d.a_d = 0; d.b_d = 0; d.pad = 0;
-        const int X2 = sm.X;
-        if (!sm.table_ok || X2 > 1) d.has_special = RS_KIND_NONE;
-        else {
-          d.a_s = sm.seg_agg[0].s; d.a_d = (int8_t)sm.seg_agg[0].d; d.has_special = (int8_t)X2;
-          if (X2) { d.wc = sm.seg_wc[1]; d.e1 = (int16_t)sm.seg_e[1]; d.b_s = sm.seg_agg[1].s; d.b_d = (int8_t)sm.seg_agg[1].d; }
-        }
-        a.desc2[(int64_t)col * T + tile] = d;
+      const int eA = xs_label(sp0 * kBias);
+      const double MA = xs_pow2(eA), MBv = xs_pow2(eA + 1), hqA = xs_pow2(eA - MB), hqB = xs_pow2(eA + 1 - MB);
+      double accA = 0.0, accB = 0.0;
+      bool tie = false;
+#pragma unroll
+      for (int k = 0; k < RS_ITEMS; ++k) {
+        const double qa = rs_round_q<MB>(w[k], MA), qb = rs_round_q<MB>(w[k], MBv);
+        tie |= (fabs(__dadd_rn((double)w[k], -qa)) == hqA) || (fabs(__dadd_rn((double)w[k], -qb)) == hqB);
+        accA = __dadd_rn(accA, qa);
+        accB = __dadd_rn(accB, qb);
+      }
+      const int any_tie = __syncthreads_or(tie ? 1 : 0);
+      double totA, totB;
+      const double exA = rs_block_excl_scan_d(accA, sm.dscratch, &totA);
+      const double exB = rs_block_excl_scan_d(accB, sm.dscratch, &totB);
+      if (!any_tie) {
+        double* cr = reinterpret_cast<double*>(a.tables + (int64_t)col * T + tile);
+        cr[tid] = exA + accA;            // inclusive over the threads, lower binade
+        cr[RS_NT + tid] = exB + accB;    // ... upper binade
+        d2.has_special = RS_KIND_CROSS; d2.e0 = (int16_t)eA; d2.a_s = totA; d2.b_s = totB;
+        __threadfence();
       }
     }
+    if (tid == 0) a.desc2[(int64_t)col * T + tile] = d2;
   }
   if (tid == 0 || (table_ok && X > 1)) __threadfence();  // table and descriptor stores precede the ticket
   __syncthreads();
