@@ -71,6 +71,8 @@ struct ResampleArgs {
   struct FusedSlot* fslots; // (B, tiles_per_col) resample_fused_kernel: tile sums tagged with the launch epoch
   int32_t presanitized;    // 1: the log-weights were stored by the step / state kernels, nan_to_num (utils.py:57) already applied
   int32_t force_benign;    // 1: the host skipped describe_kernel (quantised weights, n <= 2^23, Philox offsets): benign by construction
+  int32_t t_host;          // resample_fused_kernel: the move index (== ctrl->t), passed by the host to keep it off the critical path
+  unsigned long long epoch_host;  // resample_fused_kernel: launch tag of the slots, unique per launch and never 0
 };
 __device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { RS_OUT_ANCESTORS = 0, RS_OUT_CUMSUM = 1 };
@@ -1105,17 +1107,15 @@ __global__ void __launch_bounds__(RS_NT, 4) expand_kernel(ResampleArgs a) {
 // sum them exactly, and expand as expand_kernel does.  No normalised weights in memory, no serial tail, one launch per resampling.
 __global__ void __launch_bounds__(RS_NT, 4) resample_fused_kernel(ResampleArgs a) {
   __shared__ __align__(16) ExpandSmem sm;
-  __shared__ int s_id;
   const int tid = threadIdx.x;
-  pdl_wait();
-  if (tid == 0) s_id = (int)atomicAdd(&a.ctrl->tile_counter, 1u);
+  // tile id = block id: blocks of a 1-D grid are dispatched in increasing order, so every predecessor a tile polls is resident or
+  // finished (the assumption CUB's decoupled look-back makes too) - no atomic ticket, hence no global round trip before the loads
+  const int T = a.tiles_per_col;
+  const int col = (int)blockIdx.x / T, tile = (int)blockIdx.x % T;
 #pragma unroll
   for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-  if (tid == 0) sm.carry = -1;
-  __syncthreads();
-  const int T = a.tiles_per_col;
-  const int col = s_id / T, tile = s_id % T;
-  if (col >= a.B) return;
+  if (tid == 0) sm.carry = -1;  // (ordered before the marks by the barriers of the block scan below)
+  pdl_wait();
   // independent loads first
   float w[RS_ITEMS];
   {
@@ -1127,8 +1127,8 @@ __global__ void __launch_bounds__(RS_NT, 4) resample_fused_kernel(ResampleArgs a
     }
   }
   const ColStats st = a.stats[col];
-  const unsigned long long epoch = a.ctrl->epoch;
-  const int t_now = a.ctrl->t;
+  const unsigned long long epoch = a.epoch_host;
+  const int t_now = a.t_host;
   if (!st.resample) return;
   const float m = a.use_rw ? st.m_rw : st.m_lw, iz = a.use_rw ? st.inv_z_rw : st.inv_z_lw;
   const int32_t n = (int32_t)a.n;

@@ -142,6 +142,8 @@ struct smcb_filter {
   const double* U_in = nullptr;
   float *eps_out = nullptr, *u_out = nullptr, *w_out = nullptr;
   int t_host = 0, y_base = 0, y_count = 0;
+  const float* y_dev = nullptr;         // observations on the device (set_observations)
+  unsigned long long fused_epoch = 0;   // tags the tile-sum slots of resample_fused_kernel, bumped per launch
   bool folded_for_next = false;
   int64_t launches = 0;
 };
@@ -350,6 +352,7 @@ static int push_ctrl(smcb_filter* f, const float* y_dev, cudaStream_t s) {
   struct { int32_t t, y_base, y_count; } head = {f->t_host, f->y_base, f->y_count};
   CU(cudaMemcpyAsync(f->ctrl, &head, sizeof(head), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync((char*)f->ctrl + offsetof(Ctrl, y), &y_dev, sizeof(y_dev), cudaMemcpyHostToDevice, s));
+  f->y_dev = y_dev;
   return SMCB_OK;
 }
 
@@ -398,6 +401,9 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   const int t = f->t_host;
   if (t - f->y_base < 0 || t - f->y_base >= f->y_count) return fail(SMCB_ESTATE, "no observation set for this move");
   StepArgs a = make_args(f);
+  a.t_host = t;
+  a.y_t = f->y_dev ? f->y_dev + (int64_t)(t - f->y_base) * f->OD : nullptr;
+  a.y_next = (f->y_dev && t + 1 - f->y_base < f->y_count) ? f->y_dev + (int64_t)(t + 1 - f->y_base) * f->OD : nullptr;
   if (ev) cudaEventRecord(ev[0], s);
   if (apf && !f->folded_for_next) {  // apf.py:27-29 evaluated now because the previous move could not fold it
     launch_preweight(f, a, s);
@@ -422,6 +428,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   static const bool no_fused = getenv("SMCB_NO_FUSED") != nullptr;
   if (f->cfg.resampler == SMCB_SYSTEMATIC && r.quantize && f->n <= (1 << 23) && !f->u_in && !no_fused) {
     r.fslots = f->fslots;
+    r.t_host = t; r.epoch_host = ++f->fused_epoch;
     launch_pdl(resample_fused_kernel, dim3(r.tiles_per_col * r.B), dim3(RS_NT), s, r);
     f->launches++;
     if (ev) { cudaEventRecord(ev[2], s); cudaEventRecord(ev[3], s); cudaEventRecord(ev[4], s); }

@@ -41,6 +41,10 @@ struct StepArgs {
   float* latest_mean; float* latest_var; float* latest_ll; float* ll_total;  // (B, D), (B, D), (B), (B)
   int32_t fin_mode;
   long long* dbg;                    // optional diagnostics (SMCB_DEBUG_TIMELINE)
+  // step_kernel only: what the host knows at launch time, so that the prologue has no chain of dependent loads (ctrl->t -> ctrl->y -> y[t])
+  int32_t t_host;                    // == ctrl->t when the kernel runs
+  const float* y_t;                  // observation of this move (NULL: none)
+  const float* y_next;               // observation of the next move (NULL: unknown -> no folded look-ahead)
 };
 __device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
@@ -436,6 +440,7 @@ struct FinPre {
   ColStats st;
   bool observed;   // y_t is present
   bool fold;       // y_{t+1} is present and the look-ahead is folded
+  float ll_total;  // running log-likelihood before this move
 };
 template <int OD>
 __device__ __forceinline__ FinPre fin_preload(const StepArgs& a, int col, int mode, int t) {
@@ -444,6 +449,7 @@ __device__ __forceinline__ FinPre fin_preload(const StepArgs& a, int col, int mo
   float y[OD];
   p.observed = (mode != FIN_STATE) && st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
   p.fold = (mode == FIN_STEP) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), y);
+  p.ll_total = a.ll_total[col];
   return p;
 }
 
@@ -541,7 +547,7 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
         }
       }
       a.latest_ll[col] = ll;
-      if (mode == FIN_STEP) a.ll_total[col] += ll;
+      if (mode == FIN_STEP) a.ll_total[col] = pre.ll_total + ll;
       if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
     }
     if (mode == FIN_STEP) {
@@ -643,12 +649,12 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   pdl_wait();
   if (a.dbg && tid == 0) atomicMin((unsigned long long*)&a.dbg[11], (unsigned long long)st_now());
   __syncthreads();
-  const int t = a.ctrl->t;
+  const int t = a.t_host;
   float y[OD], yn[OD];
-  const bool observed = st_load_obs<OD>(st_obs(a.ctrl, t, OD), y);
-  const bool fold = (ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(st_obs(a.ctrl, t + 1, OD), yn);
+  const bool observed = st_load_obs<OD>(a.y_t, y);
+  const bool fold = (ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(a.y_next, yn);
   const ColStats st = a.stats[col];
-  if (tid == 0) { fin_pre.st = st; fin_pre.observed = observed; fin_pre.fold = fold; }  // for the finalizing block's tail
+  if (tid == 0) { fin_pre.st = st; fin_pre.observed = observed; fin_pre.fold = fold; fin_pre.ll_total = a.ll_total[col]; }  // for the finalizing block's tail
   if (a.dbg && tid == 0 && blockIdx.x == 0) a.dbg[14] = st_now();
   // SISR resamples when the ESS test fired (sisr.py:19-26), the APF on every observed step (apf.py:29-34, filters/base.py:213)
   const bool resampled = (ALG == SMCB_ALG_APF) ? observed : (st.resample != 0);
