@@ -101,13 +101,19 @@ def load_library():
     with _lock:
         if _lib is not None:
             return _lib
-        if _stale():
+        alt = os.environ.get("SMCB_LIB_PATH")  # diagnostics: an alternative build of the same sources (tools/variants.py)
+        if alt:
+            lib_path = alt
+        elif _stale():
+            lib_path = LIB_PATH
             try:
                 build_library()
             except (SmcbError, FileNotFoundError) as e:
                 if not os.path.exists(LIB_PATH):
                     raise SmcbError(f"libsmcb200.so is missing and could not be built ({e}); pyfilter_b200 has no CPU fallback")
-        lib = C.CDLL(LIB_PATH)
+        else:
+            lib_path = LIB_PATH
+        lib = C.CDLL(lib_path)
         for name, restype, argtypes in SYMBOLS:
             fn = getattr(lib, name)
             fn.restype = restype
