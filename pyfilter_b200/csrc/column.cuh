@@ -1,0 +1,240 @@
+// column_kernel: ONE block owns ONE column (one independent filter of at most RS_TILE = 4096 particles) for a whole run of moves.
+//
+// The multi-kernel pipeline (resample_fused_kernel -> step_kernel, step.cuh / resample.cuh) pays two launches and about ten dependent
+// global round trips per move (normalisers, tile sums, tickets, partials): ~9 us per move however small the column is.  The batch of
+// independent filters of SMC2 / NESS (BASELINE.json configs[4]: 4096 state particles x 1024 theta, filters/base.py:93-119) is exactly
+// the regime where that floor dominates.  Here the column never leaves the SM between moves: particles in shared memory, log-weights
+// in registers, normalisers in shared memory; a move is  weights -> block scan -> systematic expansion (the SAME rs_mark_pass /
+// rs_emit_ancestors as resample_fused_kernel, single tile, so n_in = 0) -> gather from shared memory -> proposal / weights (the SAME
+// Proposal<> and model functions as step_kernel, same Philox counters) -> block reduction -> fin_apply.  Global memory sees the
+// history rows every move and the state once at the end.  The host launches it instead of the pipeline whenever it applies
+// (smcb_api.cu: column_path_ok); results differ from the pipeline only through the order of the float32 reductions.
+#pragma once
+#include "step.cuh"
+#include "resample.cuh"
+
+struct ColumnArgs {
+  StepArgs s;           // buffers, parameters, history (s.t_host = first move of this launch)
+  int32_t steps;        // moves to run
+  int32_t y_avail;      // observations available from y (>= steps); move k may fold the next look-ahead iff k + 1 < y_avail
+  const float* y;       // (y_avail, OD): observation of move s.t_host + k at y + k * OD
+  const float* u_in;    // optional injected systematic offsets (B)
+  float* u_out;         // optional dump of the offsets used (B)
+  float* w_out;         // optional dump of the normalised resampling weights (B, ld)
+  int32_t quantize;     // must be 1: rounding-free weights
+};
+
+template <int D>
+struct ColumnSmem {
+  float Ps[SMCB_NPARAM];
+  Fin4Scratch<1 + 2 * D> f4;
+  ColStats st;
+};
+
+template <int MODEL, int PROP, int ALG>
+__global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
+  typedef Model<MODEL> M;
+  constexpr int D = M::D, OD = M::OD;
+  __shared__ __align__(16) ExpandSmem sm;        // marks (stage), ancestors (c_tile reused as int32), scan scratch
+  __shared__ ColumnSmem<D> cs;
+  extern __shared__ __align__(16) float ck_xs[];  // (D, RS_TILE) particles of the column
+  const StepArgs& a = c.s;
+  const int tid = threadIdx.x, col = blockIdx.x;
+  const int32_t n = (int32_t)a.n;
+  const int32_t gbase = tid * RS_ITEMS;
+  int32_t* anc_s = reinterpret_cast<int32_t*>(sm.c_tile);
+  if (tid < SMCB_NPARAM) cs.Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
+  if (tid == 0) cs.st = a.stats[col];
+  const float* Ps = cs.Ps;
+  float ll_total = a.ll_total[col];
+  const float nf = (float)a.n, inv_n = 1.0f / (float)a.n;
+  const double nd = (double)n, nfd = (double)(float)a.n;
+  const float one4[4] = {1.f, 1.f, 1.f, 1.f};
+  float* lwrow = a.lw + (int64_t)col * a.ld;
+  float* rwrow = a.rw + (int64_t)col * a.ld;
+  int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
+
+  // ---- the column comes on chip
+  float lw[RS_ITEMS], rw[RS_ITEMS];
+  {
+    const int t0 = a.t_host;
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+      const float4 q = *reinterpret_cast<const float4*>(lwrow + gbase + 4 * v);
+      lw[4 * v] = q.x; lw[4 * v + 1] = q.y; lw[4 * v + 2] = q.z; lw[4 * v + 3] = q.w;
+      const float4 r = *reinterpret_cast<const float4*>(rwrow + gbase + 4 * v);
+      rw[4 * v] = r.x; rw[4 * v + 1] = r.y; rw[4 * v + 2] = r.z; rw[4 * v + 3] = r.w;
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        *reinterpret_cast<float4*>(ck_xs + d * RS_TILE + gbase + 4 * v) =
+            *reinterpret_cast<const float4*>(a.xbuf[t0 & 1] + ((int64_t)d * a.B + col) * a.ld + gbase + 4 * v);
+    }
+  }
+  __syncthreads();
+
+  for (int k = 0; k < c.steps; ++k) {
+    const int t = a.t_host + k;
+    const ColStats st = cs.st;
+    float y[OD], yn[OD];
+    const bool observed = st_load_obs<OD>(c.y + (int64_t)k * OD, y);
+    const bool fold = (ALG == SMCB_ALG_APF) && a.fold && (k + 1 < c.y_avail) && st_load_obs<OD>(c.y + (int64_t)(k + 1) * OD, yn);
+    const bool resampled = (ALG == SMCB_ALG_APF) ? observed : (st.resample != 0);
+
+    // ---- systematic resampling of the column (resample_fused_kernel with a single tile)
+    if (resampled && st.resample) {
+#pragma unroll
+      for (int r = 0; r < FB_ROWS; ++r) *reinterpret_cast<int4*>(&sm.stage[(r * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+      if (tid == 0) sm.carry = -1;
+      const float m = (ALG == SMCB_ALG_APF) ? st.m_rw : st.m_lw, iz = (ALG == SMCB_ALG_APF) ? st.inv_z_rw : st.inv_z_lw;
+      float w[RS_ITEMS];
+      double tsum = 0.0;
+#pragma unroll
+      for (int j = 0; j < RS_ITEMS; ++j) {
+        float x = smcb_weight((ALG == SMCB_ALG_APF) ? rw[j] : lw[j], m, iz);
+        if (gbase + j >= n) x = 0.f;
+        const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);  // multiple of 2^-52: the column is benign
+        w[j] = (float)xd;
+        tsum += xd;
+      }
+      if (c.w_out) {
+        float* dst = c.w_out + (int64_t)col * a.ld + gbase;
+#pragma unroll
+        for (int v = 0; v < RS_ITEMS / 4; ++v)
+          reinterpret_cast<float4*>(dst)[v] = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+      }
+      double tot;
+      const double S0 = rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);
+      float u;
+      if (c.u_in) u = c.u_in[col];
+      else {
+        const Philox4 r4 = philox4x32_10((uint32_t)col, 0u, (uint32_t)t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        u = smcb_u01(r4.x);
+      }
+      if (c.u_out && tid == 0) c.u_out[col] = u;
+      int32_t lo_thread = 0;
+      if (tid) lo_thread = (gbase - 1 >= n - 1) ? n : xs_count_fast((float)S0, u, n, nd, nfd);
+      auto mark = [&](int32_t wb, bool first) -> int32_t {
+        return rs_mark_pass<53, true, true>(w, S0, 0.0, nullptr, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, sm);
+      };
+      rs_emit_ancestors(sm, mark, 0, anc_s);   // n <= RS_TILE < FB_WIN: always a single window
+      __syncthreads();
+    }
+
+    // ---- the move itself (step_kernel's body on this thread's RS_ITEMS particles)
+    StepAcc<D> mom; mom.init();
+    StepAcc1 r2; r2.init();
+    StepAcc1 r3; r3.init();
+    float shift[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) shift[d] = st.shift[d];
+    float xnew[D][RS_ITEMS];
+#pragma unroll
+    for (int g = 0; g < RS_ITEMS / 4; ++g) {
+      const int32_t i0 = gbase + 4 * g;
+      int anc[4] = {i0, i0 + 1, i0 + 2, i0 + 3};
+      if (resampled) {
+        const int4 q = *reinterpret_cast<const int4*>(anc_s + i0);
+        anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
+      }
+      const bool live = i0 < n, full = i0 + 4 <= n;
+      if (live && (resampled || ALG == SMCB_ALG_APF))   // sisr.py:32 / apf.py:18-23
+        *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+      if (!full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q >= n) anc[q] = 0;
+      }
+      float lwp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!resampled) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lwp[q] = lw[4 * g + q];
+      }
+      float xa[D][4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xa[d][q] = ck_xs[d * RS_TILE + anc[q]];
+      }
+      float z[D][4];
+      if (live) st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
+      else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) { z[d][0] = z[d][1] = z[d][2] = z[d][3] = 0.f; }
+      }
+      float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float xk[D], zk[D], xo[D], inc, g_anc;
+#pragma unroll
+        for (int d = 0; d < D; ++d) { xk[d] = xa[d][q]; zk[d] = z[d][q]; }
+        Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) xn[d][q] = xo[d];
+        float lwv;
+        if (!observed) lwv = lwp[q];
+        else if (ALG == SMCB_ALG_APF) lwv = __fsub_rn(inc, g_anc);   // apf.py:43
+        else lwv = __fadd_rn(inc, lwp[q]);                           // sisr.py:52
+        lwn[q] = lwv;
+        inc4[q] = inc;
+        wprev[q] = 0.f;
+        if (ALG == SMCB_ALG_SISR) wprev[q] = resampled ? inv_n : smcb_weight(lwp[q], st.m_lw, st.inv_z_lw);
+        gnx[q] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        lwn[q] = st_sanitize(lwn[q]);                                // utils.py:57
+        rwn[q] = fold ? st_sanitize(__fadd_rn(gnx[q], lwn[q])) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        lw[4 * g + q] = lwn[q];
+        if (fold) rw[4 * g + q] = rwn[q];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = xn[d][q];
+      }
+      if (!full) {  // padding contributes nothing
+#pragma unroll
+        for (int q = 0; q < 4; ++q) if (i0 + q >= n) { lwn[q] = -INFINITY; rwn[q] = -INFINITY; inc4[q] = -INFINITY; }
+      }
+      if (live) {
+        mom.add4(lwn, xn, shift);
+        if (fold) r2.add4(rwn, one4);
+        if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
+      }
+    }
+    SoftAcc<1 + 2 * D> A;
+    SoftAcc<1> Q, R2, R3;
+    mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
+    softacc4_block_reduce(A, Q, R2, R3, cs.f4);   // its barriers also separate this move's gathers from the stores below
+    if (tid == 0) {
+      FinPre pre;
+      pre.st = st; pre.observed = observed; pre.fold = fold; pre.ll_total = ll_total;
+      ColStats stn = st;
+      ll_total += fin_apply<D, OD, ALG>(a, col, FIN_STEP, t, A, Q, R2, R3, pre, stn);
+      cs.st = stn;
+    }
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        *reinterpret_cast<float4*>(ck_xs + d * RS_TILE + gbase + 4 * v) =
+            make_float4(xnew[d][4 * v], xnew[d][4 * v + 1], xnew[d][4 * v + 2], xnew[d][4 * v + 3]);
+    }
+    __syncthreads();
+  }
+
+  // ---- the column goes back to global memory
+  {
+    const int t1 = a.t_host + c.steps;
+    const bool rw_valid = (ALG == SMCB_ALG_APF) && cs.st.fold_valid;
+#pragma unroll
+    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+      *reinterpret_cast<float4*>(lwrow + gbase + 4 * v) = make_float4(lw[4 * v], lw[4 * v + 1], lw[4 * v + 2], lw[4 * v + 3]);
+      if (rw_valid) *reinterpret_cast<float4*>(rwrow + gbase + 4 * v) = make_float4(rw[4 * v], rw[4 * v + 1], rw[4 * v + 2], rw[4 * v + 3]);
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+        *reinterpret_cast<float4*>(a.xbuf[t1 & 1] + ((int64_t)d * a.B + col) * a.ld + gbase + 4 * v) =
+            *reinterpret_cast<const float4*>(ck_xs + d * RS_TILE + gbase + 4 * v);
+    }
+    if (col == 0 && tid == 0) a.ctrl->t = t1;
+  }
+}

@@ -10,6 +10,7 @@
 #include "../../include/smcb200.h"
 #include "resample.cuh"
 #include "step.cuh"
+#include "column.cuh"
 #include "operators.cuh"
 
 static thread_local std::string g_err;
@@ -465,9 +466,67 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
   return SMCB_OK;
 }
 
+// ---- resident-column path: one block per column runs all `steps` moves in one launch (column.cuh) -----------------------------------
+static bool column_path_ok(const smcb_filter* f) {
+  if (getenv("SMCB_NO_COLUMN")) return false;   // diagnostics / tests: force the multi-kernel pipeline
+  if (f->n > RS_TILE || f->cfg.resampler != SMCB_SYSTEMATIC || f->cfg.exact_weights) return false;
+  if (f->cfg.algorithm == SMCB_APF && !f->cfg.fold_lookahead) return false;
+  return true;
+}
+
+template <int MODEL, int PROP>
+static cudaError_t launch_column_alg(int alg, int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
+  cudaError_t e;
+  if (alg == SMCB_SISR) {
+    e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, SMCB_ALG_SISR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e == cudaSuccess) column_kernel<MODEL, PROP, SMCB_ALG_SISR><<<B, RS_NT, dyn, s>>>(c);
+  } else {
+    e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, SMCB_ALG_APF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e == cudaSuccess) column_kernel<MODEL, PROP, SMCB_ALG_APF><<<B, RS_NT, dyn, s>>>(c);
+  }
+  return e;
+}
+
+static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
+  const bool apf = f->cfg.algorithm == SMCB_APF;
+  const int t = f->t_host;
+  if (steps < 1) return SMCB_OK;
+  if (t - f->y_base < 0 || t + steps - 1 - f->y_base >= f->y_count || !f->y_dev) return fail(SMCB_ESTATE, "no observation set for this move");
+  StepArgs a = make_args(f);
+  a.t_host = t;
+  if (apf && !f->folded_for_next) {  // apf.py:27-29 evaluated now because the previous move could not fold it
+    launch_preweight(f, a, s);
+    launch_finalize(f, a, FIN_PREWEIGHT, s);
+  }
+  ColumnArgs c;
+  memset(&c, 0, sizeof(c));
+  c.s = a;
+  c.steps = steps;
+  c.y = f->y_dev + (int64_t)(t - f->y_base) * f->OD;
+  c.y_avail = f->y_count - (t - f->y_base);
+  c.u_in = f->u_in; c.u_out = f->u_out; c.w_out = f->w_out; c.quantize = 1;
+  const size_t dyn = sizeof(float) * (size_t)f->D * RS_TILE;
+  const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
+  cudaError_t e = cudaSuccess;
+  switch (f->cfg.model) {
+    case 0: e = prop ? launch_column_alg<0, 1>(alg, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, f->B, dyn, s, c); break;
+    case 1: e = prop ? launch_column_alg<1, 1>(alg, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, f->B, dyn, s, c); break;
+    case 2: e = launch_column_alg<2, 0>(alg, f->B, dyn, s, c); break;
+    case 3: e = launch_column_alg<3, 0>(alg, f->B, dyn, s, c); break;
+  }
+  if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
+  f->launches++;
+  const int t1 = t + steps;
+  f->folded_for_next = apf && f->cfg.fold_lookahead && (t1 - f->y_base) < f->y_count;
+  f->t_host = t1;
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
 extern "C" int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream) {
   if (!f) return fail(SMCB_EINVAL, "null handle");
   cudaStream_t s = (cudaStream_t)stream;
+  if (column_path_ok(f)) return run_column(f, steps, s);
   for (int k = 0; k < steps; ++k) {
     int rc = run_one(f, s, nullptr);
     if (rc) return rc;

@@ -453,6 +453,63 @@ __device__ __forceinline__ FinPre fin_preload(const StepArgs& a, int col, int mo
   return p;
 }
 
+// The single-thread part of FIN_STATE / FIN_STEP: the folded sums of a column -> ColStats, moments, likelihood increment, history rows.
+// Shared by finalize_column (multi-kernel pipeline) and column_kernel (one block owns the column).  Returns the new statistics in `st`
+// (also stored to a.stats[col]) and the likelihood increment of the move.
+template <int D, int OD, int ALG>
+__device__ __forceinline__ float fin_apply(const StepArgs& a, int col, int mode, int t, const SoftAcc<1 + 2 * D>& A, const SoftAcc<1>& Q,
+                                           const SoftAcc<1>& R2, const SoftAcc<1>& R3, const FinPre& pre, ColStats& st) {
+  const float nf = (float)a.n;
+  const bool observed = (mode == FIN_STEP) && pre.observed;
+  const float ll_aux_prev = st.ll_aux;
+  st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
+  // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
+  const float zz = (Q.m == -INFINITY) ? 0.f : Q.s[0] * __expf(Q.m - 2.f * A.m);
+  st.ess = (A.s[0] * A.s[0]) / zz;
+  float mean[D], var[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const float dm = A.s[1 + d] * st.inv_z_lw;            // E[x - shift]
+    mean[d] = st.shift[d] + dm;
+    var[d] = fmaxf(A.s[1 + D + d] * st.inv_z_lw - dm * dm, 0.f);
+  }
+  float ll = 0.f;
+  if (mode == FIN_STEP && observed) {
+    if (ALG == SMCB_ALG_SISR) ll = R3.m + logf(R3.s[0]);                       // filters/particle/utils.py:16-22
+    else ll = (A.m + logf(A.s[0]) - logf(nf)) + ll_aux_prev;                   // apf.py:44
+  }
+  // next step's resampling decision and (APF) folded normalisers
+  st.fold_valid = 0;
+  if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
+  else {
+    st.resample = 0;  // set by the pre-weight pass unless the look-ahead was folded below
+    const bool fold = pre.fold;
+    if (fold) {
+      st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
+      st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
+      st.fold_valid = 1;
+      st.resample = 1;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) st.shift[d] = mean[d];
+  a.stats[col] = st;
+  const int rowi = (mode == FIN_STEP) ? t + 1 : t;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    a.latest_mean[col * D + d] = mean[d];
+    a.latest_var[col * D + d] = var[d];
+    if (a.hist_mean && rowi < a.hist_rows) {
+      a.hist_mean[((int64_t)rowi * a.B + col) * D + d] = mean[d];
+      a.hist_var[((int64_t)rowi * a.B + col) * D + d] = var[d];
+    }
+  }
+  a.latest_ll[col] = ll;
+  if (mode == FIN_STEP) a.ll_total[col] = pre.ll_total + ll;
+  if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
+  return ll;
+}
+
 template <int D, int OD, int ALG>
 __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int mode, int t, FinSmem<D>& fs, const FinPre& pre) {
   const int tid = threadIdx.x;
@@ -502,53 +559,7 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       st.fold_valid = 1;
       a.stats[col] = st;
     } else {
-      const bool observed = (mode == FIN_STEP) && pre.observed;
-      const float ll_aux_prev = st.ll_aux;
-      st.m_lw = A.m; st.z_lw = A.s[0]; st.inv_z_lw = 1.0f / A.s[0];
-      // Q.m may differ from 2*A.m by rounding of the merges: bring sum e^2 to the reference point 2*A.m
-      const float zz = (Q.m == -INFINITY) ? 0.f : Q.s[0] * __expf(Q.m - 2.f * A.m);
-      st.ess = (A.s[0] * A.s[0]) / zz;
-      float mean[D], var[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const float dm = A.s[1 + d] * st.inv_z_lw;            // E[x - shift]
-        mean[d] = st.shift[d] + dm;
-        var[d] = fmaxf(A.s[1 + D + d] * st.inv_z_lw - dm * dm, 0.f);
-      }
-      float ll = 0.f;
-      if (mode == FIN_STEP && observed) {
-        if (ALG == SMCB_ALG_SISR) ll = R3.m + logf(R3.s[0]);                       // filters/particle/utils.py:16-22
-        else ll = (A.m + logf(A.s[0]) - logf(nf)) + ll_aux_prev;                   // apf.py:44
-      }
-      // next step's resampling decision and (APF) folded normalisers
-      st.fold_valid = 0;
-      if (ALG == SMCB_ALG_SISR) st.resample = (st.ess < a.ess_threshold * nf) ? 1 : 0;   // sisr.py:18-19
-      else {
-        st.resample = 0;  // set by the pre-weight pass unless the look-ahead was folded below
-        const bool fold = pre.fold;
-        if (fold) {
-          st.m_rw = R2.m; st.z_rw = R2.s[0]; st.inv_z_rw = 1.0f / R2.s[0];
-          st.ll_aux = logf(R2.s[0]) + (R2.m - A.m) - logf(A.s[0]);
-          st.fold_valid = 1;
-          st.resample = 1;
-        }
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) st.shift[d] = mean[d];
-      a.stats[col] = st;
-      const int rowi = (mode == FIN_STEP) ? t + 1 : t;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        a.latest_mean[col * D + d] = mean[d];
-        a.latest_var[col * D + d] = var[d];
-        if (a.hist_mean && rowi < a.hist_rows) {
-          a.hist_mean[((int64_t)rowi * a.B + col) * D + d] = mean[d];
-          a.hist_var[((int64_t)rowi * a.B + col) * D + d] = var[d];
-        }
-      }
-      a.latest_ll[col] = ll;
-      if (mode == FIN_STEP) a.ll_total[col] = pre.ll_total + ll;
-      if (a.hist_ll && rowi < a.hist_rows) a.hist_ll[(int64_t)rowi * a.B + col] = ll;
+      fin_apply<D, OD, ALG>(a, col, mode, t, A, Q, R2, R3, pre, st);
     }
     if (mode == FIN_STEP) {
       if (a.B == 1 || atomicAdd(&a.ctrl->ticket, 1) == a.B - 1) {  // every column is finalized, hence every block has read ctrl->t
