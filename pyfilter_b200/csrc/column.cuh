@@ -24,25 +24,34 @@ struct ColumnArgs {
   int32_t quantize;     // must be 1: rounding-free weights
 };
 
-template <int D>
+template <int NT, int D>
 struct ColumnSmem {
+  int32_t stage[RS_TILE];       // marks of the expansion, then (in place: single window) the ancestors
+  double dscratch[33];          // block scan
+  int32_t wtot[NT / 32];
+  int32_t carry, n_out;
   float Ps[SMCB_NPARAM];
-  Fin4Scratch<1 + 2 * D> f4;
+  Fin4Scratch<1 + 2 * D, NT> f4;
   ColStats st;
 };
 
-template <int MODEL, int PROP, int ALG>
-__global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
+// NT threads per column, ITEMS = RS_TILE / NT consecutive particles per thread; MINB resident blocks per SM bound the registers
+// (512 x 8 particles: two blocks per SM at 64 registers for large batches, one block at 128 registers when there are fewer columns
+// than SMs - a lone block is latency bound and wants the instruction-level parallelism).  Threads whose particles are all padding
+// (n < RS_TILE) skip the arithmetic.
+template <int MODEL, int PROP, int ALG, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
   typedef Model<MODEL> M;
   constexpr int D = M::D, OD = M::OD;
-  __shared__ __align__(16) ExpandSmem sm;        // marks (stage), ancestors (c_tile reused as int32), scan scratch
-  __shared__ ColumnSmem<D> cs;
+  constexpr int ITEMS = RS_TILE / NT, ROWS = ITEMS / 4;
+  static_assert(ITEMS % 4 == 0 && ROWS >= 1, "a thread owns whole groups of four particles (one Philox block each)");
+  __shared__ __align__(16) ColumnSmem<NT, D> cs;
   extern __shared__ __align__(16) float ck_xs[];  // (D, RS_TILE) particles of the column
   const StepArgs& a = c.s;
   const int tid = threadIdx.x, col = blockIdx.x;
   const int32_t n = (int32_t)a.n;
-  const int32_t gbase = tid * RS_ITEMS;
-  int32_t* anc_s = reinterpret_cast<int32_t*>(sm.c_tile);
+  const int32_t gbase = tid * ITEMS;
+  int32_t* anc_s = cs.stage;
   if (tid < SMCB_NPARAM) cs.Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
   if (tid == 0) cs.st = a.stats[col];
   const float* Ps = cs.Ps;
@@ -55,11 +64,11 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
   int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
 
   // ---- the column comes on chip
-  float lw[RS_ITEMS], rw[RS_ITEMS];
+  float lw[ITEMS], rw[ITEMS];
   {
     const int t0 = a.t_host;
 #pragma unroll
-    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+    for (int v = 0; v < ITEMS / 4; ++v) {
       const float4 q = *reinterpret_cast<const float4*>(lwrow + gbase + 4 * v);
       lw[4 * v] = q.x; lw[4 * v + 1] = q.y; lw[4 * v + 2] = q.z; lw[4 * v + 3] = q.w;
       const float4 r = *reinterpret_cast<const float4*>(rwrow + gbase + 4 * v);
@@ -83,27 +92,32 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
     // ---- systematic resampling of the column (resample_fused_kernel with a single tile)
     if (resampled && st.resample) {
 #pragma unroll
-      for (int r = 0; r < FB_ROWS; ++r) *reinterpret_cast<int4*>(&sm.stage[(r * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-      if (tid == 0) sm.carry = -1;
+      for (int r = 0; r < ROWS; ++r) *reinterpret_cast<int4*>(&cs.stage[(r * NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+      if (tid == 0) cs.carry = -1;
       const float m = (ALG == SMCB_ALG_APF) ? st.m_rw : st.m_lw, iz = (ALG == SMCB_ALG_APF) ? st.inv_z_rw : st.inv_z_lw;
-      float w[RS_ITEMS];
+      float w[ITEMS];
       double tsum = 0.0;
+      const bool tlive = gbase < n;   // some of this thread's particles exist
 #pragma unroll
-      for (int j = 0; j < RS_ITEMS; ++j) {
-        float x = smcb_weight((ALG == SMCB_ALG_APF) ? rw[j] : lw[j], m, iz);
-        if (gbase + j >= n) x = 0.f;
-        const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);  // multiple of 2^-52: the column is benign
-        w[j] = (float)xd;
-        tsum += xd;
+      for (int j = 0; j < ITEMS; ++j) w[j] = 0.f;
+      if (tlive) {
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          float x = smcb_weight((ALG == SMCB_ALG_APF) ? rw[j] : lw[j], m, iz);
+          if (gbase + j >= n) x = 0.f;
+          const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);  // multiple of 2^-52: the column is benign
+          w[j] = (float)xd;
+          tsum += xd;
+        }
       }
       if (c.w_out) {
         float* dst = c.w_out + (int64_t)col * a.ld + gbase;
 #pragma unroll
-        for (int v = 0; v < RS_ITEMS / 4; ++v)
+        for (int v = 0; v < ITEMS / 4; ++v)
           reinterpret_cast<float4*>(dst)[v] = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
       }
       double tot;
-      const double S0 = rs_block_excl_scan_d(tsum, sm.core.dscratch, &tot);
+      const double S0 = rs_block_excl_scan_d<NT>(tsum, cs.dscratch, &tot);
       float u;
       if (c.u_in) u = c.u_in[col];
       else {
@@ -114,22 +128,23 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
       int32_t lo_thread = 0;
       if (tid) lo_thread = (gbase - 1 >= n - 1) ? n : xs_count_fast((float)S0, u, n, nd, nfd);
       auto mark = [&](int32_t wb, bool first) -> int32_t {
-        return rs_mark_pass<53, true, true>(w, S0, 0.0, nullptr, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, sm);
+        if (!tlive) return n;   // nothing but padding: every count is n, no marks
+        return rs_mark_pass<53, true, true, ITEMS, RS_TILE>(w, S0, 0.0, nullptr, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, cs);
       };
-      rs_emit_ancestors(sm, mark, 0, anc_s);   // n <= RS_TILE < FB_WIN: always a single window
+      rs_emit_ancestors<NT, ROWS>(cs, mark, 0, anc_s);   // n <= RS_TILE = the window: a single pass, ancestors replace the marks in place
       __syncthreads();
     }
 
-    // ---- the move itself (step_kernel's body on this thread's RS_ITEMS particles)
+    // ---- the move itself (step_kernel's body on this thread's ITEMS particles)
     StepAcc<D> mom; mom.init();
     StepAcc1 r2; r2.init();
     StepAcc1 r3; r3.init();
     float shift[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) shift[d] = st.shift[d];
-    float xnew[D][RS_ITEMS];
+    float xnew[D][ITEMS];
 #pragma unroll
-    for (int g = 0; g < RS_ITEMS / 4; ++g) {
+    for (int g = 0; g < ITEMS / 4; ++g) {
       const int32_t i0 = gbase + 4 * g;
       int anc[4] = {i0, i0 + 1, i0 + 2, i0 + 3};
       if (resampled) {
@@ -137,7 +152,15 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
         anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
       }
       const bool live = i0 < n, full = i0 + 4 <= n;
-      if (live && (resampled || ALG == SMCB_ALG_APF))   // sisr.py:32 / apf.py:18-23
+      if (!live) {  // padding only
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = 0.f;
+        }
+        continue;
+      }
+      if (resampled || ALG == SMCB_ALG_APF)   // sisr.py:32 / apf.py:18-23
         *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
       if (!full) {
 #pragma unroll
@@ -155,11 +178,7 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
         for (int d = 0; d < D; ++d) xa[d][q] = ck_xs[d * RS_TILE + anc[q]];
       }
       float z[D][4];
-      if (live) st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
-      else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) { z[d][0] = z[d][1] = z[d][2] = z[d][3] = 0.f; }
-      }
+      st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
       float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -195,11 +214,9 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) if (i0 + q >= n) { lwn[q] = -INFINITY; rwn[q] = -INFINITY; inc4[q] = -INFINITY; }
       }
-      if (live) {
-        mom.add4(lwn, xn, shift);
-        if (fold) r2.add4(rwn, one4);
-        if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
-      }
+      mom.add4(lwn, xn, shift);
+      if (fold) r2.add4(rwn, one4);
+      if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
     }
     SoftAcc<1 + 2 * D> A;
     SoftAcc<1> Q, R2, R3;
@@ -213,7 +230,7 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
       cs.st = stn;
     }
 #pragma unroll
-    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+    for (int v = 0; v < ITEMS / 4; ++v) {
 #pragma unroll
       for (int d = 0; d < D; ++d)
         *reinterpret_cast<float4*>(ck_xs + d * RS_TILE + gbase + 4 * v) =
@@ -227,7 +244,7 @@ __global__ void __launch_bounds__(RS_NT, 2) column_kernel(ColumnArgs c) {
     const int t1 = a.t_host + c.steps;
     const bool rw_valid = (ALG == SMCB_ALG_APF) && cs.st.fold_valid;
 #pragma unroll
-    for (int v = 0; v < RS_ITEMS / 4; ++v) {
+    for (int v = 0; v < ITEMS / 4; ++v) {
       *reinterpret_cast<float4*>(lwrow + gbase + 4 * v) = make_float4(lw[4 * v], lw[4 * v + 1], lw[4 * v + 2], lw[4 * v + 3]);
       if (rw_valid) *reinterpret_cast<float4*>(rwrow + gbase + 4 * v) = make_float4(rw[4 * v], rw[4 * v + 1], rw[4 * v + 2], rw[4 * v + 3]);
 #pragma unroll

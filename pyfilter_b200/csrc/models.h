@@ -42,6 +42,17 @@ enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 #define P_X0_LOC 21          // .. +2 (three dims)
 #define P_X0_SCALE 24        // .. +2
 
+// sin(v) for the drift of the sine diffusion: explicit two-constant reduction to [-pi, pi] (exact products through fma), then the SFU.
+// Absolute error <= 2^-20.9 ~ 5e-7 on the reduced argument (PTX sin.approx.ftz.f32) against ~27 instructions of sinf() with its slow
+// path; the drift is multiplied by dt, so the state moves by < 1e-7 - an ulp of x - and the parity tolerances (2e-6 on x_t) hold.
+// One function for every kernel: the APF recomputes g(x_anc) from the gathered state and needs identical bits at every call site.
+__device__ __forceinline__ float smcb_sin(float v) {
+  const float k = __fadd_rn(fmaf(v, 0.15915494309189535f, 12582912.f), -12582912.f);  // nearest integer to v / (2 pi)
+  float r = fmaf(k, -6.2831854820251465f, v);                                           // v - k * fl32(2 pi)
+  r = fmaf(k, 1.7484555314695172e-7f, r);                                               // ... - k * (2 pi - fl32(2 pi))
+  return __sinf(r);
+}
+
 __device__ __forceinline__ float smcb_normal_lp(float v, float loc, float inv2var, float lognorm) {
   float d = __fsub_rn(v, loc);
   return __fsub_rn(__fmul_rn(-__fmul_rn(d, d), inv2var), lognorm);
@@ -73,7 +84,7 @@ template <> struct Model<SMCB_MODEL_SINE_EM> {
   static constexpr int D = 1, OD = 1;
   static constexpr bool LINEAR_OBS = true;
   __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
-    loc[0] = __fadd_rn(x[0], __fmul_rn(sinf(__fsub_rn(x[0], P[0])), P[2]));
+    loc[0] = __fadd_rn(x[0], __fmul_rn(smcb_sin(__fsub_rn(x[0], P[0])), P[2]));
     scale = P[1];
   }
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {

@@ -86,7 +86,8 @@ struct OpMinU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint3
 #define RS_BENIGN_MIN_BITS 0x31000000u  // 2^-29
 
 // exclusive block scan of one double per thread (blockDim.x == RS_NT); *total = sum over the block
-__device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch /*>=8*/, double* total) {
+template <int NT = RS_NT>
+__device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch /*>= NT/32*/, double* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double inc = v;
 #pragma unroll
@@ -99,7 +100,7 @@ __device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch
   __syncthreads();
   double off = 0.0, tot = 0.0;
 #pragma unroll
-  for (int k = 0; k < RS_NT / 32; ++k) {
+  for (int k = 0; k < NT / 32; ++k) {
     const double s = scratch[k];
     off += (k < wid) ? s : 0.0;
     tot += s;
@@ -876,22 +877,22 @@ struct ExpandSmem {
 
 // Counts of this thread's particles; every particle with offspring marks its first slot inside the window [wb, wb + FB_WIN).
 // FAST: cumulative weights on the fly, c_j = fl32(S0 + sum_{i<=j} RN_q(w_i)); otherwise they are read from shared memory.
-template <int MB, bool FAST, bool BENIGN>
-__device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[RS_ITEMS], double S0, double M, const float* c_thread, int32_t lo,
+template <int MB, bool FAST, bool BENIGN, int ITEMS = RS_ITEMS, int WIN = FB_WIN, typename SM = ExpandSmem>
+__device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[ITEMS], double S0, double M, const float* c_thread, int32_t lo,
                                                 int32_t gbase, int32_t wb, bool first, float u, int32_t n, float nf, double nd,
-                                                double nfd, bool fast_ok, ExpandSmem& sm) {
+                                                double nfd, bool fast_ok, SM& sm) {
   double run = S0;
 #pragma unroll
-  for (int j = 0; j < RS_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     float c;
     if (FAST) {
       run = __dadd_rn(run, BENIGN ? (double)w[j] : rs_round_q<MB>(w[j], M));
       c = (float)run;
     } else c = c_thread[j];
     int32_t hi = BENIGN ? xs_count_fast(c, u, n, nd, nfd) : rs_count_any(c, u, n, nf, nd, nfd, fast_ok);
-    if (gbase + RS_ITEMS >= n) hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
+    if (gbase + ITEMS >= n) hi = (gbase + j >= n - 1) ? n : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
     const int32_t r = lo - wb;
-    if (hi > lo && (uint32_t)r < (uint32_t)FB_WIN) sm.stage[r] = gbase + j;
+    if (hi > lo && (uint32_t)r < (uint32_t)WIN) sm.stage[r] = gbase + j;
     if (!first && hi > lo && r < 0 && hi > wb) sm.carry = gbase + j;  // its slots began in an earlier window (one such particle at most)
     lo = max(lo, hi);
   }
@@ -900,37 +901,38 @@ __device__ __forceinline__ int32_t rs_mark_pass(const float (&w)[RS_ITEMS], doub
 
 // ---- ancestors of one tile from the marks: the tile owns the output slots [n_in, n_out) ----------------------------------------------
 // `mark(wb, first)` runs the mark pass for the window starting at slot wb and returns the thread's last count.
-template <typename Mark>
-__device__ __forceinline__ void rs_emit_ancestors(ExpandSmem& sm, Mark mark, int32_t n_in, int32_t* anc) {
+template <int NT = RS_NT, int ROWS = FB_ROWS, typename SM = ExpandSmem, typename Mark>
+__device__ __forceinline__ void rs_emit_ancestors(SM& sm, Mark mark, int32_t n_in, int32_t* anc) {
+  constexpr int WIN = NT / 32 * ROWS * 32 * 4;  // output slots per window (FB_WIN for the defaults)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int32_t wb0 = n_in & ~3;
   {
     const int32_t last = mark(wb0, true);
-    if (tid == RS_NT - 1) sm.n_out = last;
+    if (tid == NT - 1) sm.n_out = last;
   }
   __syncthreads();
   const int32_t n_out = sm.n_out;
 
   int32_t carry = -1;
-  for (int32_t wb = wb0; wb < n_out; wb += FB_WIN) {
+  for (int32_t wb = wb0; wb < n_out; wb += WIN) {
     if (wb != wb0) {  // rare: more than one window of offspring
       __syncthreads();
 #pragma unroll
-      for (int k = 0; k < FB_ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * RS_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
+      for (int k = 0; k < ROWS; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
       if (tid == 0) sm.carry = -1;
       __syncthreads();
       mark(wb, false);
       __syncthreads();
       carry = max(carry, sm.carry);
     }
-    const int32_t wlen = min(FB_WIN, n_out - wb);
-    // last mark at or before every slot; warp `wid` owns FB_ROWS rows of 32 int4, row k = int4 [(wid*FB_ROWS + k)*32, +32)
-    int4 m[FB_ROWS];
-    int32_t cin[FB_ROWS];
+    const int32_t wlen = min(WIN, n_out - wb);
+    // last mark at or before every slot; warp `wid` owns ROWS rows of 32 int4, row k = int4 [(wid*ROWS + k)*32, +32)
+    int4 m[ROWS];
+    int32_t cin[ROWS];
     int32_t wrun = -1;  // last mark seen by this warp so far
 #pragma unroll
-    for (int k = 0; k < FB_ROWS; ++k) {
-      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+    for (int k = 0; k < ROWS; ++k) {
+      const int i4 = (wid * ROWS + k) * 32 + lane;
       m[k] = *reinterpret_cast<const int4*>(&sm.stage[i4 * 4]);
       const int32_t v = max(max(m[k].x, m[k].y), max(m[k].z, m[k].w));
       const uint32_t bal = __ballot_sync(0xffffffffu, v >= 0);
@@ -945,15 +947,15 @@ __device__ __forceinline__ void rs_emit_ancestors(ExpandSmem& sm, Mark mark, int
     int32_t cw = carry;  // last mark before this warp's rows
     int32_t call = carry;
 #pragma unroll
-    for (int k = 0; k < RS_NT / 32; ++k) {
+    for (int k = 0; k < NT / 32; ++k) {
       const int32_t t = sm.wtot[k];
       if (k < wid) cw = max(cw, t);
       call = max(call, t);
     }
     carry = call;
 #pragma unroll
-    for (int k = 0; k < FB_ROWS; ++k) {
-      const int i4 = (wid * FB_ROWS + k) * 32 + lane;
+    for (int k = 0; k < ROWS; ++k) {
+      const int i4 = (wid * ROWS + k) * 32 + lane;
       const int32_t s0 = wb + i4 * 4;
       if (i4 * 4 < wlen) {
         int4 o;

@@ -474,17 +474,20 @@ static bool column_path_ok(const smcb_filter* f) {
   return true;
 }
 
-template <int MODEL, int PROP>
-static cudaError_t launch_column_alg(int alg, int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
-  cudaError_t e;
-  if (alg == SMCB_SISR) {
-    e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, SMCB_ALG_SISR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e == cudaSuccess) column_kernel<MODEL, PROP, SMCB_ALG_SISR><<<B, RS_NT, dyn, s>>>(c);
-  } else {
-    e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, SMCB_ALG_APF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    if (e == cudaSuccess) column_kernel<MODEL, PROP, SMCB_ALG_APF><<<B, RS_NT, dyn, s>>>(c);
-  }
+template <int MODEL, int PROP, int ALG, int NT, int MINB>
+static cudaError_t launch_column_nt(int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
+  cudaError_t e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, ALG, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e == cudaSuccess) column_kernel<MODEL, PROP, ALG, NT, MINB><<<B, NT, dyn, s>>>(c);
   return e;
+}
+template <int MODEL, int PROP>
+static cudaError_t launch_column_alg(int alg, int minb, int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
+  if (alg == SMCB_SISR) {
+    if (minb == 1) return launch_column_nt<MODEL, PROP, SMCB_ALG_SISR, 512, 1>(B, dyn, s, c);
+    return launch_column_nt<MODEL, PROP, SMCB_ALG_SISR, 512, 2>(B, dyn, s, c);
+  }
+  if (minb == 1) return launch_column_nt<MODEL, PROP, SMCB_ALG_APF, 512, 1>(B, dyn, s, c);
+  return launch_column_nt<MODEL, PROP, SMCB_ALG_APF, 512, 2>(B, dyn, s, c);
 }
 
 static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
@@ -507,12 +510,15 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   c.u_in = f->u_in; c.u_out = f->u_out; c.w_out = f->w_out; c.quantize = 1;
   const size_t dyn = sizeof(float) * (size_t)f->D * RS_TILE;
   const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
+  // 512 threads x 8 particles; fewer columns than SMs: one block per SM with twice the registers, otherwise two blocks per SM
+  int nt = (f->B <= 148) ? 1 : 2;
+  if (const char* v = getenv("SMCB_COLUMN_MINB")) nt = atoi(v) == 1 ? 1 : 2;   // diagnostics
   cudaError_t e = cudaSuccess;
   switch (f->cfg.model) {
-    case 0: e = prop ? launch_column_alg<0, 1>(alg, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, f->B, dyn, s, c); break;
-    case 1: e = prop ? launch_column_alg<1, 1>(alg, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, f->B, dyn, s, c); break;
-    case 2: e = launch_column_alg<2, 0>(alg, f->B, dyn, s, c); break;
-    case 3: e = launch_column_alg<3, 0>(alg, f->B, dyn, s, c); break;
+    case 0: e = prop ? launch_column_alg<0, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, nt, f->B, dyn, s, c); break;
+    case 1: e = prop ? launch_column_alg<1, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, nt, f->B, dyn, s, c); break;
+    case 2: e = launch_column_alg<2, 0>(alg, nt, f->B, dyn, s, c); break;
+    case 3: e = launch_column_alg<3, 0>(alg, nt, f->B, dyn, s, c); break;
   }
   if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
   f->launches++;

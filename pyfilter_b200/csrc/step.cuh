@@ -125,14 +125,14 @@ __device__ __forceinline__ void softacc_block_reduce(SoftAcc<K>& a, SoftAcc<K>* 
 }
 
 // the four accumulators of the step in one pass (three barriers instead of twelve); results valid in thread 0
-template <int K>
+template <int K, int NT = ST_NT>
 struct Fin4Scratch {
-  float m[4][ST_NT / 32];
-  float a[K][ST_NT / 32];
-  float q[ST_NT / 32], r2[ST_NT / 32], r3[ST_NT / 32];
+  float m[4][NT / 32];
+  float a[K][NT / 32];
+  float q[NT / 32], r2[NT / 32], r3[NT / 32];
 };
-template <int K>
-__device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>& Q, SoftAcc<1>& R2, SoftAcc<1>& R3, Fin4Scratch<K>& sc) {
+template <int K, int NT = ST_NT>
+__device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>& Q, SoftAcc<1>& R2, SoftAcc<1>& R3, Fin4Scratch<K, NT>& sc) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float mb[4] = {A.m, Q.m, R2.m, R3.m};
 #pragma unroll
@@ -149,7 +149,7 @@ __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>&
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
 #pragma unroll
-    for (int w = 0; w < ST_NT / 32; ++w) mb[i] = fmaxf(mb[i], sc.m[i][w]);
+    for (int w = 0; w < NT / 32; ++w) mb[i] = fmaxf(mb[i], sc.m[i][w]);
   }
   const float sA = (A.m == -INFINITY) ? 0.f : __expf(A.m - mb[0]);
   const float sQ = (Q.m == -INFINITY) ? 0.f : __expf(Q.m - mb[1]);
@@ -171,12 +171,12 @@ __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>&
     for (int k = 0; k < K; ++k) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < ST_NT / 32; ++w) t += sc.a[k][w];
+      for (int w = 0; w < NT / 32; ++w) t += sc.a[k][w];
       A.s[k] = t;
     }
     float tq = 0.f, t2 = 0.f, t3 = 0.f;
 #pragma unroll
-    for (int w = 0; w < ST_NT / 32; ++w) { tq += sc.q[w]; t2 += sc.r2[w]; t3 += sc.r3[w]; }
+    for (int w = 0; w < NT / 32; ++w) { tq += sc.q[w]; t2 += sc.r2[w]; t3 += sc.r3[w]; }
     Q.s[0] = tq; R2.s[0] = t2; R3.s[0] = t3;
   }
 }

@@ -34,13 +34,22 @@ def one(T, cfg):
     import pyfilter_b200 as pf
     from pyfilter_b200 import timeseries as ts
     from pyfilter_b200.filters.particle import APF, SISR, proposals
-    model, cls, prop, res, N = {"c3": ("sv_ar1", APF, proposals.Bootstrap, pf.resampling.systematic, 4_000_000),
+    model, cls, prop, res, N, *batch = {"c3": ("sv_ar1", APF, proposals.Bootstrap, pf.resampling.systematic, 4_000_000),
+                                "c1": ("lg_ar1", SISR, proposals.Bootstrap, pf.resampling.systematic, 1_000),
+                                "c5s": ("sine_em", APF, proposals.Bootstrap, pf.resampling.systematic, 4096, 128),
+                                "c5": ("sine_em", APF, proposals.Bootstrap, pf.resampling.systematic, 4096, 1024),
                                 "c2": ("sine_em", APF, proposals.LinearGaussianObservations, pf.resampling.systematic, 1_000_000),
                                 "c4": ("lorenz63_em", SISR, proposals.Bootstrap, pf.resampling.multinomial, 2_000_000),
                                 "c4s": ("lorenz63_em", SISR, proposals.Bootstrap, pf.resampling.systematic, 2_000_000)}[cfg]
     g = torch.Generator().manual_seed(123)
     _, y = ts.build(model).sample_states(T + 24, generator=g)
-    f = cls(ts.build(model), N, proposal=prop(), resampling=res, seed=7)
+    kw = {}
+    if batch:
+        torch.manual_seed(123)
+        kw = dict(gamma=torch.randn(batch[0]), sigma=torch.exp(0.5 * torch.randn(batch[0])))
+    f = cls(ts.build(model, **kw), N, proposal=prop(), resampling=res, seed=7)
+    if batch:
+        f.set_batch_shape(torch.Size(batch))
     e = f._get_engine(T + 30)
     yd = y.float().reshape(T + 24, -1).cuda().contiguous()
     e.initialize(); e.set_observations(yd, 0); e.run(20); torch.cuda.synchronize()
