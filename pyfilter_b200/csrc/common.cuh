@@ -84,6 +84,12 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// warp maximum in ONE instruction (sm_100a: redux.sync.max.f32 -> CREDUX.MAX.F32); inputs are never NaN here
+__device__ __forceinline__ float warp_redux_max(float v) {
+  float r;
+  asm volatile("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(r) : "f"(v));
+  return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

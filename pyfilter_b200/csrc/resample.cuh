@@ -99,11 +99,17 @@ __device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch
   if (lane == 31) scratch[wid] = inc;
   __syncthreads();
   double off = 0.0, tot = 0.0;
+  if (NT > 256) {  // one lane per warp: cost independent of the block size (exact in any order for the rounding-free weights)
+    const double s = (lane < NT / 32) ? scratch[lane] : 0.0;
+    tot = warp_sum(s);
+    off = warp_sum((lane < wid) ? s : 0.0);
+  } else {
 #pragma unroll
-  for (int k = 0; k < NT / 32; ++k) {
-    const double s = scratch[k];
-    off += (k < wid) ? s : 0.0;
-    tot += s;
+    for (int k = 0; k < NT / 32; ++k) {
+      const double s = scratch[k];
+      off += (k < wid) ? s : 0.0;
+      tot += s;
+    }
   }
   *total = tot;
   return off + (inc - v);
@@ -944,15 +950,10 @@ __device__ __forceinline__ void rs_emit_ancestors(SM& sm, Mark mark, int32_t n_i
     }
     if (lane == 0) sm.wtot[wid] = wrun;
     __syncthreads();
-    int32_t cw = carry;  // last mark before this warp's rows
-    int32_t call = carry;
-#pragma unroll
-    for (int k = 0; k < NT / 32; ++k) {
-      const int32_t t = sm.wtot[k];
-      if (k < wid) cw = max(cw, t);
-      call = max(call, t);
-    }
-    carry = call;
+    // last mark before this warp's rows / in the whole window: one lane per warp, integer redux
+    const int32_t wt = (lane < NT / 32) ? sm.wtot[lane] : -1;
+    const int32_t cw = max(carry, __reduce_max_sync(0xffffffffu, (lane < wid) ? wt : -1));
+    carry = max(carry, __reduce_max_sync(0xffffffffu, wt));
 #pragma unroll
     for (int k = 0; k < ROWS; ++k) {
       const int i4 = (wid * ROWS + k) * 32 + lane;

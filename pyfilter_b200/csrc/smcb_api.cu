@@ -483,9 +483,11 @@ static cudaError_t launch_column_nt(int B, size_t dyn, cudaStream_t s, const Col
 template <int MODEL, int PROP>
 static cudaError_t launch_column_alg(int alg, int minb, int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
   if (alg == SMCB_SISR) {
+    if (minb == 0) return launch_column_nt<MODEL, PROP, SMCB_ALG_SISR, 1024, 1>(B, dyn, s, c);
     if (minb == 1) return launch_column_nt<MODEL, PROP, SMCB_ALG_SISR, 512, 1>(B, dyn, s, c);
     return launch_column_nt<MODEL, PROP, SMCB_ALG_SISR, 512, 2>(B, dyn, s, c);
   }
+  if (minb == 0) return launch_column_nt<MODEL, PROP, SMCB_ALG_APF, 1024, 1>(B, dyn, s, c);
   if (minb == 1) return launch_column_nt<MODEL, PROP, SMCB_ALG_APF, 512, 1>(B, dyn, s, c);
   return launch_column_nt<MODEL, PROP, SMCB_ALG_APF, 512, 2>(B, dyn, s, c);
 }
@@ -512,7 +514,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
   // 512 threads x 8 particles; fewer columns than SMs: one block per SM with twice the registers, otherwise two blocks per SM
   int nt = (f->B <= 148) ? 1 : 2;
-  if (const char* v = getenv("SMCB_COLUMN_MINB")) nt = atoi(v) == 1 ? 1 : 2;   // diagnostics
+  if (const char* v = getenv("SMCB_COLUMN_MINB")) nt = atoi(v);   // diagnostics: 0 = 1024 threads x 4, 1 = 512 x 8 one block per SM, 2 = 512 x 8 two per SM
   cudaError_t e = cudaSuccess;
   switch (f->cfg.model) {
     case 0: e = prop ? launch_column_alg<0, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, nt, f->B, dyn, s, c); break;

@@ -115,12 +115,10 @@ __device__ __forceinline__ void softacc_block_reduce(SoftAcc<K>& a, SoftAcc<K>* 
     for (int k = 0; k < K; ++k) scratch[wid].s[k] = a.s[k];
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (wid == 0) {  // same fold as softacc4_block_reduce (one lane per warp, butterfly): the pre-weight pass and the folded look-ahead
+                   // of the step kernel must produce the same normaliser bit for bit
 #pragma unroll
-    for (int w = 1; w < ST_NT / 32; ++w) {
-#pragma unroll
-      for (int k = 0; k < K; ++k) a.s[k] += scratch[w].s[k];
-    }
+    for (int k = 0; k < K; ++k) a.s[k] = warp_sum((lane < ST_NT / 32) ? scratch[lane].s[k] : 0.f);
   }
 }
 
@@ -133,13 +131,13 @@ struct Fin4Scratch {
 };
 template <int K, int NT = ST_NT>
 __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>& Q, SoftAcc<1>& R2, SoftAcc<1>& R3, Fin4Scratch<K, NT>& sc) {
+  // Cost per thread is independent of the block size: the NT/32 per-warp values are folded by every warp with one lane per value
+  // (redux for the maxima) instead of a loop over the warps in every thread.
+  static_assert(NT <= 1024, "one lane per warp");
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float mb[4] = {A.m, Q.m, R2.m, R3.m};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int o = 16; o; o >>= 1) mb[i] = fmaxf(mb[i], __shfl_xor_sync(0xffffffffu, mb[i], o));
-  }
+  for (int i = 0; i < 4; ++i) mb[i] = warp_redux_max(mb[i]);
   __syncthreads();
   if (lane == 0) {
 #pragma unroll
@@ -147,10 +145,7 @@ __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>&
   }
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) mb[i] = fmaxf(mb[i], sc.m[i][w]);
-  }
+  for (int i = 0; i < 4; ++i) mb[i] = warp_redux_max((lane < NT / 32) ? sc.m[i][lane] : -INFINITY);
   const float sA = (A.m == -INFINITY) ? 0.f : __expf(A.m - mb[0]);
   const float sQ = (Q.m == -INFINITY) ? 0.f : __expf(Q.m - mb[1]);
   const float s2 = (R2.m == -INFINITY) ? 0.f : __expf(R2.m - mb[2]);
@@ -166,18 +161,13 @@ __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>&
   }
   __syncthreads();
   A.m = mb[0]; Q.m = mb[1]; R2.m = mb[2]; R3.m = mb[3];
-  if (threadIdx.x == 0) {
+  if (wid == 0) {  // the warp of thread 0 folds the per-warp sums, one lane per warp
+    const bool have = lane < NT / 32;
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < NT / 32; ++w) t += sc.a[k][w];
-      A.s[k] = t;
-    }
-    float tq = 0.f, t2 = 0.f, t3 = 0.f;
-#pragma unroll
-    for (int w = 0; w < NT / 32; ++w) { tq += sc.q[w]; t2 += sc.r2[w]; t3 += sc.r3[w]; }
-    Q.s[0] = tq; R2.s[0] = t2; R3.s[0] = t3;
+    for (int k = 0; k < K; ++k) A.s[k] = warp_sum(have ? sc.a[k][lane] : 0.f);
+    Q.s[0] = warp_sum(have ? sc.q[lane] : 0.f);
+    R2.s[0] = warp_sum(have ? sc.r2[lane] : 0.f);
+    R3.s[0] = warp_sum(have ? sc.r3[lane] : 0.f);
   }
 }
 

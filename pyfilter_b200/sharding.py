@@ -36,6 +36,38 @@ def gather_loglikelihood(ll_local: torch.Tensor, batch: int, group=None) -> torc
     return torch.cat([o[: h - l] for o, (l, h) in zip(out, sizes)])
 
 
+class LogLikelihoodGather:
+    """The per-move exchange of the theta-sharded loop without per-call allocations: every rank contributes ``width`` floats
+    (its shard padded to the widest one) to ONE preallocated ``(world * width,)`` buffer through ``all_gather_into_tensor``
+    (a single NCCL kernel, no list of outputs, no concatenation); ``__call__`` returns a view of that buffer in column order when
+    the shards are equal, else the compacted copy.  Same result as :func:`gather_loglikelihood`."""
+
+    def __init__(self, batch: int, device, dtype=torch.float32, group=None):
+        import torch.distributed as dist
+
+        self.group, self.batch = group, batch
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.sizes = [column_shard(batch, r, self.world) for r in range(self.world)]
+        self.width = max(hi - lo for lo, hi in self.sizes)
+        self.even = all(hi - lo == self.width for lo, hi in self.sizes)
+        self.send = torch.zeros(self.width, dtype=dtype, device=device)
+        self.recv = torch.empty(self.world * self.width, dtype=dtype, device=device)
+
+    def __call__(self, ll_local: torch.Tensor) -> torch.Tensor:
+        import torch.distributed as dist
+
+        lo, hi = self.sizes[self.rank]
+        if ll_local.numel() != hi - lo:
+            raise ValueError("local vector does not match this rank's shard")
+        src = ll_local if (self.even and ll_local.is_contiguous()) else self.send
+        if src is self.send:
+            self.send[: hi - lo].copy_(ll_local)
+        dist.all_gather_into_tensor(self.recv, src, group=self.group)
+        if self.even:
+            return self.recv
+        return torch.cat([self.recv[r * self.width: r * self.width + (h - l)] for r, (l, h) in enumerate(self.sizes)])
+
+
 def theta_ess(ll_total: torch.Tensor) -> torch.Tensor:
     """ESS of the theta-particles from their accumulated log-likelihoods (reference utils.py:8-20 on the theta weights)."""
     w = torch.softmax(ll_total - ll_total.max(), dim=0)

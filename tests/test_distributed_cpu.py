@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from pyfilter_b200.sharding import column_shard, gather_loglikelihood, theta_ess
+from pyfilter_b200.sharding import LogLikelihoodGather, column_shard, gather_loglikelihood, theta_ess
 
 
 def test_column_shard_partitions_every_batch():
@@ -30,6 +30,9 @@ def _worker(rank, world, port, batch, q):
         lo, hi = column_shard(batch, rank, world)
         got = gather_loglikelihood(full[lo:hi].clone(), batch)
         ok = torch.equal(got, full) and abs(float(theta_ess(got)) - float(theta_ess(full))) < 1e-6
+        gather = LogLikelihoodGather(batch, "cpu")   # the preallocated single-buffer form bench.py uses per move
+        for rep in range(2):
+            ok = ok and torch.equal(gather(full[lo:hi].clone() + rep), full + rep)
         # timing reduction used by bench.py: max over ranks
         tmax = torch.tensor([float(rank + 1)])
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
