@@ -143,81 +143,92 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
 #pragma unroll
     for (int d = 0; d < D; ++d) shift[d] = st.shift[d];
     float xnew[D][ITEMS];
+    // the steady state (observed, resampled, look-ahead folded, plain Philox noise) runs a copy of the loop with those facts as
+    // compile-time constants (same reason as in step_kernel: the uniform per-particle branches otherwise become convergence regions)
+    const bool observed_rt = observed, fold_rt = fold, resampled_rt = resampled;
+    auto groups = [&](auto fast_tag) {
+      constexpr bool FAST = decltype(fast_tag)::value;
+      const bool observed = FAST ? true : observed_rt;
+      const bool fold = FAST ? (ALG == SMCB_ALG_APF) : fold_rt;
+      const bool resampled = FAST ? true : resampled_rt;
 #pragma unroll
-    for (int g = 0; g < ITEMS / 4; ++g) {
-      const int32_t i0 = gbase + 4 * g;
-      int anc[4] = {i0, i0 + 1, i0 + 2, i0 + 3};
-      if (resampled) {
-        const int4 q = *reinterpret_cast<const int4*>(anc_s + i0);
-        anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
-      }
-      const bool live = i0 < n, full = i0 + 4 <= n;
-      if (!live) {  // padding only
+      for (int g = 0; g < ITEMS / 4; ++g) {
+        const int32_t i0 = gbase + 4 * g;
+        int anc[4] = {i0, i0 + 1, i0 + 2, i0 + 3};
+        if (resampled) {
+          const int4 q = *reinterpret_cast<const int4*>(anc_s + i0);
+          anc[0] = q.x; anc[1] = q.y; anc[2] = q.z; anc[3] = q.w;
+        }
+        const bool live = i0 < n, full = i0 + 4 <= n;
+        if (!live) {  // padding only
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = 0.f;
+          }
+          continue;
+        }
+        if (resampled || ALG == SMCB_ALG_APF)   // sisr.py:32 / apf.py:18-23
+          *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+        if (!full) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (i0 + q >= n) anc[q] = 0;
+        }
+        float lwp[4] = {0.f, 0.f, 0.f, 0.f};
+        if (!resampled) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) lwp[q] = lw[4 * g + q];
+        }
+        float xa[D][4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
 #pragma unroll
-          for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = 0.f;
+          for (int d = 0; d < D; ++d) xa[d][q] = ck_xs[d * RS_TILE + anc[q]];
         }
-        continue;
+        float z[D][4];
+        st_noise4<D, FAST>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
+        float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float xk[D], zk[D], xo[D], inc, g_anc;
+#pragma unroll
+          for (int d = 0; d < D; ++d) { xk[d] = xa[d][q]; zk[d] = z[d][q]; }
+          Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+#pragma unroll
+          for (int d = 0; d < D; ++d) xn[d][q] = xo[d];
+          float lwv;
+          if (!observed) lwv = lwp[q];
+          else if (ALG == SMCB_ALG_APF) lwv = __fsub_rn(inc, g_anc);   // apf.py:43
+          else lwv = __fadd_rn(inc, lwp[q]);                           // sisr.py:52
+          lwn[q] = lwv;
+          inc4[q] = inc;
+          wprev[q] = 0.f;
+          if (ALG == SMCB_ALG_SISR) wprev[q] = resampled ? inv_n : smcb_weight(lwp[q], st.m_lw, st.inv_z_lw);
+          gnx[q] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          lwn[q] = st_sanitize(lwn[q]);                                // utils.py:57
+          rwn[q] = fold ? st_sanitize(__fadd_rn(gnx[q], lwn[q])) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          lw[4 * g + q] = lwn[q];
+          if (fold) rw[4 * g + q] = rwn[q];
+#pragma unroll
+          for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = xn[d][q];
+        }
+        if (!full) {  // padding contributes nothing
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (i0 + q >= n) { lwn[q] = -INFINITY; rwn[q] = -INFINITY; inc4[q] = -INFINITY; }
+        }
+        mom.add4(lwn, xn, shift);
+        if (fold) r2.add4(rwn, one4);
+        if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
       }
-      if (resampled || ALG == SMCB_ALG_APF)   // sisr.py:32 / apf.py:18-23
-        *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
-      if (!full) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q >= n) anc[q] = 0;
-      }
-      float lwp[4] = {0.f, 0.f, 0.f, 0.f};
-      if (!resampled) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) lwp[q] = lw[4 * g + q];
-      }
-      float xa[D][4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) xa[d][q] = ck_xs[d * RS_TILE + anc[q]];
-      }
-      float z[D][4];
-      st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
-      float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float xk[D], zk[D], xo[D], inc, g_anc;
-#pragma unroll
-        for (int d = 0; d < D; ++d) { xk[d] = xa[d][q]; zk[d] = z[d][q]; }
-        Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) xn[d][q] = xo[d];
-        float lwv;
-        if (!observed) lwv = lwp[q];
-        else if (ALG == SMCB_ALG_APF) lwv = __fsub_rn(inc, g_anc);   // apf.py:43
-        else lwv = __fadd_rn(inc, lwp[q]);                           // sisr.py:52
-        lwn[q] = lwv;
-        inc4[q] = inc;
-        wprev[q] = 0.f;
-        if (ALG == SMCB_ALG_SISR) wprev[q] = resampled ? inv_n : smcb_weight(lwp[q], st.m_lw, st.inv_z_lw);
-        gnx[q] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        lwn[q] = st_sanitize(lwn[q]);                                // utils.py:57
-        rwn[q] = fold ? st_sanitize(__fadd_rn(gnx[q], lwn[q])) : 0.f;
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        lw[4 * g + q] = lwn[q];
-        if (fold) rw[4 * g + q] = rwn[q];
-#pragma unroll
-        for (int d = 0; d < D; ++d) xnew[d][4 * g + q] = xn[d][q];
-      }
-      if (!full) {  // padding contributes nothing
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (i0 + q >= n) { lwn[q] = -INFINITY; rwn[q] = -INFINITY; inc4[q] = -INFINITY; }
-      }
-      mom.add4(lwn, xn, shift);
-      if (fold) r2.add4(rwn, one4);
-      if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
-    }
+    };
+    if (observed_rt && resampled_rt && (ALG != SMCB_ALG_APF || fold_rt) && !a.eps_in && !a.eps_out) groups(std::true_type{});
+    else groups(std::false_type{});
     SoftAcc<1 + 2 * D> A;
     SoftAcc<1> Q, R2, R3;
     mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);

@@ -26,6 +26,22 @@ XS_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
   Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
 }
 
+// the same generator with the ten round keys precomputed (kernel arguments: they become constant-bank operands of the xor instead of
+// twenty uniform additions per call)
+XS_HD void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t* keys /*20*/) {
+  for (int r = 0; r < 10; ++r) { keys[2 * r] = k0; keys[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+XS_HD Philox4 philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t* keys) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = smcb_mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = smcb_mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    uint32_t n0 = hi1 ^ c1 ^ keys[2 * r], n2 = hi0 ^ c3 ^ keys[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  Philox4 o; o.x = c0; o.y = c1; o.z = c2; o.w = c3; return o;
+}
+
 // purposes (counter word 3)
 #define SMCB_RNG_TRANSITION 0u   // + state dimension
 #define SMCB_RNG_INIT 8u         // + state dimension

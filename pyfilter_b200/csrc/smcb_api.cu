@@ -205,7 +205,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   {
     const int64_t chunk = ST_NT * ST_VEC;
     const int64_t nchunks = (f->n + chunk - 1) / chunk;
-    int64_t cap = (148 * 4) / f->B;  // one resident wave of step-kernel blocks (4 per SM)
+    int64_t cap = (148 * SMCB_ST_MINB) / f->B;  // one resident wave of step-kernel blocks
     if (cap < 1) cap = 1;
     f->iters = (int)((nchunks + cap - 1) / cap);
     f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);
@@ -284,6 +284,7 @@ static StepArgs make_args(smcb_filter* f) {
   a.P = f->P_dev; a.xbuf[0] = f->xbuf[0]; a.xbuf[1] = f->xbuf[1]; a.lw = f->lw; a.rw = f->rw;
   a.anc = f->anc; a.prev_inds = f->prev_inds; a.stats = f->stats; a.partials = f->partials; a.ctrl = f->ctrl; a.col_ticket = f->col_ticket;
   a.eps_in = f->eps_in; a.eps_out = f->eps_out; a.seed = f->cfg.seed;
+  philox_round_keys((uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), a.pkeys);
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
   a.dbg = f->dbg;

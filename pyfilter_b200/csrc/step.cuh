@@ -9,11 +9,15 @@
 // Layout: state is SoA  x[dim][column][particle]  (pitch ld), weights  lw[column][particle]; one thread owns 4 consecutive
 // particles of one column so every global access except the ancestor gather is a coalesced 128-bit transaction.
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "philox.h"
 
 #define ST_NT 256
 #define ST_VEC 4
+#ifndef SMCB_ST_MINB
+#define SMCB_ST_MINB 4   // resident step-kernel blocks per SM the register budget is sized for (one wave = 148 * SMCB_ST_MINB blocks)
+#endif
 
 struct StepArgs {
   int64_t n, ld;
@@ -45,6 +49,7 @@ struct StepArgs {
   int32_t t_host;                    // == ctrl->t when the kernel runs
   const float* y_t;                  // observation of this move (NULL: none)
   const float* y_next;               // observation of the next move (NULL: unknown -> no folded look-ahead)
+  uint32_t pkeys[20];                // Philox round keys of `seed` (philox_round_keys)
 };
 __device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
@@ -275,18 +280,18 @@ __device__ __forceinline__ bool st_load_obs(const float* p, float* y) {  // fals
   return !all_nan;
 }
 
-template <int D>
+template <int D, bool PLAIN = false>  // PLAIN: the caller knows that no draws are injected or dumped
 __device__ __forceinline__ void st_noise4(const StepArgs& a, int col, int64_t i0, int t, uint32_t purpose, float (&z)[D][4]) {
 #pragma unroll
   for (int d = 0; d < D; ++d) {
-    if (a.eps_in) {
+    if (!PLAIN && a.eps_in) {
       const float4 q = *reinterpret_cast<const float4*>(a.eps_in + ((int64_t)d * a.B + col) * a.ld + i0);
       z[d][0] = q.x; z[d][1] = q.y; z[d][2] = q.z; z[d][3] = q.w;
     } else {
-      Philox4 r = philox4x32_10((uint32_t)(i0 >> 2), (uint32_t)col, (uint32_t)t, purpose + d, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      Philox4 r = philox4x32_10_keys((uint32_t)(i0 >> 2), (uint32_t)col, (uint32_t)t, purpose + d, a.pkeys);
       smcb_normal4(r, z[d]);
     }
-    if (a.eps_out)
+    if (!PLAIN && a.eps_out)
       *reinterpret_cast<float4*>(a.eps_out + ((int64_t)d * a.B + col) * a.ld + i0) = make_float4(z[d][0], z[d][1], z[d][2], z[d][3]);
   }
 }
@@ -637,7 +642,7 @@ struct StepAcc1 {
 };
 
 template <int MODEL, int PROP, int ALG>
-__global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
+__global__ void __launch_bounds__(ST_NT, SMCB_ST_MINB) step_kernel(StepArgs a) {
   typedef Model<MODEL> M;
   constexpr int D = M::D, OD = M::OD;
   __shared__ float Ps[SMCB_NPARAM];
@@ -675,94 +680,110 @@ __global__ void __launch_bounds__(ST_NT, 4) step_kernel(StepArgs a) {
   int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
   float* lwrow = a.lw + (int64_t)col * a.ld;
   float* rwrow = a.rw + (int64_t)col * a.ld;
+  // keep the row pointers in registers: re-deriving them from (column, pitch, buffer index) inside the loop costs ~5 instructions per access
+#pragma unroll
+  for (int d = 0; d < D; ++d) { asm volatile("" : "+l"(xprev[d])); asm volatile("" : "+l"(xnext[d])); }
+  asm volatile("" : "+l"(ancrow)); asm volatile("" : "+l"(pirow)); asm volatile("" : "+l"(lwrow)); asm volatile("" : "+l"(rwrow));
 
   StepAcc<D> mom; mom.init();
   StepAcc1 r2; r2.init();   // APF: folded resampling weights
   StepAcc1 r3; r3.init();   // SISR: likelihood increment
 
   const int32_t stride = a.blocks_per_col * (ST_NT * ST_VEC);
-  int32_t i0 = (blockIdx.x * ST_NT + tid) * ST_VEC;
-  int4 ancq = make_int4(i0, i0 + 1, i0 + 2, i0 + 3);
-  if (resampled && i0 < n) ancq = *reinterpret_cast<const int4*>(ancrow + i0);
-  for (int it = 0; it < a.iters; ++it, i0 += stride) {
-    if (i0 >= n) break;
-    const bool full = i0 + 4 <= n;
-    int anc[4] = {ancq.x, ancq.y, ancq.z, ancq.w};
-    {  // fetch the next group's ancestors while this one is processed
-      const int32_t inext = i0 + stride;
-      ancq = make_int4(inext, inext + 1, inext + 2, inext + 3);
-      if (resampled && it + 1 < a.iters && inext < n) ancq = *reinterpret_cast<const int4*>(ancrow + inext);
-    }
-    if (resampled) {
-      *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
-      if (!full) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) if (i0 + k >= n) anc[k] = 0;
+  const int32_t ilast = (int32_t)a.ld - 4;  // last group of the padded row
+  // The steady state (observed move, resampled, look-ahead folded, no injected or dumped noise) gets its own copy of the loop with
+  // those facts as compile-time constants: the per-particle `if (observed)` / `fold ? .. : ..` are warp-uniform but the compiler
+  // cannot know it and wraps each in a convergence region.
+  const bool observed_rt = observed, fold_rt = fold, resampled_rt = resampled;
+  auto run_loop = [&](auto fast_tag) {
+    constexpr bool FAST = decltype(fast_tag)::value;
+    const bool observed = FAST ? true : observed_rt;
+    const bool fold = FAST ? (ALG == SMCB_ALG_APF) : fold_rt;
+    const bool resampled = FAST ? true : resampled_rt;
+    int32_t i0 = (blockIdx.x * ST_NT + tid) * ST_VEC;
+    int4 ancq = make_int4(i0, i0 + 1, i0 + 2, i0 + 3);
+    if (resampled && i0 < n) ancq = *reinterpret_cast<const int4*>(ancrow + i0);
+    for (int it = 0; it < a.iters; ++it, i0 += stride) {
+      if (i0 >= n) break;
+      const bool full = i0 + 4 <= n;
+      int anc[4] = {i0, i0 + 1, i0 + 2, i0 + 3};
+      if (resampled) {  // fetch the next group's ancestors while this one is processed: clamped into the padded row, no branch per lane
+        anc[0] = ancq.x; anc[1] = ancq.y; anc[2] = ancq.z; anc[3] = ancq.w;
+        ancq = *reinterpret_cast<const int4*>(ancrow + min(i0 + stride, ilast));
       }
-    } else if (ALG == SMCB_ALG_APF) {
-      *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);  // apf.py:18-23 arange
-    }
-    float lwp[4] = {0.f, 0.f, 0.f, 0.f};
-    if (!resampled) {  // weights carry over (sisr.py:52 without the reset of :34; particle/state.py:42)
-      const float4 q = *reinterpret_cast<const float4*>(lwrow + i0);
-      lwp[0] = q.x; lwp[1] = q.y; lwp[2] = q.z; lwp[3] = q.w;
-    }
-    float xa[D][4];
+      if (resampled) {
+        *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);
+        if (!full) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+          for (int k = 0; k < 4; ++k) if (i0 + k >= n) anc[k] = 0;
+        }
+      } else if (ALG == SMCB_ALG_APF) {
+        *reinterpret_cast<int4*>(pirow + i0) = make_int4(anc[0], anc[1], anc[2], anc[3]);  // apf.py:18-23 arange
+      }
+      float lwp[4] = {0.f, 0.f, 0.f, 0.f};
+      if (!resampled) {  // weights carry over (sisr.py:52 without the reset of :34; particle/state.py:42)
+        const float4 q = *reinterpret_cast<const float4*>(lwrow + i0);
+        lwp[0] = q.x; lwp[1] = q.y; lwp[2] = q.z; lwp[3] = q.w;
+      }
+      float xa[D][4];
 #pragma unroll
-      for (int d = 0; d < D; ++d) xa[d][k] = __ldg(xprev[d] + anc[k]);
-    }
-    float z[D][4];
-    st_noise4<D>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) xa[d][k] = __ldg(xprev[d] + anc[k]);
+      }
+      float z[D][4];
+      st_noise4<D, FAST>(a, col, i0, t, SMCB_RNG_TRANSITION, z);
 
-    float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
+      float xn[D][4], lwn[4], rwn[4], gnx[4], inc4[4], wprev[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      float xk[D], zk[D], xo[D], inc, g_anc;
+      for (int k = 0; k < 4; ++k) {
+        float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
-      for (int d = 0; d < D; ++d) { xk[d] = xa[d][k]; zk[d] = z[d][k]; }
-      Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+        for (int d = 0; d < D; ++d) { xk[d] = xa[d][k]; zk[d] = z[d][k]; }
+        Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
-      for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
-      float lw;
-      if (!observed) lw = lwp[k];
-      else if (ALG == SMCB_ALG_APF) lw = __fsub_rn(inc, g_anc);   // apf.py:43
-      else lw = __fadd_rn(inc, lwp[k]);                           // sisr.py:52
-      lwn[k] = lw;
-      inc4[k] = inc;
-      if (ALG == SMCB_ALG_SISR) wprev[k] = resampled ? inv_n : smcb_weight(lwp[k], st.m_lw, st.inv_z_lw);
-      gnx[k] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
-    }
-    {  // nan_to_num (utils.py:57) only when something in the group is not finite: a sum of four finite floats can overflow at worst
-      const float chk = fabsf(lwn[0]) + fabsf(lwn[1]) + fabsf(lwn[2]) + fabsf(lwn[3]);
-      if (!(chk < INFINITY)) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) lwn[k] = st_sanitize(lwn[k]);
+        for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
+        float lw;
+        if (!observed) lw = lwp[k];
+        else if (ALG == SMCB_ALG_APF) lw = __fsub_rn(inc, g_anc);   // apf.py:43
+        else lw = __fadd_rn(inc, lwp[k]);                           // sisr.py:52
+        lwn[k] = lw;
+        inc4[k] = inc;
+        if (ALG == SMCB_ALG_SISR) wprev[k] = resampled ? inv_n : smcb_weight(lwp[k], st.m_lw, st.inv_z_lw);
+        gnx[k] = fold ? Proposal<MODEL, PROP>::pre_weight(yn, xo, Ps) : 0.f;
       }
+      {  // nan_to_num (utils.py:57) only when something in the group is not finite: a sum of four finite floats can overflow at worst
+        const float chk = fabsf(lwn[0]) + fabsf(lwn[1]) + fabsf(lwn[2]) + fabsf(lwn[3]);
+        if (!(chk < INFINITY)) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) rwn[k] = __fadd_rn(gnx[k], lwn[k]);
-      if (fold) {
-        const float chk2 = fabsf(rwn[0]) + fabsf(rwn[1]) + fabsf(rwn[2]) + fabsf(rwn[3]);
-        if (!(chk2 < INFINITY)) {
+          for (int k = 0; k < 4; ++k) lwn[k] = st_sanitize(lwn[k]);
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) rwn[k] = st_sanitize(rwn[k]);
+        for (int k = 0; k < 4; ++k) rwn[k] = __fadd_rn(gnx[k], lwn[k]);
+        if (fold) {
+          const float chk2 = fabsf(rwn[0]) + fabsf(rwn[1]) + fabsf(rwn[2]) + fabsf(rwn[3]);
+          if (!(chk2 < INFINITY)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rwn[k] = st_sanitize(rwn[k]);
+          }
         }
       }
-    }
 #pragma unroll
-    for (int d = 0; d < D; ++d) *reinterpret_cast<float4*>(xnext[d] + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
-    if (!fold || a.store_lw) *reinterpret_cast<float4*>(lwrow + i0) = make_float4(lwn[0], lwn[1], lwn[2], lwn[3]);
-    if (fold) *reinterpret_cast<float4*>(rwrow + i0) = make_float4(rwn[0], rwn[1], rwn[2], rwn[3]);
+      for (int d = 0; d < D; ++d) *reinterpret_cast<float4*>(xnext[d] + i0) = make_float4(xn[d][0], xn[d][1], xn[d][2], xn[d][3]);
+      if (!fold || a.store_lw) *reinterpret_cast<float4*>(lwrow + i0) = make_float4(lwn[0], lwn[1], lwn[2], lwn[3]);
+      if (fold) *reinterpret_cast<float4*>(rwrow + i0) = make_float4(rwn[0], rwn[1], rwn[2], rwn[3]);
 
-    if (!full) {  // the tail of the column: padding contributes nothing
+      if (!full) {  // the tail of the column: padding contributes nothing
 #pragma unroll
-      for (int k = 0; k < 4; ++k) if (i0 + k >= n) { lwn[k] = -INFINITY; rwn[k] = -INFINITY; inc4[k] = -INFINITY; }
+        for (int k = 0; k < 4; ++k) if (i0 + k >= n) { lwn[k] = -INFINITY; rwn[k] = -INFINITY; inc4[k] = -INFINITY; }
+      }
+      mom.add4(lwn, xn, shift);
+      if (fold) r2.add4(rwn, one4);
+      if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
     }
-    mom.add4(lwn, xn, shift);
-    if (fold) r2.add4(rwn, one4);
-    if (ALG == SMCB_ALG_SISR && observed) r3.add4(inc4, wprev);
-  }
+  };
+  if (observed_rt && resampled_rt && (ALG != SMCB_ALG_APF || fold_rt) && !a.eps_in && !a.eps_out) run_loop(std::true_type{});
+  else run_loop(std::false_type{});
   if (a.dbg && tid == 0) atomicMax((unsigned long long*)&a.dbg[15], (unsigned long long)st_now());
   SoftAcc<1 + 2 * D> A;
   SoftAcc<1> Q, R2, R3;
