@@ -35,8 +35,8 @@ struct Ctrl {
   int32_t y_base;       // time index of y[0]
   int32_t y_count;      // observations available at y
   int32_t ticket;       // last-block-done counter of the finalize kernel
-  uint32_t epoch;       // bumped once per move; tags the slots of resample_fused_kernel so they never need clearing
-  uint32_t tile_counter;
+  uint32_t epoch;       // unused (the slot tag of resample_fused_kernel is a kernel argument: ResampleArgs.epoch_host)
+  uint32_t tile_counter;  // unused (tile id = block id)
   int32_t slow_tiles;   // diagnostics: tiles that took the sequential fallback of the exact scan
   int32_t lb_fail;      // reserved
   const float* y;       // (y_count, OD) observations on device

@@ -62,9 +62,12 @@ XS_HD double smcb_u01_double(uint32_t hi, uint32_t lo) {
 // four N(0,1) draws from one Philox block (two Box-Muller pairs)
 __device__ __forceinline__ void smcb_normal4(const Philox4& r, float (&z)[4]) {
   float u0 = smcb_u01_open(r.x), u1 = smcb_u01(r.y), u2 = smcb_u01_open(r.z), u3 = smcb_u01(r.w);
-  float ra, rb;  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): two SFU operations each
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-1.3862943611198906f * __log2f(u0)));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-1.3862943611198906f * __log2f(u2)));
+  float ra, rb, l0, l2;  // sqrt(-2 ln u) = sqrt(-2 ln2 * lg2 u): two SFU operations each
+  // u0, u2 >= 2^-25 are normal numbers: the .ftz form returns the same bits as __log2f without its scaling code for denormals
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(u0));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u2));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(ra) : "f"(-1.3862943611198906f * l0));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rb) : "f"(-1.3862943611198906f * l2));
   float s0, c0, s1, c1;
   __sincosf(6.283185307179586f * u1, &s0, &c0);
   __sincosf(6.283185307179586f * u3, &s1, &c1);

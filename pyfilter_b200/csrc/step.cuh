@@ -560,8 +560,6 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       if (a.B == 1 || atomicAdd(&a.ctrl->ticket, 1) == a.B - 1) {  // every column is finalized, hence every block has read ctrl->t
         a.ctrl->ticket = 0;
         a.ctrl->t = t + 1;
-        a.ctrl->tile_counter = 0;   // arm the next resampling launch (resample_fused_kernel: tile ids, slot tags)
-        a.ctrl->epoch += 1;
       }
     }
   }
@@ -571,7 +569,6 @@ template <int D, int OD, int ALG>
 __global__ void __launch_bounds__(ST_NT) finalize_kernel(StepArgs a) {
   __shared__ FinSmem<D> fs;
   const int t = a.ctrl->t;
-  if (blockIdx.x == 0 && threadIdx.x == 0) { a.ctrl->tile_counter = 0; a.ctrl->epoch += 1; }  // arm the next resampling launch
   const FinPre pre = fin_preload<OD>(a, blockIdx.x, a.fin_mode, t);
   finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, t, fs, pre);
 }
