@@ -8,6 +8,7 @@
 #include <random>
 #include <algorithm>
 #include "../../pyfilter_b200/csrc/scan_tile.h"
+#include "../../pyfilter_b200/csrc/philox.h"
 
 template <int MB>
 static std::vector<float> seq_cumsum(const std::vector<float>& w) {
@@ -208,8 +209,26 @@ static bool check_integer_transducers(std::mt19937_64& rng) {
   return true;
 }
 
+// philox4x32_10_keys (round keys precomputed on the host and passed as kernel arguments) is the same generator as philox4x32_10
+static bool check_philox_keys(std::mt19937_64& rng) {
+  for (int it = 0; it < 200000; ++it) {
+    const uint32_t c0 = (uint32_t)rng(), c1 = (uint32_t)rng(), c2 = (uint32_t)rng(), c3 = (uint32_t)rng();
+    const uint64_t seed = rng();
+    uint32_t keys[20];
+    philox_round_keys((uint32_t)seed, (uint32_t)(seed >> 32), keys);
+    const Philox4 a = philox4x32_10(c0, c1, c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const Philox4 b = philox4x32_10_keys(c0, c1, c2, c3, keys);
+    if (a.x != b.x || a.y != b.y || a.z != b.z || a.w != b.w) { fprintf(stderr, "FAILED philox keys at %d\n", it); return false; }
+  }
+  // known answer of Philox4x32-10 (Random123 kat_vectors: counter = key = 0)
+  const Philox4 z = philox4x32_10(0u, 0u, 0u, 0u, 0u, 0u);
+  if (z.x != 0x6627e8d5u || z.y != 0xe169c58du || z.z != 0xbc57ac4cu || z.w != 0x9b00dbd8u) { fprintf(stderr, "FAILED philox KAT %08x %08x %08x %08x\n", z.x, z.y, z.z, z.w); return false; }
+  return true;
+}
+
 int main(int argc, char** argv) {
   std::mt19937_64 rng(12345);
+  if (!check_philox_keys(rng)) return 1;
   if (!check_count_fast(rng)) return 1;
   if (!check_integer_transducers<53>(rng) || !check_integer_transducers<24>(rng)) return 1;
   size_t big = argc > 1 ? (size_t)atol(argv[1]) : (size_t)1 << 20;

@@ -66,7 +66,7 @@ def test_unsupported_combinations_raise():
 
 def test_exact_scan_host_arithmetic(tmp_path):
     """tests/host/test_exact_scan.cpp: the tile algorithm, the probe counts and the integer transducers against the plain
-    sequential definitions (g++, no GPU)."""
+    sequential definitions; Philox4x32-10 against the Random123 known answer and the keyed variant the kernels use (g++, no GPU)."""
     exe = str(tmp_path / "test_exact_scan")
     subprocess.run(["g++", "-O2", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host", "test_exact_scan.cpp")], check=True)
     out = subprocess.run([exe, "200000"], capture_output=True, text=True, timeout=600)
