@@ -144,9 +144,40 @@ def resampling_cases():
     print("wrote resampling.npz with", len(cases), "arrays")
 
 
+def residual_cases():
+    """``pyfilter.resampling.residual`` (resampling.py:66-105, 1-D only): weights, the float64 uniforms its multinomial part drew
+    (recovered by re-winding the generator) and the indices it returned.  Own file and own seed so that resampling.npz is untouched."""
+    R = load_reference_resampling()
+    residual, normalize = R["resampling"].residual, R["utils"].normalize
+    torch.manual_seed(321)
+    cases = {}
+    specs = [("n300", 300, 1.0), ("n1000_heavy", 1000, 6.0), ("n4096", 4096, 2.0), ("n33", 33, 0.3), ("n65536", 65536, 3.0)]
+    for name, n, std in specs:
+        W = normalize(torch.randn(n) * std)
+        rng = torch.get_rng_state()
+        idx = residual(W.clone(), normalized=True)
+        after = torch.get_rng_state()
+        m = n - int((n * W).floor().sum())
+        torch.set_rng_state(rng)
+        U = torch.empty((1, m), dtype=torch.float64).uniform_() if m else torch.empty((1, 0), dtype=torch.float64)
+        assert torch.equal(torch.get_rng_state(), after), name
+        cases[f"res_{name}_W"], cases[f"res_{name}_U"], cases[f"res_{name}_idx"] = _np(W), _np(U[0]), _np(idx)
+    # nothing left for the multinomial part: uniform weights (every floor is 1) and a one-hot column (floor = N)
+    n = 64
+    for name, W in (("uniform", torch.full((n,), 1.0 / n)), ("onehot", torch.nn.functional.one_hot(torch.tensor(5), n).float())):
+        cases[f"res_{name}_W"], cases[f"res_{name}_U"] = _np(W), np.zeros(0)
+        cases[f"res_{name}_idx"] = _np(residual(W.clone(), normalized=True))
+    np.savez_compressed(os.path.join(OUT, "residual.npz"), **cases)
+    print("wrote residual.npz with", len(cases), "arrays")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "residual":   # added later: leaves the other files as they are
+        residual_cases()
+        return
     resampling_cases()
+    residual_cases()
     filter_case("c1_sisr_boot", "lg_ar1", {}, "sisr", "bootstrap", "systematic", 1000, 0, 12, 123)
     filter_case("c1_sisr_boot_b3_nan", "lg_ar1", {}, "sisr", "bootstrap", "systematic", 193, 3, 10, 124, nan_steps=(4,))
     filter_case("c1_sisr_lgo", "lg_ar1", {}, "sisr", "linear_gaussian", "systematic", 257, 0, 8, 125)

@@ -52,7 +52,7 @@ def get_ess(weights: torch.Tensor, normalized: bool = False) -> torch.Tensor:
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# resampling                                                                                     resampling.py:8-65
+# resampling                                                                                     resampling.py:8-105
 # ----------------------------------------------------------------------------------------------------------------------
 def _wrapped(f, w: torch.Tensor, normalized: bool, **kwargs) -> torch.Tensor:
     """``resampling.py:8-21``.  1-D input calls ``f(w, *kwargs)`` - i.e. keyword *names* are splatted
@@ -89,6 +89,57 @@ def systematic(w: torch.Tensor, normalized: bool = False, u: Optional[torch.Tens
 def multinomial(w: torch.Tensor, normalized: bool = False) -> torch.Tensor:
     """``pyfilter.resampling.multinomial`` (``resampling.py:55-65``): ``torch.multinomial(W, N, replacement=True)``."""
     return _wrapped(lambda ww: torch.multinomial(ww, ww.shape[-1], replacement=True), w, normalized)
+
+
+def _residual_1d(w: torch.Tensor) -> torch.Tensor:
+    """``resampling.py:78-105`` on a 1-D tensor of normalised weights: ``floor(N w_i)`` deterministic copies of every particle
+    (in particle order), the remaining ``N - sum floor`` slots drawn by ``torch.multinomial`` from the fractional parts
+    (divided by the number of deterministic copies, resampling.py:88 - multinomial normalises anyway)."""
+    if w.dim() > 1:
+        raise NotImplementedError("Not implemented for multidimensional arrays!")
+    n = w.shape[-1]
+    mw = n * w
+    floored = mw.floor()
+    res = mw - floored
+    out = torch.ones_like(w, dtype=torch.long)
+    numelems = floored.sum(-1)
+    res = res / numelems
+    intpart = floored.long()
+    ranged = torch.arange(n, dtype=intpart.dtype) * out
+    modded = ranged.repeat_interleave(intpart)
+    aslong = int(numelems.long())
+    out[:aslong] = modded
+    if aslong == n:
+        return out
+    out[aslong:] = torch.multinomial(res, n - aslong, replacement=True)
+    return out
+
+
+def residual(w: torch.Tensor, normalized: bool = False) -> torch.Tensor:
+    """``pyfilter.resampling.residual`` (``resampling.py:66-105``); 1-D only, like the reference."""
+    return _wrapped(_residual_1d, w, normalized)
+
+
+def residual_restated(W: np.ndarray, U: np.ndarray) -> np.ndarray:
+    """Numpy restatement of ``residual`` for one column of normalised float32 weights, given the float64 uniforms ``U`` the
+    multinomial part consumes in draw order (``len(U) = N - sum floor(N w)``): float32 products ``N w`` and floors, the
+    fractional parts divided (float32) by the number of deterministic copies, then ``multinomial_restated``'s rule on them
+    (sequential float32 prefix sum divided by its last element, left search in double).  What a CUDA kernel must reproduce."""
+    W = np.asarray(W, dtype=np.float32)
+    n = W.shape[0]
+    mw = (np.float32(n) * W).astype(np.float32)
+    floored = np.floor(mw).astype(np.float32)
+    counts = floored.astype(np.int64)
+    k = int(counts.sum())
+    out = np.ones(n, dtype=np.int64)
+    out[:k] = np.repeat(np.arange(n, dtype=np.int64), counts)
+    if k == n:
+        return out
+    res = ((mw - floored).astype(np.float32) / np.float32(k)).astype(np.float32)
+    c = sequential_cumsum(res, np.float32)
+    c = (c / c[-1]).astype(np.float32)
+    out[k:] = np.searchsorted(c.astype(np.float64), np.asarray(U, dtype=np.float64)[: n - k], side="left")
+    return out
 
 
 def sequential_cumsum(w: np.ndarray, acc_dtype, out_dtype=np.float32) -> np.ndarray:

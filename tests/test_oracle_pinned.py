@@ -7,7 +7,7 @@ import torch
 
 from oracle import smc_oracle as O
 from oracle.ref_loader import reference_available
-from tests.golden_util import filter_cases, load_filter_case, load_resampling, model_params
+from tests.golden_util import filter_cases, load_filter_case, load_residual, load_resampling, model_params
 
 
 def test_resampling_golden_systematic():
@@ -30,6 +30,37 @@ def test_resampling_golden_multinomial():
         W, U, idx = g[f"mul_{name}_W"], g[f"mul_{name}_U"], g[f"mul_{name}_idx"]
         for b in range(W.shape[1]):
             assert np.array_equal(O.multinomial_restated(W[:, b], U[:, b]), idx[:, b]), (name, b)
+
+
+def test_resampling_golden_residual():
+    """``pyfilter.resampling.residual`` (resampling.py:66-105; SURVEY.md 8(f) f4 - oracle only so far, no CUDA path yet): the numpy
+    restatement reproduces the reference's indices from the weights and the float64 uniforms its multinomial part drew."""
+    g = load_residual()
+    names = sorted({k[4:-2] for k in g if k.startswith("res_") and k.endswith("_W")})
+    assert len(names) >= 7
+    for name in names:
+        W, U, idx = g[f"res_{name}_W"], g[f"res_{name}_U"], g[f"res_{name}_idx"]
+        assert np.array_equal(O.residual_restated(W, U), idx), name
+        n = W.shape[0]
+        counts = np.floor(np.float32(n) * W).astype(np.int64)
+        assert np.array_equal(np.bincount(idx[: counts.sum()], minlength=n), counts), name   # deterministic part
+    with pytest.raises(NotImplementedError):
+        O.residual(torch.rand(10, 2))
+
+
+@pytest.mark.skipif(not reference_available(), reason="needs /root/reference (build container)")
+def test_residual_bitwise_vs_reference():
+    from oracle.ref_loader import load_reference_resampling
+
+    ref = load_reference_resampling()["resampling"].residual
+    for seed, n, std in [(1, 500, 1.0), (2, 4096, 4.0), (3, 17, 0.1)]:
+        torch.manual_seed(seed)
+        lw = torch.randn(n) * std
+        torch.manual_seed(100 + seed)
+        a = ref(lw.clone())
+        torch.manual_seed(100 + seed)
+        b = O.residual(lw.clone())
+        assert torch.equal(a, b), seed
 
 
 def test_normalize_golden():
