@@ -28,7 +28,7 @@ def _np(t):
     return t.detach().cpu().numpy().copy()
 
 
-def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed, nan_steps=()):
+def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed, nan_steps=(), prefix="filter"):
     pf = load_reference()
     from pyfilter.filters.particle import APF, SISR, proposals as pr
     from pyfilter import resampling as RR
@@ -89,7 +89,7 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
     out = {k: np.stack(v) for k, v in rec.items()}
     out.update(y=_np(y), x0=x0, N=N, B=B, T=T, seed=seed, model=model_name, alg=alg, proposal=proposal,
                resampler=resampler, params_json=np.array(repr(params)))
-    np.savez_compressed(os.path.join(OUT, f"filter_{tag}.npz"), **out)
+    np.savez_compressed(os.path.join(OUT, f"{prefix}_{tag}.npz"), **out)
     print("wrote", tag, {k: v.shape for k, v in out.items() if hasattr(v, "shape") and v.ndim > 0 and k in ("x", "lw", "U")})
 
 
@@ -171,10 +171,21 @@ def residual_cases():
     print("wrote residual.npz with", len(cases), "arrays")
 
 
+def oracle_only_cases():
+    """Rows of SURVEY.md 8(f) whose oracle exists before their CUDA path: files named ``oracleonly_*.npz`` so that the GPU parity
+    tests (which iterate ``filter_*.npz``) do not pick them up.  f2: multi-dimensional LinearGaussianObservations on Lorenz-63
+    (examples/lorenz.ipynb:214)."""
+    filter_case("c4_apf_lgo_sys", "lorenz63_em", {}, "apf", "linear_gaussian", "systematic", 400, 0, 8, 131, prefix="oracleonly")
+    filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132, prefix="oracleonly")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "residual":   # added later: leaves the other files as they are
         residual_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "oracle_only":
+        oracle_only_cases()
         return
     resampling_cases()
     residual_cases()

@@ -395,6 +395,9 @@ class Lorenz63(Model):
         self.inc_scale = math.sqrt(self.dt)
         self.x0_mean = _t([-5.91652, -5.52332, 24.5723])
         self.x0_scale = math.sqrt(10.0) * torch.ones(3)
+        # the same observation as a LinearStateSpaceModel (examples/lorenz.ipynb:105-117): y = b + A x + s nu, A (2, 3), b, s (1,)
+        s1 = self.obs_s.reshape(-1)[:1] if self.obs_s.dim() else self.obs_s.unsqueeze(-1)
+        self.linear_obs = (_t([[self.obs_a, 0.0, 0.0], [0.0, 0.0, self.obs_a]]), torch.zeros_like(s1), s1)
 
     def _p(self, p):  # parameter (B,) -> broadcast against (N,B)
         return p
@@ -440,7 +443,10 @@ def lgo_sample_and_weight(model: Model, y, x_prev, z):
     """``proposals/linear.py:38-55`` + ``proposals/utils.py:219-267`` + ``proposals/base.py:45-50`` for a SCALAR
     state and observation: optimal Gaussian kernel ``N(k, P)``, ``P = 1/(sigma^-2 + a^2 s^-2)``,
     ``k = P (sigma^-2 m + a s^-2 (y - b))``; weight ``log p(y|x') + log p(x'|x) - log N(x'; k, P)``."""
-    assert model.state_dim == 0 and model.obs_dim == 0 and model.linear_obs is not None
+    assert model.linear_obs is not None
+    if model.state_dim > 0:
+        return _lgo_sample_and_weight_nd(model, y, x_prev, z)
+    assert model.obs_dim == 0
     a, b, s = model.linear_obs
     mean, scale = model.mean_scale(x_prev)
     h_var_inv = scale.pow(-2.0)
@@ -465,10 +471,64 @@ def lgo_sample_and_weight(model: Model, y, x_prev, z):
 def lgo_pre_weight(model: Model, y, x_prev):
     """``proposals/linear.py:57-86`` for scalar state/observation: ``log N(y; b + a x_{t-1}, sqrt(s^2 + a^2 sigma^2))``
     (centred on the PREVIOUS state, Appendix A-8)."""
+    if model.state_dim > 0:
+        return _lgo_pre_weight_nd(model, y, x_prev)
     a, b, s = model.linear_obs
     _, h_scale = model.mean_scale(x_prev)
     cov = s.pow(2.0) + a * h_scale.pow(2.0) * a
     return normal_log_prob(y, b + a * x_prev, cov.sqrt())
+
+
+def _diag_from_flat(v: torch.Tensor, dim: int) -> torch.Tensor:
+    """``utils.py:23-46`` for a vector event shape: ``eye(dim) * v.unsqueeze(-1)``."""
+    return torch.eye(dim, dtype=v.dtype) * v.unsqueeze(-1)
+
+
+def _lgo_sample_and_weight_nd(model: Model, y, x_prev, z):
+    """``proposals/linear.py:38-55`` + ``proposals/utils.py:219-267`` + ``proposals/base.py:45-50`` for a VECTOR state (d) and a
+    vector observation (m), as in examples/lorenz.ipynb:214 (oracle only so far).  With ``A (m, d)``,
+    ``(mean, sigma) = mean_scale(x)``: ``P = (diag(sigma^-2) + A^T diag(s^-2) A)^-1``, ``k = P (sigma^-2 mean + A^T diag(s^-2) (y - b))``,
+    ``x' = k + chol(P) z``; weight ``log p(y|x') + log p(x'|x) - log N(x'; k, P)``.  Same torch ops in the same order as the
+    reference (batched ``inverse``, ``cholesky_ex``, ``MultivariateNormal.log_prob``)."""
+    from torch.distributions import AffineTransform, Independent, MultivariateNormal, Normal, TransformedDistribution
+    from torch.linalg import cholesky_ex
+
+    a, b, s = model.linear_obs
+    d, m = model.state_dim, model.obs_dim
+    mean, scale = model.mean_scale(x_prev)
+    h_var_inv = scale.pow(-2.0)
+    o_var_inv = s.pow(-2.0)
+    yc = y - b
+    # find_optimal_density
+    c_t = a.transpose(-2, -1)
+    o_inv_cov = _diag_from_flat(o_var_inv, m)
+    t_2 = c_t.matmul(o_inv_cov).matmul(a)
+    cov = (_diag_from_flat(h_var_inv, d) + t_2).inverse()
+    t_1 = h_var_inv * mean
+    t_2 = o_inv_cov.matmul(yc)
+    t_3 = c_t.matmul(t_2.unsqueeze(-1))
+    k_mean = cov.matmul(t_1.unsqueeze(-1) + t_3).squeeze(-1)
+    kernel = MultivariateNormal(k_mean, scale_tril=cholesky_ex(cov)[0], validate_args=False)
+    # MultivariateNormal.rsample: loc + scale_tril @ eps
+    x_new = kernel.loc + torch.matmul(kernel._unbroadcasted_scale_tril, z.unsqueeze(-1)).squeeze(-1)
+    # _weight_with_kernel
+    y_lp = Independent(Normal(b + (a @ x_new.unsqueeze(-1)).squeeze(-1), s, validate_args=False), 1).log_prob(y)
+    inc = Independent(Normal(torch.zeros(d), _t(model.inc_scale).expand(d), validate_args=False), 1)
+    x_lp = TransformedDistribution(inc, AffineTransform(mean, scale, event_dim=1), validate_args=False).log_prob(x_new)
+    return x_new, y_lp + x_lp - kernel.log_prob(x_new)
+
+
+def _lgo_pre_weight_nd(model: Model, y, x_prev):
+    """``proposals/linear.py:57-86``, vector case: ``log N(y; b + A x_{t-1}, diag(s^2) + A diag(sigma^2) A^T)``."""
+    from torch.distributions import MultivariateNormal
+    from torch.linalg import cholesky_ex
+
+    a, b, s = model.linear_obs
+    d, m = model.state_dim, model.obs_dim
+    _, h_scale = model.mean_scale(x_prev)
+    cov = _diag_from_flat(s.pow(2.0), m) + a.matmul(_diag_from_flat(h_scale.pow(2.0), d)).matmul(a.transpose(-2, -1))
+    o_loc = b + (a @ x_prev.unsqueeze(-1)).squeeze(-1)
+    return MultivariateNormal(o_loc, scale_tril=cholesky_ex(cov)[0], validate_args=False).log_prob(y)
 
 
 PROPOSALS = {

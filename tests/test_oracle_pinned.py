@@ -7,7 +7,7 @@ import torch
 
 from oracle import smc_oracle as O
 from oracle.ref_loader import reference_available
-from tests.golden_util import filter_cases, load_filter_case, load_residual, load_resampling, model_params
+from tests.golden_util import filter_cases, load_filter_case, load_residual, load_resampling, model_params, oracle_only_cases
 
 
 def test_resampling_golden_systematic():
@@ -90,9 +90,11 @@ def test_reference_kat_systematic():
         assert (inds[i] == exp).all()
 
 
-@pytest.mark.parametrize("tag", filter_cases())
+@pytest.mark.parametrize("tag", filter_cases() + ["oracleonly:" + t for t in oracle_only_cases()])
 def test_teacher_forced_steps_match_reference(tag):
-    g = load_filter_case(tag)
+    """Every golden file, incl. the ``oracleonly_*`` ones (multi-dimensional LinearGaussianObservations on Lorenz-63, SURVEY.md 8(f)
+    f2: the oracle is pinned, the CUDA path is not built yet)."""
+    g = load_filter_case(tag.split(":")[1], prefix="oracleonly") if tag.startswith("oracleonly:") else load_filter_case(tag)
     model = O.build_model(g["model"], model_params(g))
     B = g["B"]
     for t in range(g["T"]):
@@ -168,5 +170,32 @@ def test_free_running_bitwise_vs_reference(alg, proposal, resampler, bshape, eve
     assert torch.equal(r.loglikelihood, o["loglikelihood"])
     assert torch.equal(r.filter_means, o["filter_means"])
     assert torch.equal(r.filter_variance, o["filter_variance"])
+    assert torch.equal(r.latest_state.timeseries_state.value, o["x"])
+    assert torch.equal(r.latest_state.previous_indices, o["prev_inds"])
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("alg", ["sisr", "apf"])
+def test_free_running_bitwise_vs_reference_lorenz_lgo(alg):
+    """LinearGaussianObservations with a 3-D state and a 2-D observation (examples/lorenz.ipynb:214) - the oracle's
+    restatement run freely against the unmodified reference on the same torch generator: identical bits."""
+    from oracle.ref_loader import load_reference
+    from oracle.ref_models import build_reference_model
+
+    load_reference()
+    from pyfilter import resampling as RR
+    from pyfilter.filters.particle import APF, SISR, proposals as pr
+
+    torch.manual_seed(6)
+    m = O.build_model("lorenz63_em")
+    _, y = m.simulate(25)
+    ssm = build_reference_model("lorenz63_em", O.DEFAULT_PARAMS["lorenz63_em"])
+    f = {"sisr": SISR, "apf": APF}[alg](ssm, 250, proposal=pr.LinearGaussianObservations(), resampling=RR.systematic)
+    torch.manual_seed(12)
+    r = f.batch_filter(y, bar=False)
+    torch.manual_seed(12)
+    o = O.batch_filter(m, alg, "linear_gaussian", y, 250, (), "systematic")
+    assert torch.equal(r.loglikelihood, o["loglikelihood"])
+    assert torch.equal(r.filter_means, o["filter_means"])
     assert torch.equal(r.latest_state.timeseries_state.value, o["x"])
     assert torch.equal(r.latest_state.previous_indices, o["prev_inds"])
