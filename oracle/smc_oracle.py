@@ -634,9 +634,10 @@ STEPS = {"sisr": sisr_step, "apf": apf_step}
 # ----------------------------------------------------------------------------------------------------------------------
 def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, particles: int,
                  batch_shape: Tuple[int, ...] = (), resampler: str = "systematic", ess_threshold: float = 0.9,
-                 x0: Optional[torch.Tensor] = None, observe_every_step: int = 1) -> Dict[str, torch.Tensor]:
+                 x0: Optional[torch.Tensor] = None, observe_every_step: int = 1, record_states: bool = False) -> Dict[str, torch.Tensor]:
     """``BaseFilter.batch_filter`` for SISR/APF using torch's global CPU generator in the reference's draw order
-    (Appendix A-15: ``u`` - only when something resamples - then the transition noise)."""
+    (Appendix A-15: ``u`` - only when something resamples - then the transition noise).  ``record_states=True`` also returns every
+    recorded state ``(x, log w, previous indices)``, the initial one included (``filters/result.py:39,119-133``)."""
     shape = (particles,) + tuple(batch_shape)
     d = (model.state_dim,) if model.state_dim else ()
     x = model.initial_sample(shape) if x0 is None else x0
@@ -646,6 +647,7 @@ def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, p
     ll_total = torch.zeros(tuple(batch_shape))
     mean, var = filter_mean_and_variance(x, normalize(lw.clone()), model.state_dim)
     means, variances = [mean], [var]
+    states = [(x, lw, inds)]
     nb = int(np.prod(batch_shape)) if batch_shape else 1
     # filters/base.py:204-210: before an observation is used, the filter propagates (predict + propagate, no weighting, no
     # likelihood, nothing recorded) until the time index of the state is a multiple of `observe_every_step`
@@ -685,8 +687,28 @@ def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, p
         ll_total = ll_total + out["ll"]
         means.append(out["mean"])
         variances.append(out["var"])
-    return {"loglikelihood": ll_total, "filter_means": torch.stack(means), "filter_variance": torch.stack(variances),
-            "x": x, "lw": lw, "prev_inds": inds}
+        states.append((x, lw, inds))
+    res = {"loglikelihood": ll_total, "filter_means": torch.stack(means), "filter_variance": torch.stack(variances),
+           "x": x, "lw": lw, "prev_inds": inds}
+    if record_states:
+        res["states"] = states
+    return res
+
+
+def smooth_fixed_lag(states) -> torch.Tensor:
+    """``ParticleFilter._do_sample_fl`` (``filters/particle/base.py:130-146``; SURVEY.md 8(f) f3, oracle only): ancestral tracing.
+    Walk the recorded states backwards; the lineage of final particle i at time t-1 is ``previous_indices_t[lineage_t[i]]``;
+    returns the ``(T+1, N, [B], [d])`` paths.  ``states``: list of ``(x, log w, previous indices)``."""
+    x_last, _, prev_last = states[-1]
+    n = x_last.shape[0]
+    result = [x_last]
+    lineage = torch.arange(n) if prev_last.dim() == 1 else torch.arange(n).unsqueeze(-1).expand(prev_last.shape)
+    latest_prev = prev_last
+    for x_s, _, prev_s in reversed(states[:-1]):
+        lineage = _gather0(latest_prev, lineage)
+        result.append(_gather0(x_s, lineage))
+        latest_prev = prev_s
+    return torch.stack(result[::-1], dim=0)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

@@ -199,3 +199,30 @@ def test_free_running_bitwise_vs_reference_lorenz_lgo(alg):
     assert torch.equal(r.filter_means, o["filter_means"])
     assert torch.equal(r.latest_state.timeseries_state.value, o["x"])
     assert torch.equal(r.latest_state.previous_indices, o["prev_inds"])
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name,alg,bshape", [("sine_em", "sisr", ()), ("lorenz63_em", "sisr", ()), ("sine_em", "apf", (3,))])
+def test_fixed_lag_smoothing_bitwise_vs_reference(name, alg, bshape):
+    """``smooth(states, method="fl")`` (filters/particle/base.py:130-146) - ancestral tracing over the recorded
+    states - restated in the oracle and compared bit for bit with the unmodified reference on the same generator."""
+    from oracle.ref_loader import load_reference
+    from oracle.ref_models import build_reference_model
+
+    load_reference()
+    from pyfilter import resampling as RR
+    from pyfilter.filters.particle import APF, SISR, proposals as pr
+
+    torch.manual_seed(8)
+    m = O.build_model(name)
+    _, y = m.simulate(15)
+    ssm = build_reference_model(name, O.DEFAULT_PARAMS[name])
+    f = {"sisr": SISR, "apf": APF}[alg](ssm, 200, proposal=pr.Bootstrap(), resampling=RR.systematic, record_states=True)
+    f.set_batch_shape(torch.Size(bshape))
+    torch.manual_seed(13)
+    r = f.batch_filter(y, bar=False)
+    ref = f.smooth(r.states, method="fl")
+    torch.manual_seed(13)
+    o = O.batch_filter(m, alg, "bootstrap", y, 200, bshape, "systematic", record_states=True)
+    got = O.smooth_fixed_lag(o["states"])
+    assert ref.shape == got.shape and torch.equal(ref, got)
