@@ -749,3 +749,30 @@ def build_model(name: str, params: Optional[dict] = None) -> Model:
     p = dict(DEFAULT_PARAMS[name])
     p.update(params or {})
     return _CLASSES[name](**p)
+
+
+def smooth_ffbs(model: Model, states, resampler: str = "systematic") -> torch.Tensor:
+    """``ParticleFilter._do_sample_ffbs`` (``filters/particle/base.py:105-128``; SURVEY.md 8(f) f3, oracle only), restated as written in
+    the reference (its own comment says "Something is wrong here": the backward weights are taken as they are).  Draws from torch's
+    global generator in the reference's order: the resampler's offset for the last state, then one Categorical draw per earlier
+    state.  ``states``: list of ``(x, log w, previous indices)``; non-batched filters only (the reference's batched branch moves axes
+    in a way its own shapes do not support)."""
+    from torch.distributions import AffineTransform, Categorical, Independent, Normal, TransformedDistribution
+
+    x_last, lw_last, _ = states[-1]
+    assert lw_last.dim() == 1, "non-batched only"
+    idx = systematic(lw_last.clone()) if resampler == "systematic" else multinomial(lw_last.clone())
+    res = [_gather0(x_last, idx)]
+    d = model.state_dim
+    for x_s, lw_s, _ in reversed(states[:-1]):
+        loc, scale = model.mean_scale(x_s)
+        if d:
+            inc = Independent(Normal(torch.zeros(d), _t(model.inc_scale).expand(d), validate_args=False), 1)
+        else:
+            inc = Normal(0.0, _t(model.inc_scale), validate_args=False)
+        density = TransformedDistribution(inc, AffineTransform(loc, scale, event_dim=1 if d else 0), validate_args=False)
+        w_state = density.log_prob(res[-1].unsqueeze(1))   # (N_smoothed, N_particles)
+        weights = lw_s.unsqueeze(0) + w_state
+        indices = Categorical(logits=weights).sample()
+        res.append(_gather0(x_s, indices))
+    return torch.stack(res[::-1], dim=0)

@@ -226,3 +226,28 @@ def test_fixed_lag_smoothing_bitwise_vs_reference(name, alg, bshape):
     o = O.batch_filter(m, alg, "bootstrap", y, 200, bshape, "systematic", record_states=True)
     got = O.smooth_fixed_lag(o["states"])
     assert ref.shape == got.shape and torch.equal(ref, got)
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("name", ["sine_em", "lorenz63_em"])
+def test_ffbs_smoothing_bitwise_vs_reference(name):
+    """``smooth(states, method="ffbs")`` (filters/particle/base.py:105-128) restated in the oracle, same generator, same bits."""
+    from oracle.ref_loader import load_reference
+    from oracle.ref_models import build_reference_model
+
+    load_reference()
+    from pyfilter import resampling as RR
+    from pyfilter.filters.particle import SISR, proposals as pr
+
+    torch.manual_seed(9)
+    m = O.build_model(name)
+    _, y = m.simulate(10)
+    ssm = build_reference_model(name, O.DEFAULT_PARAMS[name])
+    f = SISR(ssm, 150, proposal=pr.Bootstrap(), resampling=RR.systematic, record_states=True)
+    torch.manual_seed(14)
+    r = f.batch_filter(y, bar=False)
+    ref = f.smooth(r.states, method="ffbs")
+    torch.manual_seed(14)
+    o = O.batch_filter(m, "sisr", "bootstrap", y, 150, (), "systematic", record_states=True)
+    got = O.smooth_ffbs(m, o["states"])
+    assert ref.shape == got.shape and torch.equal(ref, got)
