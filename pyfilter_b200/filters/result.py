@@ -72,20 +72,40 @@ class FilterResult(dict):
     def resample(self, indices: torch.Tensor, entire_history=True):
         self._loglikelihood.copy_(self._loglikelihood[indices])
         if entire_history:
+            # new tensors, not the reference's in-place `tens.copy_(tens[indices])` (filters/result.py:110-112): the latest state
+            # holds the same tensor objects as the deques and permutes them itself below - in place they would be permuted twice
             for d in (self._means, self._variances):
-                for tens in d:
-                    tens.copy_(tens[indices])
+                for i in range(len(d)):
+                    d[i] = d[i][indices]
         for s in self.states:
             s.resample(indices)
         return self
 
+    # The reference's serialisation (filters/result.py:134-156 on top of container.py:113-147): the moment deques travel as stacked
+    # tensors under "tensor_tuples" with their maxlen encoded in the key, then the latest state and the running log-likelihood.
+    _TT_KEY = "tensor_deque_{maxlen}__{name}"
+
     def state_dict(self):
-        return {"filter_means": self.filter_means, "filter_variances": self.filter_variance,
-                "state": self.latest_state.state_dict(), "log_likelihood": self.loglikelihood}
+        from collections import OrderedDict
+
+        tt = OrderedDict()
+        tt[self._TT_KEY.format(maxlen=self._means.maxlen, name="filter_means")] = self.filter_means
+        tt[self._TT_KEY.format(maxlen=self._variances.maxlen, name="filter_variances")] = self.filter_variance
+        return OrderedDict([("tensor_tuples", tt), ("state", self.latest_state.state_dict()), ("log_likelihood", self.loglikelihood)])
 
     def load_state_dict(self, sd):
-        self._means = deque(sd["filter_means"].unbind(0), maxlen=self._means.maxlen)
-        self._variances = deque(sd["filter_variances"].unbind(0), maxlen=self._variances.maxlen)
+        if "tensor_tuples" in sd:
+            for key, v in sd["tensor_tuples"].items():
+                type_, name = key.replace("tensor_", "", 1).split("__", 1)
+                maxlen = type_.split("_", 1)[1]
+                dq = deque(v.unbind(0) if v.numel() else (), maxlen=None if maxlen == "None" else int(maxlen))
+                if name == "filter_means":
+                    self._means = dq
+                elif name == "filter_variances":
+                    self._variances = dq
+        else:  # flat layout written by earlier versions of this package
+            self._means = deque(sd["filter_means"].unbind(0), maxlen=self._means.maxlen)
+            self._variances = deque(sd["filter_variances"].unbind(0), maxlen=self._variances.maxlen)
         self._loglikelihood = sd["log_likelihood"]
         assert len(self.states) == 1, "Can only handle case when we have 1 state!"
         self.latest_state.load_state_dict(sd["state"])
