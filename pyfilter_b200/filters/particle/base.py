@@ -88,7 +88,8 @@ class ParticleFilter:
     def predict(self, state):
         raise NotImplementedError("predict/correct are fused into one device step; call filter() or batch_filter()")
 
-    correct = predict
+    def correct(self, y, prediction):
+        raise NotImplementedError("predict/correct are fused into one device step; call filter() or batch_filter()")
 
     def smooth(self, states, method="ffbs"):
         raise NotImplementedError("smoothing is listed under 'next' (SURVEY.md 8(f) f3)")

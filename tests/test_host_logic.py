@@ -50,3 +50,33 @@ def test_constructor_checks_and_factory():
     assert f.particles == torch.Size([2000, 7])
     with pytest.raises(ValueError):  # same pairing rule as proposals/linear.py:32-36
         proposals.LinearGaussianObservations().set_model(ts.build("sv_ar1"))
+
+
+def test_filter_signatures_match_the_reference():
+    """Same constructor keywords / defaults and method signatures as pyfilter's particle filters (filters/particle/base.py:19-27,
+    filters/base.py:22-29), so user code switches by changing the import.  Needs the reference (build container)."""
+    import inspect
+
+    from oracle.ref_loader import load_reference, reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    load_reference()
+    from pyfilter.filters.base import BaseFilter
+    from pyfilter.filters.particle import SISR as RefSISR
+    from pyfilter.filters.particle.base import ParticleFilter
+
+    mine = inspect.signature(SISR.__init__).parameters
+    for ref_sig in (inspect.signature(ParticleFilter.__init__), inspect.signature(BaseFilter.__init__)):
+        for name, p in ref_sig.parameters.items():
+            if name in ("self", "kwargs"):
+                continue
+            assert name in mine, name
+            if p.default is not inspect.Parameter.empty and name != "resampling":
+                assert mine[name].default == p.default, name
+    assert list(mine)[:6] == ["self", "model", "particles", "resampling", "proposal", "ess_threshold"]   # positional order
+    for meth in ("batch_filter", "filter", "initialize", "initialize_with_result", "copy", "increase_particles", "set_batch_shape",
+                 "initialize_model", "smooth", "predict", "correct"):
+        a = [n for n in inspect.signature(getattr(SISR, meth)).parameters]
+        b = [n for n in inspect.signature(getattr(RefSISR, meth)).parameters]
+        assert a == b, (meth, a, b)
