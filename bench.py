@@ -252,6 +252,13 @@ def run_b200(args):
                 "whole_step": {"algorithmic_bytes_per_particle": 24, "achieved": whole, "frac": whole / peak,
                                "ms_per_step_profiled": step_ms}}
 
+    try:  # every kernel of the move against the same peak (the two hot kernels are within 2 % of each other: "dominant" can flip)
+        roofline["per_kernel"] = {k: {"ms": per[k], "algorithmic_bytes": alg_bytes[k],
+                                      "achieved": alg_bytes[k] / (per[k] * 1e-3) / 1e9, "frac": alg_bytes[k] / (per[k] * 1e-3) / 1e9 / peak}
+                                  for k in per if per[k] > 0}
+    except Exception:
+        pass
+
     line = None
     if rank == 0:
         # ---- end to end through the C ABI on host buffers (pinned), incl. H2D of y and D2H of the results
