@@ -227,13 +227,17 @@ def run_b200(args):
     prof = (C.c_float * 5)()
     _lib.check(lib.smcb_filter_profile(e.handle, P, prof, stream.cuda_stream))
     e.t += P
-    fused = (not args.exact_weights) and N <= (1 << 23) and not os.environ.get("SMCB_NO_FUSED")  # run_one's own condition
-    names = ["apf_preweight", "resample_fused_kernel" if fused else "normalize_kernel", "describe_kernel", "expand_kernel", "step_kernel"]
-    per = {n_: prof[i] / P for i, n_ in enumerate(names)}
-    if fused:  # the two slots only hold the bracketing events' own overhead
+    fused = (not args.exact_weights) and N <= (1 << 23) and not os.environ.get("SMCB_NO_FUSED")  # run_one's own conditions
+    move = (not args.exact_weights) and N <= (1 << 23) and not os.environ.get("SMCB_NO_MOVE")
+    if move:     # ONE kernel per move (csrc/move.cuh); the other slots only hold the bracketing events' own overhead
+        names = ["apf_preweight", "move_kernel", "-", "-", "-"]
+    else:
+        names = ["apf_preweight", "resample_fused_kernel" if fused else "normalize_kernel", "describe_kernel", "expand_kernel", "step_kernel"]
+    per = {n_: prof[i] / P for i, n_ in enumerate(names) if n_ != "-"}
+    if fused and not move:
         per.pop("describe_kernel"); per.pop("expand_kernel")
     # algorithmic bytes per launch: resampling = load log-weight 4 + store ancestor 4; step = ancestor 4 + gather 4 + x 4 + log-weight 4
-    alg_bytes = {"resample_fused_kernel": 8.0 * N, "normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N, "expand_kernel": 8.0 * N,
+    alg_bytes = {"move_kernel": 24.0 * N, "resample_fused_kernel": 8.0 * N, "normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N, "expand_kernel": 8.0 * N,
                  "step_kernel": 16.0 * N, "apf_preweight": 12.0 * N}
     dom = max(per, key=per.get)
     peak, peak_src = load_peaks()

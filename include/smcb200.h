@@ -65,7 +65,10 @@ typedef struct smcb_config {
                              never rounds and every column takes the chain-free path; 1: weights are exactly
                              fl32(exp(lw - max) * fl32(1/sum)) and columns with tiny weights take the transducer scan.  Either way
                              the ancestors are bit-exact for the weights used (smcb_filter_dump_noise returns them). */
-  int32_t reserved;
+  int32_t column_offset;  /* global index of this handle's column 0.  The Philox counters are (particle group, column_offset + column,
+                             move, purpose): shards of ONE batch of filters on different ranks (or handles) pass the offset of their
+                             first column so that no two columns of the batch share a random stream, and the result does not depend
+                             on how the batch is split */
 } smcb_config;
 
 typedef struct smcb_filter smcb_filter;
@@ -137,7 +140,9 @@ enum {
   SMCB_PTR_HIST_VAR = 8,   /* float (rows,B,D)  FilterResult.filter_variance                                                */
   SMCB_PTR_HIST_LL = 9,    /* float (rows,B)    per-move increments                                                         */
   SMCB_PTR_ESS = 10,       /* float (B) packed copy refreshed by smcb_filter_sync_stats                                     */
-  SMCB_PTR_X_OTHER = 11    /* float (D, B, ld)  the ping-pong twin of SMCB_PTR_X (previous particles)                       */
+  SMCB_PTR_X_OTHER = 11,   /* float (D, B, ld)  the ping-pong twin of SMCB_PTR_X (previous particles)                       */
+  SMCB_PTR_RESAMPLE_LOGW = 12 /* float (B, ld)  APF: the resampling log-weights g(y_{t+1}|x_t) + log w_t of the COMING move (apf.py:29),
+                                 valid after a move that folded the look-ahead or after the pre-weight pass                         */
 };
 int smcb_filter_ptr(smcb_filter* f, int32_t what, void** ptr_dev);
 /* gathers ESS / resample flags of every column into the packed SMCB_PTR_ESS buffer (get_ess, utils.py:8-20) */
@@ -149,6 +154,10 @@ int smcb_filter_sync_stats(smcb_filter* f, void* stream);
 /* pyfilter.utils.normalize (utils.py:49-64): NaN-safe soft-max over the particle axis; does NOT mutate the input */
 int smcb_normalize(const float* logw_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, float* out_dev,
                    int64_t out_stride_n, int64_t out_stride_b, float* ess_out_dev, void* stream);
+/* pyfilter.utils.get_ess (utils.py:8-20): ESS = 1 / sum_i W_i^2 per column, from log-weights (normalized = 0) or from normalised
+ * weights (normalized = 1) */
+int smcb_get_ess(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, int32_t normalized,
+                 float* ess_out_dev, void* stream);
 /* pyfilter.resampling.systematic (resampling.py:24-52): int64 ancestors; `u_dev` (B) overrides the sampled offsets (the
  * reference's testing hook `u=`); `normalized` mirrors the keyword of the same name */
 int smcb_systematic(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, int32_t normalized,

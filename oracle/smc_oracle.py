@@ -564,11 +564,13 @@ def _as_2d_resample(W: torch.Tensor, u, resampler: str, U=None) -> torch.Tensor:
 
 
 def sisr_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, ess_threshold=0.9,
-              resampler="systematic", U=None) -> Dict[str, torch.Tensor]:
+              resampler="systematic", U=None, force_idx=None) -> Dict[str, torch.Tensor]:
     """One ``SISR`` move (``filters/particle/sisr.py:14-56``, ``filters/base.py:188-221``) with injected noise.
 
     ``x:(N,[B],[d])``, ``lw:(N,[B])``, ``z`` unit normals shaped like ``x``, ``u:(B,)`` systematic offsets for ALL
-    columns (only the resampled ones are used).  A NaN ``y`` propagates only (``particle/state.py:38-42``)."""
+    columns (only the resampled ones are used).  A NaN ``y`` propagates only (``particle/state.py:38-42``).
+    ``force_idx`` (test hook): ancestors to use instead of the resampler's (parity tests feed the device's ancestors so that every
+    other quantity of the move can be compared even when an ulp of a weight moved one ancestor)."""
     lw = lw.clone()
     n = lw.shape[0]
     W = normalize(lw)  # sisr.py:16 (mutates lw like the reference)
@@ -577,7 +579,7 @@ def sisr_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, ess_t
     inds = prev_inds.clone()
     x_res, lw_res = x, lw
     if bool(mask.any()):
-        all_idx = _as_2d_resample(W, u, resampler, U)
+        all_idx = _as_2d_resample(W, u, resampler, U) if force_idx is None else force_idx
         if W.dim() == 1:
             inds, x_res = all_idx, _gather0(x, all_idx)
             lw_res = torch.zeros_like(lw)
@@ -602,8 +604,9 @@ def sisr_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, ess_t
     return out
 
 
-def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resampler="systematic", U=None):
-    """One ``APF`` move (``filters/particle/apf.py:16-46``) with injected noise; resamples every step."""
+def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resampler="systematic", U=None, force_idx=None):
+    """One ``APF`` move (``filters/particle/apf.py:16-46``) with injected noise; resamples every step.  ``force_idx``: see
+    :func:`sisr_step`."""
     lw = lw.clone()
     n = lw.shape[0]
     W = normalize(lw)  # apf.py:17
@@ -616,7 +619,7 @@ def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resamp
     sample_and_weight, pre_weight = PROPOSALS[proposal]
     g = pre_weight(model, y, x)  # apf.py:27
     rw = normalize(g + lw)  # apf.py:29-31 -> resampling.py:10-11
-    idx = _as_2d_resample(rw, u, resampler, U)
+    idx = _as_2d_resample(rw, u, resampler, U) if force_idx is None else force_idx
     x_res = _gather0(x, idx)  # apf.py:34
     x_new, inc = sample_and_weight(model, y, x_res, z)  # apf.py:41
     lw_new = inc - g.gather(0, idx)  # apf.py:43

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmcb200.so")
 _SOURCES = ["smcb_api.cu", "resample.cuh", "step.cuh", "operators.cuh", "common.cuh", "models.h", "philox.h", "scan_tile.h",
-            "exact_scan.h", "column.cuh"]
+            "exact_scan.h", "column.cuh", "move.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
               "-diag-suppress", "128"]
 
@@ -27,7 +27,7 @@ class smcb_config(C.Structure):
         ("particles", C.c_int64), ("batch", C.c_int32), ("n_raw_params", C.c_int32),
         ("params_host", C.POINTER(C.c_float)), ("param_cols", C.c_int32), ("ess_threshold", C.c_float),
         ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_weights", C.c_int32),
-        ("reserved", C.c_int32),
+        ("column_offset", C.c_int32),
     ]
 
 
@@ -60,6 +60,7 @@ SYMBOLS = [
     ("smcb_filter_ptr", C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     ("smcb_filter_sync_stats", C.c_int, [_P, _P]),
     ("smcb_normalize", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P]),
+    ("smcb_get_ess", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, _P]),
     ("smcb_systematic", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64,
                                   C.c_int64, _P]),
     ("smcb_multinomial", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64,
@@ -67,7 +68,7 @@ SYMBOLS = [
 ]
 
 PTR_X, PTR_LOGW, PTR_PREV_INDS, PTR_MEAN, PTR_VAR, PTR_LL, PTR_LL_TOTAL, PTR_HIST_MEAN, PTR_HIST_VAR, PTR_HIST_LL, PTR_ESS, \
-    PTR_X_OTHER = range(12)
+    PTR_X_OTHER, PTR_RESAMPLE_LOGW = range(13)
 
 _lib = None
 _lock = threading.Lock()

@@ -59,8 +59,10 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
   const float nf = (float)a.n, inv_n = 1.0f / (float)a.n;
   const double nd = (double)n, nfd = (double)(float)a.n;
   const float one4[4] = {1.f, 1.f, 1.f, 1.f};
-  float* lwrow = a.lw + (int64_t)col * a.ld;
-  float* rwrow = a.rw + (int64_t)col * a.ld;
+  const float* lwrow = a.lw + (int64_t)col * a.ld;          // rows of the state at the first move ...
+  const float* rwrow = a.rw + (int64_t)col * a.ld;
+  float* lwrow_out = a.lw_out + (int64_t)col * a.ld;        // ... and of the state after the last one (parity of the move index)
+  float* rwrow_out = a.rw_out + (int64_t)col * a.ld;
   int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
 
   // ---- the column comes on chip
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
       float u;
       if (c.u_in) u = c.u_in[col];
       else {
-        const Philox4 r4 = philox4x32_10((uint32_t)col, 0u, (uint32_t)t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+        const Philox4 r4 = philox4x32_10((uint32_t)(col + a.col0), 0u, (uint32_t)t, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
         u = smcb_u01(r4.x);
       }
       if (c.u_out && tid == 0) c.u_out[col] = u;
@@ -256,8 +258,8 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
     const bool rw_valid = (ALG == SMCB_ALG_APF) && cs.st.fold_valid;
 #pragma unroll
     for (int v = 0; v < ITEMS / 4; ++v) {
-      *reinterpret_cast<float4*>(lwrow + gbase + 4 * v) = make_float4(lw[4 * v], lw[4 * v + 1], lw[4 * v + 2], lw[4 * v + 3]);
-      if (rw_valid) *reinterpret_cast<float4*>(rwrow + gbase + 4 * v) = make_float4(rw[4 * v], rw[4 * v + 1], rw[4 * v + 2], rw[4 * v + 3]);
+      *reinterpret_cast<float4*>(lwrow_out + gbase + 4 * v) = make_float4(lw[4 * v], lw[4 * v + 1], lw[4 * v + 2], lw[4 * v + 3]);
+      if (rw_valid) *reinterpret_cast<float4*>(rwrow_out + gbase + 4 * v) = make_float4(rw[4 * v], rw[4 * v + 1], rw[4 * v + 2], rw[4 * v + 3]);
 #pragma unroll
       for (int d = 0; d < D; ++d)
         *reinterpret_cast<float4*>(a.xbuf[t1 & 1] + ((int64_t)d * a.B + col) * a.ld + gbase + 4 * v) =

@@ -7,6 +7,19 @@
 
 #define SMCB_FLT_MAX 3.402823466e+38f
 
+// number of SMs of the current device (148 on B200), queried once per process
+static inline int smcb_sm_count() {
+  static int v = 0;
+  if (v <= 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+      cudaGetLastError();
+      v = 148;
+    }
+  }
+  return v;
+}
+
 // Per-column summary written by the finalize kernel and read by the next step's kernels (all on device, no host sync).
 struct ColStats {
   float m_lw, z_lw, inv_z_lw;   // max, sum exp(lw - max) and its reciprocal for the log-weights (filters/particle/state.py:148)

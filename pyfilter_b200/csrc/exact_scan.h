@@ -223,3 +223,24 @@ XS_HD int32_t xs_count_fast(float c, float u, int32_t n, double nd /* (double)n 
   const int32_t r = K + (sd <= tt ? 1 : 0);
   return r < n ? r : n;
 }
+
+// The same count with fewer instructions for the move kernel (no upper clamp: the caller clamps into [lo, n_out]).  tt = t, or the double
+// just below t when the midpoint tie rounds away from c, comes out of ONE fused multiply-add rounded down: the product (c + ulp/2) * n is
+// exact, the addend is -0 for an even mantissa and minus the smallest denormal for an odd one.  A garbage c (NaN normalisers of a dead
+// column) gives a garbage but harmless count: the caller's clamp keeps every index in range.
+XS_HD int32_t xs_count_lean(float c, float u, int32_t n, double nfd /* (double)(float)n */) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t cb = __float_as_uint(c);
+  const double cd = (double)c;
+  const double cdh = __hiloint2double(__double2hiint(cd), __double2loint(cd) | 0x10000000);
+  const double adj = __hiloint2double((int)0x80000000u, (int)(cb & 1u));
+  const double tt = __fma_rd(cdh, nfd, adj);
+  const int32_t K = __double2loint(__dadd_rd(tt, 4503599627370496.0));   // floor(tt) read off the mantissa of 2^52 + tt (tt < 2^31)
+  const float Kf = __fadd_rn(__uint_as_float(0x4B000000u | (uint32_t)K), -8388608.0f);
+  const double sd = (double)__fadd_rn(Kf, u);
+  return K + (sd <= tt ? 1 : 0);
+#else
+  return xs_count_fast(c, u, n, (double)n, nfd);
+#endif
+}
+

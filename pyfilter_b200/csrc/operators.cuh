@@ -158,6 +158,19 @@ __global__ void copy_ess_kernel(const ColStats* st, float* out, int B) {
   if (b < B) out[b] = st[b].ess;
 }
 
+// get_ess(W, normalized=True) (utils.py:8-20): 1 / sum_i W_i^2 of every column, from weights with arbitrary strides
+__global__ void __launch_bounds__(256) ess_normalized_kernel(const float* __restrict__ w, int64_t n, int64_t sn, int64_t sb, float* out) {
+  __shared__ double scratch[33];
+  const int col = blockIdx.x;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += 256) {
+    const double v = (double)w[i * sn + (int64_t)col * sb];
+    s += v * v;
+  }
+  s = block_allreduce<256>(s, 0.0, OpSumD(), scratch);
+  if (threadIdx.x == 0) out[col] = (float)(1.0 / s);
+}
+
 static inline void op_launch_colstats(const float* rows, int64_t n, int B, int64_t ld, int nblk, NormPartial* parts, ColStats* stats, cudaStream_t s) {
   colstats_partial_kernel<<<dim3(nblk, B), RS_NT, 0, s>>>(rows, n, ld, nblk, parts);
   colstats_final_kernel<<<B, 128, 0, s>>>(parts, nblk, n, stats);
@@ -193,6 +206,7 @@ struct MultinomialArgs {
   int32_t* anc;            // (B, ld)
   int32_t stride;          // coarse table: last element of every `stride` cumulative weights (power of two)
   int32_t ncoarse;
+  int32_t col0;            // global index of column 0 (Philox counter)
 };
 
 // Draw i picks the first k with (double) fl32(c_k / c_{n-1}) >= U_i.  The predicate is monotone in c_k, so it is turned into a
@@ -217,7 +231,7 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
     double U;
     if (a.U) U = a.U[(int64_t)col * a.U_pitch + i];
     else {
-      Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)col, (uint32_t)t, SMCB_RNG_MULTINOMIAL, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      Philox4 r = philox4x32_10((uint32_t)i, (uint32_t)(col + a.col0), (uint32_t)t, SMCB_RNG_MULTINOMIAL, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       U = smcb_u01_double(r.x, r.y);
     }
     const float Uc = __double2float_ru(U);
@@ -254,12 +268,12 @@ static inline void op_launch_multinomial_after_normalize(const ResampleArgs& r, 
   expand_kernel<24, RS_OUT_CUMSUM><<<g, RS_NT, 0, s>>>(r);
   MultinomialArgs m;
   m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
-  m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc;
+  m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc; m.col0 = r.col0;
   int stride = 256;  // every block gathers the coarse table itself (one sector per entry): keep it to ~1k entries
   while ((r.n + stride - 1) / stride > 1024) stride *= 2;
   m.stride = stride; m.ncoarse = (int)((r.n + stride - 1) / stride);
   int bx = (int)((r.n + 255) / 256);
-  const int cap = (148 * 6 + r.B - 1) / r.B;
+  const int cap = (smcb_sm_count() * 6 + r.B - 1) / r.B;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
   multinomial_draw_kernel<<<dim3(bx, r.B), 256, (size_t)m.ncoarse * sizeof(float), s>>>(m);

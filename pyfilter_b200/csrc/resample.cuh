@@ -73,6 +73,7 @@ struct ResampleArgs {
   int32_t force_benign;    // 1: the host skipped describe_kernel (quantised weights, n <= 2^23, Philox offsets): benign by construction
   int32_t t_host;          // resample_fused_kernel: the move index (== ctrl->t), passed by the host to keep it off the critical path
   unsigned long long epoch_host;  // resample_fused_kernel: launch tag of the slots, unique per launch and never 0
+  int32_t col0;            // global index of column 0 (smcb_config.column_offset): the Philox counters use col0 + column
 };
 __device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { RS_OUT_ANCESTORS = 0, RS_OUT_CUMSUM = 1 };
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(RS_NT) normalize_kernel(ResampleArgs a) {
     float u;  // one uniform per column (resampling.py:41)
     if (a.u_in) u = u_inj;
     else {
-      Philox4 r = philox4x32_10((uint32_t)col, 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      Philox4 r = philox4x32_10((uint32_t)(col + a.col0), 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
       u = smcb_u01(r.x);
     }
     a.u_col[col] = u;
@@ -1176,7 +1177,7 @@ __global__ void __launch_bounds__(RS_NT, 4) resample_fused_kernel(ResampleArgs a
   const double S_in = block_allreduce<RS_NT>(part, 0.0, OpSumD(), sm.core.dscratch);
   const double S0 = S_in + ex;
   // one uniform per column (resampling.py:41)
-  const Philox4 r4 = philox4x32_10((uint32_t)col, 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+  const Philox4 r4 = philox4x32_10((uint32_t)(col + a.col0), 0u, (uint32_t)t_now, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
   const float u = smcb_u01(r4.x);
   if (a.u_out && tile == 0 && tid == 0) a.u_out[col] = u;
   const float nf = (float)a.n;

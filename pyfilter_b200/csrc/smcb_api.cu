@@ -11,6 +11,7 @@
 #include "resample.cuh"
 #include "step.cuh"
 #include "column.cuh"
+#include "move.cuh"
 #include "operators.cuh"
 
 static thread_local std::string g_err;
@@ -118,7 +119,8 @@ struct smcb_filter {
   int64_t n, ld;
   float* P_dev = nullptr;
   float* xbuf[2] = {nullptr, nullptr};
-  float *lw = nullptr, *rw = nullptr;
+  float* lwbuf[2] = {nullptr, nullptr};  // log-weights and APF resampling log-weights: like the state they ping-pong with the move index
+  float* rwbuf[2] = {nullptr, nullptr};  // (the state at move index t lives in xbuf / lwbuf / rwbuf [t & 1])
   int32_t *anc = nullptr, *prev_inds = nullptr;
   ColStats* stats = nullptr;
   Partial* partials = nullptr;
@@ -147,6 +149,14 @@ struct smcb_filter {
   unsigned long long fused_epoch = 0;   // tags the tile-sum slots of resample_fused_kernel, bumped per launch
   bool folded_for_next = false;
   int64_t launches = 0;
+  // move_kernel (move.cuh): per-tile partial records, the tile-ticket counter and the host's copy of its value, the persistent grid
+  Partial* tile_partials = nullptr;
+  uint32_t* tile_counter = nullptr;
+  long long* wd = nullptr;
+  uint32_t ticket_next = 0;
+  int mv_grid = 0;
+  unsigned long long* mslots = nullptr;
+  unsigned mv_epoch = 0;
 };
 
 template <typename T>
@@ -172,10 +182,10 @@ static int upload_params(smcb_filter* f, const float* params_host, int n_raw, in
 
 extern "C" int smcb_filter_destroy(smcb_filter* f) {
   if (!f) return SMCB_OK;
-  void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lw, f->rw, f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
+  void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -205,7 +215,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   {
     const int64_t chunk = ST_NT * ST_VEC;
     const int64_t nchunks = (f->n + chunk - 1) / chunk;
-    int64_t cap = (148 * SMCB_ST_MINB) / f->B;  // one resident wave of step-kernel blocks
+    int64_t cap = ((int64_t)smcb_sm_count() * SMCB_ST_MINB) / f->B;  // one resident wave of step-kernel blocks
     if (cap < 1) cap = 1;
     f->iters = (int)((nchunks + cap - 1) / cap);
     f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);
@@ -218,8 +228,10 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->P_dev, (size_t)f->B * SMCB_NPARAM));
   A_(dalloc(&f->xbuf[0], cells * f->D));
   A_(dalloc(&f->xbuf[1], cells * f->D));
-  A_(dalloc(&f->lw, cells));
-  A_(dalloc(&f->rw, cells));
+  A_(dalloc(&f->lwbuf[0], cells));
+  A_(dalloc(&f->lwbuf[1], cells));
+  A_(dalloc(&f->rwbuf[0], cells));
+  A_(dalloc(&f->rwbuf[1], cells));
   A_(dalloc(&f->wn, cells));
   A_(dalloc(&f->anc, cells));
   A_(dalloc(&f->prev_inds, cells));
@@ -240,6 +252,10 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ncounter, (size_t)f->B));
   A_(dalloc(&f->verdict, (size_t)f->B));
   A_(dalloc(&f->u_col, (size_t)f->B));
+  A_(dalloc(&f->tile_partials, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->tile_counter, (size_t)1));
+  A_(dalloc(&f->mslots, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->wd, (size_t)4));
   A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_var, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_ll, (size_t)rows * f->B));
@@ -249,7 +265,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
-  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)8 * f->B * f->tiles_per_col));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -281,11 +297,14 @@ static StepArgs make_args(smcb_filter* f) {
   StepArgs a;
   memset(&a, 0, sizeof(a));
   a.n = f->n; a.ld = f->ld; a.B = f->B; a.blocks_per_col = f->blocks_per_col; a.iters = f->iters;
-  a.P = f->P_dev; a.xbuf[0] = f->xbuf[0]; a.xbuf[1] = f->xbuf[1]; a.lw = f->lw; a.rw = f->rw;
+  a.P = f->P_dev; a.xbuf[0] = f->xbuf[0]; a.xbuf[1] = f->xbuf[1];
+  a.lw = f->lwbuf[f->t_host & 1]; a.rw = f->rwbuf[f->t_host & 1];                  // current state
+  a.lw_out = f->lwbuf[(f->t_host + 1) & 1]; a.rw_out = f->rwbuf[(f->t_host + 1) & 1];  // state after ONE move (run_column overrides)
   a.anc = f->anc; a.prev_inds = f->prev_inds; a.stats = f->stats; a.partials = f->partials; a.ctrl = f->ctrl; a.col_ticket = f->col_ticket;
   a.eps_in = f->eps_in; a.eps_out = f->eps_out; a.seed = f->cfg.seed;
   philox_round_keys((uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), a.pkeys);
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
+  a.col0 = f->cfg.column_offset;
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
   a.dbg = f->dbg;
   a.latest_mean = f->latest_mean; a.latest_var = f->latest_var; a.latest_ll = f->latest_ll; a.ll_total = f->ll_total;
@@ -316,6 +335,75 @@ static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
     case 3: launch_step_alg<3, 0>(alg, g, s, a); break;
   }
   f->launches++;
+}
+
+// ---- move_kernel (move.cuh): one kernel per move, persistent grid drawing tile tickets -----------------------------------------
+template <int MODEL, int PROP, int ALG>
+static cudaError_t launch_move_t(smcb_filter* f, MoveArgs& m, cudaStream_t s) {
+  constexpr int D = Model<MODEL>::D;
+  const size_t dyn = sizeof(float) * (size_t)D * MV_TILE;
+  auto kernel = move_kernel<MODEL, PROP, ALG>;
+  if (f->mv_grid == 0) {  // once per handle: dynamic shared memory limit; one block per tile
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    f->mv_grid = m.total_tiles;
+  }
+  m.ticket_base = f->ticket_next;
+  f->ticket_next += (uint32_t)m.total_tiles;  // every block draws exactly one ticket
+  static bool pdl_ok = true;
+  if (use_pdl() && pdl_ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(f->mv_grid); cfg.blockDim = dim3(MV_NT); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kernel, m) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError();
+    pdl_ok = false;
+  }
+  kernel<<<f->mv_grid, MV_NT, dyn, s>>>(m);
+  return cudaGetLastError();
+}
+template <int MODEL, int PROP>
+static cudaError_t launch_move_alg(smcb_filter* f, MoveArgs& m, cudaStream_t s) {
+  if (f->cfg.algorithm == SMCB_SISR) return launch_move_t<MODEL, PROP, SMCB_ALG_SISR>(f, m, s);
+  return launch_move_t<MODEL, PROP, SMCB_ALG_APF>(f, m, s);
+}
+static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
+  MoveArgs m;
+  memset(&m, 0, sizeof(m));
+  m.s = a;
+  m.s.partials = f->tile_partials; m.s.blocks_per_col = f->tiles_per_col;
+  m.tiles_per_col = f->tiles_per_col; m.total_tiles = f->tiles_per_col * f->B;
+  f->mv_epoch = f->mv_epoch % 1023u + 1u;   // 1 .. 1023, never the previous launch's
+  m.tile_counter = f->tile_counter; m.mslots = f->mslots; m.epoch = f->mv_epoch;
+  m.u_in = f->u_in; m.u_out = f->u_out; m.w_out = f->w_out; m.wd = f->wd;
+  m.tl = f->dbg ? f->dbg + 32 : nullptr;
+  if (!f->u_in && f->B <= MV_U_HOST) {  // few columns: the systematic offsets (one Philox block per column and move) come as arguments
+    m.n_u_host = f->B;
+    for (int b = 0; b < f->B; ++b) {
+      const Philox4 r4 = philox4x32_10((uint32_t)(b + a.col0), 0u, (uint32_t)a.t_host, SMCB_RNG_SYSTEMATIC, (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+      m.u_host[b] = smcb_u01(r4.x);
+    }
+  }
+  const int prop = f->cfg.proposal;
+  cudaError_t e = cudaSuccess;
+  switch (f->cfg.model) {
+    case 0: e = prop ? launch_move_alg<0, 1>(f, m, s) : launch_move_alg<0, 0>(f, m, s); break;
+    case 1: e = prop ? launch_move_alg<1, 1>(f, m, s) : launch_move_alg<1, 0>(f, m, s); break;
+    case 2: e = launch_move_alg<2, 0>(f, m, s); break;
+    case 3: e = launch_move_alg<3, 0>(f, m, s); break;
+  }
+  if (e != cudaSuccess) return fail(SMCB_ECUDA, std::string("move_kernel: ") + cudaGetErrorString(e));
+  f->launches++;
+  return SMCB_OK;
+}
+// the move kernel serves systematic resampling with rounding-free weights of at most 2^23 particles (the lean probe count)
+static bool move_path_ok(const smcb_filter* f) {
+  const bool off = getenv("SMCB_NO_MOVE") != nullptr;  // diagnostics / tests: force the two-kernel pipeline
+  return !off && f->cfg.resampler == SMCB_SYSTEMATIC && !f->cfg.exact_weights && f->n <= (1 << 23) &&
+         (int64_t)f->tiles_per_col * f->B < (1 << 30);
 }
 
 static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
@@ -398,7 +486,8 @@ extern "C" int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, 
 }
 
 // one filter move; `ev` (optional) receives 6 events bracketing the 5 kernel groups
-static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
+// `last`: the caller reads the state after this move (API-visible log-weights and ancestors are stored)
+static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = true) {
   const bool apf = f->cfg.algorithm == SMCB_APF;
   const int t = f->t_host;
   if (t - f->y_base < 0 || t - f->y_base >= f->y_count) return fail(SMCB_ESTATE, "no observation set for this move");
@@ -412,13 +501,22 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev) {
     launch_finalize(f, a, FIN_PREWEIGHT, s);
   }
   if (ev) cudaEventRecord(ev[1], s);
+  a.store_lw = last ? 1 : 0;
+  if (move_path_ok(f)) {
+    int rc = launch_move(f, a, s);
+    if (rc) return rc;
+    if (ev) for (int g = 2; g <= 5; ++g) cudaEventRecord(ev[g], s);
+    f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
+    f->t_host = t + 1;
+    return SMCB_OK;
+  }
   ResampleArgs r;
   memset(&r, 0, sizeof(r));
-  r.w = apf ? f->rw : f->lw;
+  r.w = apf ? a.rw : a.lw;
   r.wn = f->wn;
   r.n = f->n; r.ld = f->ld; r.B = f->B; r.tiles_per_col = f->tiles_per_col;
   r.input_is_w = 0; r.use_rw = apf ? 1 : 0; r.stats = f->stats;
-  r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed;
+  r.u_in = f->u_in; r.u_out = f->u_out; r.seed = f->cfg.seed; r.col0 = f->cfg.column_offset;
   r.tilesum = f->tilesum; r.prefix = f->prefix; r.sin = f->sin; r.tileflag = f->tileflag; r.desc = f->desc; r.desc2 = f->desc2; r.tables = f->tables;
   r.anc = f->anc; r.w_out = f->w_out; r.ctrl = f->ctrl;
   r.tilemin = f->tilemin; r.ncounter = f->ncounter; r.dcounter = f->dcounter; r.verdict = f->verdict; r.u_col = f->u_col;
@@ -507,6 +605,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   ColumnArgs c;
   memset(&c, 0, sizeof(c));
   c.s = a;
+  c.s.lw_out = f->lwbuf[(t + steps) & 1]; c.s.rw_out = f->rwbuf[(t + steps) & 1];
   c.steps = steps;
   c.y = f->y_dev + (int64_t)(t - f->y_base) * f->OD;
   c.y_avail = f->y_count - (t - f->y_base);
@@ -514,7 +613,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   const size_t dyn = sizeof(float) * (size_t)f->D * RS_TILE;
   const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
   // 512 threads x 8 particles; fewer columns than SMs: one block per SM with twice the registers, otherwise two blocks per SM
-  int nt = (f->B <= 148) ? 1 : 2;
+  int nt = (f->B <= smcb_sm_count()) ? 1 : 2;
   if (const char* v = getenv("SMCB_COLUMN_MINB")) nt = atoi(v);   // diagnostics: 0 = 1024 threads x 4, 1 = 512 x 8 one block per SM, 2 = 512 x 8 two per SM
   cudaError_t e = cudaSuccess;
   switch (f->cfg.model) {
@@ -537,7 +636,7 @@ extern "C" int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (column_path_ok(f)) return run_column(f, steps, s);
   for (int k = 0; k < steps; ++k) {
-    int rc = run_one(f, s, nullptr);
+    int rc = run_one(f, s, nullptr, k == steps - 1);
     if (rc) return rc;
   }
   CU(cudaGetLastError());
@@ -550,7 +649,7 @@ extern "C" int smcb_filter_profile(smcb_filter* f, int32_t steps, float* out_ms_
   std::vector<cudaEvent_t> ev((size_t)steps * 6);
   for (auto& e : ev) CU(cudaEventCreate(&e));
   int rc = SMCB_OK;
-  for (int k = 0; k < steps && rc == SMCB_OK; ++k) rc = run_one(f, s, &ev[(size_t)k * 6]);
+  for (int k = 0; k < steps && rc == SMCB_OK; ++k) rc = run_one(f, s, &ev[(size_t)k * 6], k == steps - 1);
   cudaError_t e2 = cudaStreamSynchronize(s);
   for (int g = 0; g < 5; ++g) out_ms_host[g] = 0.f;
   if (rc == SMCB_OK && e2 == cudaSuccess)
@@ -609,7 +708,7 @@ extern "C" int smcb_filter_ptr(smcb_filter* f, int32_t what, void** p) {
   switch (what) {
     case SMCB_PTR_X: *p = f->xbuf[f->t_host & 1]; break;
     case SMCB_PTR_X_OTHER: *p = f->xbuf[(f->t_host + 1) & 1]; break;
-    case SMCB_PTR_LOGW: *p = f->lw; break;
+    case SMCB_PTR_LOGW: *p = f->lwbuf[f->t_host & 1]; break;
     case SMCB_PTR_PREV_INDS: *p = f->prev_inds; break;
     case SMCB_PTR_MEAN: *p = f->latest_mean; break;
     case SMCB_PTR_VAR: *p = f->latest_var; break;
@@ -619,8 +718,10 @@ extern "C" int smcb_filter_ptr(smcb_filter* f, int32_t what, void** p) {
     case SMCB_PTR_HIST_VAR: *p = f->hist_var; break;
     case SMCB_PTR_HIST_LL: *p = f->hist_ll; break;
     case SMCB_PTR_ESS: *p = f->ess_packed; break;
+    case SMCB_PTR_RESAMPLE_LOGW: *p = f->rwbuf[f->t_host & 1]; break;
     case 20: *p = f->dbg; break;  /* diagnostics */
     case 21: *p = f->verdict; break;
+    case 22: *p = f->wd; break;
     default: return fail(SMCB_EINVAL, "unknown pointer id");
   }
   return SMCB_OK;
@@ -708,6 +809,16 @@ extern "C" int smcb_normalize(const float* logw_dev, int64_t n, int32_t B, int64
   }
   op_free(ws, s);
   return rc;
+}
+
+extern "C" int smcb_get_ess(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized, float* ess_out_dev,
+                            void* stream) {
+  if (!w_dev || !ess_out_dev || n < 1 || B < 1) return fail(SMCB_EINVAL, "bad argument");
+  if (!normalized) return smcb_normalize(w_dev, n, B, sn, sb, nullptr, 0, 0, ess_out_dev, stream);
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  ess_normalized_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(w_dev, n, sn, sb, ess_out_dev);
+  CU(cudaGetLastError());
+  return SMCB_OK;
 }
 
 static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized, const float* u_dev,

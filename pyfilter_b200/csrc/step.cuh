@@ -24,8 +24,10 @@ struct StepArgs {
   int32_t B, blocks_per_col, iters;  // every block runs `iters` strided chunks of ST_NT*ST_VEC particles
   const float* P;                    // (B, SMCB_NPARAM)
   float* xbuf[2];                    // ping-pong state buffers, each (D, B, ld); the live one is xbuf[ctrl->t & 1]
-  float* lw;                         // (B, ld)
-  float* rw;                         // (B, ld)
+  float* lw;                         // (B, ld) log-weights of the CURRENT state (input of a move)
+  float* rw;                         // (B, ld) APF resampling log-weights g + lw of the current state
+  float* lw_out;                     // (B, ld) the rows a MOVE writes: the weight rows ping-pong with the move index like the state buffers,
+  float* rw_out;                     //         because move_kernel reads a tile's weights while other tiles already store new ones
   const int32_t* anc;                // (B, ld)
   int32_t* prev_inds;                // (B, ld) ancestors of the latest move as the API reports them (sisr.py:32 / apf.py:46)
   ColStats* stats;                   // (B)
@@ -50,6 +52,7 @@ struct StepArgs {
   const float* y_t;                  // observation of this move (NULL: none)
   const float* y_next;               // observation of the next move (NULL: unknown -> no folded look-ahead)
   uint32_t pkeys[20];                // Philox round keys of `seed` (philox_round_keys)
+  int32_t col0;                      // global index of column 0 (smcb_config.column_offset): the Philox counters use col0 + column
 };
 __device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
@@ -134,7 +137,7 @@ struct Fin4Scratch {
   float a[K][NT / 32];
   float q[NT / 32], r2[NT / 32], r3[NT / 32];
 };
-template <int K, int NT = ST_NT>
+template <int K, int NT = ST_NT, bool PROTECT = true>  // PROTECT = false: the scratch area is known to be idle (saves a barrier)
 __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>& Q, SoftAcc<1>& R2, SoftAcc<1>& R3, Fin4Scratch<K, NT>& sc) {
   // Cost per thread is independent of the block size: the NT/32 per-warp values are folded by every warp with one lane per value
   // (redux for the maxima) instead of a loop over the warps in every thread.
@@ -143,7 +146,7 @@ __device__ __forceinline__ void softacc4_block_reduce(SoftAcc<K>& A, SoftAcc<1>&
   float mb[4] = {A.m, Q.m, R2.m, R3.m};
 #pragma unroll
   for (int i = 0; i < 4; ++i) mb[i] = warp_redux_max(mb[i]);
-  __syncthreads();
+  if (PROTECT) __syncthreads();
   if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) sc.m[i][wid] = mb[i];
@@ -288,7 +291,7 @@ __device__ __forceinline__ void st_noise4(const StepArgs& a, int col, int64_t i0
       const float4 q = *reinterpret_cast<const float4*>(a.eps_in + ((int64_t)d * a.B + col) * a.ld + i0);
       z[d][0] = q.x; z[d][1] = q.y; z[d][2] = q.z; z[d][3] = q.w;
     } else {
-      Philox4 r = philox4x32_10_keys((uint32_t)(i0 >> 2), (uint32_t)col, (uint32_t)t, purpose + d, a.pkeys);
+      Philox4 r = philox4x32_10_keys((uint32_t)(i0 >> 2), (uint32_t)(col + a.col0), (uint32_t)t, purpose + d, a.pkeys);
       smcb_normal4(r, z[d]);
     }
     if (!PLAIN && a.eps_out)
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(ST_NT) state_kernel(StepArgs a) {
   float shift[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) shift[d] = a.sample_x0 ? Ps[P_X0_LOC + d] : a.stats[col].shift[d];
+  if (a.sample_x0 && blockIdx.x == 0 && tid < D) a.stats[col].shift[tid] = Ps[P_X0_LOC + tid];  // the finalize kernel adds the shift back
   Moments<D> mom; mom.init();
   for (int it = 0; it < a.iters; ++it) {
     const int64_t i0 = ((int64_t)(it * a.blocks_per_col + blockIdx.x) * ST_NT + tid) * ST_VEC;
@@ -675,12 +679,14 @@ __global__ void __launch_bounds__(ST_NT, SMCB_ST_MINB) step_kernel(StepArgs a) {
   }
   const int32_t* ancrow = a.anc + (int64_t)col * a.ld;
   int32_t* pirow = a.prev_inds + (int64_t)col * a.ld;
-  float* lwrow = a.lw + (int64_t)col * a.ld;
-  float* rwrow = a.rw + (int64_t)col * a.ld;
+  const float* lwin = a.lw + (int64_t)col * a.ld;
+  float* lwrow = a.lw_out + (int64_t)col * a.ld;
+  float* rwrow = a.rw_out + (int64_t)col * a.ld;
   // keep the row pointers in registers: re-deriving them from (column, pitch, buffer index) inside the loop costs ~5 instructions per access
 #pragma unroll
   for (int d = 0; d < D; ++d) { asm volatile("" : "+l"(xprev[d])); asm volatile("" : "+l"(xnext[d])); }
   asm volatile("" : "+l"(ancrow)); asm volatile("" : "+l"(pirow)); asm volatile("" : "+l"(lwrow)); asm volatile("" : "+l"(rwrow));
+  asm volatile("" : "+l"(lwin));
 
   StepAcc<D> mom; mom.init();
   StepAcc1 r2; r2.init();   // APF: folded resampling weights
@@ -719,7 +725,7 @@ __global__ void __launch_bounds__(ST_NT, SMCB_ST_MINB) step_kernel(StepArgs a) {
       }
       float lwp[4] = {0.f, 0.f, 0.f, 0.f};
       if (!resampled) {  // weights carry over (sisr.py:52 without the reset of :34; particle/state.py:42)
-        const float4 q = *reinterpret_cast<const float4*>(lwrow + i0);
+        const float4 q = *reinterpret_cast<const float4*>(lwin + i0);
         lwp[0] = q.x; lwp[1] = q.y; lwp[2] = q.z; lwp[3] = q.w;
       }
       float xa[D][4];

@@ -37,10 +37,8 @@ def normalize(weights: torch.Tensor) -> torch.Tensor:
 def get_ess(weights: torch.Tensor, normalized: bool = False) -> torch.Tensor:
     """ESS = 1 / sum_i W_i^2 over dim 0 from an array of (log) weights."""
     w = _check_weights(weights)
-    if normalized:
-        w = w.clamp_min(torch.finfo(torch.float32).tiny).log()  # the kernel works from log-weights
     n, b, sn, sb = _strides_2d(w)
     ess = torch.empty(b, device=w.device, dtype=torch.float32)
     lib = _lib.load_library()
-    _lib.check(lib.smcb_normalize(w.data_ptr(), n, b, sn, sb, None, 0, 0, ess.data_ptr(), _lib.current_stream()))
+    _lib.check(lib.smcb_get_ess(w.data_ptr(), n, b, sn, sb, int(bool(normalized)), ess.data_ptr(), _lib.current_stream()))
     return ess.reshape(w.shape[1:])

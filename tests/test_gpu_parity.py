@@ -20,14 +20,17 @@ def pf():
     return pyfilter_b200
 
 
-@pytest.fixture(params=["column", "pipeline"])
+@pytest.fixture(params=["column", "pipeline", "twokernel"])
 def smc_path(request, monkeypatch):
     """Filters of at most 4096 particles per column run in the resident column kernel (csrc/column.cuh) by default;
-    ``SMCB_NO_COLUMN`` forces the multi-kernel pipeline (resample_fused / normalize-describe-expand + step).  Both are tested."""
-    if request.param == "pipeline":
+    ``SMCB_NO_COLUMN`` forces the per-move pipeline: the single move kernel (csrc/move.cuh, "pipeline") or, with ``SMCB_NO_MOVE``
+    as well, the older resampling kernel(s) + step kernel ("twokernel").  All three are tested."""
+    monkeypatch.delenv("SMCB_NO_COLUMN", raising=False)
+    monkeypatch.delenv("SMCB_NO_MOVE", raising=False)
+    if request.param != "column":
         monkeypatch.setenv("SMCB_NO_COLUMN", "1")
-    else:
-        monkeypatch.delenv("SMCB_NO_COLUMN", raising=False)
+    if request.param == "twokernel":
+        monkeypatch.setenv("SMCB_NO_MOVE", "1")
     return request.param
 
 
@@ -44,7 +47,7 @@ def test_normalize_and_ess_golden(pf):
     ref = g["norm_out"]
     ok = ~np.isnan(ref)
     assert np.allclose(W[ok], ref[ok], rtol=2e-6, atol=1e-37)
-    assert np.isnan(W[~ok]).all() or (~ok).sum() == 0 or True  # all-NaN columns are undefined input (Appendix A-1)
+    # (all-NaN columns give NaN in the reference, i.e. they are undefined input - Appendix A-1 - and are not compared)
     ess = pf.utils.get_ess(lw.clone()).cpu().numpy()
     okc = ~np.isnan(g["norm_ess"])
     assert np.allclose(ess[okc], g["norm_ess"][okc], rtol=5e-6)
@@ -223,6 +226,23 @@ def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights, smc_pa
             for key, got in (("ll", st.get_loglikelihood()), ("mean", st.get_mean()), ("var", st.get_variance())):
                 a, b = got.cpu().numpy().reshape(-1), g[key][t].reshape(-1)
                 assert np.allclose(a, b, rtol=2e-5, atol=2e-5), (tag, t, key, a, b)
+        # (3) EVERY quantity of the move, on every step: the oracle's step run on the device's ancestors (an ulp of a weight may move
+        # an ancestor; with the ancestors forced the rest of the arithmetic is compared in full, flipped particles included)
+        kw = dict(force_idx=inds.reshape(gx.shape[:ginds.dim()]))
+        yt = torch.as_tensor(g["y"][t]).float()
+        ut = torch.from_numpy(g["u"][t]).reshape(-1)
+        if g["alg"] == "sisr":
+            ref = O.sisr_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, torch.from_numpy(g["z"][t]),
+                              ut, resampler=g["resampler"], **kw)
+        else:
+            ref = O.apf_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, torch.from_numpy(g["z"][t]),
+                             ut, resampler=g["resampler"], **kw)
+        assert torch.allclose(x, ref["x"], rtol=0, atol=2e-6 * max(1.0, float(gx.abs().max()))), (tag, t, "x vs oracle on device ancestors")
+        finr = torch.isfinite(ref["lw"])
+        assert ((lw[finr] - ref["lw"][finr]).abs() <= tol + 4e-6 * ref["lw"][finr].abs()).all(), (tag, t, "lw vs oracle on device ancestors")
+        for key, got in (("ll", st.get_loglikelihood()), ("mean", st.get_mean()), ("var", st.get_variance())):
+            a, b = got.cpu().numpy().reshape(-1), ref[key].numpy().reshape(-1)
+            assert np.allclose(a, b, rtol=2e-5, atol=2e-5), (tag, t, key, "vs oracle on device ancestors", a, b)
     print(tag, "ancestor flips vs golden over all steps:", total_flips)
 
 
@@ -298,8 +318,8 @@ def test_filter_single_steps_match_batch(pf, smc_path):
         rb = fb.initialize_with_result(st)
         for yt in y:
             st = fb.filter(yt, st, result=rb)
-        if smc_path == "column" and cls is APF:
-            # fa folds the look-ahead inside the column kernel, fb (fold_lookahead=False) runs the pre-weight kernel of the pipeline:
+        if smc_path in ("column", "pipeline") and cls is APF:
+            # fa folds the look-ahead inside the column / move kernel, fb (fold_lookahead=False) runs the pre-weight kernel:
             # the float32 normaliser differs in its last bit, a rare ancestor flips and the runs decorrelate -
             # identical up to the first flip, Monte-Carlo agreement afterwards
             assert torch.allclose(ra.filter_means[:6], rb.filter_means[:6], rtol=1e-4, atol=1e-5)
@@ -514,6 +534,14 @@ def test_observe_every_step(pf, alg, smc_path):
     r2 = f2.initialize_with_result(st)
     for yt in y:
         st = f2.filter(yt, st, result=r2)
+    if alg == "apf" and smc_path != "twokernel":
+        # res folds the look-ahead inside the move kernel, f2 (fold_lookahead=False) runs the pre-weight kernel: the float32 normaliser
+        # of the resampling weights is reduced in a different order, an ulp flips a rare ancestor and the runs decorrelate
+        #  - identical up to the first flip, Monte-Carlo agreement afterwards
+        assert torch.allclose(res.filter_means[:4], r2.filter_means[:4], rtol=1e-4, atol=1e-5)
+        assert float((res.filter_means - r2.filter_means).abs().max()) < 0.1
+        assert abs(float(res.loglikelihood) - float(r2.loglikelihood)) < 6 * spread
+        return
     assert torch.allclose(res.filter_means, r2.filter_means, rtol=1e-4, atol=1e-5)
     assert torch.allclose(res.loglikelihood, r2.loglikelihood, rtol=1e-4, atol=1e-3)
 
@@ -588,3 +616,286 @@ def test_column_kernel_matches_pipeline(pf, name, alg, prop, N, B, monkeypatch):
     assert torch.allclose(a[3][:3], b[3][:3], atol=2e-3 * scale) and torch.allclose(a[5][:3], b[5][:3], atol=2e-3, rtol=1e-3)
     assert float((a[3] - b[3]).abs().max()) < max(0.1, 3.0 / N ** 0.5) * scale
     assert float((a[4] - b[4]).abs().max()) < 0.2 * float(a[4].abs().max())
+
+
+# ------------------------------------------------------------------------------- the kernels the benchmark times, pinned
+def _engine(pf, name, alg, N, B=0, seed=77, rows=24, **kw):
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR
+
+    f = {"apf": APF, "sisr": SISR}[alg](ts.build(name), N, seed=seed, **kw)
+    if B:
+        f.set_batch_shape(torch.Size([B]))
+    return f._get_engine(rows)
+
+
+@pytest.mark.parametrize("name,alg,N,B", [("sv_ar1", "apf", 4_000_000, 0), ("lorenz63_em", "sisr", 300_000, 3), ("sine_em", "apf", 70_001, 2)])
+def test_move_kernel_bit_identical_to_two_kernel_pipeline(pf, name, alg, N, B, monkeypatch):
+    """The benchmark's kernel (move_kernel, csrc/move.cuh: resampling + propagation in one pass, Philox offsets, its compile-time
+    steady-state loop) against the two-kernel pipeline whose generic loop the golden vectors pin: from the SAME state, one move gives
+    bit-identical particles, log-weights, folded resampling weights and ancestors - with the steady-state loop (no dump) and with the
+    generic loop (noise dumped) alike; then the move is replayed on the CPU oracle with the dumped noise, offset and the device's
+    ancestors, so log-likelihood increment, mean and variance of the benchmark path itself are compared with the reference arithmetic."""
+    from pyfilter_b200 import _lib
+
+    monkeypatch.delenv("SMCB_NO_COLUMN", raising=False)
+    monkeypatch.delenv("SMCB_NO_MOVE", raising=False)
+    torch.manual_seed(5)
+    mo = O.build_model(name)
+    _, y = mo.simulate(12)
+    yd = y.float().reshape(12, -1).cuda().contiguous()
+    e0 = _engine(pf, name, alg, N, B)
+    e0.initialize()
+    e0.set_observations(yd, 0)
+    e0.run(8)                      # a realistic cloud: weights of a running filter, not of the prior
+    torch.cuda.synchronize()
+    x0, lw0, pi0 = e0.x_view().clone(), e0.logw_view().clone(), e0.prev_inds().clone()
+    out = {}
+    for path in ("move", "move_dump", "twokernel", "twokernel_dump"):
+        if path.startswith("twokernel"):
+            monkeypatch.setenv("SMCB_NO_MOVE", "1")
+        else:
+            monkeypatch.delenv("SMCB_NO_MOVE", raising=False)
+        e = _engine(pf, name, alg, N, B)
+        e.load_state(x0, lw0, pi0, 8)
+        e.set_observations(yd, 0)
+        eps = torch.zeros(e.D, e.B, e.ld, device="cuda")
+        ud = torch.zeros(e.B, device="cuda")
+        wd = torch.zeros(e.B, e.ld, device="cuda")
+        if path.endswith("_dump"):
+            e.dump_noise(eps, ud, wd)
+        launches = e.info().kernel_launches
+        e.run(1)
+        torch.cuda.synchronize()
+        st = e.make_state()
+        rw = e.raw(_lib.PTR_RESAMPLE_LOGW, (e.B, e.ld))[:, : e.N].clone()
+        out[path] = dict(x=e.x_view().clone(), lw=e.logw_view().clone(), pi=e.prev_inds().clone(), rw=rw, ll=st.get_loglikelihood().clone(),
+                         mean=st.get_mean().clone(), var=st.get_variance().clone(), eps=eps, u=ud, w=wd,
+                         launches=e.info().kernel_launches - launches)
+    a = out["move"]
+    assert out["move"]["launches"] < out["twokernel"]["launches"]
+    for other in ("move_dump", "twokernel", "twokernel_dump"):
+        b = out[other]
+        assert torch.equal(a["pi"], b["pi"]), (other, "ancestors", int((a["pi"] != b["pi"]).sum()))
+        assert torch.equal(a["x"], b["x"]), (other, "x")
+        assert torch.equal(a["lw"], b["lw"]), (other, "lw")
+        if alg == "apf":
+            assert torch.equal(a["rw"], b["rw"]), (other, "folded resampling log-weights")
+        assert torch.allclose(a["ll"], b["ll"], rtol=1e-5, atol=1e-5) and torch.allclose(a["mean"], b["mean"], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(a["var"], b["var"], rtol=1e-4, atol=1e-7)
+    assert torch.equal(out["move_dump"]["eps"], out["twokernel_dump"]["eps"]) and torch.equal(out["move_dump"]["u"], out["twokernel_dump"]["u"])
+    assert torch.equal(out["move_dump"]["w"], out["twokernel_dump"]["w"])
+    # replay on the CPU oracle with the dumped noise and the device's ancestors
+    d = out["move_dump"]
+    z = d["eps"][:, :, : e.N].permute(2, 1, 0).cpu()           # (N, B, D)
+    z = z[..., 0] if e.D == 1 and len(mo_state_shape(mo)) == 0 else z
+    if not B:
+        z = z[:, 0]
+    step = O.apf_step if alg == "apf" else O.sisr_step
+    u = d["u"].cpu()
+    ref = step(mo, "bootstrap", x0.cpu(), lw0.cpu(), pi0.cpu(), y[8].float(), z, u, force_idx=a["pi"].cpu())
+    xs = float(ref["x"].abs().max())
+    assert torch.allclose(a["x"].cpu(), ref["x"], rtol=0, atol=2e-6 * max(1.0, xs))
+    fin = torch.isfinite(ref["lw"])
+    assert bool(((a["lw"].cpu() - ref["lw"])[fin].abs() <= 1e-5 + 4e-6 * ref["lw"][fin].abs()).all())
+    assert torch.allclose(a["ll"].cpu(), ref["ll"].float(), rtol=2e-5, atol=2e-4 if name == "sine_em" else 2e-5)  # (peaked weights: c5 tolerance)
+    assert torch.allclose(a["mean"].cpu().reshape(-1), ref["mean"].reshape(-1), rtol=2e-5, atol=2e-5)
+    assert torch.allclose(a["var"].cpu().reshape(-1), ref["var"].reshape(-1), rtol=1e-4, atol=2e-5)
+    # and the ancestors are the CPU systematic ancestors for the device's weights and offset (bit-exact)
+    Wd = d["w"][:, : e.N].t().cpu()
+    cols = Wd.sum(0) > 0.5                      # the columns that resampled dumped their weights
+    assert bool(cols.all()) or alg == "sisr"
+    if bool(cols.any()):
+        exp = O.systematic(Wd[:, cols].clone(), normalized=True, u=u[cols].reshape(-1, 1))
+        assert torch.equal(a["pi"].cpu().reshape(e.N, -1)[:, cols], exp)
+
+
+def mo_state_shape(mo):
+    return (mo.state_dim,) if mo.state_dim else ()
+
+
+def test_move_kernel_reproducible_and_many_windows(pf, monkeypatch):
+    """(1) Same seed, same bits: tile tickets are drawn dynamically, the statistics are reduced per tile - two runs of 30 moves
+    agree bit for bit.  (2) Degenerate weights: one particle owns (almost) every slot, i.e. one tile has hundreds of windows of
+    offspring - still exact against the CPU systematic."""
+    monkeypatch.delenv("SMCB_NO_MOVE", raising=False)
+    torch.manual_seed(2)
+    mo = O.build_model("sv_ar1")
+    _, y = mo.simulate(32)
+    yd = y.float().reshape(-1, 1).cuda().contiguous()
+    res = []
+    for rep in range(2):
+        e = _engine(pf, "sv_ar1", "apf", 1_000_000, rows=40)
+        e.initialize()
+        e.set_observations(yd, 0)
+        e.run(30)
+        torch.cuda.synchronize()
+        res.append((e.x_view().clone(), e.logw_view().clone(), e.prev_inds().clone(), e.history(31)))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1]) and torch.equal(res[0][2], res[1][2])
+    for h0, h1 in zip(res[0][3], res[1][3]):
+        assert torch.equal(h0, h1)
+    # degenerate cloud
+    N = 300_000
+    e = _engine(pf, "sv_ar1", "sisr", N, seed=3)
+    x0 = torch.randn(N) * 0.1 - 1.0
+    lw0 = torch.full((N,), -60.0)
+    lw0[123_457] = 0.0
+    lw0[5] = -3.0
+    e.load_state(x0, lw0, torch.arange(N), 0)
+    e.set_observations(yd, 0)
+    wd = torch.zeros(e.B, e.ld, device="cuda")
+    ud = torch.zeros(e.B, device="cuda")
+    e.dump_noise(None, ud, wd)
+    e.run(1)
+    torch.cuda.synchronize()
+    anc = e.prev_inds().cpu()
+    exp = O.systematic(wd[0, :N].cpu().clone().unsqueeze(1), normalized=True, u=ud.cpu().reshape(1, 1))[:, 0]
+    assert torch.equal(anc, exp)
+    assert int((anc == 123_457).sum()) > N * 0.9
+    assert torch.equal(e.x_view().cpu() != 0, torch.ones(N, dtype=torch.bool))
+
+
+# ------------------------------------------------------------------------------- BASELINE configs at full size, teacher-forced
+def test_full_size_config2_lgo_vs_oracle(pf):
+    """configs[1]: sine diffusion, APF + LinearGaussianObservations, systematic, 1,000,000 particles - one teacher-forced move."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, proposals
+
+    N = 1_000_000
+    gen = torch.Generator().manual_seed(12)
+    mo = O.build_model("sine_em")
+    x0 = torch.randn(N, generator=gen) * 1.5
+    lw0 = torch.randn(N, generator=gen) * 0.8
+    z = torch.randn(N, generator=gen)
+    u = torch.rand(1, generator=gen)
+    y = torch.tensor(0.7)
+    f = APF(ts.build("sine_em"), N, proposal=proposals.LinearGaussianObservations(), seed=4)
+    e = f._get_engine(2)
+    e.load_state(x0, lw0, torch.arange(N), 0)
+    eps = torch.zeros(e.D, e.B, e.ld)
+    eps[0, 0, :N] = z
+    e.set_noise(eps.cuda(), u.cuda(), None)
+    wdump = torch.zeros(e.B, e.ld, device="cuda")
+    e.dump_noise(None, None, wdump)
+    e.set_observations(y.reshape(1, 1).cuda(), 0)
+    e.run(1)
+    torch.cuda.synchronize()
+    st = e.make_state()
+    anc = st.previous_indices.cpu()
+    Wd = wdump[0, :N].cpu()
+    assert torch.equal(anc, O.systematic(Wd.clone().unsqueeze(1), normalized=True, u=u.reshape(1, 1))[:, 0])
+    ref0 = O.apf_step(mo, "linear_gaussian", x0, lw0, torch.arange(N), y, z, u=u)
+    assert torch.allclose(Wd, ref0["resample_W"], rtol=2e-5, atol=2.3e-16)
+    # s = 0.1 makes the weights peaked: a relative 1e-6 on a heavy weight moves the cumulative sum by a whole probe spacing (1e-6), so
+    # against the oracle's OWN (ulp-different) weights most ancestors sit one or two places away - close, not equal
+    assert float((anc - ref0["prev_inds"]).abs().float().mean()) < 50.0
+    ref = O.apf_step(mo, "linear_gaussian", x0, lw0, torch.arange(N), y, z, u=u, force_idx=anc)
+    assert torch.allclose(st.timeseries_state.value.cpu(), ref["x"], rtol=0, atol=2e-6 * max(1.0, float(ref["x"].abs().max())))
+    fin = torch.isfinite(ref["lw"])
+    assert bool(((st.weights.cpu() - ref["lw"])[fin].abs() <= 3e-5 + 4e-6 * ref["lw"][fin].abs()).all())
+    assert abs(float(st.get_loglikelihood()) - float(ref["ll"])) <= 2e-5 + 2e-5 * abs(float(ref["ll"]))
+    assert torch.allclose(st.get_mean().cpu().reshape(-1), ref["mean"].reshape(-1), rtol=2e-5, atol=2e-5)
+    assert torch.allclose(st.get_variance().cpu().reshape(-1), ref["var"].reshape(-1), rtol=1e-4, atol=2e-5)
+
+
+def test_full_size_config4_multinomial_vs_oracle(pf):
+    """configs[3]: Lorenz-63, SISR + Bootstrap, multinomial resampling, 2,000,000 particles - one teacher-forced move with injected
+    float64 uniforms: ancestors bit-exact against the restated torch.multinomial for the device's weights."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import SISR
+
+    N = 2_000_000
+    gen = torch.Generator().manual_seed(14)
+    mo = O.build_model("lorenz63_em")
+    loc, scale = mo.initial_loc_scale()
+    x0 = loc + scale * torch.randn(N, 3, generator=gen)
+    y = torch.tensor([0.8 * -5.9 + 0.3, 0.8 * 24.5 - 0.2])
+    lw0 = mo.obs_log_prob(y, x0).float() * 0.25          # uneven enough for the ESS test to fire
+    z = torch.randn(N, 3, generator=gen)
+    U = torch.rand(N, dtype=torch.float64, generator=gen)
+    f = SISR(ts.build("lorenz63_em"), N, resampling=pf.resampling.multinomial, seed=4)
+    e = f._get_engine(2)
+    e.load_state(x0, lw0, torch.arange(N), 0)
+    eps = torch.zeros(e.D, e.B, e.ld)
+    eps[:, 0, :N] = z.t()
+    Ub = torch.zeros(e.B, e.ld, dtype=torch.float64)
+    Ub[0, :N] = U
+    e.set_noise(eps.cuda(), None, Ub.cuda())
+    wdump = torch.zeros(e.B, e.ld, device="cuda")
+    e.dump_noise(None, None, wdump)
+    _, flags = e.ess()
+    torch.cuda.synchronize()
+    assert bool(flags.cpu() > 0), "the test state must trigger resampling"
+    e.set_observations(y.reshape(1, 2).cuda(), 0)
+    e.run(1)
+    torch.cuda.synchronize()
+    st = e.make_state()
+    anc = st.previous_indices.cpu()
+    Wd = wdump[0, :N].cpu()
+    exp = torch.from_numpy(O.multinomial_restated(Wd.numpy(), U.numpy()))
+    assert torch.equal(anc, exp)
+    ref = O.sisr_step(mo, "bootstrap", x0, lw0, torch.arange(N), y, z, None, resampler="multinomial", U=U.numpy(), force_idx=anc)
+    assert bool(ref["resampled"])
+    assert torch.allclose(st.timeseries_state.value.cpu(), ref["x"], rtol=0, atol=2e-6 * float(ref["x"].abs().max()))
+    fin = torch.isfinite(ref["lw"])
+    assert bool(((st.weights.cpu() - ref["lw"])[fin].abs() <= 1e-5 + 4e-6 * ref["lw"][fin].abs()).all())
+    assert abs(float(st.get_loglikelihood()) - float(ref["ll"])) <= 2e-5 + 2e-5 * abs(float(ref["ll"]))
+    # At 2 M particles the reference's OWN float32 reductions are 2.3e-5 (relative) away from the float64 value of the same sums
+    # (measured with the oracle on this cloud: the soft-max normaliser), so the comparison with it is made at 1e-4 and the device's
+    # moments are also held against the float64 moments of the device's own particles and log-weights
+    assert torch.allclose(st.get_mean().cpu().reshape(-1), ref["mean"].reshape(-1), rtol=1e-4, atol=2e-4)
+    assert torch.allclose(st.get_variance().cpu().reshape(-1), ref["var"].reshape(-1), rtol=3e-4, atol=2e-4)
+    Wd64 = torch.softmax(st.weights.cpu().double(), 0).unsqueeze(-1)
+    xd64 = st.timeseries_state.value.cpu().double()
+    m64 = (Wd64 * xd64).sum(0)
+    v64 = (Wd64 * (xd64 - m64) ** 2).sum(0)
+    assert torch.allclose(st.get_mean().cpu().reshape(-1).double(), m64, rtol=3e-5, atol=1e-5)
+    assert torch.allclose(st.get_variance().cpu().reshape(-1).double(), v64, rtol=1e-4, atol=1e-5)
+    assert e.info().slow_tiles >= 0
+
+
+@pytest.mark.parametrize("name,B", [("lg_ar1", 0), ("sv_ar1", 3), ("lorenz63_em", 2)])
+def test_initialize(pf, name, B):
+    """``ParticleFilter.initialize`` (filters/particle/base.py:87-103): x_0 = loc + scale * z for the dumped unit normals (bit for
+    bit), z ~ N(0, 1), log w = 0, log-likelihood 0, previous indices = arange, history row 0 = mean / variance of x_0."""
+    N = 200_000
+    e = _engine(pf, name, "sisr", N, B, seed=9)
+    eps = torch.zeros(e.D, e.B, e.ld, device="cuda")
+    e.dump_noise(eps, None, None)
+    e.initialize()
+    torch.cuda.synchronize()
+    st = e.make_state()
+    x = st.timeseries_state.value.cpu()
+    mo = O.build_model(name)
+    loc, scale = mo.initial_loc_scale()
+    z = eps[:, :, :N].permute(2, 1, 0).cpu()                      # (N, B, D)
+    zz = z.reshape(-1).double()
+    assert abs(float(zz.mean())) < 5.0 / zz.numel() ** 0.5 and abs(float(zz.std()) - 1.0) < 5.0 / zz.numel() ** 0.5
+    assert abs(float((zz ** 3).mean())) < 0.05 and abs(float((zz ** 4).mean()) - 3.0) < 0.1
+    xe = (loc.float() + scale.float() * z).reshape(N, e.B, e.D)
+    got = x.reshape(N, e.B, e.D)
+    assert torch.allclose(got, xe, rtol=1e-6, atol=1e-6)   # (the device derives the stationary scale in double precision)
+    assert int(st.timeseries_state.time_index) == 0
+    assert torch.equal(st.weights.cpu(), torch.zeros(st.weights.shape))
+    assert torch.equal(st.get_loglikelihood().cpu(), torch.zeros(st.get_loglikelihood().shape))
+    pi = st.previous_indices.cpu()
+    ar = torch.arange(N)
+    assert torch.equal(pi, ar if not B else ar.unsqueeze(1).expand(N, B))
+    m = got.double().mean(0)
+    v = got.double().var(0, unbiased=False)
+    assert torch.allclose(st.get_mean().cpu().reshape(e.B, e.D).double(), m, rtol=2e-5, atol=2e-5)
+    assert torch.allclose(st.get_variance().cpu().reshape(e.B, e.D).double(), v, rtol=1e-4, atol=1e-6)
+    hm, hv, hl = e.history(1)
+    assert torch.allclose(hm.reshape(-1).cpu(), st.get_mean().reshape(-1).cpu()) and float(hl.abs().max()) == 0.0
+
+
+def test_get_ess_normalized(pf):
+    """``get_ess(W, normalized=True)`` (utils.py:8-20) against the oracle."""
+    gen = torch.Generator().manual_seed(3)
+    lw = torch.randn(50_000, 4, generator=gen) * 2
+    W = O.normalize(lw.clone())
+    ref = O.get_ess(W, normalized=True)
+    got = pf.utils.get_ess(W.cuda(), normalized=True).cpu()
+    assert torch.allclose(got, ref, rtol=5e-6)
+    got1 = pf.utils.get_ess(W[:, 0].contiguous().cuda(), normalized=True).cpu()
+    assert torch.allclose(got1, ref[0], rtol=5e-6)
