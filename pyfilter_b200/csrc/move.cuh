@@ -32,7 +32,7 @@
 #define MV_PER 20                             // window slots per thread in the "last mark" scan
 #define MV_WIN (MV_NT * MV_PER)               // 5120 output slots per window
 #define MV_U_HOST 8
-#define MV_LB 8                               // look-back: slots per lane in flight
+#define MV_LB 4                               // look-back: slots per thread in flight
 #ifndef SMCB_MV_MINB
 #define SMCB_MV_MINB 4
 #endif
@@ -46,6 +46,9 @@ struct MoveArgs {
   uint32_t* tile_counter;
   unsigned long long* mslots; // (B, tiles_per_col) tile sums tagged with the launch epoch, ONE 64-bit word each: a sum of weights that are
                               // multiples of 2^-52 below 2 is a 54-bit integer count of quanta, the 10 bits above it carry the tag
+  unsigned long long* gslots; // (B, ceil(tiles_per_col / 32)) group totals, same format
+  uint32_t* gcount;           // (B, ceil(tiles_per_col / 32)) publications per group (reset with the handle's state)
+  uint32_t launch_index;      // move launches since that reset: a group's counter stands at launch_index * members when the launch starts
   unsigned long long epoch;   // tag of this launch in [1, 1023], different from the previous launch's (every tile of every launch
                               // rewrites its slot, so a slot never holds a tag older than one launch)
   const float* u_in;          // optional injected systematic offsets (B)
@@ -61,7 +64,7 @@ template <int D>
 struct MoveSmem {
   int32_t stage[MV_WIN];      // marks, then (in place) the ancestors of the window; identity tiles: the carried log-weights
   double scan_a[MV_NT / 32];  // every collective of the tile has its own scratch area: no "protect the reuse" barriers
-  double s_in;                // exact sum of the preceding tiles (look-back warp -> everybody)
+  unsigned long long lb;      // look-back: quanta of the tiles before this one (warp 0 -> everybody)
   int32_t wtot[MV_NT / 32];
   int32_t carry;
   int32_t ticket, is_last;
@@ -73,7 +76,7 @@ struct MoveSmem {
 
 // a block-uniform flag / value the compiler can SEE is uniform (vote / redux result): branches on it need no divergence handling
 // and the collectives behind them no re-convergence
-#define MV_STAMP(k) do { if (c.tl && tid == 0) c.tl[(int64_t)ticket * 8 + (k)] = st_now(); } while (0)
+#define MV_STAMP(k) do { if (c.tl && tid == 0) c.tl[(int64_t)ticket * 16 + (k)] = st_now(); } while (0)
 __device__ __forceinline__ bool mv_uniform(bool f) { return __all_sync(0xffffffffu, f) != 0; }
 __device__ __forceinline__ int32_t mv_uniform(int32_t v) { return __reduce_max_sync(0xffffffffu, v); }
 
@@ -99,51 +102,107 @@ __device__ __forceinline__ double mv_block_excl_scan(double v, double* scratch, 
   *total = tot;
   return off + (inc - v);
 }
-// the look-back of one warp: exact sum of the tile sums published by the tiles before `tile` (MV_LB slots per lane in flight).
-// Out of line: only warp 0 of a block pays for the registers of the loads in flight.
+// ---- publishing a tile sum and looking back, two levels -------------------------------------------------------------------------
+// A tile sum is a count of quanta (2^-52) in 54 bits under a 10-bit launch tag, written with ONE atomic exchange at the L2.  Tiles form
+// groups of 32; every tile also bumps its group's counter, and the tile that completes a group adds the 32 sums up and publishes the
+// group total the same way.  A tile then needs at most one group total per earlier group and the sums of its group mates before it:
+// two loads per lane of ONE warp for up to 1024 tiles.  (Measured on the way: 256 polling threads per block, or a warp polling every
+// predecessor, flood the L2 with strong loads and delay the very publications they wait for - up to 20 us per tile.)
 #define MV_SLOT_MASK ((1ull << 54) - 1ull)
-__device__ __noinline__ double mv_lookback(const unsigned long long* slots, int tile, unsigned long long epoch, long long* wd) {
+#define MV_GROUP 32
+#define MV_GPAD 16   // a group's total / counter sits alone in a 128-byte line: hundreds of tiles poll and bump them at the same time
+__device__ __forceinline__ unsigned long long mv_ld_strong(const unsigned long long* p) {  // a STRONG load at gpu scope
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long mv_wait_slot(const unsigned long long* p, unsigned long long v, unsigned long long epoch, int& waited) {
+  while ((v >> 54) != epoch) {
+#ifdef MV_SLEEP
+    __nanosleep(MV_SLEEP);
+#endif
+    v = mv_ld_strong(p);
+    ++waited;
+  }
+  return v & MV_SLOT_MASK;
+}
+__device__ __forceinline__ unsigned long long mv_warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// executed by warp 0 of the block; `quanta` = this tile's sum (valid in lane 0); returns the sum of all tiles before `tile` (every lane)
+__device__ __forceinline__ unsigned long long mv_publish_lookback(unsigned long long* slots, unsigned long long* gslots, uint32_t* gcount,
+                                                                   int tile, int T, unsigned long long quanta, unsigned long long epoch,
+                                                                   uint32_t launch_index, long long* wd, long long* tlrow) {
   const int lane = threadIdx.x & 31;
-  unsigned long long part = 0ull;   // integer quanta: exact in any order
+#define MV_LSTAMP(k) do { if (tlrow && lane == 0) tlrow[k] = st_now(); } while (0)
+  const int g = tile / MV_GROUP, r = tile - g * MV_GROUP;
+  const int members = min(MV_GROUP, T - g * MV_GROUP);
+  uint32_t old = 0;
+  if (lane == 0) {
+    atomicExch(slots + tile, (epoch << 54) | (quanta & MV_SLOT_MASK));
+    old = atomicAdd(gcount + g * MV_GPAD * 2, 1u) - launch_index * (uint32_t)members;   // every tile of every launch bumps its group exactly once:
+  }                                                                        // relative to the launch the counter runs 0 .. members - 1
+  MV_LSTAMP(8);
+  // the loads of the look-back go out while the counter's old value is on its way
+  const unsigned long long* pm = slots + g * MV_GROUP + lane;
+  unsigned long long vm = (lane < r) ? mv_ld_strong(pm) : (epoch << 54);
+  unsigned long long acc = 0ull;
   int waited = 0;
-  const long long t_begin = wd ? st_now() : 0;
-  for (int q0 = tile - 1 - lane; q0 >= 0; q0 -= 32 * MV_LB) {
-    unsigned long long v[MV_LB];
-#pragma unroll
-    for (int j = 0; j < MV_LB; ++j) {
-      const int q = q0 - 32 * j;
-      v[j] = (q >= 0) ? __ldcg(slots + q) : (epoch << 54);
-    }
-#pragma unroll
-    for (int j = 0; j < MV_LB; ++j) {
-      const int q = q0 - 32 * j;
-      while ((v[j] >> 54) != epoch) {
-        __nanosleep(20);
-        v[j] = __ldcg(slots + q);
-        ++waited;
+  for (int g0 = 0; g0 < g; g0 += 32) {   // one round per 32 earlier groups (1024 tiles)
+    const unsigned long long* pg = gslots + (int64_t)(g0 + lane) * MV_GPAD;
+    const unsigned long long vg = (g0 + lane < g) ? mv_ld_strong(pg) : (epoch << 54);
+    if (g0 == 0) {  // first round: this is where the group is completed, before anything is waited for
+      const bool closer = __shfl_sync(0xffffffffu, old + 1u == (uint32_t)members ? 1 : 0, 0) != 0;
+      MV_LSTAMP(9);
+      if (closer) {
+        unsigned long long vc = (lane < members) ? mv_ld_strong(slots + g * MV_GROUP + lane) : (epoch << 54);
+        vc = mv_wait_slot(slots + g * MV_GROUP + lane, vc, epoch, waited);
+        vc = mv_warp_sum_u64(vc);
+        if (lane == 0) atomicExch(gslots + (int64_t)g * MV_GPAD, (epoch << 54) | (vc & MV_SLOT_MASK));
       }
-      part += v[j] & MV_SLOT_MASK;
+    }
+    if (g0 == 0) MV_LSTAMP(10);
+    acc += mv_wait_slot(pg, vg, epoch, waited);
+  }
+  MV_LSTAMP(11);
+  if (g == 0) {  // (the loop above did not run: group 0 is completed here)
+    const bool closer = __shfl_sync(0xffffffffu, old + 1u == (uint32_t)members ? 1 : 0, 0) != 0;
+    if (closer) {
+      unsigned long long vc = (lane < members) ? mv_ld_strong(slots + lane) : (epoch << 54);
+      vc = mv_wait_slot(slots + lane, vc, epoch, waited);
+      vc = mv_warp_sum_u64(vc);
+      if (lane == 0) atomicExch(gslots, (epoch << 54) | (vc & MV_SLOT_MASK));
     }
   }
-  if (wd) {  // diagnostics: tiles that had to wait, re-polls, time spent looking back (ns, lane 0)
-    if (waited) atomicAdd((unsigned long long*)&wd[2], (unsigned long long)waited);
-    if (lane == 0) { atomicAdd((unsigned long long*)&wd[3], (unsigned long long)(st_now() - t_begin)); if (waited) atomicAdd((unsigned long long*)&wd[0], 1ull); }
-  }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-  return (double)part * 2.220446049250313e-16;   // quanta * 2^-52: exact (the sum of a column is below 2)
+  acc += mv_wait_slot(pm, vm, epoch, waited);
+  MV_LSTAMP(12);
+  if (tlrow && lane == 0) tlrow[13] = (long long)waited;
+  if (wd && waited) atomicAdd((unsigned long long*)&wd[2], (unsigned long long)waited);   // diagnostics: re-polls
+  return mv_warp_sum_u64(acc);
+}
+// a tile that does not resample still keeps its slot's tag and its group's counter in step
+__device__ __forceinline__ void mv_publish_idle(unsigned long long* slots, unsigned long long* gslots, uint32_t* gcount, int tile, int T,
+                                                unsigned long long epoch, uint32_t launch_index) {
+  const int g = tile / MV_GROUP;
+  const int members = min(MV_GROUP, T - g * MV_GROUP);
+  atomicExch(slots + tile, epoch << 54);
+  const uint32_t old = atomicAdd(gcount + g * MV_GPAD * 2, 1u) - launch_index * (uint32_t)members;
+  if (old + 1u == (uint32_t)members) atomicExch(gslots + (int64_t)g * MV_GPAD, epoch << 54);
 }
 
 // weights of this thread's 16 particles, rounded to multiples of 2^-52 (exactly what normalize_kernel / resample_fused_kernel compute)
 template <bool INNER>
-__device__ __forceinline__ double mv_weights(const float (&win)[MV_ITEMS], float m, float iz, int32_t gbase, int32_t n, double (&wq)[MV_ITEMS]) {
+__device__ __forceinline__ double mv_weights(const float (&win)[MV_ITEMS], float m, float iz, int32_t gbase, int32_t n, float (&wq)[MV_ITEMS]) {
   double tsum = 0.0;
 #pragma unroll
   for (int j = 0; j < MV_ITEMS; ++j) {
     float x = smcb_weight(win[j], m, iz);
     if (!INNER && gbase + j >= n) x = 0.f;
-    wq[j] = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);
-    tsum += wq[j];
+    const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);
+    wq[j] = (float)xd;   // exact: a multiple of 2^-52 below 2^-29 has at most 23 significant bits (kept as float: registers)
+    tsum += xd;
   }
   return tsum;
 }
@@ -159,13 +218,13 @@ __device__ __forceinline__ int32_t mv_count(float c, float u, int32_t n, int32_t
 // CHECK = false: the whole tile fits the window (n_out - wb <= MV_WIN), no range test per particle.
 // A mark is the index of the particle INSIDE the tile (the gather of x_{t-1} needs nothing else).
 template <bool INNER, bool CHECK, bool FIRST, bool LEAN, typename SM>
-__device__ __forceinline__ void mv_mark(const double (&wq)[MV_ITEMS], double S0, int32_t lo, int32_t gbase, int32_t wb, float u,
+__device__ __forceinline__ void mv_mark(const float (&wq)[MV_ITEMS], double S0, int32_t lo, int32_t gbase, int32_t wb, float u,
                                         int32_t n, int32_t n_out, double nfd, SM& sm) {
   double run = S0;
   const int32_t lbase = (int32_t)threadIdx.x * MV_ITEMS;
 #pragma unroll
   for (int j = 0; j < MV_ITEMS; ++j) {
-    run = __dadd_rn(run, wq[j]);
+    run = __dadd_rn(run, (double)wq[j]);
     int32_t hi = mv_count<LEAN>((float)run, u, n, n_out, nfd);
     if (!INNER) hi = (gbase + j >= n - 1) ? n_out : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1 (n_out == n here)
     const int32_t r = lo - wb;
@@ -191,7 +250,7 @@ __device__ __noinline__ void mv_remark(const float* wsrc, float m, float iz, dou
     const float4 q = __ldg(reinterpret_cast<const float4*>(wsrc) + v);
     win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
   }
-  double wq[MV_ITEMS];
+  float wq[MV_ITEMS];
   mv_weights<false>(win, m, iz, gbase, n, wq);
   if (lean) {
     if (first) mv_mark<false, true, true, true>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
@@ -266,15 +325,14 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   }
 #pragma unroll
   for (int k = 0; k < MV_PER / 4; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * MV_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-  float y[OD], yn[OD];
-  const bool observed = mv_uniform(st_load_obs<OD>(a.y_t, y));
-  const bool fold = mv_uniform((ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(a.y_next, yn));
+  bool observed, fold;
+  {  // only the flags now; the values are fetched again behind the marks (registers are scarce while the weights are live)
+    float y0[OD], y1[OD];
+    observed = mv_uniform(st_load_obs<OD>(a.y_t, y0));
+    fold = mv_uniform((ALG == SMCB_ALG_APF) && a.fold && st_load_obs<OD>(a.y_next, y1));
+  }
   const int32_t n = (int32_t)a.n;
-  const float inv_n = 1.0f / (float)a.n;
   const double nfd = (double)(float)a.n;
-  const float one4[4] = {1.f, 1.f, 1.f, 1.f};
-  const float* Ps = sm.Ps;
-  const bool plain_noise = !a.eps_in && !a.eps_out;
   __syncthreads();
   const int ticket = mv_uniform(sm.ticket);
   const int col = ticket / T, tile = ticket - col * T;
@@ -283,16 +341,6 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   const int32_t tile_base = tile * MV_TILE;
   const int32_t gbase = tile_base + tid * MV_ITEMS;
   const int64_t rowoff = (int64_t)col * a.ld;
-  float* const lwrow = a.lw_out + rowoff;
-  float* const rwrow = a.rw_out + rowoff;
-  int32_t* const pirow = a.prev_inds + rowoff;
-  const float* xprev[D];
-  float* xnext[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) {
-    xprev[d] = a.xbuf[t & 1] + ((int64_t)d * a.B + col) * a.ld;
-    xnext[d] = a.xbuf[(t + 1) & 1] + ((int64_t)d * a.B + col) * a.ld;
-  }
   const bool use_rw = (ALG == SMCB_ALG_APF) && observed;
   const float* const winrow = (use_rw ? a.rw : a.lw) + rowoff;
   // the lean probe count needs u == 0 or u >= 2^-64 (exact_scan.h); Philox offsets are multiples of 2^-24
@@ -310,26 +358,22 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
     win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
   }
   const float4* stp = reinterpret_cast<const float4*>(a.stats + col);
-  const float4 st0 = stp[0], st1 = stp[1], st2 = stp[2];   // m_lw z_lw inv_z_lw m_rw | z_rw inv_z_rw ess resample | shift[3] ll_aux
+  const float4 st0 = stp[0], st1 = stp[1];   // m_lw z_lw inv_z_lw m_rw | z_rw inv_z_rw ess resample
 #pragma unroll
   for (int d = 0; d < D; ++d) {
 #pragma unroll
     for (int v = 0; v < MV_ITEMS / 4; ++v) {
       const int e = (v * MV_NT + tid) * 4;
-      *reinterpret_cast<float4*>(mv_x + d * MV_TILE + e) = __ldg(reinterpret_cast<const float4*>(xprev[d] + tile_base + e));
+      *reinterpret_cast<float4*>(mv_x + d * MV_TILE + e) =
+          __ldg(reinterpret_cast<const float4*>(a.xbuf[t & 1] + ((int64_t)d * a.B + col) * a.ld + tile_base + e));
     }
   }
   if (tid < (int)(sizeof(ColStats) / 4)) reinterpret_cast<float*>(&sm.fin_pre.st)[tid] = reinterpret_cast<const float*>(a.stats + col)[tid];
   if (tid == 32) { sm.fin_pre.observed = observed; sm.fin_pre.fold = fold; sm.fin_pre.ll_total = a.ll_total[col]; }
-  const float st_m_lw = st0.x, st_inv_z_lw = st0.z;
   // SISR resamples when the ESS test fired (sisr.py:19-26), the APF on every observed step (apf.py:29-34, filters/base.py:213)
   const bool resampled = (ALG == SMCB_ALG_APF) ? observed : mv_uniform(__float_as_int(st1.w) != 0);
   const float wm = use_rw ? st0.w : st0.x;
   const float wiz = use_rw ? st1.y : st0.z;
-  const float shift3[3] = {st2.x, st2.y, st2.z};
-  float shift[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) shift[d] = shift3[d];
   if (c.u_out && resampled && tile == 0 && tid == 0) c.u_out[col] = u;
 
   int32_t n_in, n_out, wb0;
@@ -337,30 +381,25 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   int32_t lo_thread = 0;
   if (resampled) {
     const bool inner = mv_uniform(tile_base + MV_TILE <= n - 1);  // neither padding nor the last particle of the column in this tile
-    double wq[MV_ITEMS];
+    float wq[MV_ITEMS];
     const double tsum = inner ? mv_weights<true>(win, wm, wiz, gbase, n, wq) : mv_weights<false>(win, wm, wiz, gbase, n, wq);
     if (c.w_out) {
       float* dst = c.w_out + rowoff + gbase;
 #pragma unroll
       for (int v = 0; v < MV_ITEMS / 4; ++v)
-        reinterpret_cast<float4*>(dst)[v] = make_float4((float)wq[4 * v], (float)wq[4 * v + 1], (float)wq[4 * v + 2], (float)wq[4 * v + 3]);
+        reinterpret_cast<float4*>(dst)[v] = make_float4(wq[4 * v], wq[4 * v + 1], wq[4 * v + 2], wq[4 * v + 3]);
     }
     double tot;
     const double ex = mv_block_excl_scan(tsum, sm.scan_a, &tot);
-    const unsigned long long* slots = c.mslots + (int64_t)col * T;
-    if (tid == 0)  // publish: ONE 64-bit exchange at the L2 (no store lingering in the SM's write path, no fence) carries sum and tag
-      atomicExch(c.mslots + (int64_t)col * T + tile, (c.epoch << 54) | (__double2ull_rn(tot * 4503599627370496.0) & MV_SLOT_MASK));
+    const int G = (T + MV_GROUP - 1) / MV_GROUP;
     MV_STAMP(2);
-    // exact sum of the preceding tiles (any order: the weights are multiples of 2^-52).  ONE warp looks back, eight slots per lane in
-    // flight at a time: 256 polling threads per block times ~600 resident blocks queue up on the few cache lines that hold the slots
-    // (measured: 5 us between the last publication and the last tile knowing its prefix), a single round of coalesced 512-byte
-    // reads does not.
     if (tid < 32) {
-      const double part = mv_lookback(slots, tile, c.epoch, c.wd);
-      if (tid == 0) sm.s_in = part;
+      const unsigned long long before = mv_publish_lookback(c.mslots + (int64_t)col * T, c.gslots + (int64_t)col * G * MV_GPAD, c.gcount + (int64_t)col * G * MV_GPAD * 2,
+                                                            tile, T, __double2ull_rn(tot * 4503599627370496.0), c.epoch, c.launch_index, c.wd, c.tl ? c.tl + (int64_t)ticket * 16 : nullptr);
+      if (tid == 0) sm.lb = before;
     }
     __syncthreads();
-    const double S_in = sm.s_in;
+    const double S_in = (double)sm.lb * 2.220446049250313e-16;   // quanta * 2^-52: exact (the sum of a column is below 2)
     MV_STAMP(3);
     S0 = S_in + ex;
     // the tile owns the output slots [n_in, n_out): known before the marks, so the common single-window tile marks without range tests
@@ -383,7 +422,10 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
     }
     __syncthreads();
   } else {  // identity ancestors; the carried log-weights travel through the window
-    if (tid == 0) atomicExch(c.mslots + (int64_t)col * T + tile, c.epoch << 54);  // (keeps the slot's tag one launch old at most)
+    if (tid == 0) {
+      const int G = (T + MV_GROUP - 1) / MV_GROUP;
+      mv_publish_idle(c.mslots + (int64_t)col * T, c.gslots + (int64_t)col * G * MV_GPAD, c.gcount + (int64_t)col * G * MV_GPAD * 2, tile, T, c.epoch, c.launch_index);
+    }
     n_in = tile_base;
     n_out = min(tile_base + MV_TILE, n);
     wb0 = tile_base;
@@ -394,7 +436,25 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   }
 
   MV_STAMP(4);
-  // ---- the move itself over the tile's output slots [n_in, n_out), window by window
+  // ---- the move itself over the tile's output slots [n_in, n_out), window by window.  What only this phase needs is fetched now.
+  float y[OD], yn[OD];
+  st_load_obs<OD>(a.y_t, y);
+  if (fold) st_load_obs<OD>(a.y_next, yn);
+  const float* Ps = sm.Ps;
+  const float inv_n = 1.0f / (float)a.n;
+  const float one4[4] = {1.f, 1.f, 1.f, 1.f};
+  const bool plain_noise = !a.eps_in && !a.eps_out;
+  const ColStats& stc = sm.fin_pre.st;   // the column's statistics before the move (shared-memory copy made with the tile loads)
+  const float st_m_lw = stc.m_lw, st_inv_z_lw = stc.inv_z_lw;
+  float shift[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) shift[d] = stc.shift[d];
+  float* const lwrow = a.lw_out + rowoff;
+  float* const rwrow = a.rw_out + rowoff;
+  int32_t* const pirow = a.prev_inds + rowoff;
+  float* xnext[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) xnext[d] = a.xbuf[(t + 1) & 1] + ((int64_t)d * a.B + col) * a.ld;
   StepAcc<D> mom; mom.init();
   StepAcc1 r2; r2.init();   // APF: folded resampling weights
   StepAcc1 r3; r3.init();   // SISR: likelihood increment
@@ -516,7 +576,8 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   MV_STAMP(6);
   pdl_trigger();  // the successor may be scheduled while the last block folds the partials
 
-  // ---- per-tile partial record; the block that completes the column folds them
+  // ---- per-tile partial record.  The records are folded by finalize_kernel, launched right behind this kernel (programmatic
+  //      dependent launch): a block neither fences nor takes a ticket before it leaves (measured: 1.5 us per block)
   SoftAcc<1 + 2 * D> A;
   SoftAcc<1> Q, R2, R3;
   mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
@@ -526,14 +587,6 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
     st_write_partial1(p, A, Q);
     p.m2 = R2.m; p.z2 = R2.s[0];
     p.m3 = R3.m; p.z3 = R3.s[0];
-    __threadfence();
-    sm.is_last = (atomicAdd(&a.col_ticket[col], 1) == T - 1);
-  }
-  __syncthreads();
-  if (sm.is_last) {
-    if (tid == 0) a.col_ticket[col] = 0;
-    __threadfence();
-    finalize_column<D, OD, ALG>(a, col, FIN_STEP, t, sm.fin, sm.fin_pre);
   }
   MV_STAMP(7);
 }

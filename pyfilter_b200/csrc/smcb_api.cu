@@ -155,8 +155,10 @@ struct smcb_filter {
   long long* wd = nullptr;
   uint32_t ticket_next = 0;
   int mv_grid = 0;
-  unsigned long long* mslots = nullptr;
+  unsigned long long *mslots = nullptr, *gslots = nullptr;
+  uint32_t* gcount = nullptr;
   unsigned mv_epoch = 0;
+  uint32_t mv_launches = 0;   // move_kernel launches since the group counters were cleared
 };
 
 template <typename T>
@@ -185,7 +187,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gslots, f->gcount};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -255,6 +257,8 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->tile_partials, (size_t)f->B * f->tiles_per_col));
   A_(dalloc(&f->tile_counter, (size_t)1));
   A_(dalloc(&f->mslots, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->gslots, (size_t)f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD));
+  A_(dalloc(&f->gcount, (size_t)f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD * 2));
   A_(dalloc(&f->wd, (size_t)4));
   A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_var, (size_t)rows * f->B * f->D));
@@ -265,7 +269,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
-  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)8 * f->B * f->tiles_per_col));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)16 * f->B * f->tiles_per_col));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -377,7 +381,8 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   m.s.partials = f->tile_partials; m.s.blocks_per_col = f->tiles_per_col;
   m.tiles_per_col = f->tiles_per_col; m.total_tiles = f->tiles_per_col * f->B;
   f->mv_epoch = f->mv_epoch % 1023u + 1u;   // 1 .. 1023, never the previous launch's
-  m.tile_counter = f->tile_counter; m.mslots = f->mslots; m.epoch = f->mv_epoch;
+  m.tile_counter = f->tile_counter; m.mslots = f->mslots; m.gslots = f->gslots; m.gcount = f->gcount; m.epoch = f->mv_epoch;
+  m.launch_index = f->mv_launches++;
   m.u_in = f->u_in; m.u_out = f->u_out; m.w_out = f->w_out; m.wd = f->wd;
   m.tl = f->dbg ? f->dbg + 32 : nullptr;
   if (!f->u_in && f->B <= MV_U_HOST) {  // few columns: the systematic offsets (one Philox block per column and move) come as arguments
@@ -424,15 +429,24 @@ static void launch_state(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   f->launches++;
 }
 
-static void launch_finalize(smcb_filter* f, StepArgs a, int mode, cudaStream_t s) {
+static void launch_finalize(smcb_filter* f, StepArgs a, int mode, cudaStream_t s, bool pdl = false) {
   a.fin_mode = mode;
   const bool apf = f->cfg.algorithm == SMCB_APF;
-  if (f->D == 1) {
-    if (apf) finalize_kernel<1, 1, SMCB_ALG_APF><<<f->B, ST_NT, 0, s>>>(a);
-    else finalize_kernel<1, 1, SMCB_ALG_SISR><<<f->B, ST_NT, 0, s>>>(a);
+  const dim3 g(f->B), b(ST_NT);
+  if (pdl) {  // behind move_kernel: overlaps the launch with the last tiles of the move
+    if (f->D == 1) {
+      if (apf) launch_pdl(finalize_kernel<1, 1, SMCB_ALG_APF>, g, b, s, a);
+      else launch_pdl(finalize_kernel<1, 1, SMCB_ALG_SISR>, g, b, s, a);
+    } else {
+      if (apf) launch_pdl(finalize_kernel<3, 2, SMCB_ALG_APF>, g, b, s, a);
+      else launch_pdl(finalize_kernel<3, 2, SMCB_ALG_SISR>, g, b, s, a);
+    }
+  } else if (f->D == 1) {
+    if (apf) finalize_kernel<1, 1, SMCB_ALG_APF><<<g, b, 0, s>>>(a);
+    else finalize_kernel<1, 1, SMCB_ALG_SISR><<<g, b, 0, s>>>(a);
   } else {
-    if (apf) finalize_kernel<3, 2, SMCB_ALG_APF><<<f->B, ST_NT, 0, s>>>(a);
-    else finalize_kernel<3, 2, SMCB_ALG_SISR><<<f->B, ST_NT, 0, s>>>(a);
+    if (apf) finalize_kernel<3, 2, SMCB_ALG_APF><<<g, b, 0, s>>>(a);
+    else finalize_kernel<3, 2, SMCB_ALG_SISR><<<g, b, 0, s>>>(a);
   }
   f->launches++;
 }
@@ -456,6 +470,8 @@ extern "C" int smcb_filter_initialize(smcb_filter* f, void* stream) {
   if (rc) return rc;
   CU(cudaMemsetAsync(f->ll_total, 0, sizeof(float) * f->B, s));
   CU(cudaMemsetAsync(f->stats, 0, sizeof(ColStats) * f->B, s));
+  CU(cudaMemsetAsync(f->gcount, 0, sizeof(uint32_t) * f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD * 2, s));
+  f->mv_launches = 0;
   StepArgs a = make_args(f);
   a.sample_x0 = 1;
   launch_state(f, a, s);
@@ -505,6 +521,11 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
   if (move_path_ok(f)) {
     int rc = launch_move(f, a, s);
     if (rc) return rc;
+    {  // the per-tile records of the move are folded by a one-block-per-column kernel chained behind it
+      StepArgs fa = a;
+      fa.partials = f->tile_partials; fa.blocks_per_col = f->tiles_per_col;
+      launch_finalize(f, fa, FIN_STEP, s, true);
+    }
     if (ev) for (int g = 2; g <= 5; ++g) cudaEventRecord(ev[g], s);
     f->folded_for_next = apf && f->cfg.fold_lookahead && (t + 1 - f->y_base) < f->y_count;
     f->t_host = t + 1;

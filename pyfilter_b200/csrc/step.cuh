@@ -572,6 +572,8 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
 template <int D, int OD, int ALG>
 __global__ void __launch_bounds__(ST_NT) finalize_kernel(StepArgs a) {
   __shared__ FinSmem<D> fs;
+  pdl_trigger();  // (launched behind move_kernel with programmatic serialisation: the next move's blocks may take their places now)
+  pdl_wait();
   const int t = a.ctrl->t;
   const FinPre pre = fin_preload<OD>(a, blockIdx.x, a.fin_mode, t);
   finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, t, fs, pre);

