@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define SMCB_VERSION 100
+#define SMCB_VERSION 200
 
 enum { SMCB_OK = 0, SMCB_EINVAL = -1, SMCB_ECUDA = -2, SMCB_ENODEVICE = -3, SMCB_EUNSUPPORTED = -4, SMCB_ESTATE = -5 };
 
@@ -87,6 +87,9 @@ typedef struct smcb_info {
 
 /* library */
 int smcb_version(void);
+/* (sizeof(smcb_config) << 16) | sizeof(smcb_info) of the BUILT library: a binding compares it with its own view of the structs before
+ * it passes one (a stale binary next to newer sources otherwise reads them with the wrong layout) */
+int smcb_abi_signature(void);
 const char* smcb_last_error(void);
 int smcb_device_count(void);
 

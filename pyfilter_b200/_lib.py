@@ -17,6 +17,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-diag-suppress", "128"]
 
 
+ABI_VERSION = 200  # SMCB_VERSION of include/smcb200.h
+
+
 class SmcbError(RuntimeError):
     pass
 
@@ -43,6 +46,7 @@ class smcb_info(C.Structure):
 _P = C.c_void_p
 SYMBOLS = [
     ("smcb_version", C.c_int, []),
+    ("smcb_abi_signature", C.c_int, []),
     ("smcb_last_error", C.c_char_p, []),
     ("smcb_device_count", C.c_int, []),
     ("smcb_filter_create", C.c_int, [C.POINTER(smcb_config), C.POINTER(_P)]),
@@ -103,6 +107,7 @@ def load_library():
         if _lib is not None:
             return _lib
         alt = os.environ.get("SMCB_LIB_PATH")  # diagnostics: an alternative build of the same sources (tools/variants.py)
+        stale_note = None
         if alt:
             lib_path = alt
         elif _stale():
@@ -112,13 +117,27 @@ def load_library():
             except (SmcbError, FileNotFoundError) as e:
                 if not os.path.exists(LIB_PATH):
                     raise SmcbError(f"libsmcb200.so is missing and could not be built ({e}); pyfilter_b200 has no CPU fallback")
+                stale_note = f"libsmcb200.so is OLDER than its sources and could not be rebuilt ({str(e)[:200]})"
         else:
             lib_path = LIB_PATH
         lib = C.CDLL(lib_path)
         for name, restype, argtypes in SYMBOLS:
-            fn = getattr(lib, name)
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                raise SmcbError(f"{lib_path} does not export {name}: the binary does not match include/smcb200.h"
+                                + (f" ({stale_note})" if stale_note else ""))
             fn.restype = restype
             fn.argtypes = argtypes
+        # the binary must have been built from THIS interface: version and struct layout
+        sig = (C.sizeof(smcb_config) << 16) | C.sizeof(smcb_info)
+        if lib.smcb_version() != ABI_VERSION or lib.smcb_abi_signature() != sig:
+            raise SmcbError(f"{lib_path} was built from another version of include/smcb200.h (version {lib.smcb_version()} vs {ABI_VERSION}, "
+                            f"struct signature {lib.smcb_abi_signature():#x} vs {sig:#x}); rebuild it with pyfilter_b200._lib.build_library(force=True)")
+        if stale_note:
+            import warnings
+
+            warnings.warn(stale_note + "; its interface matches, its kernels may not", RuntimeWarning)
         _lib = lib
         return lib
 

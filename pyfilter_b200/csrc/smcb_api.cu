@@ -48,6 +48,7 @@ static void launch_pdl(K kernel, dim3 grid, dim3 block, cudaStream_t s, const A&
 }
 
 extern "C" int smcb_version(void) { return SMCB_VERSION; }
+extern "C" int smcb_abi_signature(void) { return (int)((sizeof(smcb_config) << 16) | sizeof(smcb_info)); }
 extern "C" const char* smcb_last_error(void) { return g_err.c_str(); }
 extern "C" int smcb_device_count(void) {
   int n = 0;

@@ -20,7 +20,7 @@ class ParticleFilter:
     def __init__(self, model, particles: int, resampling: Callable = _resampling.systematic, proposal: Union[str, Proposal] = None,
                  ess_threshold=0.9, record_states=False, record_moments=True, nan_strategy: str = "skip",
                  record_intermediary_states: bool = False, seed: int = None, fold_lookahead: bool = True,
-                 exact_weights: bool = False):
+                 exact_weights: bool = False, column_offset: int = 0):
         if not (isinstance(model, StateSpaceModel) or callable(model)):
             raise ValueError("`model` must be a `StateSpaceModel` or a callable that returns one!")
         builder = callable(model) and not isinstance(model, StateSpaceModel)
@@ -42,6 +42,13 @@ class ParticleFilter:
         self._fold = fold_lookahead
         self._engine: Engine = None
         self._exact_weights = bool(exact_weights)  # see include/smcb200.h: smcb_config.exact_weights
+        # Random streams: the Philox key is `seed`, the counter (particle group, column_offset + column, move, purpose).  Shards of ONE
+        # batch of filters (ranks of a theta-sharded SMC2 run, pyfilter_b200.sharding) pass the global index of their first column as
+        # `column_offset` with the SAME seed: no two columns share a stream and the result does not depend on the split.  Every new
+        # engine of a filter (history growth, set_batch_shape, increase_particles) and every copy() derives a fresh sub-seed.
+        self._column_offset = int(column_offset)
+        self._generation = 0   # engines created so far
+        self._copies = 0
 
     # ---- reference surface
     @property
@@ -80,7 +87,9 @@ class ParticleFilter:
         res = type(self)(model=self._model_builder, particles=self._base_particles[0], resampling=self._resampler,
                          proposal=self._proposal.copy(), ess_threshold=self._resample_threshold,  # sic: base.py:165 (Appendix A-12)
                          record_states=self.record_states, record_moments=self.record_moments, nan_strategy=self._nan_strategy,
-                         record_intermediary_states=self._record_intermediary, seed=self._seed, fold_lookahead=self._fold, exact_weights=self._exact_weights)
+                         record_intermediary_states=self._record_intermediary, seed=self._derive_seed(0x9E3779B9 + self._copies),
+                         fold_lookahead=self._fold, exact_weights=self._exact_weights, column_offset=self._column_offset)
+        self._copies += 1
         res._model = self._model
         res.set_batch_shape(self.batch_shape)
         return res
@@ -95,20 +104,35 @@ class ParticleFilter:
         raise NotImplementedError("smoothing is listed under 'next' (SURVEY.md 8(f) f3)")
 
     # ---- engine management
+    def _derive_seed(self, salt: int) -> int:
+        """SplitMix64 of (seed, salt): sub-seeds of copies and of re-created engines (None stays None: drawn from torch's generator)."""
+        if self._seed is None:
+            return None
+        z = (int(self._seed) + (salt + 1) * 0x9E3779B97F4A7C15) & (2**64 - 1)
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & (2**64 - 1)
+        return (z ^ (z >> 31)) & (2**62 - 1)
+
     def _get_engine(self, history_rows: int) -> Engine:
         assert self._model is not None, "Model has not been initialized!"
         self._proposal.set_model(self._model)
         e = self._engine
         if e is None or e.history_rows < history_rows:
-            seed = self._seed if self._seed is not None else int(torch.randint(0, 2**62, (1,)).item())
+            if self._seed is None:
+                seed = int(torch.randint(0, 2**62, (1,)).item())
+            else:  # the first engine uses the seed itself (two filters built with the same seed agree), later ones a sub-seed
+                seed = self._seed if self._generation == 0 else self._derive_seed(self._generation)
+            self._generation += 1
             n = int(self._base_particles[0])
             e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS[self._resampler], n,
-                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_weights)
+                       self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_weights,
+                       self._column_offset)
             self._engine = e
         return e
 
     def _adopt(self, engine: Engine, state: ParticleFilterCorrection):
         if not state.is_live(engine):
+            state._check_live("particles and weights")   # a stale view of this engine's buffers cannot be adopted: it raises
             engine.load_state(state.timeseries_state.value, state.weights, state.previous_indices,
                               int(state.timeseries_state.time_index))
 
@@ -178,7 +202,10 @@ class ParticleFilter:
         else:
             e.run(M)
         means, variances, ll = e.history(t0 + M + 1)
-        rows = torch.as_tensor([t0 + 1 + mv for mv in observed], device=means.device)  # history row of a move = its index + 1
+        # history row of a move = its index + 1; with record_intermediary_states the propagate-only moves of observe_every_step are
+        # recorded as well (filters/base.py:207-208; their likelihood increments are zero)
+        kept = range(M) if self._record_intermediary else observed
+        rows = torch.as_tensor([t0 + 1 + mv for mv in kept], device=means.device)
         result.extend_moments(means[rows], variances[rows])
         result._loglikelihood = result._loglikelihood + ll[rows].sum(0)
         result._states.append(e.make_state())

@@ -10,7 +10,7 @@ from ...timeseries import StateSpaceModel, TimeseriesState
 class Engine:
     def __init__(self, model: StateSpaceModel, proposal_id: int, algorithm_id: int, resampler_id: int, particles: int,
                  batch_shape: torch.Size, ess_threshold: float, seed: int, history_rows: int, fold_lookahead: bool = True,
-                 exact_weights: bool = False):
+                 exact_weights: bool = False, column_offset: int = 0):
         _lib.require_cuda()
         self.lib = _lib.load_library()
         self.model = model
@@ -28,6 +28,7 @@ class Engine:
         cfg.history_rows = int(history_rows)
         cfg.fold_lookahead = int(bool(fold_lookahead))
         cfg.exact_weights = int(bool(exact_weights))
+        cfg.column_offset = int(column_offset)   # global index of column 0: the Philox counters use column_offset + column
         self._params_keepalive = params
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)))
@@ -139,6 +140,8 @@ class Engine:
         from .state import ParticleFilterCorrection
 
         x = TimeseriesState(torch.tensor(self.t), self.x_view(), self.event_shape)
+        # x / log-weights are zero-copy views of the LIVE device buffers (valid until the engine moves again: `is_live`); a state that is
+        # kept (FilterResult with record_states, a state handed back to filter() later) is detached at append time (filters/result.py)
         return ParticleFilterCorrection(x, self.logw_view(), self.small(_lib.PTR_LL, False), self.prev_inds,
                                         self.small(_lib.PTR_MEAN, True), self.small(_lib.PTR_VAR, True), engine=self,
                                         stamp=self.stamp)

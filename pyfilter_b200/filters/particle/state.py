@@ -15,12 +15,29 @@ class ParticleFilterCorrection(dict):
                  engine=None, stamp=None):
         super().__init__()
         self["_x"], self["_w"], self["_ll"], self["_mean"], self["_var"] = x, w, ll, mean, var
-        self._prev_inds = prev_inds  # int64 tensor or a zero-argument callable producing it (widening is lazy)
+        # same key as the reference (particle/state.py:155,162); an int64 tensor, or - while the state is the engine's live one - a
+        # zero-argument callable that widens the device's int32 ancestors on first use
+        dict.__setitem__(self, "_prev_inds", prev_inds)
         self._engine, self._stamp = engine, stamp
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if key == "_prev_inds" and callable(v):
+            self._check_live("previous_indices")
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def _check_live(self, what):
+        e = self._engine
+        if e is not None and self._stamp != e.stamp:
+            raise RuntimeError(f"this state's {what} are views of device buffers that later filter moves have overwritten; keep a state "
+                               "with .detach_copy() (FilterResult does so when record_states is set) before the filter moves again")
 
     # -- reference accessors
     @property
     def timeseries_state(self) -> TimeseriesState:
+        self._check_live("particles")
         return self["_x"]
 
     def get_timeseries_state(self) -> TimeseriesState:
@@ -28,13 +45,12 @@ class ParticleFilterCorrection(dict):
 
     @property
     def weights(self) -> torch.Tensor:
+        self._check_live("log-weights")
         return self["_w"]
 
     @property
     def previous_indices(self) -> torch.Tensor:
-        if callable(self._prev_inds):
-            self._prev_inds = self._prev_inds()
-        return self._prev_inds
+        return self["_prev_inds"]
 
     def get_loglikelihood(self):
         return self["_ll"]
@@ -53,6 +69,7 @@ class ParticleFilterCorrection(dict):
         return self._engine is engine and engine is not None and self._stamp == engine.stamp
 
     def detach_copy(self) -> "ParticleFilterCorrection":
+        self._check_live("particles and weights")
         x = self.timeseries_state
         return ParticleFilterCorrection(TimeseriesState(x.time_index.clone(), x.value.clone(), x.event_shape), self.weights.clone(),
                                         self["_ll"].clone(), self.previous_indices.clone(), self["_mean"].clone(),
@@ -62,7 +79,7 @@ class ParticleFilterCorrection(dict):
     def resample(self, indices):
         self["_x"] = self.timeseries_state.copy(values=self.timeseries_state.value[:, indices])
         self["_w"] = self.weights[:, indices]
-        self._prev_inds = self.previous_indices[:, indices]
+        self["_prev_inds"] = self.previous_indices[:, indices]
         self["_mean"] = self["_mean"][indices]
         self["_var"] = self["_var"][indices]
         self._engine = None
@@ -72,7 +89,7 @@ class ParticleFilterCorrection(dict):
             mine = self.detach_copy()
             for k in ("_x", "_w", "_ll", "_mean", "_var"):
                 self[k] = mine[k]
-            self._prev_inds, self._engine = mine.previous_indices, None
+            self["_prev_inds"], self._engine = mine.previous_indices, None
         self["_x"].value[:, mask] = other.timeseries_state.value[:, mask]
         self["_w"][:, mask] = other.weights[:, mask]
         self["_ll"][mask] = other.get_loglikelihood()[mask]
@@ -92,7 +109,7 @@ class ParticleFilterCorrection(dict):
         assert self.timeseries_state.value.shape == values.shape, "Seems like you're loading a different shape"
         self["_x"] = TimeseriesState(state_dict["_x"]["time_index"], values, self.timeseries_state.event_shape)
         self["_w"], self["_ll"] = state_dict["_w"], state_dict["_ll"]
-        self._prev_inds = state_dict["_prev_inds"]
+        self["_prev_inds"] = state_dict["_prev_inds"]
         self["_mean"], self["_var"] = state_dict["_mean"], state_dict["_var"]
         self._engine = None
 

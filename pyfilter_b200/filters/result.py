@@ -50,8 +50,11 @@ class FilterResult(dict):
         self._means.append(state.get_mean())
         self._variances.append(state.get_variance())
         self._loglikelihood = self._loglikelihood + state.get_loglikelihood()
-        if self._states.maxlen != 1 and len(self._states) > 0:
-            self._states[-1] = self._states[-1].detach_copy()  # older states must not alias the engine's live buffers
+        # A state straight from the engine holds zero-copy VIEWS of the device buffers, which the next move overwrites (particles and
+        # weights ping-pong, the ancestors are rewritten in place).  A result that keeps more than the latest state therefore takes its
+        # copy NOW, while the views still show this state - not when the next one arrives.
+        if self._states.maxlen != 1 and getattr(state, "_engine", None) is not None:
+            state = state.detach_copy()
         self._states.append(state)
         return self
 

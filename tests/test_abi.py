@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/smcb200.h but not exported"
         assert n in bound, f"{n} has no ctypes prototype in pyfilter_b200/_lib.py"
-    assert lib.smcb_version() == 100
+    assert lib.smcb_version() == 200
 
 
 def test_struct_layouts_match_header():

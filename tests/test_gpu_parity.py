@@ -898,3 +898,63 @@ def test_get_ess_normalized(pf):
     assert torch.allclose(got, ref, rtol=5e-6)
     got1 = pf.utils.get_ess(W[:, 0].contiguous().cuda(), normalized=True).cpu()
     assert torch.allclose(got1, ref[0], rtol=5e-6)
+
+
+# ------------------------------------------------------------------------------------------------ recorded states (result objects)
+@pytest.mark.parametrize("alg", ["sisr", "apf"])
+def test_record_states_hold_their_own_move(pf, alg, smc_path):
+    """``record_states=True`` (filters/result.py:39,119-133): every recorded state shows the particles, log-weights and ancestors of ITS
+    move, not of a later one (the device buffers are rewritten by every move: the result copies a state when it is appended).  The
+    recorded states are compared with a second filter of the same seed that is stepped by hand and copied after every move, and a
+    stale view of the device buffers refuses to be read."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR
+
+    torch.manual_seed(4)
+    _, y = O.build_model("sine_em").simulate(9)
+    y[4] = float("nan")
+    cls = {"sisr": SISR, "apf": APF}[alg]
+    N = 6000
+    fa = cls(ts.build("sine_em"), N, seed=31, record_states=True)
+    ra = fa.batch_filter(y, bar=False)
+    assert len(ra.states) == 10
+    fb = cls(ts.build("sine_em"), N, seed=31)
+    eb = fb._get_engine(12)
+    eb.initialize()
+    eb.set_observations(y.float().reshape(-1, 1).cuda().contiguous(), 0)
+    live = eb.make_state()
+    copies = [live.detach_copy()]
+    for _ in range(9):
+        eb.run(1)
+        copies.append(eb.make_state().detach_copy())
+    for i, (sa, sb) in enumerate(zip(ra.states, copies)):
+        assert int(sa.timeseries_state.time_index) == i
+        assert torch.equal(sa.timeseries_state.value, sb.timeseries_state.value), i
+        assert torch.equal(sa.weights, sb.weights), i
+        assert torch.equal(sa.previous_indices, sb.previous_indices), i
+        assert torch.equal(sa["_prev_inds"], sb["_prev_inds"])
+    # consecutive recorded states differ (they are not all views of the last one)
+    assert not torch.equal(ra.states[3].timeseries_state.value, ra.states[9].timeseries_state.value)
+    with pytest.raises(RuntimeError):
+        live.weights   # the engine has moved nine times since this view was made
+
+
+def test_record_intermediary_moments(pf):
+    """``record_intermediary_states=True`` with ``observe_every_step = 3`` (filters/base.py:207-208): the result also carries the moments
+    of the propagate-only moves - one row per move - whether or not the states themselves are recorded."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF
+
+    torch.manual_seed(6)
+    _, y = O.build_model("sine_em").simulate(7)
+    k = 3
+    fa = APF(ts.build("sine_em", observe_every_step=k), 5000, seed=3, record_intermediary_states=True)
+    ra = fa.batch_filter(y, bar=False)
+    fb = APF(ts.build("sine_em", observe_every_step=k), 5000, seed=3, record_intermediary_states=True, record_states=True)
+    rb = fb.batch_filter(y, bar=False)
+    moves = 1 + 6 * k
+    assert ra.filter_means.shape[0] == moves + 1 == rb.filter_means.shape[0]
+    assert len(rb.states) == moves + 1
+    assert torch.allclose(ra.loglikelihood, rb.loglikelihood, rtol=1e-4, atol=1e-3)
+    fc = APF(ts.build("sine_em", observe_every_step=k), 5000, seed=3)
+    assert fc.batch_filter(y, bar=False).filter_means.shape[0] == 8
