@@ -296,11 +296,11 @@ def bench_smc2(world, rank, dist, K=250, W=10):
     lo, hi = column_shard(THETA, rank, world)
     torch.manual_seed(123)
     gamma, sigma = torch.randn(THETA), torch.exp(0.5 * torch.randn(THETA))   # theta ~ prior
-    y = simulate("sine_em", 2 * (W + K) + 4)
+    y = simulate("sine_em", 5 * (W + K) + 16)
     y_dev = y.reshape(-1, 1).cuda().contiguous()
     f = APF(ts.build("sine_em", gamma=gamma[lo:hi], sigma=sigma[lo:hi]), N, seed=123, column_offset=lo)
     f.set_batch_shape(torch.Size([hi - lo]))
-    e = f._get_engine(2 * (W + K) + 8)
+    e = f._get_engine(5 * (W + K) + 20)
     stream = torch.cuda.current_stream()
     e.initialize()
     e.set_observations(y_dev, 0)
@@ -320,26 +320,60 @@ def bench_smc2(world, rank, dist, K=250, W=10):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t)
 
-    def online(moves):
+    # (1) the exchange as NCCL collective (torch.distributed): the baseline
+    def online_nccl(moves):
+        if not dist:
+            e.run_stepwise(moves)   # (the loop in C: no exchange on one GPU)
+            return
         for _ in range(moves):
             e.run(1)
-            if dist:
-                gather(ll_view)
+            gather(ll_view)
 
-    def batch(moves):
+    def batch_nccl(moves):
         e.run(moves)
         if dist:
             gather(ll_tot_view)
 
-    online(W)
-    ms_online = timed(lambda: online(K))
-    batch(W)
-    ms_batch = timed(lambda: batch(K))
+    online_nccl(W)
+    ms_online_nccl = timed(lambda: online_nccl(K))
+    batch_nccl(W)
+    ms_batch_nccl = timed(lambda: batch_nccl(K))
     res = {"workload": "sine_em APF bootstrap systematic, 1024 theta x 4096 particles (BASELINE.json configs[4]), theta columns sharded over the ranks",
-           "scaling": "strong", "theta_per_gpu": hi - lo, "moves": K,
-           "batch": {"us_per_move": ms_batch * 1e3 / K, "value": THETA * N * K / (ms_batch * 1e-3), "unit": UNIT},
-           "online": {"us_per_move": ms_online * 1e3 / K, "value": THETA * N * K / (ms_online * 1e-3), "unit": UNIT,
-                      "exchange": "torch.distributed all_gather_into_tensor of the (B_local,) increments after every move" if dist else "none (1 GPU)"}}
+           "scaling": "strong", "theta_per_gpu": hi - lo, "moves": K}
+    ms_online, ms_batch, how = ms_online_nccl, ms_batch_nccl, "none (1 GPU)"
+    if dist:
+        res["nccl_exchange"] = {"batch_us_per_move": ms_batch_nccl * 1e3 / K, "online_us_per_move": ms_online_nccl * 1e3 / K,
+                                "what": "torch.distributed all_gather_into_tensor of the (B_local,) values after every launch"}
+        how = "NCCL all_gather_into_tensor"
+        try:
+            # (2) the exchange inside the finalising kernel: (value, tag) stores into every rank's buffer over NVLink peer memory
+            from pyfilter_b200.sharding import PeerExchange
+
+            px = PeerExchange(e, THETA, lo)
+
+            def online_peer(moves):
+                e.run_stepwise(moves)   # one launch per move + the reader of the exchange after every move, the loop in C
+
+            def batch_peer(moves):
+                e.run(moves)
+                px.wait()
+
+            online_peer(W)
+            ms_online = timed(lambda: online_peer(K))
+            batch_peer(W)
+            ms_batch = timed(lambda: batch_peer(K))
+            how = "peer-memory stores from the finalising kernel (no collective launch) + one reader kernel per exchange"
+            # every rank must hold the same totals
+            e.run(1)
+            _, tot = px.wait()
+            chk = tot.clone()
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+            res["peer_exchange_consistent"] = bool(torch.equal(chk, tot))
+        except Exception as ex:
+            res["peer_exchange_error"] = repr(ex)[:300]
+    res["batch"] = {"us_per_move": ms_batch * 1e3 / K, "value": THETA * N * K / (ms_batch * 1e-3), "unit": UNIT}
+    res["online"] = {"us_per_move": ms_online * 1e3 / K, "value": THETA * N * K / (ms_online * 1e-3), "unit": UNIT}
+    res["exchange"] = how
     # speed-up against this box's own 1-GPU run (the driver runs N = 1, 2, 4, 8 back to back on one box)
     memo = os.path.join("/tmp", "smcb_smc2_n1.json")
     if rank == 0:
@@ -509,7 +543,7 @@ def run_b200(args):
         # one move = ONE launch of the dominant kernel (plus its one-block finalize, chained with programmatic dependent launch).  The
         # events of smcb_filter_profile sit between the kernels and break that overlap, so the kernel's average launch duration is
         # taken from the timed region itself: K back-to-back moves on the launching stream (the bracketed figure is kept next to it)
-        per["move_kernel"] = ms / K - per.get("apf_preweight", 0.0) * 0.0
+        per["move_kernel"] = ms / K
     # algorithmic bytes per launch: whole move = 16 + 8 d per particle; resampling = load log-weight 4 + store ancestor 4;
     # step = ancestor 4 + gather 4 + x 4 + log-weight 4
     alg_bytes = {"move_kernel": 24.0 * N, "resample_fused_kernel": 8.0 * N, "normalize_kernel": 8.0 * N, "describe_kernel": 4.0 * N,

@@ -113,6 +113,10 @@ int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, int32_t cou
  * for the next `steps` observations set above; NaN observations propagate only (filters/base.py:213-214). */
 int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream);
 
+/* the online pattern of SMC2 / NESS (inference/sequential/smc2.py:53-65, ness.py:56): `steps` launches of ONE move each; when an exchange
+ * is attached (below) every move is followed by the reader of that exchange */
+int smcb_filter_run_stepwise(smcb_filter* f, int32_t steps, void* stream);
+
 /* measurement aid: runs `steps` moves like smcb_filter_run with CUDA events around every kernel group and returns the summed
  * device time in milliseconds: out_ms_host[0..4] = {APF pre-weight (+finalize), normalize, describe (+chain), expand, fused
  * step}.  Synchronises the stream. */
@@ -123,6 +127,19 @@ int smcb_filter_profile(smcb_filter* f, int32_t steps, float* out_ms_host, void*
  * (row 0 is zero) and the total log-likelihood (B).  Any output pointer may be NULL.  Synchronises the stream. */
 int smcb_filter_batch_filter_host(smcb_filter* f, const float* y_host, int32_t T, float* means_host, float* vars_host,
                                   float* ll_steps_host, float* ll_total_host, void* stream);
+
+/* Shards of ONE batch of filters on several GPUs (the theta-particles of SMC2 / NESS split by columns): the per-column
+ * log-likelihood values every rank needs for the theta-level ESS test (inference/sequential/state.py:35-44, smc2.py:59-63) are stored
+ * by the finalising kernel straight into every rank's buffer over NVLink peer memory - no collective launch.  `peer_ptrs_host[r]` is
+ * the device address of rank r's buffer as mapped into THIS process (torch symmetric memory / cudaIpc: plumbing), each at least
+ * 2 * 2 * total_columns * 8 bytes and zeroed; `rank` is this handle's position, `first_column` the global index of its column 0.
+ * From then on the move that ends every smcb_filter_run publishes (increment of the last move, running total) of its columns.
+ * NULL detaches. */
+int smcb_filter_attach_exchange(smcb_filter* f, const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, int32_t total_columns,
+                                int32_t first_column);
+/* enqueues the reader of the latest exchange: waits (on the device, polling this rank's buffer) until the values of every column of
+ * the batch have arrived and returns a dense device array (2, total_columns): row 0 the increments, row 1 the totals */
+int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* stream);
 
 /* parity hooks: inject the transition noise (D, B, ld) / systematic offsets (B) / multinomial uniforms
  * (B, ld) float64, or dump the ones the kernels generated and the normalised weights (B, ld) the resampler consumed.  NULL

@@ -57,8 +57,11 @@ SYMBOLS = [
     ("smcb_filter_refresh_state", C.c_int, [_P, C.c_int32, _P]),
     ("smcb_filter_set_observations", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P]),
     ("smcb_filter_run", C.c_int, [_P, C.c_int32, _P]),
+    ("smcb_filter_run_stepwise", C.c_int, [_P, C.c_int32, _P]),
     ("smcb_filter_profile", C.c_int, [_P, C.c_int32, _P, _P]),
     ("smcb_filter_batch_filter_host", C.c_int, [_P, _P, C.c_int32, _P, _P, _P, _P, _P]),
+    ("smcb_filter_attach_exchange", C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("smcb_filter_exchange_wait", C.c_int, [_P, C.POINTER(_P), _P]),
     ("smcb_filter_set_noise", C.c_int, [_P, _P, _P, _P]),
     ("smcb_filter_dump_noise", C.c_int, [_P, _P, _P, _P]),
     ("smcb_filter_ptr", C.c_int, [_P, C.c_int32, C.POINTER(_P)]),

@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
     if (resampled && st.resample) {
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) *reinterpret_cast<int4*>(&cs.stage[(r * NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-      if (tid == 0) cs.carry = -1;
       const float m = (ALG == SMCB_ALG_APF) ? st.m_rw : st.m_lw, iz = (ALG == SMCB_ALG_APF) ? st.inv_z_rw : st.inv_z_lw;
       float w[ITEMS];
       double tsum = 0.0;
@@ -119,7 +118,7 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
           reinterpret_cast<float4*>(dst)[v] = make_float4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
       }
       double tot;
-      const double S0 = rs_block_excl_scan_d<NT>(tsum, cs.dscratch, &tot);
+      const double S0 = rs_block_excl_scan_d<NT, false>(tsum, cs.dscratch, &tot);   // (dscratch was last read several barriers ago)
       float u;
       if (c.u_in) u = c.u_in[col];
       else {
@@ -127,14 +126,23 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
         u = smcb_u01(r4.x);
       }
       if (c.u_out && tid == 0) c.u_out[col] = u;
-      int32_t lo_thread = 0;
-      if (tid) lo_thread = (gbase - 1 >= n - 1) ? n : xs_count_fast((float)S0, u, n, nd, nfd);
-      auto mark = [&](int32_t wb, bool first) -> int32_t {
-        if (!tlive) return n;   // nothing but padding: every count is n, no marks
-        return rs_mark_pass<53, true, true, ITEMS, RS_TILE>(w, S0, 0.0, nullptr, lo_thread, gbase, wb, first, u, n, nf, nd, nfd, true, cs);
-      };
-      rs_emit_ancestors<NT, ROWS>(cs, mark, 0, anc_s);   // n <= RS_TILE = the window: a single pass, ancestors replace the marks in place
+      // counts of this thread's particles (exact_scan.h: xs_count_lean; the column is one window, so a mark needs no range test) and
+      // the "last mark" scan in place: the ancestors replace the marks
+      int32_t lo = 0;
+      if (tid) lo = (gbase - 1 >= n - 1) ? n : max(0, min(xs_count_lean((float)S0, u, n, nfd), n));
+      if (tlive) {
+        double run = S0;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+          run = __dadd_rn(run, (double)w[j]);
+          int32_t hi = min(xs_count_lean((float)run, u, n, nfd), n);
+          hi = (gbase + j >= n - 1) ? n : hi;   // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1
+          if (hi > lo) cs.stage[lo] = gbase + j;
+          lo = max(lo, hi);
+        }
+      }
       __syncthreads();
+      rs_emit_blocked<NT, ITEMS>(cs, -1);
     }
 
     // ---- the move itself (step_kernel's body on this thread's ITEMS particles)
@@ -234,13 +242,15 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
     SoftAcc<1 + 2 * D> A;
     SoftAcc<1> Q, R2, R3;
     mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
-    softacc4_block_reduce(A, Q, R2, R3, cs.f4);   // its barriers also separate this move's gathers from the stores below
+    softacc4_block_reduce<1 + 2 * D, NT, false>(A, Q, R2, R3, cs.f4);   // its barriers also separate this move's gathers from the stores below
     if (tid == 0) {
       FinPre pre;
       pre.st = st; pre.observed = observed; pre.fold = fold; pre.ll_total = ll_total;
       ColStats stn = st;
-      ll_total += fin_apply<D, OD, ALG>(a, col, FIN_STEP, t, A, Q, R2, R3, pre, stn);
+      const float ll = fin_apply<D, OD, ALG>(a, col, FIN_STEP, t, A, Q, R2, R3, pre, stn);
+      ll_total += ll;
       cs.st = stn;
+      if (k == c.steps - 1) smcb_exchange_publish(a.xch, col, ll, ll_total);   // the values of the launch's last move go to every rank
     }
 #pragma unroll
     for (int v = 0; v < ITEMS / 4; ++v) {

@@ -56,6 +56,31 @@ struct Ctrl {
   int64_t lb_windows;   // reserved
 };
 
+// Exchange of the per-column log-likelihood values between the GPUs that hold shards of ONE batch of filters (theta-sharded SMC2 /
+// NESS): the kernel that finalises a column stores (value, sequence tag) pairs straight into EVERY rank's buffer
+// over NVLink peer memory - one 8-byte store per rank and value: the pair is written atomically, so no fence, no flag and no
+// collective launch is needed; the reader polls the tags (exchange_wait_kernel).  Buffers: torch symmetric memory (plumbing),
+// layout  slot[parity = seq & 1][kind: 0 = increment of the last move, 1 = running total][global column]  of 8 bytes each.
+#define SMCB_MAX_PEERS 8
+struct ExchangeArgs {
+  unsigned long long* peer[SMCB_MAX_PEERS];  // base of every rank's buffer (this rank's own included), NULL when no exchange is attached
+  int32_t world;
+  int32_t total;        // columns of the whole batch
+  int32_t lo;           // global index of this rank's first column
+  uint32_t seq;         // sequence number of the exchange this launch publishes (>= 1); 0: do not publish
+};
+__device__ __forceinline__ void smcb_exchange_publish(const ExchangeArgs& x, int col, float ll, float ll_total) {
+  if (!x.seq) return;
+  const int64_t base = (int64_t)(x.seq & 1u) * 2 * x.total + x.lo + col;
+  const unsigned long long a = ((unsigned long long)x.seq << 32) | (unsigned long long)__float_as_uint(ll);
+  const unsigned long long b = ((unsigned long long)x.seq << 32) | (unsigned long long)__float_as_uint(ll_total);
+  for (int r = 0; r < x.world; ++r) {
+    unsigned long long* p = x.peer[r] + base;
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(a) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p + x.total), "l"(b) : "memory");
+  }
+}
+
 // Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
 // while its predecessor in the stream drains; pdl_wait() blocks until the predecessor has completed and its writes are visible
 // (a no-op for ordinary launches), pdl_trigger() lets the successor's blocks be scheduled once every block has called it or exited.

@@ -261,41 +261,6 @@ __device__ __noinline__ void mv_remark(const float* wsrc, float m, float iz, dou
   }
 }
 
-// "last mark at or before every slot" over the window in shared memory; the ancestors replace the marks in place.  A thread owns
-// MV_PER consecutive slots: running maximum in registers, one warp scan of the per-thread maxima, one cross-warp step.
-template <typename SM>
-__device__ __forceinline__ int32_t mv_emit(SM& sm, int32_t carry) {
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  int4 m[MV_PER / 4];
-#pragma unroll
-  for (int k = 0; k < MV_PER / 4; ++k) m[k] = *reinterpret_cast<const int4*>(&sm.stage[tid * MV_PER + 4 * k]);
-  int32_t v = -1;
-#pragma unroll
-  for (int k = 0; k < MV_PER / 4; ++k) v = max(max(v, max(m[k].x, m[k].y)), max(m[k].z, m[k].w));
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
-    if (lane >= o) v = max(v, t);
-  }
-  int32_t run = __shfl_up_sync(0xffffffffu, v, 1);
-  if (lane == 0) run = -1;
-  if (lane == 31) sm.wtot[wid] = v;
-  __syncthreads();
-  const int32_t wt = (lane < MV_NT / 32) ? sm.wtot[lane] : -1;
-  run = max(run, max(carry, __reduce_max_sync(0xffffffffu, (lane < wid) ? wt : -1)));
-  carry = max(carry, __reduce_max_sync(0xffffffffu, wt));
-#pragma unroll
-  for (int k = 0; k < MV_PER / 4; ++k) {
-    m[k].x = run = max(run, m[k].x);
-    m[k].y = run = max(run, m[k].y);
-    m[k].z = run = max(run, m[k].z);
-    m[k].w = run = max(run, m[k].w);
-    *reinterpret_cast<int4*>(&sm.stage[tid * MV_PER + 4 * k]) = m[k];
-  }
-  __syncthreads();
-  return carry;
-}
-
 template <int MODEL, int PROP, int ALG>
 __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   typedef Model<MODEL> M;
@@ -566,7 +531,7 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
           __syncthreads();
           carry = max(carry, sm.carry);
         }
-        carry = mv_emit(sm, carry);
+        carry = rs_emit_blocked<MV_NT, MV_PER>(sm, carry);
         if (wb == wb0) MV_STAMP(5);
       }
       if (fast) run_window(std::true_type{}, wb, wlen);

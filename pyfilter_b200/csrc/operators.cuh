@@ -183,6 +183,25 @@ static inline void op_launch_copy_ess(const ColStats* st, float* out, int B, cud
   copy_ess_kernel<<<(B + 127) / 128, 128, 0, s>>>(st, out, B);
 }
 
+// ---- reader of the peer-memory exchange (common.cuh: smcb_exchange_publish) ------------------------------------------------------------
+// Polls the (value, tag) pairs of exchange `seq` in this rank's buffer until every column of the batch has arrived (strong system-scope
+// loads: the pairs are written by other GPUs) and writes the values out densely: out[0 .. total) increments, out[total .. 2 total) totals.
+__global__ void __launch_bounds__(256) exchange_wait_kernel(const unsigned long long* buf, int total, uint32_t seq, float* out, long long* spins) {
+  const unsigned long long* base = buf + (int64_t)(seq & 1u) * 2 * total;
+  long long n = 0;
+  for (int i = threadIdx.x; i < 2 * total; i += blockDim.x) {
+    unsigned long long v;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(base + i) : "memory");
+      if ((uint32_t)(v >> 32) == seq) break;
+      __nanosleep(100);
+      ++n;
+    }
+    out[i] = __uint_as_float((uint32_t)v);
+  }
+  if (spins && n) atomicAdd((unsigned long long*)spins, (unsigned long long)n);
+}
+
 // ---- systematic ------------------------------------------------------------------------------------------------------------------
 static inline void op_launch_systematic(const ResampleArgs& r, cudaStream_t s) {
   const dim3 g(r.tiles_per_col, r.B);

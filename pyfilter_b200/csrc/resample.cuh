@@ -87,7 +87,7 @@ struct OpMinU { __device__ __forceinline__ uint32_t operator()(uint32_t a, uint3
 #define RS_BENIGN_MIN_BITS 0x31000000u  // 2^-29
 
 // exclusive block scan of one double per thread (blockDim.x == RS_NT); *total = sum over the block
-template <int NT = RS_NT>
+template <int NT = RS_NT, bool PROTECT = true>  // PROTECT = false: `scratch` is known to be idle (saves a barrier)
 __device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch /*>= NT/32*/, double* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   double inc = v;
@@ -96,7 +96,7 @@ __device__ __forceinline__ double rs_block_excl_scan_d(double v, double* scratch
     const double t = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += t;
   }
-  __syncthreads();
+  if (PROTECT) __syncthreads();
   if (lane == 31) scratch[wid] = inc;
   __syncthreads();
   double off = 0.0, tot = 0.0;
@@ -975,6 +975,43 @@ __device__ __forceinline__ void rs_emit_ancestors(SM& sm, Mark mark, int32_t n_i
       }
     }
   }
+}
+
+// "last mark at or before every slot" over a window of NT * PER slots in shared memory (sm.stage); the ancestors replace the marks
+// in place.  A thread owns PER consecutive slots: running maximum in registers, one warp scan of the per-thread maxima, one cross-warp
+// step (sm.wtot: NT / 32 ints).  `carry` = last mark of the windows before this one; returns it updated.  All NT threads call.
+template <int NT, int PER, typename SM>
+__device__ __forceinline__ int32_t rs_emit_blocked(SM& sm, int32_t carry) {
+  static_assert(PER % 4 == 0, "a thread reads whole int4");
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  int4 m[PER / 4];
+#pragma unroll
+  for (int k = 0; k < PER / 4; ++k) m[k] = *reinterpret_cast<const int4*>(&sm.stage[tid * PER + 4 * k]);
+  int32_t v = -1;
+#pragma unroll
+  for (int k = 0; k < PER / 4; ++k) v = max(max(v, max(m[k].x, m[k].y)), max(m[k].z, m[k].w));
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v = max(v, t);
+  }
+  int32_t run = __shfl_up_sync(0xffffffffu, v, 1);
+  if (lane == 0) run = -1;
+  if (lane == 31) sm.wtot[wid] = v;
+  __syncthreads();
+  const int32_t wt = (lane < NT / 32) ? sm.wtot[lane] : -1;
+  run = max(run, max(carry, __reduce_max_sync(0xffffffffu, (lane < wid) ? wt : -1)));
+  carry = max(carry, __reduce_max_sync(0xffffffffu, wt));
+#pragma unroll
+  for (int k = 0; k < PER / 4; ++k) {
+    m[k].x = run = max(run, m[k].x);
+    m[k].y = run = max(run, m[k].y);
+    m[k].z = run = max(run, m[k].z);
+    m[k].w = run = max(run, m[k].w);
+    *reinterpret_cast<int4*>(&sm.stage[tid * PER + 4 * k]) = m[k];
+  }
+  __syncthreads();
+  return carry;
 }
 
 template <int MB, int OUT>

@@ -160,6 +160,11 @@ struct smcb_filter {
   uint32_t* gcount = nullptr;
   unsigned mv_epoch = 0;
   uint32_t mv_launches = 0;   // move_kernel launches since the group counters were cleared
+  // peer-memory exchange of the per-column log-likelihoods (smcb_filter_attach_exchange)
+  ExchangeArgs xch = {};
+  uint32_t xch_seq = 0;       // exchanges published so far
+  int xch_rank = 0;
+  float* xch_out = nullptr;   // (2, total) dense copy made by smcb_filter_exchange_wait
 };
 
 template <typename T>
@@ -188,7 +193,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gslots, f->gcount};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gslots, f->gcount, f->xch_out};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -310,6 +315,7 @@ static StepArgs make_args(smcb_filter* f) {
   philox_round_keys((uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), a.pkeys);
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
   a.col0 = f->cfg.column_offset;
+  a.xch = f->xch; a.xch.seq = 0;   // set by the launch that finalises the last move of a run
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
   a.dbg = f->dbg;
   a.latest_mean = f->latest_mean; a.latest_var = f->latest_var; a.latest_ll = f->latest_ll; a.ll_total = f->ll_total;
@@ -519,6 +525,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
   }
   if (ev) cudaEventRecord(ev[1], s);
   a.store_lw = last ? 1 : 0;
+  if (last && f->xch.peer[0]) a.xch.seq = ++f->xch_seq;   // the move that ends a run publishes its columns' log-likelihoods to every rank
   if (move_path_ok(f)) {
     int rc = launch_move(f, a, s);
     if (rc) return rc;
@@ -597,7 +604,12 @@ static bool column_path_ok(const smcb_filter* f) {
 
 template <int MODEL, int PROP, int ALG, int NT, int MINB>
 static cudaError_t launch_column_nt(int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
-  cudaError_t e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, ALG, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  static size_t set_for = 0;   // the attribute is set once per instantiation (a driver call per launch costs microseconds on the online path)
+  cudaError_t e = cudaSuccess;
+  if (set_for < dyn) {
+    e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, ALG, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e == cudaSuccess) set_for = dyn;
+  }
   if (e == cudaSuccess) column_kernel<MODEL, PROP, ALG, NT, MINB><<<B, NT, dyn, s>>>(c);
   return e;
 }
@@ -624,6 +636,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
     launch_preweight(f, a, s);
     launch_finalize(f, a, FIN_PREWEIGHT, s);
   }
+  if (f->xch.peer[0]) a.xch.seq = ++f->xch_seq;
   ColumnArgs c;
   memset(&c, 0, sizeof(c));
   c.s = a;
@@ -662,6 +675,23 @@ extern "C" int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream) {
     if (rc) return rc;
   }
   CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* stream);
+// SMC2 / NESS drive the filter one observation at a time and look at the likelihood increments after every move (smc2.py:53-65,
+// ness.py:56): `steps` launches of one move each; with an exchange attached every move is followed by the reader of that exchange.
+extern "C" int smcb_filter_run_stepwise(smcb_filter* f, int32_t steps, void* stream) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  for (int k = 0; k < steps; ++k) {
+    int rc = smcb_filter_run(f, 1, stream);
+    if (rc) return rc;
+    if (f->xch.peer[0]) {
+      float* out = nullptr;
+      rc = smcb_filter_exchange_wait(f, &out, stream);
+      if (rc) return rc;
+    }
+  }
   return SMCB_OK;
 }
 
@@ -711,6 +741,38 @@ extern "C" int smcb_filter_batch_filter_host(smcb_filter* f, const float* y_host
   if (ll_steps_host) CU(cudaMemcpyAsync(ll_steps_host, f->hist_ll, sizeof(float) * rows * f->B, cudaMemcpyDeviceToHost, s));
   if (ll_total_host) CU(cudaMemcpyAsync(ll_total_host, f->ll_total, sizeof(float) * f->B, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_attach_exchange(smcb_filter* f, const uint64_t* peer_ptrs_host, int32_t world, int32_t rank, int32_t total_columns,
+                                           int32_t first_column) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  if (!peer_ptrs_host) {  // detach
+    f->xch = ExchangeArgs{}; f->xch_seq = 0;
+    return SMCB_OK;
+  }
+  if (world < 1 || world > SMCB_MAX_PEERS || rank < 0 || rank >= world) return fail(SMCB_EINVAL, "world size must be 1 .. 8, rank inside it");
+  if (total_columns < f->B || first_column < 0 || first_column + f->B > total_columns) return fail(SMCB_EINVAL, "this rank's columns do not fit the batch");
+  ExchangeArgs x = {};
+  for (int r = 0; r < world; ++r) {
+    if (!peer_ptrs_host[r]) return fail(SMCB_EINVAL, "null peer buffer");
+    x.peer[r] = (unsigned long long*)(uintptr_t)peer_ptrs_host[r];
+  }
+  x.world = world; x.total = total_columns; x.lo = first_column; x.seq = 0;
+  if (f->xch_out) { cudaFree(f->xch_out); f->xch_out = nullptr; }
+  CU(cudaMalloc((void**)&f->xch_out, sizeof(float) * 2 * (size_t)total_columns));
+  f->xch = x; f->xch_seq = 0; f->xch_rank = rank;
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* stream) {
+  if (!f || !out_dev) return fail(SMCB_EINVAL, "null argument");
+  if (!f->xch.peer[0] || !f->xch_seq) return fail(SMCB_ESTATE, "no exchange attached or nothing published yet");
+  unsigned long long* mine = f->xch.peer[f->xch_rank];   // the buffer the peers (and this rank) stored into
+  exchange_wait_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mine, f->xch.total, f->xch_seq, f->xch_out, f->wd ? f->wd + 3 : nullptr);
+  f->launches++;
+  CU(cudaGetLastError());
+  *out_dev = f->xch_out;
   return SMCB_OK;
 }
 

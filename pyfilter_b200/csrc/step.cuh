@@ -52,6 +52,7 @@ struct StepArgs {
   const float* y_t;                  // observation of this move (NULL: none)
   const float* y_next;               // observation of the next move (NULL: unknown -> no folded look-ahead)
   uint32_t pkeys[20];                // Philox round keys of `seed` (philox_round_keys)
+  ExchangeArgs xch;                  // peer-memory exchange of the per-column log-likelihoods (common.cuh); xch.seq == 0: none
   int32_t col0;                      // global index of column 0 (smcb_config.column_offset): the Philox counters use col0 + column
 };
 __device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
@@ -558,7 +559,8 @@ __device__ __forceinline__ void finalize_column(const StepArgs& a, int col, int 
       st.fold_valid = 1;
       a.stats[col] = st;
     } else {
-      fin_apply<D, OD, ALG>(a, col, mode, t, A, Q, R2, R3, pre, st);
+      const float ll = fin_apply<D, OD, ALG>(a, col, mode, t, A, Q, R2, R3, pre, st);
+      if (mode == FIN_STEP) smcb_exchange_publish(a.xch, col, ll, pre.ll_total + ll);
     }
     if (mode == FIN_STEP) {
       if (a.B == 1 || atomicAdd(&a.ctrl->ticket, 1) == a.B - 1) {  // every column is finalized, hence every block has read ctrl->t

@@ -121,6 +121,12 @@ class Engine:
         self.t += steps
         self.stamp += 1
 
+    def run_stepwise(self, steps: int):
+        """``steps`` launches of one move each (the online pattern of SMC2 / NESS), the loop itself in C."""
+        _lib.check(self.lib.smcb_filter_run_stepwise(self.handle, steps, _lib.current_stream()))
+        self.t += steps
+        self.stamp += 1
+
     def set_noise(self, eps=None, u=None, U=None):
         self._noise_keep = (eps, u, U)
         _lib.check(self.lib.smcb_filter_set_noise(self.handle, eps.data_ptr() if eps is not None else None,

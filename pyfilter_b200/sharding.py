@@ -68,6 +68,61 @@ class LogLikelihoodGather:
         return torch.cat([self.recv[r * self.width: r * self.width + (h - l)] for r, (l, h) in enumerate(self.sizes)])
 
 
+class PeerExchange:
+    """The per-move exchange of the theta-sharded loop WITHOUT a collective launch: the kernel that finalises a column stores its
+    log-likelihood increment and running total (each with a sequence tag, one 8-byte store) straight into every rank's buffer over
+    NVLink peer memory (``smcb_filter_attach_exchange``, include/smcb200.h); :meth:`wait` enqueues the small reader that polls this
+    rank's buffer until all columns of the batch have arrived and returns ``(increments, totals)``, each ``(batch,)`` in column order.
+
+    The buffers are torch symmetric memory (``torch.distributed._symmetric_memory``: allocation and address exchange are plumbing);
+    ``buffers=`` takes ordinary CUDA tensors instead - one per rank, all visible to this process - which is how the single-GPU tests
+    emulate several ranks.  Protocol: every rank calls ``wait()`` after every ``run()`` that publishes (two buffers alternate by
+    parity of the sequence number, so a rank may be one exchange ahead of a peer, not two)."""
+
+    def __init__(self, engine, batch: int, first_column: int, group=None, buffers=None, rank: int = None):
+        import ctypes as C
+
+        from . import _lib
+
+        self.engine, self.batch = engine, int(batch)
+        words = 2 * 2 * self.batch   # [parity][increment | total][column], 8 bytes each
+        if buffers is None:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm_mem
+
+            group = group if group is not None else dist.group.WORLD
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+            self._buf = symm_mem.empty(words, dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+            self._buf.zero_()
+            self._hdl = symm_mem.rendezvous(self._buf, group)
+            ptrs = [int(p) for p in self._hdl.buffer_ptrs]
+            torch.cuda.synchronize()
+            dist.barrier(group)   # every buffer is zeroed before anybody stores into it
+        else:
+            self.world, self.rank = len(buffers), int(rank)
+            for b in buffers:
+                assert b.is_cuda and b.dtype == torch.int64 and b.numel() >= words
+            self._buf = buffers
+            ptrs = [int(b.data_ptr()) for b in buffers]
+        arr = (C.c_uint64 * self.world)(*ptrs)
+        _lib.check(engine.lib.smcb_filter_attach_exchange(engine.handle, arr, self.world, self.rank, self.batch, int(first_column)))
+
+    def wait(self):
+        import ctypes as C
+
+        from . import _lib
+
+        out = C.c_void_p()
+        _lib.check(self.engine.lib.smcb_filter_exchange_wait(self.engine.handle, C.byref(out), _lib.current_stream()))
+        t = _lib.as_tensor(out.value, (2, self.batch), "<f4", self.engine)
+        return t[0], t[1]
+
+    def close(self):
+        from . import _lib
+
+        _lib.check(self.engine.lib.smcb_filter_attach_exchange(self.engine.handle, None, 0, 0, 0, 0))
+
+
 def theta_ess(ll_total: torch.Tensor) -> torch.Tensor:
     """ESS of the theta-particles from their accumulated log-likelihoods (reference utils.py:8-20 on the theta weights)."""
     w = torch.softmax(ll_total - ll_total.max(), dim=0)

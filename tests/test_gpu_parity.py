@@ -958,3 +958,51 @@ def test_record_intermediary_moments(pf):
     assert torch.allclose(ra.loglikelihood, rb.loglikelihood, rtol=1e-4, atol=1e-3)
     fc = APF(ts.build("sine_em", observe_every_step=k), 5000, seed=3)
     assert fc.batch_filter(y, bar=False).filter_means.shape[0] == 8
+
+
+# ------------------------------------------------------------------------------------------------ theta shards: peer-memory exchange
+@pytest.mark.parametrize("N,online", [(4096, True), (4096, False), (20_000, True)])
+def test_peer_exchange_emulated_ranks(pf, N, online):
+    """The exchange of the theta-sharded loop (include/smcb200.h: smcb_filter_attach_exchange): the finalising kernel stores (value, tag)
+    pairs into every rank's buffer.  Two "ranks" are emulated on one GPU - two shards of one batch of 10 columns, two handles, two
+    buffers - and every rank must read the log-likelihood increments and totals of ALL columns exactly as the shards computed them,
+    move after move (N = 4096: the resident column kernel, online and whole runs; N = 20000: move kernel + finalize kernel).  The
+    shards pass their global column offset, so the run also equals ONE unsharded filter on the same seed, bit for bit."""
+    from pyfilter_b200 import _lib, timeseries as ts
+    from pyfilter_b200.filters.particle import APF
+    from pyfilter_b200.sharding import PeerExchange, column_shard
+
+    THETA, world = 10, 2
+    gen = torch.Generator().manual_seed(5)
+    gamma, sigma = torch.randn(THETA, generator=gen) * 0.3, torch.exp(0.3 * torch.randn(THETA, generator=gen))
+    torch.manual_seed(3)
+    _, y = O.build_model("sine_em").simulate(13)
+    yd = y.float().reshape(-1, 1).cuda().contiguous()
+    bufs = [torch.zeros(2 * 2 * THETA, dtype=torch.int64, device="cuda") for _ in range(world)]
+    engines, xs = [], []
+    for r in range(world):
+        lo, hi = column_shard(THETA, r, world)
+        f = APF(ts.build("sine_em", gamma=gamma[lo:hi], sigma=sigma[lo:hi]), N, seed=77, column_offset=lo)
+        f.set_batch_shape(torch.Size([hi - lo]))
+        e = f._get_engine(16)
+        e.initialize()
+        e.set_observations(yd, 0)
+        engines.append((e, lo, hi))
+        xs.append(PeerExchange(e, THETA, lo, buffers=bufs, rank=r))
+    whole = APF(ts.build("sine_em", gamma=gamma, sigma=sigma), N, seed=77)
+    whole.set_batch_shape(torch.Size([THETA]))
+    ew = whole._get_engine(16)
+    ew.initialize()
+    ew.set_observations(yd, 0)
+    for steps in ([1] * 6 if online else [4, 5, 3]):
+        for e, _, _ in engines:
+            e.run(steps)
+        ew.run(steps)
+        got = [x.wait() for x in xs]
+        torch.cuda.synchronize()
+        inc = torch.cat([e.raw(_lib.PTR_LL, (e.B,)).clone() for e, _, _ in engines])
+        tot = torch.cat([e.raw(_lib.PTR_LL_TOTAL, (e.B,)).clone() for e, _, _ in engines])
+        for a, b in got:
+            assert torch.equal(a, inc) and torch.equal(b, tot)
+        assert torch.equal(tot, ew.raw(_lib.PTR_LL_TOTAL, (THETA,))), "sharded run differs from the unsharded one"
+    assert torch.isfinite(tot).all()
