@@ -168,6 +168,38 @@ int smcb_filter_ptr(smcb_filter* f, int32_t what, void** ptr_dev);
 /* gathers ESS / resample flags of every column into the packed SMCB_PTR_ESS buffer (get_ess, utils.py:8-20) */
 int smcb_filter_sync_stats(smcb_filter* f, void* stream);
 
+/* the proposal plug-in surface (filters/particle/proposals/base.py:52-85) as stand-alone passes of the handle's proposal over a caller's
+ * particles `x_dev` (D, B, ld) in the handle's layout (NULL: the handle's current particles); y_dev is ONE observation (obs_dim) on the
+ * device.  pre_weight -> log p(y | .) as the APF uses it (apf.py:27; proposals/base.py:69-85, proposals/linear.py:57-86) into out_dev
+ * (B, ld).  sample_and_weight -> proposed particles (D, B, ld) and weight increments (B, ld) (proposals/bootstrap.py:10-14,
+ * proposals/linear.py:38-55); `eps_dev` (D, B, ld) injects the N(0,1) draws, NULL draws them from Philox at move index `t`. */
+int smcb_filter_pre_weight(smcb_filter* f, const float* y_dev, const float* x_dev, float* out_dev, void* stream);
+int smcb_filter_sample_and_weight(smcb_filter* f, const float* y_dev, const float* x_dev, const float* eps_dev, int32_t t, float* x_out_dev,
+                                  float* w_out_dev, void* stream);
+/* relative ESS threshold of the coming SISR moves (filters/particle/base.py:42); a negative value switches resampling off, a value above 1
+ * forces it - SISR.correct (sisr.py:50-56) propagates a prediction that SISR.predict has already resampled */
+int smcb_filter_set_ess_threshold(smcb_filter* f, float relative_threshold);
+/* ParticleFilterCorrection.predict_path (particle/state.py:173-174 -> model.sample_states(num_steps, x_0)): every particle of `x_dev`
+ * (NULL: the current ones) simulated `steps` transitions ahead with its observations: x_out_dev (steps, D, B, ld), y_out_dev (steps,
+ * obs_dim, B, ld).  A Philox stream of its own (the filter's noise is not replayed). */
+int smcb_filter_predict_path(smcb_filter* f, int32_t steps, const float* x_dev, float* x_out_dev, float* y_out_dev, void* stream);
+
+/* one backward step of forward-filtering backward-sampling as the reference writes it (filters/particle/base.py:105-128) for a
+ * non-batched filter: for every smoothed particle i (its value at the later time: xnext_dev[i]) an index is drawn from
+ * Categorical(logits = lw + log p(xnext_i | x)) over the N particles x_dev (N, D) of the earlier state with log-weights lw_dev (N) -
+ * by inversion of the cumulative unnormalised probabilities with the uniform U_dev[i] (float64, NULL: Philox(seed, t)); idx_out_dev (N)
+ * int64 and x_out_dev (N, D) = x[idx].  Reference layout, contiguous.  O(N^2), like the reference. */
+int smcb_filter_ffbs_step(smcb_filter* f, const float* x_dev, const float* lw_dev, const float* xnext_dev, const double* U_dev, uint64_t seed,
+                          int32_t t, int64_t* idx_out_dev, float* x_out_dev, void* stream);
+
+/* theta-level operations of SMC2 / PMMH on the RESIDENT state of a handle (columns = theta-particles): FilterResult.resample
+ * (filters/result.py:76-95, particle/state.py:150-158): column b <- column idx_dev[b] (int64 (B)) for particles, log-weights, APF
+ * resampling weights, ancestors, statistics, running log-likelihood, latest moments and - with entire_history - the moment / likelihood
+ * history rows; FilterResult.exchange (filters/result.py:97-117, particle/state.py:160-168): column b of `dst` <- column b of `src` where
+ * mask_dev[b] != 0 (uint8 (B)); both handles must hold the same shapes and stand at the same move index. */
+int smcb_filter_resample_columns(smcb_filter* f, const int64_t* idx_dev, int32_t entire_history, void* stream);
+int smcb_filter_exchange_columns(smcb_filter* dst, smcb_filter* src, const uint8_t* mask_dev, void* stream);
+
 /* stand-alone operators ......................................................................................................
  * All take a weight matrix with element strides (stride_n, stride_b): the reference's particle-major (N,B) tensor has
  * (B, 1); a single column has (1, 0).  `out_dev` strides are given the same way. */
@@ -187,6 +219,18 @@ int smcb_systematic(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, 
 int smcb_multinomial(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, int32_t normalized,
                      const double* U_dev, uint64_t seed, int64_t* out_dev, int64_t out_stride_n, int64_t out_stride_b,
                      void* stream);
+
+/* pyfilter.resampling.residual (resampling.py:68-105) on NORMALISED weights: floor(n w) deterministic copies in particle order, then
+ * multinomial draws (torch.multinomial CPU semantics, as smcb_multinomial) on the fractional parts; `U_dev` (B, n) float64 uniforms in
+ * draw order override Philox.  (The reference implements one column only; columns are independent here.) */
+int smcb_residual(const float* w_dev, int64_t n, int32_t B, int64_t stride_n, int64_t stride_b, const double* U_dev, uint64_t seed,
+                  int64_t* out_dev, int64_t out_stride_n, int64_t out_stride_b, void* stream);
+/* filters.utils.batched_gather (filters/utils.py:4-21) on the reference's layout, contiguous: out[i, b, :] = x[idx[i, b], b, :] with
+ * x (n, B, D) float32 and idx (n, B) int64.  With `prev_dev` (n, B) int64 the index is first pushed one generation back and written
+ * back, idx[i, b] <- prev[idx[i, b], b]: one backward step of fixed-lag smoothing (ancestral tracing, filters/particle/base.py:130-146).
+ * Synchronises the stream (an index out of range is an error, as in torch.gather). */
+int smcb_batched_gather(const float* x_dev, int64_t n, int32_t B, int32_t D, int64_t* idx_dev, const int64_t* prev_dev, float* out_dev,
+                        void* stream);
 
 #ifdef __cplusplus
 }

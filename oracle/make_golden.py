@@ -172,11 +172,11 @@ def residual_cases():
 
 
 def oracle_only_cases():
-    """Rows of SURVEY.md 8(f) whose oracle exists before their CUDA path: files named ``oracleonly_*.npz`` so that the GPU parity
-    tests (which iterate ``filter_*.npz``) do not pick them up.  f2: multi-dimensional LinearGaussianObservations on Lorenz-63
-    (examples/lorenz.ipynb:214)."""
-    filter_case("c4_apf_lgo_sys", "lorenz63_em", {}, "apf", "linear_gaussian", "systematic", 400, 0, 8, 131, prefix="oracleonly")
-    filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132, prefix="oracleonly")
+    """f2: multi-dimensional LinearGaussianObservations on Lorenz-63 (examples/lorenz.ipynb:214).  Written as ``oracleonly_*.npz``
+    while the oracle existed before the CUDA path; the kernel exists now (csrc/step.cuh, ProposalLGO<.., true>) and the files are
+    part of the GPU parity set (``filter_*.npz``).  A ``prefix="oracleonly"`` keeps a future row out of the GPU tests the same way."""
+    filter_case("c4_apf_lgo_sys", "lorenz63_em", {}, "apf", "linear_gaussian", "systematic", 400, 0, 8, 131)
+    filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132)
 
 
 def main():

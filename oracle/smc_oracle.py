@@ -779,3 +779,26 @@ def smooth_ffbs(model: Model, states, resampler: str = "systematic") -> torch.Te
         indices = Categorical(logits=weights).sample()
         res.append(_gather0(x_s, indices))
     return torch.stack(res[::-1], dim=0)
+
+
+def ffbs_backward_indices(model: Model, x_s, lw_s, x_later, U) -> torch.Tensor:
+    """One backward step of ``_do_sample_ffbs`` (``filters/particle/base.py:112-122``) with the ``Categorical(logits=...).sample()`` draw
+    replaced by the inversion it stands for, on replayed uniforms: the logits are computed exactly as in :func:`smooth_ffbs` (float32,
+    the reference's own ops), the probabilities are accumulated in float64 and smoothed particle ``i`` takes the first index whose
+    cumulative probability reaches ``U_i`` times the total.  What the CUDA kernel (csrc/plugin.cuh, ffbs_step_kernel) is compared with;
+    the two may differ where ``U_i`` lies within float32 rounding of a boundary."""
+    from torch.distributions import AffineTransform, Independent, Normal, TransformedDistribution
+
+    d = model.state_dim
+    loc, scale = model.mean_scale(x_s)
+    if d:
+        inc = Independent(Normal(torch.zeros(d), _t(model.inc_scale).expand(d), validate_args=False), 1)
+    else:
+        inc = Normal(0.0, _t(model.inc_scale), validate_args=False)
+    density = TransformedDistribution(inc, AffineTransform(loc, scale, event_dim=1 if d else 0), validate_args=False)
+    w_state = density.log_prob(x_later.unsqueeze(1))   # (N_smoothed, N_particles)
+    weights = (lw_s.unsqueeze(0) + w_state).double()
+    p = (weights - weights.max(-1, keepdim=True).values).exp()
+    c = p.cumsum(-1)
+    target = (torch.as_tensor(U, dtype=torch.float64) * c[:, -1]).unsqueeze(-1)
+    return torch.searchsorted(c, target).squeeze(-1).clamp(max=x_s.shape[0] - 1)

@@ -72,6 +72,15 @@ SYMBOLS = [
                                   C.c_int64, _P]),
     ("smcb_multinomial", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, _P, C.c_uint64, _P, C.c_int64,
                                    C.c_int64, _P]),
+    ("smcb_filter_pre_weight", C.c_int, [_P, _P, _P, _P, _P]),
+    ("smcb_filter_sample_and_weight", C.c_int, [_P, _P, _P, _P, C.c_int32, _P, _P, _P]),
+    ("smcb_filter_set_ess_threshold", C.c_int, [_P, C.c_float]),
+    ("smcb_filter_predict_path", C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
+    ("smcb_filter_resample_columns", C.c_int, [_P, _P, C.c_int32, _P]),
+    ("smcb_filter_exchange_columns", C.c_int, [_P, _P, _P, _P]),
+    ("smcb_residual", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_uint64, _P, C.c_int64, C.c_int64, _P]),
+    ("smcb_batched_gather", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
+    ("smcb_filter_ffbs_step", C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, C.c_int32, _P, _P, _P]),
 ]
 
 PTR_X, PTR_LOGW, PTR_PREV_INDS, PTR_MEAN, PTR_VAR, PTR_LL, PTR_LL_TOTAL, PTR_HIST_MEAN, PTR_HIST_VAR, PTR_HIST_LL, PTR_ESS, \

@@ -10,7 +10,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#define SMCB_NPARAM 28
+#define SMCB_NPARAM 32
 #define SMCB_LOG_SQRT_2PI 0.9189385332046727f
 
 enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_NUM_MODELS = 4 };
@@ -41,6 +41,14 @@ enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 #define P_INC_SCALE 20       // std of the increment distribution (1 or sqrt(dt))
 #define P_X0_LOC 21          // .. +2 (three dims)
 #define P_X0_SCALE 24        // .. +2
+// multi-dimensional LinearGaussianObservations of the Lorenz model (examples/lorenz.ipynb:214): with y = a (x1, x3) + s nu the matrices
+// of proposals/utils.py:219-267 are DIAGONAL - P = diag(p, 1/sigma^-2, p), p = 1/(sigma^-2 + a^2 s^-2) - so slots 8..18 serve the two
+// observed coordinates with (a, s) = (obs_a, obs_s) and these four the unobserved one
+#define P_LGO_COV1 27        // fl32(1 / sigma^-2)
+#define P_LGO_KSTD1 28       // sqrt of it
+#define P_LGO_K1_INV2VAR 29
+#define P_LGO_K1_LOGNORM 30
+#define P_LGO_OBS_S 31        // Lorenz: obs_s itself (slots 6, 7 hold the derived constants of its density)
 
 // sin(v) for the drift of the sine diffusion: explicit two-constant reduction to [-pi, pi] (exact products through fma), then the SFU.
 // Absolute error <= 2^-20.9 ~ 5e-7 on the reduced argument (PTX sin.approx.ftz.f32) against ~27 instructions of sinf() with its slow
@@ -77,6 +85,10 @@ template <> struct Model<SMCB_MODEL_LG_AR1> {
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
   }
+  // y = b + a x + s v   (sample of build_density(x): ParticleFilterCorrection.predict_path, particle/state.py:173-174)
+  __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
+    y[0] = __fadd_rn(__fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), __fmul_rn(P[P_OBS_S], v[0]));
+  }
 };
 
 // ---- configs 2 and 5: Euler-Maruyama of dx = sin(x - gamma) dt + sigma dW;  y = b + a x + s nu      (reference README.md:44-67)
@@ -89,6 +101,9 @@ template <> struct Model<SMCB_MODEL_SINE_EM> {
   }
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
+  }
+  __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
+    y[0] = __fadd_rn(__fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), __fmul_rn(P[P_OBS_S], v[0]));
   }
 };
 
@@ -107,13 +122,16 @@ template <> struct Model<SMCB_MODEL_SV_AR1> {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(-x[0], 1.4426950408889634f)));
     return fmaf(-hy2, e, fmaf(-0.5f, x[0], -SMCB_LOG_SQRT_2PI));  // explicit fma: the same bits at every call site
   }
+  __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
+    y[0] = __fmul_rn(__expf(__fmul_rn(0.5f, x[0])), v[0]);
+  }
 };
 
 // ---- config 4: Euler-Maruyama Lorenz-63, y = obs_a (x^1, x^3) + obs_s nu                      (reference examples/lorenz.ipynb:53-117)
 //      P: 0 s, 1 r, 2 b, 3 sigma, 4 dt, 5 obs_a, 6 inv2var, 7 lognorm (per component)
 template <> struct Model<SMCB_MODEL_LORENZ63_EM> {
   static constexpr int D = 3, OD = 2;
-  static constexpr bool LINEAR_OBS = false;
+  static constexpr bool LINEAR_OBS = true;   // y = a (x1, x3) + s nu: a LinearStateSpaceModel in the notebook (lorenz.ipynb:105-117)
   __device__ static __forceinline__ void loc_scale(const float* x, const float* P, float* loc, float& scale) {
     float f0 = __fmul_rn(-P[0], __fsub_rn(x[0], x[1]));
     float f1 = __fsub_rn(__fsub_rn(__fmul_rn(P[1], x[0]), x[1]), __fmul_rn(x[0], x[2]));
@@ -127,5 +145,9 @@ template <> struct Model<SMCB_MODEL_LORENZ63_EM> {
     float l0 = smcb_normal_lp(y[0], __fmul_rn(P[5], x[0]), P[6], P[7]);
     float l1 = smcb_normal_lp(y[1], __fmul_rn(P[5], x[2]), P[6], P[7]);
     return __fadd_rn(l0, l1);
+  }
+  __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
+    y[0] = __fadd_rn(__fmul_rn(P[5], x[0]), __fmul_rn(P[P_LGO_OBS_S], v[0]));
+    y[1] = __fadd_rn(__fmul_rn(P[5], x[2]), __fmul_rn(P[P_LGO_OBS_S], v[1]));
   }
 };

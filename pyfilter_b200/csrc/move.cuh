@@ -29,26 +29,40 @@
 #define MV_NT 256
 #define MV_ITEMS 16
 #define MV_TILE (MV_NT * MV_ITEMS)            // == RS_TILE: the row pitch is a multiple of it
-#define MV_PER 20                             // window slots per thread in the "last mark" scan
+#define MV_PER 20                             // window slots per thread in the "last mark" scan (largest tile class)
 #define MV_WIN (MV_NT * MV_PER)               // 5120 output slots per window
+// Tile classes.  A tile is MV_NT threads x ITEMS consecutive particles with ITEMS in {16, 12, 8, 4}; its window holds MV_NT * (ITEMS + 4)
+// output slots.  A column is cut into t1 tiles of items1 particles per thread followed by tiles of items2 <= items1 (MoveArgs).  Measured
+// (tools/geom_sweep.py, profiles/README.md): a tile costs a fixed part worth about 8 particles per thread, and the machine behaves like a
+// throughput device once it is full - 4,000,000 particles as 977 tiles of 4096 take 40.6 us, as 592 x 4096 + 513 x 3072 ("two full waves")
+// 42.4 us, as 1303 x 3072 47.2 us - so the host keeps 4096-particle tiles and only cuts the remainder of a column finer when the last
+// wave would leave more than three quarters of the block slots idle (2,000,000 x 3-D particles: 489 tiles on 444 slots, 38.2 -> 36.8 us).
+#define MV_WIN_OF(items) (MV_NT * ((items) + 4))
 #define MV_U_HOST 8
 #define MV_LB 4                               // look-back: slots per thread in flight
+// resident blocks per SM the register budget is sized for.  Scalar state (37 KB of shared memory per block): 5 blocks of 51 registers
+// measured 2 % faster than 4 of 64 and 13 % faster than 3 of 85 (tools/variants.py: 39.9 / 40.7 / 46.0 us per 4M-particle move) - the
+// kernel hides latency with warps, not with registers.  Three state dimensions: 70 KB per block, three blocks fit whatever the registers.
 #ifndef SMCB_MV_MINB
-#define SMCB_MV_MINB 4
+#define SMCB_MV_MINB 5
+#endif
+#ifndef SMCB_MV_MINB3
+#define SMCB_MV_MINB3 3
 #endif
 static_assert(MV_TILE == RS_TILE, "tiles of the move kernel are the resampling tiles");
 
 struct MoveArgs {
   StepArgs s;                 // buffers, parameters, history; s.partials = per-tile records (B, tiles_per_col), s.blocks_per_col = tiles_per_col
-  int32_t tiles_per_col;
+  int32_t tiles_per_col;      // t1 + (tiles of the second class)
   int32_t total_tiles;        // B * tiles_per_col
+  int32_t t1, items1, items2; // tile classes of a column: tiles [0, t1) hold MV_NT * items1 particles each, the others MV_NT * items2
   uint32_t ticket_base;       // value of *tile_counter when this launch starts (the counter is never reset: wrap-around arithmetic)
   uint32_t* tile_counter;
   unsigned long long* mslots; // (B, tiles_per_col) tile sums tagged with the launch epoch, ONE 64-bit word each: a sum of weights that are
                               // multiples of 2^-52 below 2 is a 54-bit integer count of quanta, the 10 bits above it carry the tag
-  unsigned long long* gslots; // (B, ceil(tiles_per_col / 32)) group totals, same format
-  uint32_t* gcount;           // (B, ceil(tiles_per_col / 32)) publications per group (reset with the handle's state)
-  uint32_t launch_index;      // move launches since that reset: a group's counter stands at launch_index * members when the launch starts
+  unsigned long long* gwords; // (2, B, ceil(tiles_per_col / 32) * MV_GPAD) group words (member count << 58 | quanta), two sets: launch k
+                              // uses set k & 1 and clears the other one (both zero after smcb_filter_initialize)
+  uint32_t launch_index;      // move launches since the handle's state was initialised
   unsigned long long epoch;   // tag of this launch in [1, 1023], different from the previous launch's (every tile of every launch
                               // rewrites its slot, so a slot never holds a tag older than one launch)
   const float* u_in;          // optional injected systematic offsets (B)
@@ -103,21 +117,43 @@ __device__ __forceinline__ double mv_block_excl_scan(double v, double* scratch, 
   return off + (inc - v);
 }
 // ---- publishing a tile sum and looking back, two levels -------------------------------------------------------------------------
-// A tile sum is a count of quanta (2^-52) in 54 bits under a 10-bit launch tag, written with ONE atomic exchange at the L2.  Tiles form
-// groups of 32; every tile also bumps its group's counter, and the tile that completes a group adds the 32 sums up and publishes the
-// group total the same way.  A tile then needs at most one group total per earlier group and the sums of its group mates before it:
-// two loads per lane of ONE warp for up to 1024 tiles.  (Measured on the way: 256 polling threads per block, or a warp polling every
+// A tile sum is a count of quanta (2^-52) in 54 bits.  Tiles form groups of 32.  A tile publishes twice, with two fire-and-forget
+// memory operations and NO return value to wait for: (1) its own slot = (launch tag << 54) | quanta, one 64-bit store; (2) a 64-bit
+// reduction  (1 << 58) | quanta  onto its group's word - the word counts its members in the top six bits and adds their quanta up below, so
+// "the group total is complete" is readable from the word itself.  A tile then needs one group word per earlier group and the slots of its
+// group mates before it: two loads per lane of ONE warp for up to 1024 tiles, all issued right behind the publication - the look-back of
+// a tile whose predecessors are done is one L2 round trip.  The group words exist twice; launch k uses set k & 1 and the first tile of
+// every group clears the other set's word for launch k + 1 (every block of launch k - 1, the last user of that set, had finished before
+// launch k passed its grid dependency).  (Measured on the way: a counter whose old value picks a "closing" tile that adds the group up
+// and publishes the total costs three dependent round trips, 4-5 us per tile; 256 polling threads per block, or a warp polling every
 // predecessor, flood the L2 with strong loads and delay the very publications they wait for - up to 20 us per tile.)
 #define MV_SLOT_MASK ((1ull << 54) - 1ull)
 #define MV_GROUP 32
-#define MV_GPAD 16   // a group's total / counter sits alone in a 128-byte line: hundreds of tiles poll and bump them at the same time
+#define MV_GPAD 16   // a group's word sits alone in a 128-byte line: hundreds of tiles poll and bump them at the same time
+#define MV_GCOUNT_SHIFT 58
 __device__ __forceinline__ unsigned long long mv_ld_strong(const unsigned long long* p) {  // a STRONG load at gpu scope
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void mv_st_strong(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void mv_red_add(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long mv_wait_slot(const unsigned long long* p, unsigned long long v, unsigned long long epoch, int& waited) {
   while ((v >> 54) != epoch) {
+#ifdef MV_SLEEP
+    __nanosleep(MV_SLEEP);
+#endif
+    v = mv_ld_strong(p);
+    ++waited;
+  }
+  return v & MV_SLOT_MASK;
+}
+__device__ __forceinline__ unsigned long long mv_wait_group(const unsigned long long* p, unsigned long long v, int& waited) {
+  while ((v >> MV_GCOUNT_SHIFT) != (unsigned long long)MV_GROUP) {   // every group BEFORE a tile's own is full
 #ifdef MV_SLEEP
     __nanosleep(MV_SLEEP);
 #endif
@@ -131,73 +167,48 @@ __device__ __forceinline__ unsigned long long mv_warp_sum_u64(unsigned long long
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// executed by warp 0 of the block; `quanta` = this tile's sum (valid in lane 0); returns the sum of all tiles before `tile` (every lane)
-__device__ __forceinline__ unsigned long long mv_publish_lookback(unsigned long long* slots, unsigned long long* gslots, uint32_t* gcount,
-                                                                   int tile, int T, unsigned long long quanta, unsigned long long epoch,
-                                                                   uint32_t launch_index, long long* wd, long long* tlrow) {
+// executed by warp 0 of the block; `quanta` = this tile's sum (valid in lane 0); returns the sum of all tiles before `tile` (every lane).
+// `gw` = this launch's set of group words of the column, `gw_next` = the other set.
+__device__ __forceinline__ unsigned long long mv_publish_lookback(unsigned long long* slots, unsigned long long* gw, unsigned long long* gw_next,
+                                                                   int tile, unsigned long long quanta, unsigned long long epoch,
+                                                                   long long* wd, long long* tlrow) {
   const int lane = threadIdx.x & 31;
 #define MV_LSTAMP(k) do { if (tlrow && lane == 0) tlrow[k] = st_now(); } while (0)
   const int g = tile / MV_GROUP, r = tile - g * MV_GROUP;
-  const int members = min(MV_GROUP, T - g * MV_GROUP);
-  uint32_t old = 0;
   if (lane == 0) {
-    atomicExch(slots + tile, (epoch << 54) | (quanta & MV_SLOT_MASK));
-    old = atomicAdd(gcount + g * MV_GPAD * 2, 1u) - launch_index * (uint32_t)members;   // every tile of every launch bumps its group exactly once:
-  }                                                                        // relative to the launch the counter runs 0 .. members - 1
+    mv_st_strong(slots + tile, (epoch << 54) | (quanta & MV_SLOT_MASK));
+    mv_red_add(gw + (int64_t)g * MV_GPAD, (1ull << MV_GCOUNT_SHIFT) | (quanta & MV_SLOT_MASK));
+    if (r == 0) mv_st_strong(gw_next + (int64_t)g * MV_GPAD, 0ull);
+  }
   MV_LSTAMP(8);
-  // the loads of the look-back go out while the counter's old value is on its way
   const unsigned long long* pm = slots + g * MV_GROUP + lane;
   unsigned long long vm = (lane < r) ? mv_ld_strong(pm) : (epoch << 54);
   unsigned long long acc = 0ull;
   int waited = 0;
   for (int g0 = 0; g0 < g; g0 += 32) {   // one round per 32 earlier groups (1024 tiles)
-    const unsigned long long* pg = gslots + (int64_t)(g0 + lane) * MV_GPAD;
-    const unsigned long long vg = (g0 + lane < g) ? mv_ld_strong(pg) : (epoch << 54);
-    if (g0 == 0) {  // first round: this is where the group is completed, before anything is waited for
-      const bool closer = __shfl_sync(0xffffffffu, old + 1u == (uint32_t)members ? 1 : 0, 0) != 0;
-      MV_LSTAMP(9);
-      if (closer) {
-        unsigned long long vc = (lane < members) ? mv_ld_strong(slots + g * MV_GROUP + lane) : (epoch << 54);
-        vc = mv_wait_slot(slots + g * MV_GROUP + lane, vc, epoch, waited);
-        vc = mv_warp_sum_u64(vc);
-        if (lane == 0) atomicExch(gslots + (int64_t)g * MV_GPAD, (epoch << 54) | (vc & MV_SLOT_MASK));
-      }
-    }
-    if (g0 == 0) MV_LSTAMP(10);
-    acc += mv_wait_slot(pg, vg, epoch, waited);
+    const unsigned long long* pg = gw + (int64_t)(g0 + lane) * MV_GPAD;
+    const unsigned long long vg = (g0 + lane < g) ? mv_ld_strong(pg) : ((unsigned long long)MV_GROUP << MV_GCOUNT_SHIFT);
+    acc += mv_wait_group(pg, vg, waited);
   }
   MV_LSTAMP(11);
-  if (g == 0) {  // (the loop above did not run: group 0 is completed here)
-    const bool closer = __shfl_sync(0xffffffffu, old + 1u == (uint32_t)members ? 1 : 0, 0) != 0;
-    if (closer) {
-      unsigned long long vc = (lane < members) ? mv_ld_strong(slots + lane) : (epoch << 54);
-      vc = mv_wait_slot(slots + lane, vc, epoch, waited);
-      vc = mv_warp_sum_u64(vc);
-      if (lane == 0) atomicExch(gslots, (epoch << 54) | (vc & MV_SLOT_MASK));
-    }
-  }
   acc += mv_wait_slot(pm, vm, epoch, waited);
   MV_LSTAMP(12);
   if (tlrow && lane == 0) tlrow[13] = (long long)waited;
-  if (wd && waited) atomicAdd((unsigned long long*)&wd[2], (unsigned long long)waited);   // diagnostics: re-polls
+  if (tlrow && wd && waited) atomicAdd((unsigned long long*)&wd[2], (unsigned long long)waited);   // diagnostics: re-polls
   return mv_warp_sum_u64(acc);
 }
-// a tile that does not resample still keeps its slot's tag and its group's counter in step
-__device__ __forceinline__ void mv_publish_idle(unsigned long long* slots, unsigned long long* gslots, uint32_t* gcount, int tile, int T,
-                                                unsigned long long epoch, uint32_t launch_index) {
+// a tile that does not resample only keeps the group words in step: the other set is cleared for the next launch
+__device__ __forceinline__ void mv_publish_idle(unsigned long long* gw_next, int tile) {
   const int g = tile / MV_GROUP;
-  const int members = min(MV_GROUP, T - g * MV_GROUP);
-  atomicExch(slots + tile, epoch << 54);
-  const uint32_t old = atomicAdd(gcount + g * MV_GPAD * 2, 1u) - launch_index * (uint32_t)members;
-  if (old + 1u == (uint32_t)members) atomicExch(gslots + (int64_t)g * MV_GPAD, epoch << 54);
+  if (tile - g * MV_GROUP == 0) mv_st_strong(gw_next + (int64_t)g * MV_GPAD, 0ull);
 }
 
 // weights of this thread's 16 particles, rounded to multiples of 2^-52 (exactly what normalize_kernel / resample_fused_kernel compute)
-template <bool INNER>
-__device__ __forceinline__ double mv_weights(const float (&win)[MV_ITEMS], float m, float iz, int32_t gbase, int32_t n, float (&wq)[MV_ITEMS]) {
+template <bool INNER, int ITEMS>
+__device__ __forceinline__ double mv_weights(const float (&win)[ITEMS], float m, float iz, int32_t gbase, int32_t n, float (&wq)[ITEMS]) {
   double tsum = 0.0;
 #pragma unroll
-  for (int j = 0; j < MV_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     float x = smcb_weight(win[j], m, iz);
     if (!INNER && gbase + j >= n) x = 0.f;
     const double xd = __dadd_rn(__dadd_rn(1.0, (double)x), -1.0);
@@ -217,19 +228,20 @@ __device__ __forceinline__ int32_t mv_count(float c, float u, int32_t n, int32_t
 // counts of this thread's particles; every particle with offspring marks its first slot inside the window [wb, wb + MV_WIN).
 // CHECK = false: the whole tile fits the window (n_out - wb <= MV_WIN), no range test per particle.
 // A mark is the index of the particle INSIDE the tile (the gather of x_{t-1} needs nothing else).
-template <bool INNER, bool CHECK, bool FIRST, bool LEAN, typename SM>
-__device__ __forceinline__ void mv_mark(const float (&wq)[MV_ITEMS], double S0, int32_t lo, int32_t gbase, int32_t wb, float u,
+template <bool INNER, bool CHECK, bool FIRST, bool LEAN, int ITEMS, typename SM>
+__device__ __forceinline__ void mv_mark(const float (&wq)[ITEMS], double S0, int32_t lo, int32_t gbase, int32_t wb, float u,
                                         int32_t n, int32_t n_out, double nfd, SM& sm) {
   double run = S0;
-  const int32_t lbase = (int32_t)threadIdx.x * MV_ITEMS;
+  const int32_t lbase = (int32_t)threadIdx.x * ITEMS;
+  constexpr int32_t WIN = MV_WIN_OF(ITEMS);
 #pragma unroll
-  for (int j = 0; j < MV_ITEMS; ++j) {
+  for (int j = 0; j < ITEMS; ++j) {
     run = __dadd_rn(run, (double)wq[j]);
     int32_t hi = mv_count<LEAN>((float)run, u, n, n_out, nfd);
     if (!INNER) hi = (gbase + j >= n - 1) ? n_out : hi;  // cumsum[..., -1] = 1.0 (resampling.py:49): every probe is <= 1 (n_out == n here)
     const int32_t r = lo - wb;
     if (CHECK) {
-      if (hi > lo && (uint32_t)r < (uint32_t)MV_WIN) sm.stage[r] = lbase + j;
+      if (hi > lo && (uint32_t)r < (uint32_t)WIN) sm.stage[r] = lbase + j;
       if (!FIRST && hi > lo && r < 0 && hi > wb) sm.carry = lbase + j;  // its slots began in an earlier window (one such particle at most)
     } else {
       if (hi > lo) sm.stage[r] = lbase + j;
@@ -241,28 +253,47 @@ __device__ __forceinline__ void mv_mark(const float (&wq)[MV_ITEMS], double S0, 
 // later windows of a tile with more than MV_WIN offspring, or any window when the lean count does not apply (rare: degenerate
 // weights, odd injected offsets): the weights are derived again from the log-weights (same function, same bits) instead of being
 // kept in registers across the propagation
-template <typename SM>
+template <int ITEMS, typename SM>
 __device__ __noinline__ void mv_remark(const float* wsrc, float m, float iz, double S0, int32_t lo, int32_t gbase, int32_t wb, bool first,
                                        bool lean, float u, int32_t n, int32_t n_out, double nfd, SM& sm) {
-  float win[MV_ITEMS];
+  float win[ITEMS];
 #pragma unroll
-  for (int v = 0; v < MV_ITEMS / 4; ++v) {
+  for (int v = 0; v < ITEMS / 4; ++v) {
     const float4 q = __ldg(reinterpret_cast<const float4*>(wsrc) + v);
     win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
   }
-  float wq[MV_ITEMS];
-  mv_weights<false>(win, m, iz, gbase, n, wq);
+  float wq[ITEMS];
+  mv_weights<false, ITEMS>(win, m, iz, gbase, n, wq);
   if (lean) {
-    if (first) mv_mark<false, true, true, true>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
-    else mv_mark<false, true, false, true>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
+    if (first) mv_mark<false, true, true, true, ITEMS>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
+    else mv_mark<false, true, false, true, ITEMS>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
   } else {
-    if (first) mv_mark<false, true, true, false>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
-    else mv_mark<false, true, false, false>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
+    if (first) mv_mark<false, true, true, false, ITEMS>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
+    else mv_mark<false, true, false, false, ITEMS>(wq, S0, lo, gbase, wb, u, n, n_out, nfd, sm);
+  }
+}
+template <typename SM>
+__device__ __forceinline__ void mv_remark_any(int items, const float* wsrc, float m, float iz, double S0, int32_t lo, int32_t gbase, int32_t wb,
+                                              bool first, bool lean, float u, int32_t n, int32_t n_out, double nfd, SM& sm) {
+  switch (items) {
+    case 16: mv_remark<16>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
+    case 12: mv_remark<12>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
+    case 8: mv_remark<8>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
+    default: mv_remark<4>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
+  }
+}
+template <typename SM>
+__device__ __forceinline__ int32_t mv_emit_any(int items, SM& sm, int32_t carry) {
+  switch (items) {
+    case 16: return rs_emit_blocked<MV_NT, 20>(sm, carry);
+    case 12: return rs_emit_blocked<MV_NT, 16>(sm, carry);
+    case 8: return rs_emit_blocked<MV_NT, 12>(sm, carry);
+    default: return rs_emit_blocked<MV_NT, 8>(sm, carry);
   }
 }
 
 template <int MODEL, int PROP, int ALG>
-__global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
+__global__ void __launch_bounds__(MV_NT, (Model<MODEL>::D == 1 ? SMCB_MV_MINB : SMCB_MV_MINB3)) move_kernel(MoveArgs c) {
   typedef Model<MODEL> M;
   constexpr int D = M::D, OD = M::OD;
   extern __shared__ __align__(16) float mv_x[];   // (D, MV_TILE): x_{t-1} of the tile
@@ -303,8 +334,12 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   const int col = ticket / T, tile = ticket - col * T;
   const float u = sm.u;
   if (tid < SMCB_NPARAM) sm.Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];  // (first read behind several barriers)
-  const int32_t tile_base = tile * MV_TILE;
-  const int32_t gbase = tile_base + tid * MV_ITEMS;
+  // tile class: particles per thread, first particle of the tile, slots per window
+  const int items = mv_uniform(tile < c.t1 ? c.items1 : c.items2);
+  const int32_t tile_base = (tile < c.t1) ? tile * (MV_NT * c.items1) : c.t1 * (MV_NT * c.items1) + (tile - c.t1) * (MV_NT * c.items2);
+  const int32_t tile_len = MV_NT * items;
+  const int32_t win_slots = MV_NT * (items + 4);
+  const int32_t gbase = tile_base + tid * items;
   const int64_t rowoff = (int64_t)col * a.ld;
   const bool use_rw = (ALG == SMCB_ALG_APF) && observed;
   const float* const winrow = (use_rw ? a.rw : a.lw) + rowoff;
@@ -314,14 +349,9 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   MV_STAMP(0);
   pdl_wait();
   MV_STAMP(1);
-  // ---- the tile comes on chip: resampling log-weights (blocked: a thread owns 16 consecutive particles), x_{t-1} (striped),
-  //      the column's normalisers (every thread, one broadcast transaction per warp)
-  float win[MV_ITEMS];
-#pragma unroll
-  for (int v = 0; v < MV_ITEMS / 4; ++v) {
-    const float4 q = __ldg(reinterpret_cast<const float4*>(winrow + gbase) + v);
-    win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
-  }
+  // ---- the tile comes on chip: x_{t-1} (striped), the column's normalisers (every thread, one broadcast transaction per warp), then
+  //      (per tile class) the resampling log-weights: blocked, a thread owns `items` consecutive particles.  Rows are allocated with a
+  //      tile of slack behind them: the last tile of a column may reach past the row (its surplus particles have index >= n: weight 0)
   const float4* stp = reinterpret_cast<const float4*>(a.stats + col);
   const float4 st0 = stp[0], st1 = stp[1];   // m_lw z_lw inv_z_lw m_rw | z_rw inv_z_rw ess resample
 #pragma unroll
@@ -329,8 +359,9 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
 #pragma unroll
     for (int v = 0; v < MV_ITEMS / 4; ++v) {
       const int e = (v * MV_NT + tid) * 4;
-      *reinterpret_cast<float4*>(mv_x + d * MV_TILE + e) =
-          __ldg(reinterpret_cast<const float4*>(a.xbuf[t & 1] + ((int64_t)d * a.B + col) * a.ld + tile_base + e));
+      if (e < tile_len)
+        *reinterpret_cast<float4*>(mv_x + d * MV_TILE + e) =
+            __ldg(reinterpret_cast<const float4*>(a.xbuf[t & 1] + ((int64_t)d * a.B + col) * a.ld + tile_base + e));
     }
   }
   if (tid < (int)(sizeof(ColStats) / 4)) reinterpret_cast<float*>(&sm.fin_pre.st)[tid] = reinterpret_cast<const float*>(a.stats + col)[tid];
@@ -341,63 +372,81 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   const float wiz = use_rw ? st1.y : st0.z;
   if (c.u_out && resampled && tile == 0 && tid == 0) c.u_out[col] = u;
 
-  int32_t n_in, n_out, wb0;
+  int32_t n_in = 0, n_out = 0, wb0 = 0;
   double S0 = 0.0;
   int32_t lo_thread = 0;
-  if (resampled) {
-    const bool inner = mv_uniform(tile_base + MV_TILE <= n - 1);  // neither padding nor the last particle of the column in this tile
-    float wq[MV_ITEMS];
-    const double tsum = inner ? mv_weights<true>(win, wm, wiz, gbase, n, wq) : mv_weights<false>(win, wm, wiz, gbase, n, wq);
-    if (c.w_out) {
-      float* dst = c.w_out + rowoff + gbase;
+  auto front = [&](auto items_tag) {
+    constexpr int ITEMS = decltype(items_tag)::value;
+    constexpr int32_t WIN = MV_WIN_OF(ITEMS);
+    float win[ITEMS];
 #pragma unroll
-      for (int v = 0; v < MV_ITEMS / 4; ++v)
-        reinterpret_cast<float4*>(dst)[v] = make_float4(wq[4 * v], wq[4 * v + 1], wq[4 * v + 2], wq[4 * v + 3]);
+    for (int v = 0; v < ITEMS / 4; ++v) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(winrow + gbase) + v);
+      win[4 * v] = q.x; win[4 * v + 1] = q.y; win[4 * v + 2] = q.z; win[4 * v + 3] = q.w;
     }
-    double tot;
-    const double ex = mv_block_excl_scan(tsum, sm.scan_a, &tot);
-    const int G = (T + MV_GROUP - 1) / MV_GROUP;
-    MV_STAMP(2);
-    if (tid < 32) {
-      const unsigned long long before = mv_publish_lookback(c.mslots + (int64_t)col * T, c.gslots + (int64_t)col * G * MV_GPAD, c.gcount + (int64_t)col * G * MV_GPAD * 2,
-                                                            tile, T, __double2ull_rn(tot * 4503599627370496.0), c.epoch, c.launch_index, c.wd, c.tl ? c.tl + (int64_t)ticket * 16 : nullptr);
-      if (tid == 0) sm.lb = before;
-    }
-    __syncthreads();
-    const double S_in = (double)sm.lb * 2.220446049250313e-16;   // quanta * 2^-52: exact (the sum of a column is below 2)
-    MV_STAMP(3);
-    S0 = S_in + ex;
-    // the tile owns the output slots [n_in, n_out): known before the marks, so the common single-window tile marks without range tests
-    n_in = 0;
-    if (tile) n_in = max(0, mv_uniform(lean ? mv_count<true>((float)S_in, u, n, n, nfd) : mv_count<false>((float)S_in, u, n, n, nfd)));
-    n_out = n;
-    if (inner) n_out = mv_uniform(lean ? mv_count<true>((float)(S_in + tot), u, n, n, nfd) : mv_count<false>((float)(S_in + tot), u, n, n, nfd));
-    n_out = max(n_out, n_in);
-    lo_thread = n_in;
-    if (tid) {
-      const int32_t cnt = (gbase - 1 >= n - 1) ? n_out : (lean ? mv_count<true>((float)S0, u, n, n_out, nfd) : mv_count<false>((float)S0, u, n, n_out, nfd));
-      lo_thread = max(n_in, cnt);
-    }
-    wb0 = n_in & ~3;
-    if (mv_uniform(n_out - wb0 <= MV_WIN) && lean) {
-      if (inner) mv_mark<true, false, true, true>(wq, S0, lo_thread, gbase, wb0, u, n, n_out, nfd, sm);
-      else mv_mark<false, false, true, true>(wq, S0, lo_thread, gbase, wb0, u, n, n_out, nfd, sm);
-    } else {
-      mv_remark(winrow + gbase, wm, wiz, S0, lo_thread, gbase, wb0, true, lean, u, n, n_out, nfd, sm);
-    }
-    __syncthreads();
-  } else {  // identity ancestors; the carried log-weights travel through the window
-    if (tid == 0) {
+    if (resampled) {
+      const bool inner = mv_uniform(tile_base + MV_NT * ITEMS <= n - 1);  // neither padding nor the last particle of the column in this tile
+      float wq[ITEMS];
+      const double tsum = inner ? mv_weights<true, ITEMS>(win, wm, wiz, gbase, n, wq) : mv_weights<false, ITEMS>(win, wm, wiz, gbase, n, wq);
+      if (c.w_out) {
+        float* dst = c.w_out + rowoff + gbase;
+#pragma unroll
+        for (int v = 0; v < ITEMS / 4; ++v)
+          if (gbase + 4 * v + 4 <= a.ld) reinterpret_cast<float4*>(dst)[v] = make_float4(wq[4 * v], wq[4 * v + 1], wq[4 * v + 2], wq[4 * v + 3]);
+      }
+      double tot;
+      const double ex = mv_block_excl_scan(tsum, sm.scan_a, &tot);
       const int G = (T + MV_GROUP - 1) / MV_GROUP;
-      mv_publish_idle(c.mslots + (int64_t)col * T, c.gslots + (int64_t)col * G * MV_GPAD, c.gcount + (int64_t)col * G * MV_GPAD * 2, tile, T, c.epoch, c.launch_index);
-    }
-    n_in = tile_base;
-    n_out = min(tile_base + MV_TILE, n);
-    wb0 = tile_base;
+      MV_STAMP(2);
+      if (tid < 32) {
+        unsigned long long* const gw0 = c.gwords + (int64_t)col * G * MV_GPAD;
+        const int64_t gset = (int64_t)a.B * G * MV_GPAD;
+        const unsigned long long before = mv_publish_lookback(c.mslots + (int64_t)col * T, gw0 + (c.launch_index & 1u) * gset, gw0 + ((c.launch_index + 1u) & 1u) * gset,
+                                                              tile, __double2ull_rn(tot * 4503599627370496.0), c.epoch, c.wd, c.tl ? c.tl + (int64_t)ticket * 16 : nullptr);
+        if (tid == 0) sm.lb = before;
+      }
+      __syncthreads();
+      const double S_in = (double)sm.lb * 2.220446049250313e-16;   // quanta * 2^-52: exact (the sum of a column is below 2)
+      MV_STAMP(3);
+      S0 = S_in + ex;
+      // the tile owns the output slots [n_in, n_out): known before the marks, so the common single-window tile marks without range tests
+      n_in = 0;
+      if (tile) n_in = max(0, mv_uniform(lean ? mv_count<true>((float)S_in, u, n, n, nfd) : mv_count<false>((float)S_in, u, n, n, nfd)));
+      n_out = n;
+      if (inner) n_out = mv_uniform(lean ? mv_count<true>((float)(S_in + tot), u, n, n, nfd) : mv_count<false>((float)(S_in + tot), u, n, n, nfd));
+      n_out = max(n_out, n_in);
+      lo_thread = n_in;
+      if (tid) {
+        const int32_t cnt = (gbase - 1 >= n - 1) ? n_out : (lean ? mv_count<true>((float)S0, u, n, n_out, nfd) : mv_count<false>((float)S0, u, n, n_out, nfd));
+        lo_thread = max(n_in, cnt);
+      }
+      wb0 = n_in & ~3;
+      if (mv_uniform(n_out - wb0 <= WIN) && lean) {
+        if (inner) mv_mark<true, false, true, true, ITEMS>(wq, S0, lo_thread, gbase, wb0, u, n, n_out, nfd, sm);
+        else mv_mark<false, false, true, true, ITEMS>(wq, S0, lo_thread, gbase, wb0, u, n, n_out, nfd, sm);
+      } else {
+        mv_remark<ITEMS>(winrow + gbase, wm, wiz, S0, lo_thread, gbase, wb0, true, lean, u, n, n_out, nfd, sm);
+      }
+      __syncthreads();
+    } else {  // identity ancestors; the carried log-weights travel through the window
+      if (tid == 0) {
+        const int G = (T + MV_GROUP - 1) / MV_GROUP;
+        mv_publish_idle(c.gwords + (int64_t)col * G * MV_GPAD + ((c.launch_index + 1u) & 1u) * ((int64_t)a.B * G * MV_GPAD), tile);
+      }
+      n_in = tile_base;
+      n_out = max(n_in, min(tile_base + MV_NT * ITEMS, n));
+      wb0 = tile_base;
 #pragma unroll
-    for (int v = 0; v < MV_ITEMS / 4; ++v)
-      *reinterpret_cast<float4*>(&sm.stage[tid * MV_ITEMS + 4 * v]) = make_float4(win[4 * v], win[4 * v + 1], win[4 * v + 2], win[4 * v + 3]);
-    __syncthreads();
+      for (int v = 0; v < ITEMS / 4; ++v)
+        *reinterpret_cast<float4*>(&sm.stage[tid * ITEMS + 4 * v]) = make_float4(win[4 * v], win[4 * v + 1], win[4 * v + 2], win[4 * v + 3]);
+      __syncthreads();
+    }
+  };
+  switch (items) {
+    case 16: front(std::integral_constant<int, 16>{}); break;
+    case 12: front(std::integral_constant<int, 12>{}); break;
+    case 8: front(std::integral_constant<int, 8>{}); break;
+    default: front(std::integral_constant<int, 4>{}); break;
   }
 
   MV_STAMP(4);
@@ -505,8 +554,11 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
             for (int d = 0; d < D; ++d) xnext[d][s0 + k] = xn[d][k];
             if (keep_lw) lwrow[s0 + k] = lwn[k];
             if (fold) rwrow[s0 + k] = rwn[k];
-          } else {  // not this tile's slot: contributes nothing
+          } else {  // not this tile's slot: contributes nothing (its "ancestor" may be an unset mark pointing at shared memory nobody wrote:
+                    // the weight is zero, but 0 * NaN would still poison the moment sums)
             lwn[k] = -INFINITY; rwn[k] = -INFINITY; inc4[k] = -INFINITY;
+#pragma unroll
+            for (int d = 0; d < D; ++d) xn[d][k] = 0.f;
           }
         }
       }
@@ -518,20 +570,20 @@ __global__ void __launch_bounds__(MV_NT, SMCB_MV_MINB) move_kernel(MoveArgs c) {
   if (n_out > n_in) {
     const bool fast = observed_rt && resampled_rt && (ALG != SMCB_ALG_APF || fold_rt) && plain_noise;
     int32_t carry = -1;
-    for (int32_t wb = wb0; wb < n_out; wb += MV_WIN) {
-      const int32_t wlen = min(MV_WIN, n_out - wb);
+    for (int32_t wb = wb0; wb < n_out; wb += win_slots) {
+      const int32_t wlen = min(win_slots, n_out - wb);
       if (resampled) {
         if (wb != wb0) {  // rare: more than one window of offspring
           __syncthreads();
 #pragma unroll
           for (int k = 0; k < MV_PER / 4; ++k) *reinterpret_cast<int4*>(&sm.stage[(k * MV_NT + tid) * 4]) = make_int4(-1, -1, -1, -1);
-          if (tid == 0) { sm.carry = -1; if (c.wd && wb == wb0 + MV_WIN) atomicAdd((unsigned long long*)&c.wd[1], 1ull); }
+          if (tid == 0) { sm.carry = -1; if (c.wd && wb == wb0 + win_slots) atomicAdd((unsigned long long*)&c.wd[1], 1ull); }
           __syncthreads();
-          mv_remark(winrow + gbase, wm, wiz, S0, lo_thread, gbase, wb, false, lean, u, n, n_out, nfd, sm);
+          mv_remark_any(items, winrow + gbase, wm, wiz, S0, lo_thread, gbase, wb, false, lean, u, n, n_out, nfd, sm);
           __syncthreads();
           carry = max(carry, sm.carry);
         }
-        carry = rs_emit_blocked<MV_NT, MV_PER>(sm, carry);
+        carry = mv_emit_any(items, sm, carry);
         if (wb == wb0) MV_STAMP(5);
       }
       if (fast) run_window(std::true_type{}, wb, wlen);

@@ -226,6 +226,7 @@ struct MultinomialArgs {
   int32_t stride;          // coarse table: last element of every `stride` cumulative weights (power of two)
   int32_t ncoarse;
   int32_t col0;            // global index of column 0 (Philox counter)
+  const int32_t* draw_offset;  // residual resampling: the first draw_offset[col] outputs are the deterministic copies (NULL: none)
 };
 
 // Draw i picks the first k with (double) fl32(c_k / c_{n-1}) >= U_i.  The predicate is monotone in c_k, so it is turned into a
@@ -245,8 +246,9 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
   }
   const double total = (double)__ldg(c + n - 1);
   const int t = a.ctrl->t;
+  const int64_t first = a.draw_offset ? (int64_t)a.draw_offset[col] : 0;   // draws go to anc[first ..], uniforms are consumed from 0
   __syncthreads();
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n - first; i += (int64_t)gridDim.x * blockDim.x) {
     double U;
     if (a.U) U = a.U[(int64_t)col * a.U_pitch + i];
     else {
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
       }
       ans = k0;
     }
-    a.anc[(int64_t)col * a.ld + i] = (int32_t)ans;
+    a.anc[(int64_t)col * a.ld + first + i] = (int32_t)ans;
   }
 }
 
@@ -287,7 +289,7 @@ static inline void op_launch_multinomial_after_normalize(const ResampleArgs& r, 
   expand_kernel<24, RS_OUT_CUMSUM><<<g, RS_NT, 0, s>>>(r);
   MultinomialArgs m;
   m.c = r.c_out; m.n = r.n; m.ld = r.ld; m.B = r.B; m.stats = r.stats; m.U = U; m.U_pitch = U_pitch;
-  m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc; m.col0 = r.col0;
+  m.seed = r.seed; m.ctrl = r.ctrl; m.anc = r.anc; m.col0 = r.col0; m.draw_offset = r.draw_offset;
   int stride = 256;  // every block gathers the coarse table itself (one sector per entry): keep it to ~1k entries
   while ((r.n + stride - 1) / stride > 1024) stride *= 2;
   m.stride = stride; m.ncoarse = (int)((r.n + stride - 1) / stride);

@@ -6,6 +6,7 @@
 #include <math.h>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #include "../../include/smcb200.h"
 #include "resample.cuh"
@@ -13,6 +14,7 @@
 #include "column.cuh"
 #include "move.cuh"
 #include "operators.cuh"
+#include "plugin.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -64,7 +66,7 @@ static void derive_params(int model, const double* r, float* P) {
   const double c = 0.91893853320467274178;  // log sqrt(2 pi)
   for (int i = 0; i < SMCB_NPARAM; ++i) P[i] = 0.f;
   double inc = 1.0, sigma = 1.0, a = 0, s = 1;
-  bool linear = false;
+  bool linear = false, lorenz_lgo = false;
   switch (model) {
     case SMCB_MODEL_LG_AR1:
       for (int i = 0; i < 6; ++i) P[i] = (float)r[i];
@@ -90,10 +92,27 @@ static void derive_params(int model, const double* r, float* P) {
       inc = sqrt(r[4]);
       const float m0[3] = {-5.91652f, -5.52332f, 24.5723f};
       for (int d = 0; d < 3; ++d) { P[P_X0_LOC + d] = m0[d]; P[P_X0_SCALE + d] = (float)sqrt(10.0); }
+      P[P_LGO_OBS_S] = (float)os;
+      // LinearGaussianObservations on y = a (x1, x3) + s nu: diagonal matrices (models.h), the unobserved coordinate keeps P = 1 / sigma^-2
+      sigma = r[3]; a = r[5]; s = os; lorenz_lgo = true;
       break;
     }
   }
   P[P_INC_SCALE] = (float)inc;
+  if (lorenz_lgo) {
+    const double hvi = 1.0 / (sigma * sigma), ovi = 1.0 / (s * s);
+    const double cov = 1.0 / (hvi + a * a * ovi), cov1 = 1.0 / hvi;
+    const double pre = s * s + a * a * sigma * sigma;
+    P[P_LGO_HVI] = (float)hvi; P[P_LGO_OVI] = (float)ovi;
+    P[P_LGO_COV] = (float)cov; P[P_LGO_KSTD] = (float)sqrt(cov);
+    P[P_LGO_K_INV2VAR] = (float)(1.0 / (2.0 * cov)); P[P_LGO_K_LOGNORM] = (float)(0.5 * log(cov) + c);
+    P[P_LGO_COV1] = (float)cov1; P[P_LGO_KSTD1] = (float)sqrt(cov1);
+    P[P_LGO_K1_INV2VAR] = (float)(1.0 / (2.0 * cov1)); P[P_LGO_K1_LOGNORM] = (float)(0.5 * log(cov1) + c);
+    P[P_LGO_PRE_INV2VAR] = (float)(1.0 / (2.0 * pre)); P[P_LGO_PRE_LOGNORM] = (float)(0.5 * log(pre) + c);
+    P[P_LGO_INC_INV2VAR] = (float)(1.0 / (2.0 * inc * inc));
+    P[P_LGO_INC_LOGNORM] = (float)(log(inc) + c + log(fabs(sigma)));
+    P[P_LGO_INV_SIGMA] = (float)(1.0 / sigma);
+  }
   if (linear) {
     P[P_OBS_INV2VAR] = (float)(1.0 / (2.0 * s * s));
     P[P_OBS_LOGNORM] = (float)(log(s) + c);
@@ -155,9 +174,10 @@ struct smcb_filter {
   uint32_t* tile_counter = nullptr;
   long long* wd = nullptr;
   uint32_t ticket_next = 0;
-  int mv_grid = 0;
-  unsigned long long *mslots = nullptr, *gslots = nullptr;
-  uint32_t* gcount = nullptr;
+  int mv_grid = 0;            // blocks of a move_kernel launch = B * mv_T (0: geometry not chosen yet)
+  int mv_t1 = 0, mv_items1 = 16, mv_items2 = 16, mv_T = 0;   // tile classes of a column (move.cuh, MoveArgs)
+  int mv_tiles_cap = 0;       // per-column capacity of the per-tile buffers (tiles of the smallest class)
+  unsigned long long *mslots = nullptr, *gwords = nullptr;
   unsigned mv_epoch = 0;
   uint32_t mv_launches = 0;   // move_kernel launches since the group counters were cleared
   // peer-memory exchange of the per-column log-likelihoods (smcb_filter_attach_exchange)
@@ -193,7 +213,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gslots, f->gcount, f->xch_out};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -203,7 +223,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   if (!cfg || !out) return fail(SMCB_EINVAL, "null argument");
   if (cfg->model < 0 || cfg->model >= SMCB_NUM_MODELS) return fail(SMCB_EUNSUPPORTED, "unknown model id (only the compiled zoo is supported; there is no CPU fallback)");
   if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS) return fail(SMCB_EUNSUPPORTED, "unknown proposal");
-  if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM))
+  if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM || cfg->model == SMCB_LORENZ63_EM))
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
   if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
   if (cfg->resampler != SMCB_SYSTEMATIC && cfg->resampler != SMCB_MULTINOMIAL) return fail(SMCB_EUNSUPPORTED, "unknown resampler");
@@ -229,17 +249,19 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
     f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);
   }
   const size_t cells = (size_t)f->B * f->ld;
+  const size_t slack = RS_TILE;   // the last tile of a column may read past its row (move.cuh): one tile of slack behind the last row
+  f->mv_tiles_cap = (int)((f->n + MV_NT * 4 - 1) / (MV_NT * 4)) + 1;
   const int rows = cfg->history_rows > 0 ? cfg->history_rows : 1;
   f->cfg.history_rows = rows;
   cudaError_t e = cudaSuccess;
 #define A_(call) if (e == cudaSuccess) e = (call)
   A_(dalloc(&f->P_dev, (size_t)f->B * SMCB_NPARAM));
-  A_(dalloc(&f->xbuf[0], cells * f->D));
-  A_(dalloc(&f->xbuf[1], cells * f->D));
-  A_(dalloc(&f->lwbuf[0], cells));
-  A_(dalloc(&f->lwbuf[1], cells));
-  A_(dalloc(&f->rwbuf[0], cells));
-  A_(dalloc(&f->rwbuf[1], cells));
+  A_(dalloc(&f->xbuf[0], cells * f->D + slack));
+  A_(dalloc(&f->xbuf[1], cells * f->D + slack));
+  A_(dalloc(&f->lwbuf[0], cells + slack));
+  A_(dalloc(&f->lwbuf[1], cells + slack));
+  A_(dalloc(&f->rwbuf[0], cells + slack));
+  A_(dalloc(&f->rwbuf[1], cells + slack));
   A_(dalloc(&f->wn, cells));
   A_(dalloc(&f->anc, cells));
   A_(dalloc(&f->prev_inds, cells));
@@ -260,11 +282,10 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ncounter, (size_t)f->B));
   A_(dalloc(&f->verdict, (size_t)f->B));
   A_(dalloc(&f->u_col, (size_t)f->B));
-  A_(dalloc(&f->tile_partials, (size_t)f->B * f->tiles_per_col));
+  A_(dalloc(&f->tile_partials, (size_t)f->B * f->mv_tiles_cap));
   A_(dalloc(&f->tile_counter, (size_t)1));
-  A_(dalloc(&f->mslots, (size_t)f->B * f->tiles_per_col));
-  A_(dalloc(&f->gslots, (size_t)f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD));
-  A_(dalloc(&f->gcount, (size_t)f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD * 2));
+  A_(dalloc(&f->mslots, (size_t)f->B * f->mv_tiles_cap));
+  A_(dalloc(&f->gwords, (size_t)2 * f->B * ((f->mv_tiles_cap + MV_GROUP - 1) / MV_GROUP) * MV_GPAD));
   A_(dalloc(&f->wd, (size_t)4));
   A_(dalloc(&f->hist_mean, (size_t)rows * f->B * f->D));
   A_(dalloc(&f->hist_var, (size_t)rows * f->B * f->D));
@@ -275,7 +296,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
-  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)16 * f->B * f->tiles_per_col));
+  if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)16 * f->B * (f->mv_tiles_cap > f->tiles_per_col ? f->mv_tiles_cap : f->tiles_per_col)));
 #undef A_
   if (e != cudaSuccess) {
     smcb_filter_destroy(f);
@@ -343,22 +364,63 @@ static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
     case 0: if (prop) launch_step_alg<0, 1>(alg, g, s, a); else launch_step_alg<0, 0>(alg, g, s, a); break;
     case 1: if (prop) launch_step_alg<1, 1>(alg, g, s, a); else launch_step_alg<1, 0>(alg, g, s, a); break;
     case 2: launch_step_alg<2, 0>(alg, g, s, a); break;
-    case 3: launch_step_alg<3, 0>(alg, g, s, a); break;
+    case 3: if (prop) launch_step_alg<3, 1>(alg, g, s, a); else launch_step_alg<3, 0>(alg, g, s, a); break;
   }
   f->launches++;
 }
 
-// ---- move_kernel (move.cuh): one kernel per move, persistent grid drawing tile tickets -----------------------------------------
+// ---- move_kernel (move.cuh): one kernel per move, one block per tile, tiles drawn from a ticket counter ---------------------------
+// Tile classes of a column (MoveArgs.t1 / items1 / items2).  `slots` = blocks resident at a time.  Tiles of 4096 particles (16 per
+// thread) unless the last wave of such tiles would use less than a quarter of the slots: then the columns' remainders behind the full
+// waves are cut into 1024-particle tiles (measurements: move.cuh, profiles/README.md).  SMCB_MV_GEOM="items1,items2,t1" overrides
+// (diagnostics, tools/geom_sweep.py).
+static void mv_choose_geometry(smcb_filter* f, int slots) {
+  const int64_t n = f->n;
+  const int B = f->B;
+  const int64_t L1 = (int64_t)MV_NT * 16;
+  const int64_t Tu = (n + L1 - 1) / L1;
+  int bt1 = (int)Tu, bi1 = 16, bi2 = 16, bT = (int)Tu;
+  const int64_t total = Tu * B;
+  if (total > slots && total % slots != 0 && total % slots < slots / 4) {
+    const int64_t t1 = ((total / slots) * slots) / B;   // whole waves of large tiles
+    if (t1 >= 1 && t1 < Tu) {
+      const int64_t L2 = (int64_t)MV_NT * 4;
+      const int64_t t2 = (n - t1 * L1 + L2 - 1) / L2;
+      if (t2 * B <= slots && t1 + t2 <= f->mv_tiles_cap) { bt1 = (int)t1; bi2 = 4; bT = (int)(t1 + t2); }
+    }
+  }
+  if (const char* g = getenv("SMCB_MV_GEOM")) {
+    int i1 = 16, i2 = 16, t1 = 0;
+    if (sscanf(g, "%d,%d,%d", &i1, &i2, &t1) == 3 && (i1 == 16 || i1 == 12 || i1 == 8 || i1 == 4) && (i2 == 16 || i2 == 12 || i2 == 8 || i2 == 4)) {
+      const int64_t L1 = (int64_t)MV_NT * i1, L2 = (int64_t)MV_NT * i2;
+      int64_t T1 = t1 < 0 ? 0 : t1;
+      if (T1 * L1 >= n) T1 = (n + L1 - 1) / L1;
+      const int64_t rest = n - T1 * L1;
+      const int64_t T2 = rest > 0 ? (rest + L2 - 1) / L2 : 0;
+      if (T1 + T2 <= f->mv_tiles_cap) { bt1 = (int)T1; bi1 = i1; bi2 = i2; bT = (int)(T1 + T2); }
+    }
+  }
+  f->mv_t1 = bt1; f->mv_items1 = bi1; f->mv_items2 = bi2; f->mv_T = bT;
+}
+
 template <int MODEL, int PROP, int ALG>
 static cudaError_t launch_move_t(smcb_filter* f, MoveArgs& m, cudaStream_t s) {
   constexpr int D = Model<MODEL>::D;
   const size_t dyn = sizeof(float) * (size_t)D * MV_TILE;
   auto kernel = move_kernel<MODEL, PROP, ALG>;
-  if (f->mv_grid == 0) {  // once per handle: dynamic shared memory limit; one block per tile
+  if (f->mv_grid == 0) {  // once per handle: dynamic shared memory limit, resident blocks, tile classes; one block per tile
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
-    f->mv_grid = m.total_tiles;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, MV_NT, dyn);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    mv_choose_geometry(f, per_sm * smcb_sm_count());
+    f->mv_grid = f->mv_T * f->B;
   }
+  m.t1 = f->mv_t1; m.items1 = f->mv_items1; m.items2 = f->mv_items2;
+  m.tiles_per_col = f->mv_T; m.total_tiles = f->mv_grid;
+  m.s.blocks_per_col = f->mv_T;
   m.ticket_base = f->ticket_next;
   f->ticket_next += (uint32_t)m.total_tiles;  // every block draws exactly one ticket
   static bool pdl_ok = true;
@@ -385,10 +447,9 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   MoveArgs m;
   memset(&m, 0, sizeof(m));
   m.s = a;
-  m.s.partials = f->tile_partials; m.s.blocks_per_col = f->tiles_per_col;
-  m.tiles_per_col = f->tiles_per_col; m.total_tiles = f->tiles_per_col * f->B;
+  m.s.partials = f->tile_partials;   // (tile geometry: launch_move_t)
   f->mv_epoch = f->mv_epoch % 1023u + 1u;   // 1 .. 1023, never the previous launch's
-  m.tile_counter = f->tile_counter; m.mslots = f->mslots; m.gslots = f->gslots; m.gcount = f->gcount; m.epoch = f->mv_epoch;
+  m.tile_counter = f->tile_counter; m.mslots = f->mslots; m.gwords = f->gwords; m.epoch = f->mv_epoch;
   m.launch_index = f->mv_launches++;
   m.u_in = f->u_in; m.u_out = f->u_out; m.w_out = f->w_out; m.wd = f->wd;
   m.tl = f->dbg ? f->dbg + 32 : nullptr;
@@ -405,7 +466,7 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
     case 0: e = prop ? launch_move_alg<0, 1>(f, m, s) : launch_move_alg<0, 0>(f, m, s); break;
     case 1: e = prop ? launch_move_alg<1, 1>(f, m, s) : launch_move_alg<1, 0>(f, m, s); break;
     case 2: e = launch_move_alg<2, 0>(f, m, s); break;
-    case 3: e = launch_move_alg<3, 0>(f, m, s); break;
+    case 3: e = prop ? launch_move_alg<3, 1>(f, m, s) : launch_move_alg<3, 0>(f, m, s); break;
   }
   if (e != cudaSuccess) return fail(SMCB_ECUDA, std::string("move_kernel: ") + cudaGetErrorString(e));
   f->launches++;
@@ -415,7 +476,7 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
 static bool move_path_ok(const smcb_filter* f) {
   const bool off = getenv("SMCB_NO_MOVE") != nullptr;  // diagnostics / tests: force the two-kernel pipeline
   return !off && f->cfg.resampler == SMCB_SYSTEMATIC && !f->cfg.exact_weights && f->n <= (1 << 23) &&
-         (int64_t)f->tiles_per_col * f->B < (1 << 30);
+         (int64_t)f->mv_tiles_cap * f->B < (1 << 30);
 }
 
 static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
@@ -425,7 +486,7 @@ static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) 
     case 0: if (prop) preweight_kernel<0, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<0, 0><<<g, ST_NT, 0, s>>>(a); break;
     case 1: if (prop) preweight_kernel<1, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<1, 0><<<g, ST_NT, 0, s>>>(a); break;
     case 2: preweight_kernel<2, 0><<<g, ST_NT, 0, s>>>(a); break;
-    case 3: preweight_kernel<3, 0><<<g, ST_NT, 0, s>>>(a); break;
+    case 3: if (prop) preweight_kernel<3, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<3, 0><<<g, ST_NT, 0, s>>>(a); break;
   }
   f->launches++;
 }
@@ -477,7 +538,7 @@ extern "C" int smcb_filter_initialize(smcb_filter* f, void* stream) {
   if (rc) return rc;
   CU(cudaMemsetAsync(f->ll_total, 0, sizeof(float) * f->B, s));
   CU(cudaMemsetAsync(f->stats, 0, sizeof(ColStats) * f->B, s));
-  CU(cudaMemsetAsync(f->gcount, 0, sizeof(uint32_t) * f->B * ((f->tiles_per_col + MV_GROUP - 1) / MV_GROUP) * MV_GPAD * 2, s));
+  CU(cudaMemsetAsync(f->gwords, 0, sizeof(unsigned long long) * 2 * f->B * ((f->mv_tiles_cap + MV_GROUP - 1) / MV_GROUP) * MV_GPAD, s));
   f->mv_launches = 0;
   StepArgs a = make_args(f);
   a.sample_x0 = 1;
@@ -531,7 +592,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
     if (rc) return rc;
     {  // the per-tile records of the move are folded by a one-block-per-column kernel chained behind it
       StepArgs fa = a;
-      fa.partials = f->tile_partials; fa.blocks_per_col = f->tiles_per_col;
+      fa.partials = f->tile_partials; fa.blocks_per_col = f->mv_T; fa.fin_host = 1;
       launch_finalize(f, fa, FIN_STEP, s, true);
     }
     if (ev) for (int g = 2; g <= 5; ++g) cudaEventRecord(ev[g], s);
@@ -655,7 +716,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
     case 0: e = prop ? launch_column_alg<0, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, nt, f->B, dyn, s, c); break;
     case 1: e = prop ? launch_column_alg<1, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, nt, f->B, dyn, s, c); break;
     case 2: e = launch_column_alg<2, 0>(alg, nt, f->B, dyn, s, c); break;
-    case 3: e = launch_column_alg<3, 0>(alg, nt, f->B, dyn, s, c); break;
+    case 3: e = prop ? launch_column_alg<3, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<3, 0>(alg, nt, f->B, dyn, s, c); break;
   }
   if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
   f->launches++;
@@ -945,4 +1006,228 @@ extern "C" int smcb_systematic(const float* w_dev, int64_t n, int32_t B, int64_t
 extern "C" int smcb_multinomial(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, int32_t normalized,
                                 const double* U_dev, uint64_t seed, int64_t* out_dev, int64_t osn, int64_t osb, void* stream) {
   return op_resample(w_dev, n, B, sn, sb, normalized, nullptr, U_dev, seed, out_dev, osn, osb, SMCB_MULTINOMIAL, (cudaStream_t)stream);
+}
+
+// ---- the callers and plug-ins either side of the fused move (plugin.cuh) ----------------------------------------------------------
+extern "C" int smcb_filter_set_ess_threshold(smcb_filter* f, float relative_threshold) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  f->cfg.ess_threshold = relative_threshold;
+  return SMCB_OK;
+}
+
+static int proposal_op(smcb_filter* f, int mode, const float* y_dev, const float* x_dev, const float* eps_dev, int32_t t, float* x_out, float* w_out,
+                       cudaStream_t s) {
+  if (!f || !y_dev || !w_out || (mode == 1 && !x_out)) return fail(SMCB_EINVAL, "null argument");
+  ProposalOpArgs c;
+  memset(&c, 0, sizeof(c));
+  c.s = make_args(f);
+  c.s.eps_in = eps_dev; c.s.eps_out = nullptr;
+  c.x_in = x_dev ? x_dev : f->xbuf[f->t_host & 1];
+  c.y = y_dev; c.x_out = x_out; c.w_out = w_out; c.mode = mode; c.t = t;
+  const int64_t chunk = ST_NT * ST_VEC;
+  dim3 g((unsigned)((f->n + chunk - 1) / chunk), f->B);
+  const int prop = f->cfg.proposal;
+  switch (f->cfg.model) {
+    case 0: if (prop) proposal_op_kernel<0, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<0, 0><<<g, ST_NT, 0, s>>>(c); break;
+    case 1: if (prop) proposal_op_kernel<1, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<1, 0><<<g, ST_NT, 0, s>>>(c); break;
+    case 2: proposal_op_kernel<2, 0><<<g, ST_NT, 0, s>>>(c); break;
+    case 3: if (prop) proposal_op_kernel<3, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<3, 0><<<g, ST_NT, 0, s>>>(c); break;
+  }
+  f->launches++;
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+extern "C" int smcb_filter_pre_weight(smcb_filter* f, const float* y_dev, const float* x_dev, float* out_dev, void* stream) {
+  return proposal_op(f, 0, y_dev, x_dev, nullptr, 0, nullptr, out_dev, (cudaStream_t)stream);
+}
+extern "C" int smcb_filter_sample_and_weight(smcb_filter* f, const float* y_dev, const float* x_dev, const float* eps_dev, int32_t t,
+                                             float* x_out_dev, float* w_out_dev, void* stream) {
+  return proposal_op(f, 1, y_dev, x_dev, eps_dev, t, x_out_dev, w_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int smcb_filter_predict_path(smcb_filter* f, int32_t steps, const float* x_dev, float* x_out_dev, float* y_out_dev, void* stream) {
+  if (!f || !x_out_dev || !y_out_dev || steps < 1) return fail(SMCB_EINVAL, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  PathArgs c;
+  memset(&c, 0, sizeof(c));
+  c.s = make_args(f);
+  c.x_in = x_dev ? x_dev : f->xbuf[f->t_host & 1];
+  c.x_out = x_out_dev; c.y_out = y_out_dev; c.steps = steps; c.t0 = f->t_host;
+  const int64_t chunk = ST_NT * ST_VEC;
+  dim3 g((unsigned)((f->n + chunk - 1) / chunk), f->B);
+  FOR_MODEL(f->cfg.model, (predict_path_kernel<MODEL><<<g, ST_NT, 0, s>>>(c)));
+  f->launches++;
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_batched_gather(const float* x_dev, int64_t n, int32_t B, int32_t D, int64_t* idx_dev, const int64_t* prev_dev, float* out_dev,
+                                   void* stream) {
+  if (!x_dev || !idx_dev || !out_dev || n < 1 || B < 1 || D < 1) return fail(SMCB_EINVAL, "bad argument");
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* bad = nullptr;
+  CU(cudaMallocAsync((void**)&bad, sizeof(int), s));
+  CU(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  const int64_t cells = n * B;
+  gather_lineage_kernel<<<(unsigned)((cells + 255) / 256), 256, 0, s>>>(x_dev, n, B, D, idx_dev, prev_dev, out_dev, bad);
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(bad, s);
+  if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
+  if (h) return fail(SMCB_EINVAL, "index out of range");   // torch.gather raises the same way
+  return SMCB_OK;
+}
+
+// the per-column buffers a theta-level permutation / exchange touches
+struct ColumnPlanes { float* p[8]; int planes[8]; int count; };
+static ColumnPlanes column_planes(smcb_filter* f) {
+  ColumnPlanes c;
+  const int cur = f->t_host & 1;
+  c.count = 0;
+  c.p[c.count] = f->xbuf[cur]; c.planes[c.count++] = f->D;
+  c.p[c.count] = f->lwbuf[cur]; c.planes[c.count++] = 1;
+  c.p[c.count] = f->rwbuf[cur]; c.planes[c.count++] = 1;
+  c.p[c.count] = (float*)f->prev_inds; c.planes[c.count++] = 1;
+  return c;
+}
+struct ColumnSmall { float* p; int rec, rows; };
+static int column_small(smcb_filter* f, bool history, ColumnSmall* out) {
+  int k = 0;
+  out[k++] = {(float*)f->stats, (int)(sizeof(ColStats) / 4), 1};
+  out[k++] = {f->ll_total, 1, 1};
+  out[k++] = {f->latest_mean, f->D, 1};
+  out[k++] = {f->latest_var, f->D, 1};
+  out[k++] = {f->latest_ll, 1, 1};
+  if (history) {
+    const int rows = std::min(f->cfg.history_rows, f->t_host + 1);
+    out[k++] = {f->hist_mean, f->D, rows};
+    out[k++] = {f->hist_var, f->D, rows};
+    out[k++] = {f->hist_ll, 1, rows};
+  }
+  return k;
+}
+
+extern "C" int smcb_filter_resample_columns(smcb_filter* f, const int64_t* idx_dev, int32_t entire_history, void* stream) {
+  if (!f || !idx_dev) return fail(SMCB_EINVAL, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* bad = nullptr;
+  CU(cudaMallocAsync((void**)&bad, sizeof(int), s));
+  CU(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  const ColumnPlanes cp = column_planes(f);
+  const int64_t ld4 = f->ld / 4;
+  for (int k = 0; k < cp.count; ++k) {   // out of place through a scratch copy of the plane group, then back
+    const size_t bytes = sizeof(float) * (size_t)cp.planes[k] * f->B * f->ld;
+    float* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, bytes, s));
+    dim3 g((unsigned)std::min<int64_t>((ld4 + 255) / 256, 64), f->B, cp.planes[k]);
+    column_gather_kernel<<<g, 256, 0, s>>>((const float4*)cp.p[k], (float4*)tmp, f->B, ld4, idx_dev, nullptr, bad);
+    CU(cudaMemcpyAsync(cp.p[k], tmp, bytes, cudaMemcpyDeviceToDevice, s));
+    CU(cudaFreeAsync(tmp, s));
+    f->launches++;
+  }
+  ColumnSmall sm[8];
+  const int ns = column_small(f, entire_history != 0, sm);
+  for (int k = 0; k < ns; ++k) {
+    const size_t count = (size_t)sm[k].rows * f->B * sm[k].rec;
+    float* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, count * sizeof(float), s));
+    column_gather_small_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(sm[k].p, tmp, f->B, sm[k].rec, sm[k].rows, idx_dev, nullptr);
+    CU(cudaMemcpyAsync(sm[k].p, tmp, count * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    CU(cudaFreeAsync(tmp, s));
+    f->launches++;
+  }
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(bad, s);
+  if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
+  if (h) return fail(SMCB_EINVAL, "column index out of range");
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+extern "C" int smcb_filter_exchange_columns(smcb_filter* dst, smcb_filter* src, const uint8_t* mask_dev, void* stream) {
+  if (!dst || !src || !mask_dev) return fail(SMCB_EINVAL, "null argument");
+  if (dst->B != src->B || dst->n != src->n || dst->D != src->D || dst->ld != src->ld) return fail(SMCB_EINVAL, "the two handles hold different shapes");
+  if (dst->t_host != src->t_host) return fail(SMCB_ESTATE, "the two handles are at different move indices");
+  cudaStream_t s = (cudaStream_t)stream;
+  const ColumnPlanes a = column_planes(dst), b = column_planes(src);
+  const int64_t ld4 = dst->ld / 4;
+  for (int k = 0; k < a.count; ++k) {
+    dim3 g((unsigned)std::min<int64_t>((ld4 + 255) / 256, 64), dst->B, a.planes[k]);
+    column_gather_kernel<<<g, 256, 0, s>>>((const float4*)b.p[k], (float4*)a.p[k], dst->B, ld4, nullptr, mask_dev, nullptr);
+    dst->launches++;
+  }
+  ColumnSmall sa[8], sb[8];
+  const int ns = column_small(dst, true, sa);
+  column_small(src, true, sb);
+  for (int k = 0; k < ns; ++k) {
+    const int rows = std::min(sa[k].rows, sb[k].rows);
+    const size_t count = (size_t)rows * dst->B * sa[k].rec;
+    column_gather_small_kernel<<<(unsigned)((count + 255) / 256), 256, 0, s>>>(sb[k].p, sa[k].p, dst->B, sa[k].rec, rows, nullptr, mask_dev);
+    dst->launches++;
+  }
+  dst->folded_for_next = dst->folded_for_next && src->folded_for_next;   // rw is valid only when both handles folded the look-ahead
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+
+// pyfilter.resampling.residual (resampling.py:68-105) on NORMALISED weights: deterministic copies + multinomial draws on the fractions
+extern "C" int smcb_residual(const float* w_dev, int64_t n, int32_t B, int64_t sn, int64_t sb, const double* U_dev, uint64_t seed, int64_t* out_dev,
+                             int64_t osn, int64_t osb, void* stream) {
+  if (!w_dev || !out_dev || n < 1 || B < 1) return fail(SMCB_EINVAL, "bad argument");
+  if (n > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");
+  if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
+  cudaStream_t s = (cudaStream_t)stream;
+  OpWorkspace ws;
+  int32_t *counts = nullptr, *ksum = nullptr;
+  int rc = op_prepare(ws, w_dev, n, B, sn, sb, false, s);
+  if (rc == SMCB_OK) {
+    const size_t cells = (size_t)B * ws.ld;
+    cudaError_t e = cudaMallocAsync((void**)&counts, cells * sizeof(int32_t), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&ksum, (size_t)B * sizeof(int32_t), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void**)&ws.cbuf, cells * sizeof(float), s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ws.wn, 0, cells * sizeof(float), s);
+    if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
+  }
+  if (rc == SMCB_OK) {
+    residual_counts_kernel<<<B, 1024, 0, s>>>(ws.w, n, ws.ld, counts, ws.wn, ksum);
+    residual_expand_kernel<<<B, 1024, 0, s>>>(counts, n, ws.ld, ws.anc);
+    ResampleArgs r;
+    memset(&r, 0, sizeof(r));
+    r.w = ws.wn; r.wn = ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
+    r.input_is_w = 1; r.use_rw = 0; r.stats = nullptr;
+    r.seed = seed; r.tilesum = ws.tilesum; r.anc = ws.anc; r.ctrl = ws.ctrl;
+    r.prefix = ws.prefix; r.sin = ws.sin; r.tileflag = ws.tileflag; r.desc = ws.desc; r.desc2 = ws.desc2; r.tables = ws.tables; r.dcounter = ws.dcounter;
+    r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
+    r.c_out = ws.cbuf; r.draw_offset = ksum;
+    rc = op_launch_multinomial(r, U_dev, n, s);
+    if (rc == SMCB_OK) {
+      op_launch_scatter_i64(ws.anc, n, B, ws.ld, out_dev, osn, osb, s);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
+    }
+  }
+  if (counts) cudaFreeAsync(counts, s);
+  if (ksum) cudaFreeAsync(ksum, s);
+  op_free(ws, s);
+  return rc;
+}
+
+// one backward step of FFBS (filters/particle/base.py:112-126) for a non-batched filter
+extern "C" int smcb_filter_ffbs_step(smcb_filter* f, const float* x_dev, const float* lw_dev, const float* xnext_dev, const double* U_dev, uint64_t seed,
+                                     int32_t t, int64_t* idx_out_dev, float* x_out_dev, void* stream) {
+  if (!f || !x_dev || !lw_dev || !xnext_dev || !idx_out_dev || !x_out_dev) return fail(SMCB_EINVAL, "null argument");
+  if (f->B != 1) return fail(SMCB_EUNSUPPORTED, "FFBS is implemented for non-batched filters (like the reference's working branch)");
+  cudaStream_t s = (cudaStream_t)stream;
+  FfbsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.P = f->P_dev; a.x = x_dev; a.lw = lw_dev; a.xnext = xnext_dev; a.U = U_dev; a.idx = idx_out_dev; a.xout = x_out_dev;
+  a.n = f->n; a.seed = seed; a.t = t;
+  FOR_MODEL(f->cfg.model, (ffbs_step_kernel<MODEL><<<(unsigned)f->n, 256, 0, s>>>(a)));
+  f->launches++;
+  CU(cudaGetLastError());
+  return SMCB_OK;
 }

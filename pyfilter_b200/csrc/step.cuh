@@ -46,6 +46,8 @@ struct StepArgs {
   int32_t hist_rows;
   float* latest_mean; float* latest_var; float* latest_ll; float* ll_total;  // (B, D), (B, D), (B), (B)
   int32_t fin_mode;
+  int32_t fin_host;                  // finalize_kernel: the move index and the observation pointers are the ones below (t_host, y_t, y_next) - no
+                                     // chain of dependent loads (ctrl->t -> ctrl->y -> y[t]) in front of the fold
   long long* dbg;                    // optional diagnostics (SMCB_DEBUG_TIMELINE)
   // step_kernel only: what the host knows at launch time, so that the prologue has no chain of dependent loads (ctrl->t -> ctrl->y -> y[t])
   int32_t t_host;                    // == ctrl->t when the kernel runs
@@ -239,8 +241,63 @@ struct Proposal<MODEL, SMCB_PROPOSAL_BOOTSTRAP> {
   }
 };
 
+template <int MODEL, int PROP, bool VECTOR = (Model<MODEL>::D > 1)>
+struct ProposalLGO;
 template <int MODEL>
-struct Proposal<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS> {
+struct Proposal<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS> : ProposalLGO<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS> {};
+
+// multi-dimensional LinearGaussianObservations for the Lorenz model (proposals/linear.py:38-86, proposals/utils.py:219-267 with
+// A = a [[1,0,0],[0,0,1]], examples/lorenz.ipynb:214): every matrix of find_optimal_density is diagonal, so the 3x3 inverse and the
+// Cholesky factor are per-column constants (models.h: P_LGO_*), the kernel N(k, P) factorises over the coordinates and
+// MultivariateNormal.log_prob is the sum of three scalar normal log-densities.
+template <int MODEL>
+struct ProposalLGO<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS, true> {
+  typedef Model<MODEL> M;
+  static_assert(M::D == 3 && M::OD == 2, "vector LinearGaussianObservations is compiled for the Lorenz-63 model");
+  // log N(y; A x_{t-1}, diag(s^2 + a^2 sigma^2))   (proposals/linear.py:57-86; centred on the previous state)
+  __device__ static __forceinline__ float pre_weight(const float* y, const float* x, const float* P) {
+    const float l0 = smcb_normal_lp(y[0], __fmul_rn(P[5], x[0]), P[P_LGO_PRE_INV2VAR], P[P_LGO_PRE_LOGNORM]);
+    const float l1 = smcb_normal_lp(y[1], __fmul_rn(P[5], x[2]), P[P_LGO_PRE_INV2VAR], P[P_LGO_PRE_LOGNORM]);
+    return __fadd_rn(l0, l1);
+  }
+  __device__ static __forceinline__ void sample_and_weight(const float* y, const float* xa, const float* z, const float* P,
+                                                           bool observed, float* xn, float& inc, float& g_anc) {
+    float m[3], sc;
+    M::loc_scale(xa, P, m, sc);
+    inc = 0.f; g_anc = 0.f;
+    if (!observed) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) xn[d] = __fadd_rn(m[d], __fmul_rn(sc, __fmul_rn(z[d], P[P_INC_SCALE])));
+      return;
+    }
+    // k = P (sigma^-2 m + A^T s^-2 y)
+    float k[3];
+    const float yo[3] = {y[0], 0.f, y[1]};
+    float x_lp = 0.f, k_lp = 0.f;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float t1 = __fmul_rn(P[P_LGO_HVI], m[d]);
+      if (d == 1) {
+        k[d] = __fmul_rn(P[P_LGO_COV1], t1);
+        xn[d] = __fadd_rn(k[d], __fmul_rn(P[P_LGO_KSTD1], z[d]));
+        k_lp = __fadd_rn(k_lp, smcb_normal_lp(xn[d], k[d], P[P_LGO_K1_INV2VAR], P[P_LGO_K1_LOGNORM]));
+      } else {
+        const float t3 = __fmul_rn(P[5], __fmul_rn(P[P_LGO_OVI], yo[d]));
+        k[d] = __fmul_rn(P[P_LGO_COV], __fadd_rn(t1, t3));
+        xn[d] = __fadd_rn(k[d], __fmul_rn(P[P_LGO_KSTD], z[d]));
+        k_lp = __fadd_rn(k_lp, smcb_normal_lp(xn[d], k[d], P[P_LGO_K_INV2VAR], P[P_LGO_K_LOGNORM]));
+      }
+      const float e = __fmul_rn(__fsub_rn(xn[d], m[d]), P[P_LGO_INV_SIGMA]);
+      x_lp = __fadd_rn(x_lp, smcb_normal_lp(e, 0.f, P[P_LGO_INC_INV2VAR], P[P_LGO_INC_LOGNORM]));
+    }
+    const float y_lp = M::obs_lp(y, xn, P);
+    inc = __fsub_rn(__fadd_rn(y_lp, x_lp), k_lp);
+    g_anc = pre_weight(y, xa, P);
+  }
+};
+
+template <int MODEL>
+struct ProposalLGO<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS, false> {
   typedef Model<MODEL> M;
   static_assert(M::LINEAR_OBS && M::D == 1, "LinearGaussianObservations needs y = b + a x + s nu with a scalar state");
   // proposals/linear.py:57-86: log N(y; b + a x_{t-1}, sqrt(s^2 + a^2 sigma^2))   (centred on the previous state)
@@ -576,6 +633,17 @@ __global__ void __launch_bounds__(ST_NT) finalize_kernel(StepArgs a) {
   __shared__ FinSmem<D> fs;
   pdl_trigger();  // (launched behind move_kernel with programmatic serialisation: the next move's blocks may take their places now)
   pdl_wait();
+  if (a.fin_host) {  // everything the fold needs besides the partial records is known or loadable at once
+    const int t = a.t_host;
+    FinPre pre;
+    float y[OD];
+    pre.st = a.stats[blockIdx.x];
+    pre.observed = (a.fin_mode != FIN_STATE) && st_load_obs<OD>(a.y_t, y);
+    pre.fold = (a.fin_mode == FIN_STEP) && a.fold && st_load_obs<OD>(a.y_next, y);
+    pre.ll_total = a.ll_total[blockIdx.x];
+    finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, t, fs, pre);
+    return;
+  }
   const int t = a.ctrl->t;
   const FinPre pre = fin_preload<OD>(a, blockIdx.x, a.fin_mode, t);
   finalize_column<D, OD, ALG>(a, blockIdx.x, a.fin_mode, t, fs, pre);

@@ -9,7 +9,7 @@ from ...timeseries import StateSpaceModel
 from ..result import FilterResult
 from .engine import Engine
 from .proposals import Bootstrap, Proposal
-from .state import ParticleFilterCorrection
+from .state import ParticleFilterCorrection, ParticleFilterPrediction
 
 _RESAMPLERS = {_resampling.systematic: 0, _resampling.multinomial: 1}
 
@@ -94,14 +94,61 @@ class ParticleFilter:
         res.set_batch_shape(self.batch_shape)
         return res
 
-    def predict(self, state):
-        raise NotImplementedError("predict/correct are fused into one device step; call filter() or batch_filter()")
+    # ---- the split step of the reference (filters/base.py:160-186): predict, then correct.  `filter()` / `batch_filter()` run both in ONE
+    #      fused kernel; these two exist for code written against the reference's plug-in surface and are built from the stand-alone
+    #      device passes (normalize, get_ess, the resamplers, batched_gather) and a single fused move from a loaded state.
+    def predict(self, state: ParticleFilterCorrection) -> ParticleFilterPrediction:
+        raise NotImplementedError()
 
-    def correct(self, y, prediction):
-        raise NotImplementedError("predict/correct are fused into one device step; call filter() or batch_filter()")
+    def correct(self, y: torch.Tensor, prediction: ParticleFilterPrediction) -> ParticleFilterCorrection:
+        raise NotImplementedError()
 
-    def smooth(self, states, method="ffbs"):
-        raise NotImplementedError("smoothing is listed under 'next' (SURVEY.md 8(f) f3)")
+    def _move_from(self, y, x: torch.Tensor, weights: torch.Tensor, indices: torch.Tensor, t: int, resample: bool) -> ParticleFilterCorrection:
+        """One fused move from an explicit state.  ``resample=False`` (SISR.correct: the prediction is already resampled) switches the
+        ESS rule off for this move."""
+        e = self._get_engine(2)
+        n = int(self._base_particles[0])
+        if not resample:
+            e.set_ess_threshold(-1.0)
+        try:
+            e.load_state(x, weights, indices, int(t))
+            e.set_observations(torch.as_tensor(y, dtype=torch.float32).reshape(1, -1).to("cuda").contiguous(), e.t)
+            e.run(1)
+            state = e.make_state().detach_copy()   # not a live view: a later filter() call reloads it and refreshes the statistics
+        finally:
+            e.set_ess_threshold(self._resample_threshold / n)
+        return state
+
+    def _do_sample_fl(self, states):
+        """Fixed-lag smoothing = ancestral tracing over the recorded states (filters/particle/base.py:130-146)."""
+        from ..utils import trace_back
+
+        rev = list(reversed(list(states)))
+        latest = rev[0]
+        result = [latest.timeseries_state.value]
+        n = int(self._base_particles[0])
+        lineage = torch.arange(n, device=result[0].device)
+        if self.batch_shape:
+            lineage = lineage.unsqueeze(-1).expand(self.particles).contiguous()
+        for s in rev[1:]:
+            x_s, lineage = trace_back(s.timeseries_state.value, lineage, latest.previous_indices)
+            result.append(x_s)
+            latest = s
+        return torch.stack(result[::-1], dim=0)
+
+    def _do_sample_ffbs(self, states):
+        """Forward filtering - backward sampling as the reference writes it (filters/particle/base.py:105-128)."""
+        from .smoothing import ffbs
+
+        return ffbs(self, states)
+
+    def smooth(self, states, method="ffbs") -> torch.Tensor:
+        lower_method = method.lower()
+        if lower_method == "ffbs":
+            return self._do_sample_ffbs(states)
+        if method == "fl":
+            return self._do_sample_fl(states)
+        raise NotImplementedError(f"Currently do not support '{method}'!")
 
     # ---- engine management
     def _derive_seed(self, salt: int) -> int:

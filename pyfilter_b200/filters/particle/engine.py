@@ -142,6 +142,69 @@ class Engine:
         packed = self.raw(_lib.PTR_ESS, (2, self.B)).clone()
         return self._squeeze_batch(packed[0], 0), self._squeeze_batch(packed[1], 0)
 
+    # ---- layouts: the reference's (N, [B], [d]) tensors <-> the device's SoA rows (D, B, ld)
+    def to_soa(self, x: torch.Tensor) -> torch.Tensor:
+        buf = torch.zeros((self.D, self.B, self.ld), device="cuda", dtype=torch.float32)
+        v = x.to(device="cuda", dtype=torch.float32).reshape(self.N, self.B, self.D)
+        buf[:, :, : self.N] = v.permute(2, 1, 0)
+        return buf
+
+    def from_soa(self, buf: torch.Tensor) -> torch.Tensor:
+        v = buf[:, :, : self.N].permute(2, 1, 0).contiguous()   # (N, B, D)
+        return v.reshape((self.N,) + tuple(self.batch_shape) + tuple(self.event_shape))
+
+    def from_rows(self, buf: torch.Tensor) -> torch.Tensor:
+        return buf[:, : self.N].t().contiguous().reshape((self.N,) + tuple(self.batch_shape))
+
+    def _y_dev(self, y) -> torch.Tensor:
+        return torch.as_tensor(y, dtype=torch.float32).reshape(-1).to("cuda").contiguous()
+
+    # ---- the proposal plug-in as stand-alone passes (proposals/base.py:52-85)
+    def pre_weight(self, y, x: torch.Tensor = None) -> torch.Tensor:
+        yd = self._y_dev(y)
+        xs = self.to_soa(x) if x is not None else None
+        out = torch.empty((self.B, self.ld), device="cuda", dtype=torch.float32)
+        _lib.check(self.lib.smcb_filter_pre_weight(self.handle, yd.data_ptr(), xs.data_ptr() if xs is not None else None, out.data_ptr(),
+                                                   _lib.current_stream()))
+        return self.from_rows(out)
+
+    def sample_and_weight(self, y, x: torch.Tensor = None, eps: torch.Tensor = None, t: int = None):
+        yd = self._y_dev(y)
+        xs = self.to_soa(x) if x is not None else None
+        es = self.to_soa(eps) if eps is not None else None
+        xo = torch.zeros((self.D, self.B, self.ld), device="cuda", dtype=torch.float32)
+        wo = torch.empty((self.B, self.ld), device="cuda", dtype=torch.float32)
+        _lib.check(self.lib.smcb_filter_sample_and_weight(self.handle, yd.data_ptr(), xs.data_ptr() if xs is not None else None,
+                                                          es.data_ptr() if es is not None else None, int(self.t if t is None else t),
+                                                          xo.data_ptr(), wo.data_ptr(), _lib.current_stream()))
+        return self.from_soa(xo), self.from_rows(wo)
+
+    def predict_path(self, steps: int, x: torch.Tensor = None):
+        """``model.sample_states(steps, x_0)`` for every particle: ``(steps, N, [B], [d])`` states and ``(steps, N, [B], [obs d])`` observations."""
+        xs = self.to_soa(x) if x is not None else None
+        xo = torch.empty((steps, self.D, self.B, self.ld), device="cuda", dtype=torch.float32)
+        yo = torch.empty((steps, self.OD, self.B, self.ld), device="cuda", dtype=torch.float32)
+        _lib.check(self.lib.smcb_filter_predict_path(self.handle, int(steps), xs.data_ptr() if xs is not None else None, xo.data_ptr(),
+                                                     yo.data_ptr(), _lib.current_stream()))
+        xp = xo[..., : self.N].permute(0, 3, 2, 1).contiguous().reshape((steps, self.N) + tuple(self.batch_shape) + tuple(self.event_shape))
+        obs_event = tuple(self.model.event_shape)
+        yp = yo[..., : self.N].permute(0, 3, 2, 1).contiguous().reshape((steps, self.N) + tuple(self.batch_shape) + obs_event)
+        return xp, yp
+
+    def set_ess_threshold(self, relative: float):
+        _lib.check(self.lib.smcb_filter_set_ess_threshold(self.handle, float(relative)))
+
+    # ---- theta-level operations on the resident state (SMC2 / PMMH): FilterResult.resample / exchange without leaving the device
+    def resample_columns(self, indices: torch.Tensor, entire_history: bool = True):
+        idx = indices.to(device="cuda", dtype=torch.int64).contiguous()
+        _lib.check(self.lib.smcb_filter_resample_columns(self.handle, idx.data_ptr(), int(bool(entire_history)), _lib.current_stream()))
+        self.stamp += 1
+
+    def exchange_columns(self, other: "Engine", mask: torch.Tensor):
+        m = mask.to(device="cuda", dtype=torch.uint8).contiguous()
+        _lib.check(self.lib.smcb_filter_exchange_columns(self.handle, other.handle, m.data_ptr(), _lib.current_stream()))
+        self.stamp += 1
+
     def make_state(self):
         from .state import ParticleFilterCorrection
 

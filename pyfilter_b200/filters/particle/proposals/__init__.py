@@ -1,6 +1,12 @@
-"""Proposal plug-ins (reference filters/particle/proposals/): on the device a proposal is an enum baked into the fused
-step kernel, so these classes only carry the choice and the compatibility check of the reference."""
-from ....timeseries import StateSpaceModel
+"""Proposal plug-ins (reference filters/particle/proposals/).  Inside the fused move a proposal is an enum baked into the kernel; the
+plug-in METHODS of the reference - ``pre_weight`` and ``sample_and_weight`` (proposals/base.py:52-85) - are stand-alone device passes
+of the same device functions (``smcb_filter_pre_weight`` / ``smcb_filter_sample_and_weight``, csrc/plugin.cuh), so code written
+against the reference's split step (``filter.predict`` / ``filter.correct``, a custom APF loop) runs unchanged."""
+from typing import Tuple
+
+import torch
+
+from ....timeseries import StateSpaceModel, TimeseriesState
 
 
 class Proposal:
@@ -8,15 +14,47 @@ class Proposal:
 
     def __init__(self, pre_weight_func=None):
         if pre_weight_func is not None:
-            raise NotImplementedError("custom pre-weight callables cannot run inside the fused kernel")
+            raise NotImplementedError("custom pre-weight callables cannot run inside the compiled kernels")
         self._model = None
+        self._op_engine = None
 
     def set_model(self, model: StateSpaceModel):
+        if model is not self._model:
+            self._op_engine = None
         self._model = model
         return self
 
     def copy(self) -> "Proposal":
         return type(self)()
+
+    # ---- the plug-in methods
+    def _engine_for(self, x: torch.Tensor):
+        """A handle of the right shape for the stand-alone passes (kept until the shape or the model changes)."""
+        from ..engine import Engine
+
+        assert self._model is not None, "call set_model first"
+        d = len(self._model.hidden.event_shape)
+        n = int(x.shape[0])
+        batch = torch.Size(x.shape[1: x.dim() - d])
+        e = self._op_engine
+        if e is None or e.N != n or e.batch_shape != batch:
+            e = Engine(self._model, self.proposal_id, 0, 0, n, batch, 0.9, int(torch.randint(0, 2**62, (1,)).item()), 1)
+            self._op_engine = e
+        return e
+
+    def pre_weight(self, y: torch.Tensor, x: TimeseriesState) -> torch.Tensor:
+        """``proposals/base.py:69-85`` (Bootstrap: ``log p(y | loc(x))`` with the affine pre-weight function, pre_weight_funcs.py:9-11)
+        / ``proposals/linear.py:57-86``: the log-weights the APF uses to select the particles it propagates."""
+        return self._engine_for(x.value).pre_weight(y, x.value)
+
+    def sample_and_weight(self, y: torch.Tensor, prediction, eps: torch.Tensor = None) -> Tuple[TimeseriesState, torch.Tensor]:
+        """``proposals/bootstrap.py:10-14`` / ``proposals/linear.py:38-55``: new particles and their weight increments.  ``eps``
+        (same shape as the particles) injects the N(0, 1) draws - the parity hook; otherwise they come from Philox."""
+        x = prediction.get_timeseries_state()
+        e = self._engine_for(x.value)
+        t = int(x.time_index)
+        x_new, w = e.sample_and_weight(y, x.value, eps, t)
+        return x.propagate_from(x_new), w
 
 
 class Bootstrap(Proposal):
@@ -26,7 +64,8 @@ class Bootstrap(Proposal):
 
 
 class LinearGaussianObservations(Proposal):
-    """``proposals/linear.py:13-89``: the optimal Gaussian kernel for ``y = b + a x + s nu`` (scalar state in the zoo)."""
+    """``proposals/linear.py:13-89``: the optimal Gaussian kernel for ``y = b + A x + s nu`` - scalar state, and the vector state of the
+    Lorenz model (examples/lorenz.ipynb:214), whose matrices are diagonal."""
 
     proposal_id = 1
 

@@ -10,6 +10,30 @@ from ...timeseries import TimeseriesState
 from ...utils import normalize
 
 
+class ParticleFilterPrediction:
+    """Prediction state of the particle filters (reference filters/particle/state.py:14-69): the (resampled) previous particles,
+    their log-weights and normalised weights, and the resampling indices."""
+
+    def __init__(self, prev_x: TimeseriesState, weights: torch.Tensor, normalized_weights: torch.Tensor, indices: torch.Tensor):
+        self.prev_x = prev_x
+        self.weights = weights
+        self.normalized_weights = normalized_weights
+        self.indices = indices
+
+    def get_timeseries_state(self) -> TimeseriesState:
+        return self.prev_x
+
+
+class SampledPath:
+    """What ``model.sample_states`` returns in stochproc, reduced to the accessor the reference's callers use (``get_paths``)."""
+
+    def __init__(self, x: torch.Tensor, y: torch.Tensor):
+        self._x, self._y = x, y
+
+    def get_paths(self):
+        return self._x, self._y
+
+
 class ParticleFilterCorrection(dict):
     def __init__(self, x: TimeseriesState, w: torch.Tensor, ll: torch.Tensor, prev_inds, mean: torch.Tensor, var: torch.Tensor,
                  engine=None, stamp=None):
@@ -96,6 +120,22 @@ class ParticleFilterCorrection(dict):
         self.previous_indices[:, mask] = other.previous_indices[:, mask]
         self["_mean"][mask] = other["_mean"][mask]
         self["_var"][mask] = other["_var"][mask]
+
+    def predict_path(self, model, num_steps: int) -> SampledPath:
+        """``particle/state.py:173-174``: ``model.sample_states(num_steps, x_0=self.timeseries_state)`` - every particle simulated
+        ``num_steps`` transitions ahead together with its observations (one device pass, csrc/plugin.cuh)."""
+        from .engine import Engine
+
+        x = self.timeseries_state.value
+        e = self._engine
+        if e is None or e.model is not model:
+            n = x.shape[0]
+            d = len(model.hidden.event_shape)
+            batch = tuple(x.shape[1: x.dim() - d])
+            e = Engine(model, 0, 0, 0, n, torch.Size(batch), 0.9, int(torch.randint(0, 2**62, (1,)).item()), 1)
+            e.t = int(self.timeseries_state.time_index)
+        xp, yp = e.predict_path(int(num_steps), x)
+        return SampledPath(xp, yp)
 
     def state_dict(self) -> Dict[str, Any]:
         res = OrderedDict()

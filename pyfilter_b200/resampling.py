@@ -1,4 +1,4 @@
-"""``pyfilter.resampling`` on the device (reference resampling.py:8-65).
+"""``pyfilter.resampling`` on the device (reference resampling.py:8-105).
 
 ``systematic`` returns ancestors that are bit-identical to the reference's CPU path
 (``torch.cumsum`` -> ``torch.searchsorted``) for the same normalised weights and offsets ``u``; ``multinomial`` is
@@ -74,6 +74,24 @@ def multinomial(w: torch.Tensor, normalized: bool = False, U: Optional[torch.Ten
     return out[0] if w.dim() == 1 else out.moveaxis(0, 1)
 
 
-def residual(w: torch.Tensor, normalized: bool = False) -> torch.Tensor:
-    """Out of scope (1-D only in the reference, not on the hot path)."""
-    raise NotImplementedError("residual resampling is not part of the B200 hot path")
+def residual(w: torch.Tensor, normalized: bool = False, U: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Performs residual resampling (reference resampling.py:68-105): ``floor(N W_j)`` copies of particle ``j`` in particle order,
+    then multinomial draws on the fractional parts.  One column only, like the reference.  ``U`` (float64, draw order) injects the
+    uniforms of the multinomial part; otherwise they come from Philox."""
+    if w.dim() > 1:
+        raise NotImplementedError("Not implemented for multidimensional arrays!")  # resampling.py:78-79
+    from .utils import normalize
+
+    W = _check_weights(w) if normalized else normalize(w)
+    n = W.shape[0]
+    out = torch.empty(n, device=W.device, dtype=torch.int64)
+    lib = _lib.load_library()
+    U_ptr = None
+    if U is not None:
+        U_full = torch.zeros(n, dtype=torch.float64, device=W.device)
+        U = torch.as_tensor(U, dtype=torch.float64, device=W.device).reshape(-1)
+        U_full[: U.numel()] = U
+        U_ptr = U_full.data_ptr()
+    seed = 0 if U is not None else _next_seed()
+    _lib.check(lib.smcb_residual(W.data_ptr(), n, 1, W.stride(0), 0, U_ptr, seed, out.data_ptr(), 1, n, _lib.current_stream()))
+    return out

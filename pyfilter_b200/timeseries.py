@@ -230,7 +230,7 @@ class LinearStateSpaceModel(StateSpaceModel):
             raise NotImplementedError(f"{type(hidden).__name__} with linear-Gaussian observations is not in the compiled model zoo")
         if mid == MODEL_LORENZ63_EM:
             a, s = parameters
-            super().__init__(hidden, mid, (a, s), torch.Size([2]), observe_every_step, linear=False)
+            super().__init__(hidden, mid, (a, s), torch.Size([2]), observe_every_step, linear=True)   # y = a (x1, x3) + s nu (lorenz.ipynb:105-117)
             return
         if len(event_shape) != 0:
             raise NotImplementedError("only scalar linear-Gaussian observations are in the compiled zoo")

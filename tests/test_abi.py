@@ -59,7 +59,7 @@ def test_unsupported_combinations_raise():
     import pyfilter_b200 as pf
 
     with pytest.raises(NotImplementedError):
-        pf.resampling.residual(torch.zeros(4))
+        pf.resampling.residual(torch.zeros(4, 2))  # one column only, like the reference (resampling.py:78-79)
     with pytest.raises(NotImplementedError):
         pf.filters.particle.APF(pf.timeseries.build("sv_ar1"), 100, resampling=lambda w: w)
 
