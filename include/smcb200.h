@@ -99,6 +99,9 @@ int smcb_filter_destroy(smcb_filter* f);
 /* new parameter values for an existing handle (SMC2 / PMMH rebuild the model per theta: filters/base.py:75-83) */
 int smcb_filter_set_params(smcb_filter* f, const float* params_host, int32_t n_raw_params, int32_t param_cols, void* stream);
 int smcb_filter_info(smcb_filter* f, smcb_info* out);
+/* a new Philox key for the coming moves (the proposal filter of a PMMH sweep re-filters the same data again and again:
+ * inference/batch/mcmc/utils.py:52-55 - every run needs its own random stream) */
+int smcb_filter_set_seed(smcb_filter* f, uint64_t seed);
 
 /* ParticleFilter.initialize (filters/particle/base.py:87-103): x_0 ~ p_0, log w = 0, ll = 0, prev_inds = arange; history row 0 */
 int smcb_filter_initialize(smcb_filter* f, void* stream);

@@ -313,6 +313,12 @@ extern "C" int smcb_filter_set_params(smcb_filter* f, const float* params_host, 
   return upload_params(f, params_host, n_raw, cols, (cudaStream_t)stream);
 }
 
+extern "C" int smcb_filter_set_seed(smcb_filter* f, uint64_t seed) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  f->cfg.seed = seed;
+  return SMCB_OK;
+}
+
 extern "C" int smcb_filter_info(smcb_filter* f, smcb_info* o) {
   if (!f || !o) return fail(SMCB_EINVAL, "null argument");
   o->particles = f->n; o->ld = f->ld; o->batch = f->B; o->state_dim = f->D; o->obs_dim = f->OD;

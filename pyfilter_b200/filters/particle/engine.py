@@ -191,6 +191,18 @@ class Engine:
         yp = yo[..., : self.N].permute(0, 3, 2, 1).contiguous().reshape((steps, self.N) + tuple(self.batch_shape) + obs_event)
         return xp, yp
 
+    def set_params(self, model: StateSpaceModel):
+        """New parameter values for the same compiled model (SMC2 / PMMH rebuild the model per theta: filters/base.py:75-83)."""
+        params = model.parameter_matrix(self.B)
+        self._params_keepalive = params
+        _lib.check(self.lib.smcb_filter_set_params(self.handle, C.cast(params.data_ptr(), C.POINTER(C.c_float)), params.shape[0], params.shape[1],
+                                                   _lib.current_stream()))
+        self.model = model
+        self.stamp += 1
+
+    def set_seed(self, seed: int):
+        _lib.check(self.lib.smcb_filter_set_seed(self.handle, int(seed) & (2**64 - 1)))
+
     def set_ess_threshold(self, relative: float):
         _lib.check(self.lib.smcb_filter_set_ess_threshold(self.handle, float(relative)))
 

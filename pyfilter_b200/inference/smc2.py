@@ -1,0 +1,224 @@
+"""SMC2 (Chopin et al.) on the resident batch of filters - reference inference/sequential/smc2.py:53-65 (the step), its particle
+Metropolis-Hastings rejuvenation kernel inference/sequential/kernels/mh.py:52-140 and inference/batch/mcmc/utils.py:14-77 (one PMMH
+sweep), the symmetric proposal inference/batch/mcmc/proposals/symmetric_mh.py:13-23 with inference/utils.py:42-76, and the state
+bookkeeping of inference/sequential/state.py:35-44.
+
+What runs where: the theta-particles are the COLUMNS of one ``smcb_filter`` handle (``set_batch_shape``, filters/base.py:93-119); a
+step is one fused move of all columns (csrc/column.cuh or csrc/move.cuh); theta-resampling and the accept/reject exchange permute /
+copy columns of the resident state on the device (``smcb_filter_resample_columns`` / ``smcb_filter_exchange_columns``, csrc/plugin.cuh);
+the proposal filter of a PMMH sweep is a second handle that re-filters the whole data with the candidate parameters
+(``smcb_filter_set_params``).  The theta-level arithmetic itself - ``(B,)`` weights, the ``(B, p)`` parameter cloud, a ``p x p``
+Cholesky factor - is torch on the device; the theta-level resampling and normalisation go through ``pyfilter_b200.resampling`` /
+``pyfilter_b200.utils`` like the state level.  One host synchronisation per step (the ESS test), as in the reference (smc2.py:62)."""
+import math
+from typing import Callable, Dict, List, Optional
+
+import torch
+
+from .. import _lib, resampling as _resampling, utils as _utils
+from ..filters.particle import APF
+from ..filters.particle.engine import Engine
+from .prior import ParameterContext, Prior
+
+
+class TooManyIncreases(Exception):
+    pass
+
+
+# ---- theta-level pieces (each one callable on its own: tests/test_gpu_smc2.py compares them with oracle/smc2_oracle.py) -------------
+def calc_mean_chol(x: torch.Tensor, w: torch.Tensor):
+    """``inference/utils.py:42-58``: weighted mean and the Cholesky factor of the weighted covariance of the rows of ``x`` ``(B, p)``;
+    a failed factorisation falls back to the diagonal."""
+    mean = w @ x
+    centralized = x - mean
+    cov = (w * centralized.t()).matmul(centralized)
+    chol, info = torch.linalg.cholesky_ex(cov)
+    if bool((info > 0).any()):
+        chol = cov.diag().sqrt().diag()
+    return mean, chol
+
+
+def construct_mvn(x: torch.Tensor, w: torch.Tensor, scale: float = 1.0):
+    """``inference/utils.py:61-76``: ``(mean, scale_tril)`` of the multivariate normal fitted to the weighted samples."""
+    mean, chol = calc_mean_chol(x, w)
+    return mean, scale * chol
+
+
+def mvn_sample(mean: torch.Tensor, scale_tril: torch.Tensor, eps: torch.Tensor) -> torch.Tensor:
+    """``MultivariateNormal.sample``: ``mean + scale_tril @ eps`` for every row of ``eps`` ``(B, p)``."""
+    return mean + eps @ scale_tril.t()
+
+
+def mvn_log_prob(mean: torch.Tensor, scale_tril: torch.Tensor, x: torch.Tensor) -> torch.Tensor:
+    """``MultivariateNormal(mean, scale_tril=...).log_prob(x)`` for the rows of ``x``."""
+    p = mean.shape[0]
+    z = torch.linalg.solve_triangular(scale_tril, (x - mean).t(), upper=False)
+    return -0.5 * (z * z).sum(0) - scale_tril.diagonal().log().sum() - 0.5 * p * math.log(2.0 * math.pi)
+
+
+def pmmh_accept(diff_logl: torch.Tensor, diff_prior: torch.Tensor, diff_prop: torch.Tensor, u: torch.Tensor) -> torch.Tensor:
+    """``inference/batch/mcmc/utils.py:66-67``: accept where ``log u < diff_prop + diff_prior + diff_logl``."""
+    return u.log() < (diff_prop + diff_prior + diff_logl)
+
+
+class SMC2State:
+    """``SMC2State`` (inference/sequential/state.py:10-95): theta log-weights, the ESS history, the parsed observations."""
+
+    def __init__(self, weights: torch.Tensor, engine: Engine):
+        self.w = weights
+        self.engine = engine
+        self.ess: List[float] = [float(_utils.get_ess(weights))]
+        self.parsed_data: List[torch.Tensor] = []
+        self.current_iteration = 0
+        self.rejuvenations = 0
+        self.acceptance: List[float] = []
+
+    @property
+    def loglikelihood(self) -> torch.Tensor:
+        return self.engine.raw(_lib.PTR_LL_TOTAL, (self.engine.B,))
+
+    def normalized_weights(self) -> torch.Tensor:
+        return _utils.normalize(self.w)
+
+
+class SMC2:
+    def __init__(self, model_builder: Callable[[Dict[str, torch.Tensor]], object], priors: Dict[str, Prior], particles: int,
+                 state_particles: int, filter_cls=APF, proposal=None, threshold: float = 0.2, num_steps: int = 1,
+                 acceptance_threshold: float = 0.2, max_increases: int = 5, seed: Optional[int] = None, max_observations: int = 1024,
+                 resampling=_resampling.systematic):
+        self._builder = model_builder
+        self.context = ParameterContext(priors)
+        self.particles = torch.Size([int(particles)])
+        self._n_state = int(state_particles)
+        self._filter_cls, self._proposal = filter_cls, proposal
+        self._threshold = float(threshold)            # ConstantThreshold (inference/sequential/threshold.py)
+        self._n_steps = int(num_steps)
+        self._acceptance_threshold = float(acceptance_threshold)
+        self._max_increases, self._increases = int(max_increases), 0
+        self._seed = seed
+        self._rows = int(max_observations) + 2
+        self._resampler = resampling                    # kernels/base.py:15-23
+        self._filter = None
+        self._proposal_filter = None
+        self._y_dev: torch.Tensor = None
+        self._gen = torch.Generator().manual_seed(seed if seed is not None else int(torch.randint(0, 2**62, (1,)).item()))
+
+    # ---- filters
+    def _make_filter(self, context: ParameterContext, n_state: int, salt: int):
+        model = self._builder(context.constrained())
+        f = self._filter_cls(model, n_state, proposal=self._proposal.copy() if self._proposal is not None else None,
+                             seed=None if self._seed is None else self._seed + 7919 * salt)
+        f.set_batch_shape(self.particles)
+        return f, f._get_engine(self._rows)
+
+    def _draw_seed(self) -> int:
+        return int(torch.randint(0, 2**62, (1,), generator=self._gen).item())
+
+    def initialize(self) -> SMC2State:
+        """``SequentialParticleAlgorithm.initialize`` (inference/sequential/base.py:56-67) + ``SMC2.initialize`` (smc2.py:48-51)."""
+        B = int(self.particles[0])
+        self.context.initialize_parameters(B, self._gen)
+        self._filter, e = self._make_filter(self.context, self._n_state, 0)
+        e.initialize()
+        self._y_dev = torch.full((self._rows, e.OD), float("nan"), device="cuda", dtype=torch.float32)
+        return SMC2State(torch.zeros(B, device="cuda"), e)
+
+    # ---- one observation (smc2.py:53-65)
+    def step(self, y: torch.Tensor, state: SMC2State) -> SMC2State:
+        e = state.engine
+        t = len(state.parsed_data)
+        if t + 2 > self._rows:
+            raise ValueError("more observations than `max_observations`")
+        yt = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
+        state.parsed_data.append(yt)
+        self._y_dev[t] = yt.to("cuda")
+        e.set_observations(self._y_dev[: t + 1], 0)
+        e.run(1)
+        state.w += e.raw(_lib.PTR_LL, (e.B,))                        # SequentialAlgorithmState.append (state.py:35-44)
+        ess = float(_utils.get_ess(state.w))
+        state.ess.append(ess)
+        any_nans = not bool(torch.isfinite(state.w).all())
+        if ess < self._threshold * self.particles[0] or any_nans:
+            state = self.rejuvenate(state)
+        state.current_iteration += 1
+        return state
+
+    def fit(self, y: torch.Tensor) -> SMC2State:
+        state = self.initialize()
+        for yt in torch.as_tensor(y):
+            state = self.step(yt, state)
+        return state
+
+    # ---- ParticleMetropolisHastings.update (kernels/mh.py:52-108)
+    def rejuvenate(self, state: SMC2State) -> SMC2State:
+        ctx, e = self.context, state.engine
+        B = int(self.particles[0])
+        W = state.normalized_weights()
+        indices = self._resampler(W, normalized=True)
+        kernel = construct_mvn(ctx.stack_parameters(), W, scale=1.1)      # SymmetricMH.build (symmetric_mh.py:13-23)
+        ctx.resample(indices)
+        e.resample_columns(indices, entire_history=True)                  # state.filter_state.resample(indices)
+        T = len(state.parsed_data)
+        if self._proposal_filter is None or self._proposal_filter[1].N != e.N:
+            self._proposal_filter = self._make_filter(ctx, e.N, 1 + self._increases)
+        sub_context = ctx.make_new()
+        pe = self._proposal_filter[1]
+        acceptance_rate = 0.0
+        for i in range(self._n_steps):
+            accepted = self._run_pmmh(ctx, state, kernel, pe, sub_context, T)
+            acceptance_rate = (float(accepted.float().mean()) + i * acceptance_rate) / (i + 1)
+            if acceptance_rate < self._acceptance_threshold:
+                state.acceptance.append(acceptance_rate)
+                return self._increase_states(state)
+        state.acceptance.append(acceptance_rate)
+        e.set_params(self._builder(ctx.constrained()))                    # filter_.initialize_model(context)
+        state.w.fill_(0.0)
+        state.rejuvenations += 1
+        return state
+
+    # ---- run_pmmh (inference/batch/mcmc/utils.py:14-77)
+    def _run_pmmh(self, ctx: ParameterContext, state: SMC2State, kernel, pe: Engine, sub_context: ParameterContext, T: int) -> torch.Tensor:
+        B = int(self.particles[0])
+        mean, scale_tril = kernel
+        eps = torch.randn(B, mean.shape[0], generator=self._gen).to("cuda")
+        rvs = mvn_sample(mean, scale_tril, eps)
+        sub_context.unstack_parameters(rvs)
+        pe.set_params(self._builder(sub_context.constrained()))
+        pe.set_seed(self._draw_seed())                                   # a fresh random stream for every re-filtering
+        pe.initialize()
+        pe.set_observations(self._y_dev[:T], 0)
+        pe.run(T)
+        new_ll = pe.raw(_lib.PTR_LL_TOTAL, (B,))
+        diff_logl = new_ll - state.loglikelihood
+        diff_prior = sub_context.eval_priors() - ctx.eval_priors()
+        uniform = torch.full((B,), 1.0 / B, device="cuda")               # state.replicate(new_res): zero log-weights
+        new_kernel = construct_mvn(sub_context.stack_parameters(), uniform, scale=1.1)
+        diff_prop = mvn_log_prob(*new_kernel, ctx.stack_parameters()) - mvn_log_prob(mean, scale_tril, rvs)
+        u = torch.rand(B, generator=self._gen).to("cuda")
+        accepted = pmmh_accept(diff_logl, diff_prior, diff_prop, u)
+        state.engine.exchange_columns(pe, accepted)                       # state.filter_state.exchange(new_res, accepted)
+        ctx.exchange(sub_context, accepted)
+        return accepted
+
+    # ---- _increase_states (kernels/mh.py:110-140): twice the state particles, re-filter, weights = change of the log-likelihoods
+    def _increase_states(self, state: SMC2State) -> SMC2State:
+        self._increases += 1
+        if self._increases > self._max_increases:
+            raise TooManyIncreases(f"Configuration only allows {self._max_increases}!")
+        old_ll = state.loglikelihood.clone()
+        T = len(state.parsed_data)
+        self._filter, e = self._make_filter(self.context, 2 * state.engine.N, 100 + self._increases)
+        e.initialize()
+        e.set_observations(self._y_dev[:T], 0)
+        e.run(T)
+        weight = e.raw(_lib.PTR_LL_TOTAL, (e.B,)) - old_ll
+        res = SMC2State(weight.clone(), e)
+        res.ess, res.parsed_data, res.current_iteration = state.ess, state.parsed_data, state.current_iteration
+        res.rejuvenations, res.acceptance = state.rejuvenations, state.acceptance
+        self._proposal_filter = None
+        return res
+
+    # ---- summaries
+    def posterior_mean(self, state: SMC2State) -> Dict[str, torch.Tensor]:
+        W = state.normalized_weights()
+        return {k: (W * v).sum() for k, v in self.context.constrained().items()}

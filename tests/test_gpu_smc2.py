@@ -1,0 +1,140 @@
+"""GPU tests of SMC2 on the resident batch of filters (pyfilter_b200/inference/smc2.py; reference inference/sequential/smc2.py:53-65,
+kernels/mh.py:52-140, batch/mcmc/utils.py:14-77): the theta-level pieces against the reference-generated golden vectors, and the
+algorithm end to end."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import smc2_oracle as S
+from oracle import smc_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "smc2_theta.npz")
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import pyfilter_b200 as pf
+
+    assert torch.cuda.is_available()
+    return pf
+
+
+def _builder(params):
+    from pyfilter_b200 import timeseries as ts
+
+    return ts.build("sine_em", gamma=params["gamma"], sigma=params["sigma"])
+
+
+def _priors():
+    from pyfilter_b200.inference import LogNormal, Normal
+
+    return {"gamma": Normal(0.0, 1.0), "sigma": LogNormal(0.0, 0.5)}
+
+
+@pytest.mark.parametrize("name", ["b64_p2", "b1024_p2", "b256_p3"])
+def test_theta_level_pieces_vs_reference_golden(pf, name):
+    from pyfilter_b200.inference import smc2 as M
+
+    z = np.load(GOLDEN)
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    x, lw = g[f"{name}_x"].cuda(), g[f"{name}_lw"].cuda()
+    W = pf.utils.normalize(lw.clone())
+    assert torch.allclose(W.cpu(), g[f"{name}_W"], rtol=3e-6, atol=1e-9)
+    assert torch.allclose(pf.utils.get_ess(lw.clone()).cpu(), g[f"{name}_ess"], rtol=1e-5)
+    mean, tril = M.construct_mvn(x, g[f"{name}_W"].cuda(), scale=1.1)
+    assert torch.allclose(mean.cpu(), g[f"{name}_mean"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(tril.cpu(), g[f"{name}_tril"], rtol=1e-4, atol=1e-5)
+    lp = M.mvn_log_prob(g[f"{name}_mean"].cuda(), g[f"{name}_tril"].cuda(), g[f"{name}_pts"].cuda())
+    assert torch.allclose(lp.cpu(), g[f"{name}_lp"], rtol=1e-5, atol=1e-3)
+    # theta-level resampling: the same systematic operator as the state level, bit-exact for the reference's weights and offset
+    idx = pf.resampling.systematic(g[f"{name}_W"].cuda(), normalized=True, u=g[f"{name}_u"].reshape(-1).cuda())
+    assert torch.equal(idx.cpu(), g[f"{name}_idx"])
+    eps = torch.randn(x.shape, generator=torch.Generator().manual_seed(1))
+    rv = M.mvn_sample(mean, tril, eps.cuda()).cpu()
+    assert torch.allclose(rv, g[f"{name}_mean"] + eps @ g[f"{name}_tril"].t(), rtol=1e-4, atol=1e-4)
+
+
+def test_priors_and_acceptance_vs_oracle(pf):
+    from pyfilter_b200.inference import LogNormal, Normal, ParameterContext
+    from pyfilter_b200.inference import smc2 as M
+
+    z = np.load(GOLDEN)
+    u = torch.from_numpy(z["prior_u"]).cuda()
+    assert torch.allclose(Normal(0.0, 1.0).eval_unconstrained(u).cpu(), torch.from_numpy(z["prior_normal"]), rtol=1e-5, atol=1e-5)
+    assert torch.allclose(LogNormal(0.0, 0.5).eval_unconstrained(u).cpu(), torch.from_numpy(z["prior_lognormal"]), rtol=1e-5, atol=1e-5)
+    ctx = ParameterContext(_priors()).initialize_parameters(400, torch.Generator().manual_seed(3))
+    c = ctx.constrained()
+    assert (c["sigma"] > 0).all() and ctx.stack_parameters().shape == (400, 2)
+    ref = S.normal_unconstrained_log_prob(ctx.values[:, 0].cpu(), 0.0, 1.0) + S.normal_unconstrained_log_prob(ctx.values[:, 1].cpu(), 0.0, 0.5)
+    assert torch.allclose(ctx.eval_priors().cpu(), ref, rtol=1e-5, atol=1e-5)
+    gen = torch.Generator().manual_seed(4)
+    a, b, c3 = (torch.randn(400, generator=gen) for _ in range(3))
+    uu = torch.rand(400, generator=gen)
+    got = M.pmmh_accept(a.cuda(), b.cuda(), c3.cuda(), uu.cuda()).cpu()
+    assert torch.equal(got, uu.log() < (c3 + b + a))
+
+
+def test_smc2_without_rejuvenation_is_the_batched_filter(pf):
+    """threshold = 0: the theta log-weights are the running log-likelihoods of the columns (state.py:43) and nothing else happens."""
+    from pyfilter_b200.inference import SMC2
+
+    torch.manual_seed(1)
+    _, y = O.build_model("sine_em").simulate(30)
+    alg = SMC2(_builder, _priors(), particles=32, state_particles=512, threshold=0.0, seed=11, max_observations=64)
+    state = alg.fit(y)
+    assert state.rejuvenations == 0 and len(state.ess) == 31 and state.current_iteration == 30
+    assert torch.allclose(state.w, state.loglikelihood, rtol=1e-5, atol=1e-4)
+    assert abs(state.ess[-1] - float(S.get_ess(state.w.cpu()))) < 1e-2 * state.ess[-1]
+
+
+def test_smc2_rejuvenation_end_to_end(pf):
+    """Data from sigma = 2 under a LogNormal(0, 0.5) prior (mean 1.13): the ESS falls, the PMMH kernel fires, the posterior moves to the
+    truth; after a rejuvenation the weights are reset (mh.py:107) and the filters' parameters are the accepted theta."""
+    from pyfilter_b200.filters.particle import proposals
+    from pyfilter_b200.inference import SMC2
+
+    torch.manual_seed(2)
+    truth = O.build_model("sine_em", dict(gamma=0.5, sigma=2.0))
+    _, y = truth.simulate(60)
+    # the optimal-kernel proposal: with an observation noise of 0.1 against a state noise of 0.6 the bootstrap likelihood estimate is too
+    # noisy for PMMH (std 3.5 over 14 observations at 4096 particles - the same on the CPU oracle), the README example uses it too
+    alg = SMC2(_builder, _priors(), particles=128, state_particles=256, proposal=proposals.LinearGaussianObservations(), threshold=0.5,
+               seed=5, max_observations=64)
+    state = alg.initialize()
+    fired_at = []
+    for t, yt in enumerate(y):
+        before = state.rejuvenations
+        state = alg.step(yt, state)
+        if state.rejuvenations > before:
+            fired_at.append(t)
+            assert float(state.w.abs().max()) == 0.0
+    assert len(fired_at) >= 1, state.ess
+    assert all(0.0 <= a <= 1.0 for a in state.acceptance) and max(state.acceptance) > 0.0
+    assert torch.isfinite(state.w).all() and torch.isfinite(state.loglikelihood).all()
+    post = alg.posterior_mean(state)
+    assert 1.4 < float(post["sigma"]) < 2.8, post
+    # the accepted parameters are the ones the filters run with: a fresh batched filter with the posterior cloud reproduces finite likelihoods
+    assert alg.context.values.shape == (128, 2)
+
+
+def test_smc2_particle_doubling(pf):
+    """An acceptance rate below the threshold doubles the state particles and re-filters (mh.py:110-140): forced here with an
+    acceptance threshold above 1."""
+    from pyfilter_b200.inference import SMC2
+    from pyfilter_b200.inference.smc2 import TooManyIncreases
+
+    torch.manual_seed(3)
+    _, y = O.build_model("sine_em", dict(gamma=0.0, sigma=1.5)).simulate(25)
+    alg = SMC2(_builder, _priors(), particles=64, state_particles=128, threshold=0.9, acceptance_threshold=1.01, max_increases=2, seed=7,
+               max_observations=32)
+    state = alg.initialize()
+    sizes = []
+    with pytest.raises(TooManyIncreases):
+        for yt in y:
+            state = alg.step(yt, state)
+            sizes.append(state.engine.N)
+    assert sizes[-1] == 512 and set(sizes) <= {128, 256, 512}
+    assert torch.isfinite(state.w).all()
