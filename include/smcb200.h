@@ -117,7 +117,10 @@ int smcb_filter_set_observations(smcb_filter* f, const float* y_dev, int32_t cou
 int smcb_filter_run(smcb_filter* f, int32_t steps, void* stream);
 
 /* the online pattern of SMC2 / NESS (inference/sequential/smc2.py:53-65, ness.py:56): `steps` launches of ONE move each; when an exchange
- * is attached (below) every move is followed by the reader of that exchange */
+ * is attached (below) every move also gathers that exchange - inside the move's own launch for the resident column kernel (the block
+ * that finishes a rank's move last waits for the other ranks' values), otherwise with the reader kernel behind it.  COLLECTIVE: every
+ * rank of the batch must run this call concurrently (one process per GPU); handles of several "ranks" driven from ONE stream must use
+ * smcb_filter_run + smcb_filter_exchange_wait instead. */
 int smcb_filter_run_stepwise(smcb_filter* f, int32_t steps, void* stream);
 
 /* measurement aid: runs `steps` moves like smcb_filter_run with CUDA events around every kernel group and returns the summed

@@ -22,6 +22,12 @@ struct ColumnArgs {
   float* u_out;         // optional dump of the offsets used (B)
   float* w_out;         // optional dump of the normalised resampling weights (B, ld)
   int32_t quantize;     // must be 1: rounding-free weights
+  float* xch_out;           // with an exchange attached: the block that finishes LAST on this rank also plays the reader - it polls this rank's
+  int32_t* xch_ticket;      // buffer until the values of every column of the batch (all ranks) have arrived and writes them out densely
+  int32_t xch_rank;         // ((2, total) floats) - no reader kernel behind the move (one launch per move in the online loop)
+  int32_t preweight_first;  // APF: the look-ahead of the FIRST move was not folded into the stored weights by the previous launch (online
+                            // use: y_{t+1} was unknown then) - the block evaluates apf.py:27-29 itself before the first move instead of
+                            // the host launching preweight_kernel + finalize_kernel in front (two launches per move saved)
 };
 
 template <int NT, int D>
@@ -82,6 +88,47 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
     }
   }
   __syncthreads();
+
+  if (ALG == SMCB_ALG_APF && c.preweight_first) {
+    // rw = g(y_t | x_{t-1}) + lw and its normalisers, exactly what the folded look-ahead of a previous move would have left: the same
+    // pre_weight function, the same per-thread accumulation order and the same block reduction (bit-identical to a batch run)
+    float y0[OD];
+    const bool observed0 = st_load_obs<OD>(c.y, y0);
+    StepAcc1 r2; r2.init();
+    if (observed0) {
+#pragma unroll
+      for (int g = 0; g < ITEMS / 4; ++g) {
+        const int32_t i0 = gbase + 4 * g;
+        if (i0 >= n) continue;
+        float rwn[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float xk[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) xk[d] = ck_xs[d * RS_TILE + i0 + q];
+          rwn[q] = st_sanitize(__fadd_rn(Proposal<MODEL, PROP>::pre_weight(y0, xk, Ps), lw[4 * g + q]));
+          rw[4 * g + q] = rwn[q];
+          if (i0 + q >= n) rwn[q] = -INFINITY;
+        }
+        r2.add4(rwn, one4);
+      }
+    }
+    SoftAcc<1 + 2 * D> A0; A0.init();
+    SoftAcc<1> Q0, R2, R30; Q0.init(); R30.init();
+    r2.to_softacc(R2);
+    softacc4_block_reduce<1 + 2 * D, NT, false>(A0, Q0, R2, R30, cs.f4);
+    if (tid == 0) {
+      ColStats stp = cs.st;
+      if (observed0) {
+        stp.m_rw = R2.m; stp.z_rw = R2.s[0]; stp.inv_z_rw = 1.0f / R2.s[0];
+        stp.ll_aux = logf(R2.s[0]) + (R2.m - stp.m_lw) - logf(stp.z_lw);   // log sum W exp(g), W = softmax(lw)  (apf.py:44)
+      }
+      stp.resample = observed0 ? 1 : 0;
+      stp.fold_valid = 1;
+      cs.st = stp;
+    }
+    __syncthreads();
+  }
 
   for (int k = 0; k < c.steps; ++k) {
     const int t = a.t_host + k;
@@ -276,5 +323,26 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
             *reinterpret_cast<const float4*>(ck_xs + d * RS_TILE + gbase + 4 * v);
     }
     if (col == 0 && tid == 0) a.ctrl->t = t1;
+  }
+  if (a.xch.seq && c.xch_out) {   // the last block of this rank gathers the exchange (its own rank's values were published above)
+    __shared__ int last_block;
+    if (tid == 0) {
+      const int old = atomicAdd(c.xch_ticket, 1);
+      last_block = (old == (int)gridDim.x - 1);
+      if (last_block) *c.xch_ticket = 0;
+    }
+    __syncthreads();
+    if (last_block) {
+      const unsigned long long* base = a.xch.peer[c.xch_rank] + (int64_t)(a.xch.seq & 1u) * 2 * a.xch.total;
+      for (int i = tid; i < 2 * a.xch.total; i += NT) {
+        unsigned long long v;
+        for (;;) {
+          asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(base + i) : "memory");
+          if ((uint32_t)(v >> 32) == a.xch.seq) break;
+          __nanosleep(100);
+        }
+        c.xch_out[i] = __uint_as_float((uint32_t)v);
+      }
+    }
   }
 }

@@ -185,6 +185,9 @@ struct smcb_filter {
   uint32_t xch_seq = 0;       // exchanges published so far
   int xch_rank = 0;
   float* xch_out = nullptr;   // (2, total) dense copy made by smcb_filter_exchange_wait
+  int32_t* xch_ticket = nullptr;   // column kernel: elects the block that gathers the exchange inside the move's own launch
+  uint32_t xch_inline_seq = 0;     // the exchange that launch has already gathered into xch_out
+  bool want_inline = false;        // set by smcb_filter_run_stepwise: the ranks run concurrently, a block may wait for the peers' values
 };
 
 template <typename T>
@@ -213,7 +216,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out, f->xch_ticket};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -699,13 +702,14 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   if (t - f->y_base < 0 || t + steps - 1 - f->y_base >= f->y_count || !f->y_dev) return fail(SMCB_ESTATE, "no observation set for this move");
   StepArgs a = make_args(f);
   a.t_host = t;
-  if (apf && !f->folded_for_next) {  // apf.py:27-29 evaluated now because the previous move could not fold it
-    launch_preweight(f, a, s);
-    launch_finalize(f, a, FIN_PREWEIGHT, s);
-  }
   if (f->xch.peer[0]) a.xch.seq = ++f->xch_seq;
   ColumnArgs c;
   memset(&c, 0, sizeof(c));
+  if (a.xch.seq && f->want_inline && f->xch_out && f->xch_ticket && !getenv("SMCB_NO_INLINE_EXCHANGE")) {
+    c.xch_out = f->xch_out; c.xch_ticket = f->xch_ticket; c.xch_rank = f->xch_rank;
+    f->xch_inline_seq = a.xch.seq;
+  }
+  c.preweight_first = (apf && !f->folded_for_next) ? 1 : 0;  // apf.py:27-29 evaluated by the block itself: the previous launch could not fold it
   c.s = a;
   c.s.lw_out = f->lwbuf[(t + steps) & 1]; c.s.rw_out = f->rwbuf[(t + steps) & 1];
   c.steps = steps;
@@ -751,11 +755,13 @@ extern "C" int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* 
 extern "C" int smcb_filter_run_stepwise(smcb_filter* f, int32_t steps, void* stream) {
   if (!f) return fail(SMCB_EINVAL, "null handle");
   for (int k = 0; k < steps; ++k) {
-    int rc = smcb_filter_run(f, 1, stream);
+    f->want_inline = true;   // every rank of the batch runs this loop at the same time (one process per GPU): the block that finishes a
+    int rc = smcb_filter_run(f, 1, stream);   // rank's move last may wait, inside the launch, for the values of the other ranks
+    f->want_inline = false;
     if (rc) return rc;
     if (f->xch.peer[0]) {
       float* out = nullptr;
-      rc = smcb_filter_exchange_wait(f, &out, stream);
+      rc = smcb_filter_exchange_wait(f, &out, stream);   // (no launch when the move has gathered the exchange itself)
       if (rc) return rc;
     }
   }
@@ -828,6 +834,7 @@ extern "C" int smcb_filter_attach_exchange(smcb_filter* f, const uint64_t* peer_
   x.world = world; x.total = total_columns; x.lo = first_column; x.seq = 0;
   if (f->xch_out) { cudaFree(f->xch_out); f->xch_out = nullptr; }
   CU(cudaMalloc((void**)&f->xch_out, sizeof(float) * 2 * (size_t)total_columns));
+  if (!f->xch_ticket) CU(dalloc(&f->xch_ticket, (size_t)1));
   f->xch = x; f->xch_seq = 0; f->xch_rank = rank;
   return SMCB_OK;
 }
@@ -835,6 +842,10 @@ extern "C" int smcb_filter_attach_exchange(smcb_filter* f, const uint64_t* peer_
 extern "C" int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* stream) {
   if (!f || !out_dev) return fail(SMCB_EINVAL, "null argument");
   if (!f->xch.peer[0] || !f->xch_seq) return fail(SMCB_ESTATE, "no exchange attached or nothing published yet");
+  if (f->xch_inline_seq == f->xch_seq) {   // the column kernel's last block has gathered this exchange inside the move's launch
+    *out_dev = f->xch_out;
+    return SMCB_OK;
+  }
   unsigned long long* mine = f->xch.peer[f->xch_rank];   // the buffer the peers (and this rank) stored into
   exchange_wait_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(mine, f->xch.total, f->xch_seq, f->xch_out, f->wd ? f->wd + 3 : nullptr);
   f->launches++;
