@@ -36,6 +36,15 @@ def main():
         cases[f"{name}_pts"], cases[f"{name}_lp"] = pts.numpy(), mvn.log_prob(pts).numpy()
         cases[f"{name}_ess"] = get_ess(lw.clone()).numpy()
         cases[f"{name}_u"], cases[f"{name}_idx"] = u.numpy(), idx.numpy()
+    # NESS: the jittering kernels' fit (location, scale) on a weighted cloud and theta-indices (jittering.py:140-225)
+    from pyfilter.inference.sequential.kernels.jittering import ConstantKernel, LiuWestShrinkage, NonShrinkingKernel, ShrinkingKernel
+
+    x = cases["b1024_p2_x"]; x = torch.from_numpy(x)
+    W = torch.from_numpy(cases["b1024_p2_W"]); idx = torch.from_numpy(cases["b1024_p2_idx"])
+    for kname, k in (("shrinking", ShrinkingKernel()), ("nonshrinking", NonShrinkingKernel()), ("liuwest", LiuWestShrinkage(0.98)),
+                     ("constant", ConstantKernel(0.1))):
+        loc, sc = k.fit(x.clone(), W.clone(), idx)
+        cases[f"jit_{kname}_loc"], cases[f"jit_{kname}_scale"] = loc.numpy(), torch.as_tensor(sc).float().numpy()
     uvals = torch.randn(500) * 2.0
     pn, pl = Normal(0.0, 1.0), LogNormal(0.0, 0.5)
     cases["prior_u"] = uvals.numpy()

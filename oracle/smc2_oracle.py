@@ -67,3 +67,46 @@ def normal_unconstrained_log_prob(u: torch.Tensor, loc: float, scale: float) -> 
     """``PriorMixin.eval_prior(x, constrained=False)`` (inference/prior.py:81-90) for ``Normal`` (identity bijection) and for
     ``LogNormal`` (``exp`` bijection: the unconstrained prior of ``log theta`` is ``Normal(loc, scale)``)."""
     return -((u - loc) ** 2) / (2.0 * scale * scale) - math.log(scale) - 0.5 * math.log(2.0 * math.pi)
+
+
+# ---- NESS: the jittering kernels (inference/sequential/kernels/jittering.py) -----------------------------------------------------------
+EPS = math.sqrt(torch.finfo(torch.float32).eps)   # constants.py
+
+
+def robust_var(x: torch.Tensor, w: torch.Tensor, mean: torch.Tensor = None) -> torch.Tensor:
+    """``jittering.py:49-83``."""
+    sort, sort_indices = x.sort(0)
+    cumulative_weights = w[sort_indices].cumsum(0)
+    low_indices = (cumulative_weights - 0.25).abs().argmin(0)
+    high_indices = (cumulative_weights - 0.75).abs().argmin(0)
+    iqr = (sort[high_indices].diag() - sort[low_indices].diag()) / 1.349
+    iqr2 = iqr**2
+    w = w.unsqueeze(-1)
+    if mean is None:
+        mean = (w * x).sum(0)
+    var = (w * (x - mean) ** 2).sum(0)
+    mask = iqr2 <= var
+    if mask.any():
+        var[mask] = iqr2[mask]
+    return var
+
+
+def jitter_fit(kind: str, x: torch.Tensor, w: torch.Tensor, indices: torch.Tensor, a: float = 0.98, scale: float = 0.1):
+    """``fit`` of ShrinkingKernel (jittering.py:148-158), NonShrinkingKernel (:166-173), LiuWestShrinkage (:197-203), ConstantKernel
+    (:222-225): the location and the scale of the jitter; ``jitter`` (:117-134) adds ``max(scale, EPS) * eps`` to the location."""
+    ess = 1.0 / (w * w).sum()
+    bw_fac = (1.59 * ess ** (-1 / 3)).clamp(EPS, 1 - EPS)
+    if kind == "shrinking":
+        mean = (w.unsqueeze(-1) * x).sum(0)
+        var = robust_var(x, w, mean)
+        beta = (1.0 - bw_fac**2).sqrt()
+        return (mean + beta * (x - mean))[indices], bw_fac * var.sqrt()
+    if kind == "nonshrinking":
+        return x[indices], bw_fac * robust_var(x, w).sqrt()
+    if kind == "liuwest":
+        mean = (w.unsqueeze(-1) * x).sum(0)
+        var = robust_var(x, w, mean)
+        return (x * a + (1 - a) * mean)[indices], math.sqrt(1 - a**2) * var.sqrt()
+    if kind == "constant":
+        return x[indices], torch.as_tensor(scale)
+    raise ValueError(kind)

@@ -26,12 +26,14 @@
 #include "step.cuh"
 #include "resample.cuh"
 
+#ifndef MV_NT
 #define MV_NT 256
+#endif
 #define MV_ITEMS 16
 #define MV_TILE (MV_NT * MV_ITEMS)            // == RS_TILE: the row pitch is a multiple of it
 #define MV_PER 20                             // window slots per thread in the "last mark" scan (largest tile class)
 #define MV_WIN (MV_NT * MV_PER)               // 5120 output slots per window
-// Tile classes.  A tile is MV_NT threads x ITEMS consecutive particles with ITEMS in {16, 12, 8, 4}; its window holds MV_NT * (ITEMS + 4)
+// Tile classes.  A tile is MV_NT threads x ITEMS consecutive particles with ITEMS in {16, 4}; its window holds MV_NT * (ITEMS + 4)
 // output slots.  A column is cut into t1 tiles of items1 particles per thread followed by tiles of items2 <= items1 (MoveArgs).  Measured
 // (tools/geom_sweep.py, profiles/README.md): a tile costs a fixed part worth about 8 particles per thread, and the machine behaves like a
 // throughput device once it is full - 4,000,000 particles as 977 tiles of 4096 take 40.6 us, as 592 x 4096 + 513 x 3072 ("two full waves")
@@ -49,7 +51,7 @@
 #ifndef SMCB_MV_MINB3
 #define SMCB_MV_MINB3 3
 #endif
-static_assert(MV_TILE == RS_TILE, "tiles of the move kernel are the resampling tiles");
+static_assert(RS_TILE % MV_TILE == 0, "the row pitch (a multiple of RS_TILE) is a multiple of the largest tile");
 
 struct MoveArgs {
   StepArgs s;                 // buffers, parameters, history; s.partials = per-tile records (B, tiles_per_col), s.blocks_per_col = tiles_per_col
@@ -84,7 +86,7 @@ struct MoveSmem {
   int32_t ticket, is_last;
   float u;
   float Ps[SMCB_NPARAM];
-  FinSmem<D> fin;
+  Fin4Scratch<1 + 2 * D, MV_NT> f4;
   FinPre fin_pre;
 };
 
@@ -275,21 +277,13 @@ __device__ __noinline__ void mv_remark(const float* wsrc, float m, float iz, dou
 template <typename SM>
 __device__ __forceinline__ void mv_remark_any(int items, const float* wsrc, float m, float iz, double S0, int32_t lo, int32_t gbase, int32_t wb,
                                               bool first, bool lean, float u, int32_t n, int32_t n_out, double nfd, SM& sm) {
-  switch (items) {
-    case 16: mv_remark<16>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
-    case 12: mv_remark<12>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
-    case 8: mv_remark<8>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
-    default: mv_remark<4>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm); break;
-  }
+  if (items == 16) mv_remark<16>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm);
+  else mv_remark<4>(wsrc, m, iz, S0, lo, gbase, wb, first, lean, u, n, n_out, nfd, sm);
 }
 template <typename SM>
 __device__ __forceinline__ int32_t mv_emit_any(int items, SM& sm, int32_t carry) {
-  switch (items) {
-    case 16: return rs_emit_blocked<MV_NT, 20>(sm, carry);
-    case 12: return rs_emit_blocked<MV_NT, 16>(sm, carry);
-    case 8: return rs_emit_blocked<MV_NT, 12>(sm, carry);
-    default: return rs_emit_blocked<MV_NT, 8>(sm, carry);
-  }
+  if (items == 16) return rs_emit_blocked<MV_NT, 20>(sm, carry);
+  return rs_emit_blocked<MV_NT, 8>(sm, carry);
 }
 
 template <int MODEL, int PROP, int ALG>
@@ -442,12 +436,8 @@ __global__ void __launch_bounds__(MV_NT, (Model<MODEL>::D == 1 ? SMCB_MV_MINB : 
       __syncthreads();
     }
   };
-  switch (items) {
-    case 16: front(std::integral_constant<int, 16>{}); break;
-    case 12: front(std::integral_constant<int, 12>{}); break;
-    case 8: front(std::integral_constant<int, 8>{}); break;
-    default: front(std::integral_constant<int, 4>{}); break;
-  }
+  if (items == 16) front(std::integral_constant<int, 16>{});   // (two classes are compiled: every further one costs instruction-cache
+  else front(std::integral_constant<int, 4>{});                // misses in all of them - 12 and 8 were measured and never chosen)
 
   MV_STAMP(4);
   // ---- the move itself over the tile's output slots [n_in, n_out), window by window.  What only this phase needs is fetched now.
@@ -598,7 +588,7 @@ __global__ void __launch_bounds__(MV_NT, (Model<MODEL>::D == 1 ? SMCB_MV_MINB : 
   SoftAcc<1 + 2 * D> A;
   SoftAcc<1> Q, R2, R3;
   mom.to_softacc(A, Q); r2.to_softacc(R2); r3.to_softacc(R3);
-  softacc4_block_reduce<1 + 2 * D, ST_NT, false>(A, Q, R2, R3, sm.fin.f4);
+  softacc4_block_reduce<1 + 2 * D, MV_NT, false>(A, Q, R2, R3, sm.f4);
   if (tid == 0) {
     Partial& p = a.partials[(int64_t)col * T + tile];
     st_write_partial1(p, A, Q);

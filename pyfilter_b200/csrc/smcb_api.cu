@@ -400,7 +400,7 @@ static void mv_choose_geometry(smcb_filter* f, int slots) {
   }
   if (const char* g = getenv("SMCB_MV_GEOM")) {
     int i1 = 16, i2 = 16, t1 = 0;
-    if (sscanf(g, "%d,%d,%d", &i1, &i2, &t1) == 3 && (i1 == 16 || i1 == 12 || i1 == 8 || i1 == 4) && (i2 == 16 || i2 == 12 || i2 == 8 || i2 == 4)) {
+    if (sscanf(g, "%d,%d,%d", &i1, &i2, &t1) == 3 && (i1 == 16 || i1 == 4) && (i2 == 16 || i2 == 4)) {
       const int64_t L1 = (int64_t)MV_NT * i1, L2 = (int64_t)MV_NT * i2;
       int64_t T1 = t1 < 0 ? 0 : t1;
       if (T1 * L1 >= n) T1 = (n + L1 - 1) / L1;

@@ -138,3 +138,48 @@ def test_smc2_particle_doubling(pf):
             sizes.append(state.engine.N)
     assert sizes[-1] == 512 and set(sizes) <= {128, 256, 512}
     assert torch.isfinite(state.w).all()
+
+
+@pytest.mark.parametrize("kind", ["shrinking", "nonshrinking", "liuwest", "constant"])
+def test_jitter_kernels_vs_reference_golden(pf, kind):
+    """NESS: location and scale of the jittering kernels (inference/sequential/kernels/jittering.py:140-225) on the device against what the
+    unmodified reference computed.  The running sums behind the weighted quartiles are a triangular product here and a sequential sum
+    there: a quartile may land on the neighbouring order statistic, hence the looser tolerance on the scale."""
+    from pyfilter_b200.inference import ness as NS
+
+    z = np.load(GOLDEN)
+    g = {k: torch.from_numpy(z[k]) for k in z.files}
+    x, W, idx = g["b1024_p2_x"].cuda(), g["b1024_p2_W"].cuda(), g["b1024_p2_idx"].cuda()
+    k = {"shrinking": NS.ShrinkingKernel(), "nonshrinking": NS.NonShrinkingKernel(), "liuwest": NS.LiuWestShrinkage(0.98),
+         "constant": NS.ConstantKernel(0.1)}[kind]
+    loc, sc = k.fit(x, W, idx)
+    assert torch.allclose(loc.cpu(), g[f"jit_{kind}_loc"], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(torch.as_tensor(sc).float().cpu(), g[f"jit_{kind}_scale"], rtol=5e-3, atol=1e-7)
+    eps = torch.randn(x.shape, generator=torch.Generator().manual_seed(2)).cuda()
+    j = k.jitter(x, W, idx, eps)
+    assert torch.allclose(j, loc + torch.as_tensor(sc).cuda().clamp(min=NS.EPS) * eps)
+
+
+@pytest.mark.parametrize("cls", ["ness", "fixed"])
+def test_ness_end_to_end(pf, cls):
+    """NESS / FixedWidthNESS (ness.py:59-109 with kernels/online.py:26-53) on the resident batch: the particles are jittered when due, the
+    weights are reset, the filters carry on with the jittered parameters and the posterior moves to the data (sigma = 2 under a
+    LogNormal(0, 0.5) prior)."""
+    from pyfilter_b200.filters.particle import proposals
+    from pyfilter_b200.inference import NESS, FixedWidthNESS
+
+    torch.manual_seed(4)
+    _, y = O.build_model("sine_em", dict(gamma=0.5, sigma=2.0)).simulate(80)
+    kw = dict(particles=256, state_particles=128, proposal=proposals.LinearGaussianObservations(), seed=3, max_observations=96)
+    alg = NESS(_builder, _priors(), threshold=0.9, **kw) if cls == "ness" else FixedWidthNESS(_builder, _priors(), block_len=10, **kw)
+    state = alg.initialize()
+    for yt in y:
+        before = alg.updates
+        state = alg.step(yt, state)
+        if alg.updates > before:   # the weights were reset before this move: they hold exactly this move's increments
+            assert torch.allclose(state.w, state.engine.raw(5, (256,)))
+    assert alg.updates >= (5 if cls == "ness" else 7)
+    assert torch.isfinite(state.w).all() and len(state.ess) == 81
+    post = alg.posterior_mean(state)
+    assert 1.4 < float(post["sigma"]) < 2.8, post
+    assert len(torch.unique(alg.context.values[:, 1])) > 200   # jittering keeps the cloud diverse

@@ -62,3 +62,13 @@ def test_smc2_oracle_vs_live_reference():
     ref_log = (new_kernel.log_prob(x) - ref.log_prob(new_x)) + (pr_new - pr_old) + (ll_new - ll_old)
     assert torch.allclose(log_acc, ref_log, rtol=1e-6, atol=1e-6) and torch.equal(acc, u.log() < ref_log)
     assert S.smc2_needs_rejuvenation(lw, 0.9) and not S.smc2_needs_rejuvenation(torch.zeros(50), 0.2)
+
+
+@pytest.mark.parametrize("kind", ["shrinking", "nonshrinking", "liuwest", "constant"])
+def test_jitter_kernels_oracle_vs_golden(kind):
+    """NESS: ``fit`` of the jittering kernels (inference/sequential/kernels/jittering.py:140-225) as the unmodified reference computed it."""
+    g = _g()
+    x, W, idx = g["b1024_p2_x"], g["b1024_p2_W"], g["b1024_p2_idx"]
+    loc, sc = S.jitter_fit(kind, x.clone(), W.clone(), idx)
+    assert torch.allclose(loc, g[f"jit_{kind}_loc"], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(torch.as_tensor(sc).float(), g[f"jit_{kind}_scale"], rtol=1e-5, atol=1e-8)
