@@ -252,6 +252,7 @@ def bench_configs(world, dist, moves=200):
         ("c2 sine_em APF LinearGaussianObservations systematic 1M", "sine_em", APF, proposals.LinearGaussianObservations, pf.resampling.systematic, 1_000_000, 0, 24),
         ("c4 lorenz63_em (3-D) SISR bootstrap multinomial 2M", "lorenz63_em", SISR, proposals.Bootstrap, pf.resampling.multinomial, 2_000_000, 0, 40),
         ("c4s lorenz63_em (3-D) SISR bootstrap systematic 2M", "lorenz63_em", SISR, proposals.Bootstrap, pf.resampling.systematic, 2_000_000, 0, 40),
+        ("c4l lorenz63_em (3-D) APF LinearGaussianObservations systematic 2M (examples/lorenz.ipynb:214)", "lorenz63_em", APF, proposals.LinearGaussianObservations, pf.resampling.systematic, 2_000_000, 0, 40),
         ("c5 sine_em APF bootstrap systematic 4096 x 128 theta (one GPU's shard of configs[4])", "sine_em", APF, proposals.Bootstrap, pf.resampling.systematic, 4096, 128, 24),
     ]
     peak, _ = load_peaks()
@@ -386,6 +387,33 @@ def bench_smc2(world, rank, dist, K=250, W=10):
         except Exception:
             pass
     return res
+
+
+def smc2_full_leg(T=40):
+    """The whole SMC2 algorithm (pyfilter_b200.inference.SMC2: filter moves, theta-level ESS test with its host synchronisation, PMMH
+    rejuvenation with re-filtering, accept / exchange) on BASELINE.json configs[4]'s sizes on ONE GPU: wall time per observation."""
+    import torch
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import proposals
+    from pyfilter_b200.inference import SMC2, LogNormal, Normal
+
+    THETA, N = 1024, 4096
+    y = simulate("sine_em", T)
+    alg = SMC2(lambda p: ts.build("sine_em", gamma=p["gamma"], sigma=p["sigma"]), {"gamma": Normal(0.0, 1.0), "sigma": LogNormal(0.0, 0.5)},
+               particles=THETA, state_particles=N, proposal=proposals.LinearGaussianObservations(), threshold=0.2, seed=123, max_observations=T + 2)
+    state = alg.initialize()
+    state = alg.step(y[0], state)   # warm-up (library load, first launches)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for yt in y[1:]:
+        state = alg.step(yt, state)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    post = alg.posterior_mean(state)
+    return {"workload": f"SMC2 {THETA} theta x {N} state particles (grows when the acceptance rate falls), sine_em APF LinearGaussianObservations, "
+                        f"threshold 0.2, {T - 1} observations, one GPU", "ms_per_observation": dt / (T - 1) * 1e3,
+            "rejuvenations": state.rejuvenations, "acceptance": [round(a, 3) for a in state.acceptance], "state_particles_final": state.engine.N,
+            "posterior_mean": {k: float(v) for k, v in post.items()}, "ess_final": state.ess[-1]}
 
 
 def torch_cuda_baseline(N, moves=10):
@@ -587,28 +615,41 @@ def run_b200(args):
         except Exception as ex:
             extra["smc2_shard"] = {"error": repr(ex)[:200]}
 
+    # ---- end to end through the C ABI on host buffers (pinned), incl. H2D of y and D2H of the results: every rank runs its replica,
+    #      barrier on both sides, the slowest rank's wall time counts, the value is the whole job's
+    yk = y[:K].contiguous().pin_memory()
+    means = torch.empty(K + 1, 1, 1).pin_memory()
+    varis = torch.empty(K + 1, 1, 1).pin_memory()
+    lls = torch.empty(K + 1, 1).pin_memory()
+    tot = torch.empty(1).pin_memory()
+    call = lambda T_: _lib.check(lib.smcb_filter_batch_filter_host(e.handle, yk.data_ptr(), T_, means.data_ptr(), varis.data_ptr(),
+                                                                   lls.data_ptr(), tot.data_ptr(), stream.cuda_stream))
+    call(min(K, 3))
+    l1 = e.info().kernel_launches
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+        torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    call(K)
+    dt = time.perf_counter() - t0
+    if dist:
+        tmax = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax)
     if rank == 0:
-        # ---- end to end through the C ABI on host buffers (pinned), incl. H2D of y and D2H of the results
-        yk = y[:K].contiguous().pin_memory()
-        means = torch.empty(K + 1, 1, 1).pin_memory()
-        varis = torch.empty(K + 1, 1, 1).pin_memory()
-        lls = torch.empty(K + 1, 1).pin_memory()
-        tot = torch.empty(1).pin_memory()
-        call = lambda T_: _lib.check(lib.smcb_filter_batch_filter_host(e.handle, yk.data_ptr(), T_, means.data_ptr(), varis.data_ptr(),
-                                                                       lls.data_ptr(), tot.data_ptr(), stream.cuda_stream))
-        call(min(K, 3))
-        l1 = e.info().kernel_launches
-        t0 = time.perf_counter()
-        call(K)
-        dt = time.perf_counter() - t0
-        e2e = {"value": N * K / dt, "unit": UNIT, "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 12 + 4.0 / K,
-               "api": "smcb_filter_batch_filter_host (C ABI, host buffers)", "loglikelihood": float(tot[0]),
+        e2e = {"value": world * N * K / dt, "unit": UNIT, "h2d_bytes_per_step": 4 * world, "d2h_bytes_per_step": (12 + 4.0 / K) * world,
+               "api": "smcb_filter_batch_filter_host (C ABI, host buffers), one call per rank, max over ranks", "loglikelihood": float(tot[0]),
                "gpu_launches": int(e.info().kernel_launches - l1)}
         if world == 1 and not args.headline_only:
             try:
                 extra.update(exact_weights_leg(N, y_dev, stream, min(K, 200)))
             except Exception as ex:
                 extra["exact_weights_true"] = {"error": repr(ex)[:200]}
+            try:
+                extra["smc2_full"] = smc2_full_leg()
+            except Exception as ex:
+                extra["smc2_full"] = {"error": repr(ex)[:200]}
             try:
                 extra["torch_cuda_baseline"] = torch_cuda_baseline(N)
             except Exception as ex:

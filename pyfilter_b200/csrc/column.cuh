@@ -58,7 +58,11 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
   const int32_t n = (int32_t)a.n;
   const int32_t gbase = tid * ITEMS;
   int32_t* anc_s = cs.stage;
+  // launched with programmatic stream serialisation: the blocks of the NEXT launch (the online loop is one launch per move) may take
+  // their places while this one runs; everything a predecessor kernel writes is read behind pdl_wait()
+  pdl_trigger();
   if (tid < SMCB_NPARAM) cs.Ps[tid] = a.P[(int64_t)col * SMCB_NPARAM + tid];
+  pdl_wait();
   if (tid == 0) cs.st = a.stats[col];
   const float* Ps = cs.Ps;
   float ll_total = a.ll_total[col];

@@ -680,8 +680,21 @@ static cudaError_t launch_column_nt(int B, size_t dyn, cudaStream_t s, const Col
     e = cudaFuncSetAttribute(column_kernel<MODEL, PROP, ALG, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e == cudaSuccess) set_for = dyn;
   }
-  if (e == cudaSuccess) column_kernel<MODEL, PROP, ALG, NT, MINB><<<B, NT, dyn, s>>>(c);
-  return e;
+  if (e != cudaSuccess) return e;
+  static bool pdl_ok = true;
+  if (use_pdl() && pdl_ok) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(B); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = dyn; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, column_kernel<MODEL, PROP, ALG, NT, MINB>, c) == cudaSuccess) return cudaSuccess;
+    cudaGetLastError();
+    pdl_ok = false;
+  }
+  column_kernel<MODEL, PROP, ALG, NT, MINB><<<B, NT, dyn, s>>>(c);
+  return cudaSuccess;
 }
 template <int MODEL, int PROP>
 static cudaError_t launch_column_alg(int alg, int minb, int B, size_t dyn, cudaStream_t s, const ColumnArgs& c) {
