@@ -389,6 +389,36 @@ def bench_smc2(world, rank, dist, K=250, W=10):
     return res
 
 
+def operators_leg():
+    """The Level-1 drop-ins on their own: stand-alone `systematic` / `multinomial` / `normalize` on a caller's
+    tensor, device-timed; algorithmic bytes = weights in (4 B) + int64 ancestors out (8 B) per particle (normalize: 4 + 4)."""
+    import torch
+    import pyfilter_b200 as pf
+
+    peak, _ = load_peaks()
+    out = {}
+    gen = torch.Generator().manual_seed(1)
+    for name, n, fn, bpp in (("systematic_4M", 4_000_000, lambda w: pf.resampling.systematic(w, normalized=True), 12),
+                             ("multinomial_2M", 2_000_000, lambda w: pf.resampling.multinomial(w, normalized=True), 12),
+                             ("residual_2M", 2_000_000, lambda w: pf.resampling.residual(w, normalized=True), 12),
+                             ("normalize_4M", 4_000_000, lambda w: pf.utils.normalize(w), 8)):
+        lw = (torch.randn(n, generator=gen) * 2.0).cuda()
+        w = pf.utils.normalize(lw.clone()) if name != "normalize_4M" else lw
+        fn(w); fn(w)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        ev0.record()
+        for _ in range(reps):
+            fn(w)
+        ev1.record()
+        torch.cuda.synchronize()
+        us = ev0.elapsed_time(ev1) * 1e3 / reps
+        out[name] = {"us_per_call": us, "GB/s": bpp * n / (us * 1e-6) / 1e9, "roofline_frac": bpp * n / (us * 1e-6) / 1e9 / peak,
+                     "algorithmic_bytes_per_particle": bpp}
+    return out
+
+
 def smc2_full_leg(T=40):
     """The whole SMC2 algorithm (pyfilter_b200.inference.SMC2: filter moves, theta-level ESS test with its host synchronisation, PMMH
     rejuvenation with re-filtering, accept / exchange) on BASELINE.json configs[4]'s sizes on ONE GPU: wall time per observation."""
@@ -402,17 +432,22 @@ def smc2_full_leg(T=40):
     alg = SMC2(lambda p: ts.build("sine_em", gamma=p["gamma"], sigma=p["sigma"]), {"gamma": Normal(0.0, 1.0), "sigma": LogNormal(0.0, 0.5)},
                particles=THETA, state_particles=N, proposal=proposals.LinearGaussianObservations(), threshold=0.2, seed=123, max_observations=T + 2)
     state = alg.initialize()
-    state = alg.step(y[0], state)   # warm-up (library load, first launches)
+    warm = 5
+    for yt in y[:warm]:               # warm-up: library load, first launches, and ONE forced rejuvenation (the first use of cuSOLVER /
+        state = alg.step(yt, state)   # cuBLAS for the p x p Cholesky factor of the proposal costs about a second on its own)
+    state = alg.rejuvenate(state)
+    r0 = state.rejuvenations
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for yt in y[1:]:
+    for yt in y[warm:]:
         state = alg.step(yt, state)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
+    T = T - warm + 1
     post = alg.posterior_mean(state)
     return {"workload": f"SMC2 {THETA} theta x {N} state particles (grows when the acceptance rate falls), sine_em APF LinearGaussianObservations, "
                         f"threshold 0.2, {T - 1} observations, one GPU", "ms_per_observation": dt / (T - 1) * 1e3,
-            "rejuvenations": state.rejuvenations, "acceptance": [round(a, 3) for a in state.acceptance], "state_particles_final": state.engine.N,
+            "rejuvenations": state.rejuvenations - r0, "acceptance": [round(a, 3) for a in state.acceptance], "state_particles_final": state.engine.N,
             "posterior_mean": {k: float(v) for k, v in post.items()}, "ess_final": state.ess[-1]}
 
 
@@ -646,6 +681,10 @@ def run_b200(args):
                 extra.update(exact_weights_leg(N, y_dev, stream, min(K, 200)))
             except Exception as ex:
                 extra["exact_weights_true"] = {"error": repr(ex)[:200]}
+            try:
+                extra["operators"] = operators_leg()
+            except Exception as ex:
+                extra["operators"] = {"error": repr(ex)[:200]}
             try:
                 extra["smc2_full"] = smc2_full_leg()
             except Exception as ex:

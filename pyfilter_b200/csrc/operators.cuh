@@ -59,11 +59,39 @@ __global__ void scatter_i64_kernel(const int32_t* __restrict__ rows, int64_t n, 
   }
 }
 
+// Columns that are contiguous in the caller's tensor (a 1-D tensor, or the (1, N)-strided result layout): plain coalesced copies, one
+// block per 4096 elements of a column - the 32 x 32 transposing kernels above would move 32 elements per block for a single column.
+__global__ void __launch_bounds__(256) copy_rows_contig_kernel(const float* __restrict__ in, int64_t n, int64_t sb, float* __restrict__ rows, int64_t ld) {
+  const int b = blockIdx.y;
+  const int64_t base = (int64_t)blockIdx.x * 4096;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int64_t i = base + j * 256 + threadIdx.x;
+    if (i < n) rows[(int64_t)b * ld + i] = __ldg(in + i + (int64_t)b * sb);
+  }
+}
+__global__ void __launch_bounds__(256) scatter_i64_contig_kernel(const int32_t* __restrict__ rows, int64_t n, int64_t ld, int64_t* __restrict__ out, int64_t sb) {
+  const int b = blockIdx.y;
+  const int64_t base = (int64_t)blockIdx.x * 4096;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int64_t i = base + j * 256 + threadIdx.x;
+    if (i < n) out[i + (int64_t)b * sb] = (int64_t)rows[(int64_t)b * ld + i];
+  }
+}
 static inline void op_launch_gather_rows(const float* in, int64_t n, int B, int64_t sn, int64_t sb, float* rows, int64_t ld, cudaStream_t s) {
+  if (sn == 1) {
+    copy_rows_contig_kernel<<<dim3((unsigned)((n + 4095) / 4096), B), 256, 0, s>>>(in, n, sb, rows, ld);
+    return;
+  }
   dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
   gather_rows_kernel<<<g, dim3(32, 8), 0, s>>>(in, n, B, sn, sb, rows, ld);
 }
 static inline void op_launch_scatter_i64(const int32_t* rows, int64_t n, int B, int64_t ld, int64_t* out, int64_t sn, int64_t sb, cudaStream_t s) {
+  if (sn == 1) {
+    scatter_i64_contig_kernel<<<dim3((unsigned)((n + 4095) / 4096), B), 256, 0, s>>>(rows, n, ld, out, sb);
+    return;
+  }
   dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
   scatter_i64_kernel<<<g, dim3(32, 8), 0, s>>>(rows, n, B, ld, out, sn, sb);
 }
@@ -175,7 +203,21 @@ static inline void op_launch_colstats(const float* rows, int64_t n, int B, int64
   colstats_partial_kernel<<<dim3(nblk, B), RS_NT, 0, s>>>(rows, n, ld, nblk, parts);
   colstats_final_kernel<<<B, 128, 0, s>>>(parts, nblk, n, stats);
 }
+__global__ void __launch_bounds__(256) apply_weights_contig_kernel(const float* __restrict__ rows, const ColStats* stats, int64_t n, int64_t ld, float* __restrict__ out, int64_t sb) {
+  const int b = blockIdx.y;
+  const ColStats st = stats[b];
+  const int64_t base = (int64_t)blockIdx.x * 4096;
+#pragma unroll 4
+  for (int j = 0; j < 16; ++j) {
+    const int64_t i = base + j * 256 + threadIdx.x;
+    if (i < n) out[i + (int64_t)b * sb] = smcb_weight(smcb_sanitize(rows[(int64_t)b * ld + i]), st.m_lw, st.inv_z_lw);
+  }
+}
 static inline void op_launch_apply_weights(const float* rows, const ColStats* stats, int64_t n, int B, int64_t ld, float* out, int64_t sn, int64_t sb, cudaStream_t s) {
+  if (sn == 1) {
+    apply_weights_contig_kernel<<<dim3((unsigned)((n + 4095) / 4096), B), 256, 0, s>>>(rows, stats, n, ld, out, sb);
+    return;
+  }
   dim3 g((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32));
   apply_weights_kernel<<<g, dim3(32, 8), 0, s>>>(rows, stats, n, B, ld, out, sn, sb);
 }

@@ -185,43 +185,42 @@ __global__ void column_gather_small_kernel(const float* __restrict__ src, float*
 // ---- residual resampling (resampling.py:68-105): the deterministic copies ------------------------------------------------------------
 // mw = fl32(n w), floored = floor(mw); particle j is copied floored_j times to out[cum_{j-1} .. cum_j); the fractional parts
 // (mw - floored) / k (k = sum floored, float32 division) are the weights of the multinomial part, drawn by the multinomial pipeline.
-// One block per column; n <= 2^24 (torch.multinomial's limit), so every count and sum is an exact float32 / int32.
-__global__ void __launch_bounds__(1024) residual_counts_kernel(const float* __restrict__ w, int64_t n, int64_t ld, int32_t* __restrict__ counts, float* __restrict__ frac,
-                                                               int32_t* __restrict__ ksum) {
+// Three passes over tiles of 4096 particles: counts + tile sums, exclusive scan of the tile sums (one block per column), expansion.
+// n <= 2^24 (torch.multinomial's limit), so every count and sum is an exact float32 / int32.
+#define RES_NT 256
+#define RES_ITEMS 16
+#define RES_TILE (RES_NT * RES_ITEMS)
+__global__ void __launch_bounds__(RES_NT) residual_counts_kernel(const float* __restrict__ w, int64_t n, int64_t ld, int tiles, int32_t* __restrict__ counts,
+                                                                 float* __restrict__ frac, int32_t* __restrict__ tile_sum) {
   __shared__ int32_t scratch[33];
-  const int col = blockIdx.x;
+  const int tile = blockIdx.x, col = blockIdx.y;
   const float nf = (float)n;
   int32_t local = 0;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) {
-    const float mw = __fmul_rn(nf, w[(int64_t)col * ld + i]);
-    const float fl = floorf(mw);
-    counts[(int64_t)col * ld + i] = (int32_t)fl;
-    frac[(int64_t)col * ld + i] = __fsub_rn(mw, fl);
-    local += (int32_t)fl;
+#pragma unroll
+  for (int j = 0; j < RES_ITEMS; ++j) {
+    const int64_t i = (int64_t)tile * RES_TILE + j * RES_NT + threadIdx.x;
+    if (i < n) {
+      const float mw = __fmul_rn(nf, w[(int64_t)col * ld + i]);
+      const float fl = floorf(mw);
+      counts[(int64_t)col * ld + i] = (int32_t)fl;
+      frac[(int64_t)col * ld + i] = __fsub_rn(mw, fl);
+      local += (int32_t)fl;
+    }
   }
-  const int32_t k = block_allreduce<1024>(local, 0, OpSumI(), scratch);
-  if (threadIdx.x == 0) ksum[col] = k;
-  __syncthreads();
-  const float kf = (float)k;
-  for (int64_t i = threadIdx.x; i < n; i += 1024) frac[(int64_t)col * ld + i] = __fdiv_rn(frac[(int64_t)col * ld + i], kf);
+  const int32_t k = block_allreduce<RES_NT>(local, 0, OpSumI(), scratch);
+  if (threadIdx.x == 0) tile_sum[(int64_t)col * tiles + tile] = k;
 }
-// exclusive integer scan of the counts + expansion: out[cum_{j-1} + r] = j.  One block per column walks the column in chunks of 1024 x 4.
-__global__ void __launch_bounds__(1024) residual_expand_kernel(const int32_t* __restrict__ counts, int64_t n, int64_t ld, int32_t* __restrict__ out) {
+// exclusive scan of a column's tile sums (in place) and its total k; one block per column
+__global__ void __launch_bounds__(1024) residual_scan_kernel(int32_t* __restrict__ tile_sum, int tiles, int32_t* __restrict__ ksum) {
   __shared__ int32_t wsum[32];
   __shared__ int32_t carry_s;
   const int col = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) carry_s = 0;
   __syncthreads();
-  for (int64_t base = 0; base < n; base += 4096) {
-    int32_t c[4];
-    int32_t s = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int64_t i = base + tid * 4 + k;
-      c[k] = (i < n) ? counts[(int64_t)col * ld + i] : 0;
-      s += c[k];
-    }
-    int32_t inc = s;
+  for (int base = 0; base < tiles; base += 1024) {
+    const int i = base + tid;
+    const int32_t v = (i < tiles) ? tile_sum[(int64_t)col * tiles + i] : 0;
+    int32_t inc = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -231,16 +230,43 @@ __global__ void __launch_bounds__(1024) residual_expand_kernel(const int32_t* __
     __syncthreads();
     int32_t off = carry_s;
     for (int k = 0; k < wid; ++k) off += wsum[k];
-    int32_t pos = off + inc - s;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int32_t j = (int32_t)(base + tid * 4 + k);
-      for (int r = 0; r < c[k]; ++r) out[(int64_t)col * ld + pos + r] = j;
-      pos += c[k];
-    }
+    if (i < tiles) tile_sum[(int64_t)col * tiles + i] = off + inc - v;
     __syncthreads();
     if (tid == 1023) carry_s = off + inc;
     __syncthreads();
+  }
+  if (tid == 0) ksum[col] = carry_s;
+}
+// expansion of one tile: out[offset_of_tile + exclusive_scan(counts) + r] = j, and the fractions are divided by k
+__global__ void __launch_bounds__(RES_NT) residual_expand_kernel(const int32_t* __restrict__ counts, float* __restrict__ frac, int64_t n, int64_t ld, int tiles,
+                                                                 const int32_t* __restrict__ tile_off, const int32_t* __restrict__ ksum, int32_t* __restrict__ out) {
+  __shared__ int32_t wsum[RES_NT / 32];
+  const int tile = blockIdx.x, col = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const float kf = (float)ksum[col];
+  int32_t c[RES_ITEMS];
+  int32_t s = 0;
+  const int64_t i0 = (int64_t)tile * RES_TILE + (int64_t)tid * RES_ITEMS;   // blocked: a thread owns 16 consecutive particles
+#pragma unroll
+  for (int j = 0; j < RES_ITEMS; ++j) {
+    const int64_t i = i0 + j;
+    c[j] = (i < n) ? counts[(int64_t)col * ld + i] : 0;
+    if (i < n) frac[(int64_t)col * ld + i] = __fdiv_rn(frac[(int64_t)col * ld + i], kf);
+    s += c[j];
+  }
+  int32_t inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) wsum[wid] = inc;
+  __syncthreads();
+  int32_t pos = tile_off[(int64_t)col * tiles + tile] + inc - s;
+  for (int k = 0; k < wid; ++k) pos += wsum[k];
+#pragma unroll
+  for (int j = 0; j < RES_ITEMS; ++j) {
+    for (int r = 0; r < c[j]; ++r) out[(int64_t)col * ld + pos + r] = (int32_t)(i0 + j);
+    pos += c[j];
   }
 }
 

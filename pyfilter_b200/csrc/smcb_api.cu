@@ -923,45 +923,56 @@ struct OpWorkspace {
   int64_t ld = 0; int tiles = 0, nblk = 0;
 };
 
-static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s) {
+// One slab per calling thread, kept between calls: the operators are called once per filter step by code written against the reference
+// (`resampling=` callables, normalize / get_ess on the theta level), and nineteen stream-ordered allocations plus six memsets per call
+// cost more host time than the kernels take.  The slab is reused while it is large enough and the stream is the same (work on one
+// stream is ordered, so the previous call has finished with it by the time the next one touches it); otherwise it is released on its
+// own stream and allocated anew.  The buffers that must start zeroed sit together at the front: one memset.
+struct OpSlab { char* base = nullptr; size_t bytes = 0; cudaStream_t stream = nullptr; int device = -1; };
+static thread_local OpSlab g_slab;
+
+static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s, bool want_cbuf = false) {
   ws.tiles = (int)((n + RS_TILE - 1) / RS_TILE);
   ws.ld = (int64_t)ws.tiles * RS_TILE;
   ws.nblk = ws.tiles;
   const size_t cells = (size_t)B * ws.ld;
-  CU(cudaMallocAsync((void**)&ws.w, cells * sizeof(float), s));
-  CU(cudaMallocAsync((void**)&ws.wn, cells * sizeof(float), s));
-  CU(cudaMallocAsync((void**)&ws.anc, cells * sizeof(int32_t), s));
-  CU(cudaMallocAsync((void**)&ws.tilesum, (size_t)B * ws.tiles * sizeof(double), s));
-  CU(cudaMallocAsync((void**)&ws.prefix, (size_t)B * ws.tiles * sizeof(double), s));
-  CU(cudaMallocAsync((void**)&ws.sin, (size_t)B * ws.tiles * sizeof(double), s));
-  CU(cudaMallocAsync((void**)&ws.tileflag, (size_t)B * ws.tiles * sizeof(int32_t), s));
-  CU(cudaMallocAsync((void**)&ws.desc, (size_t)B * ws.tiles * sizeof(XsDesc), s));
-  CU(cudaMallocAsync((void**)&ws.desc2, (size_t)B * ws.tiles * sizeof(XsDesc), s));
-  CU(cudaMallocAsync((void**)&ws.tables, (size_t)B * ws.tiles * sizeof(SegTable), s));
-  CU(cudaMallocAsync((void**)&ws.dcounter, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMemsetAsync(ws.dcounter, 0, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMallocAsync((void**)&ws.ctrl, sizeof(Ctrl), s));
-  CU(cudaMallocAsync((void**)&ws.stats, (size_t)B * sizeof(ColStats), s));
-  CU(cudaMallocAsync((void**)&ws.parts, (size_t)B * ws.nblk * sizeof(NormPartial), s));
-  CU(cudaMallocAsync((void**)&ws.tilemin, (size_t)B * ws.tiles * sizeof(uint32_t), s));
-  CU(cudaMallocAsync((void**)&ws.ncounter, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMallocAsync((void**)&ws.verdict, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMallocAsync((void**)&ws.u_col, (size_t)B * sizeof(float), s));
-  CU(cudaMemsetAsync(ws.ncounter, 0, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMemsetAsync(ws.verdict, 0, (size_t)B * sizeof(int32_t), s));
-  CU(cudaMemsetAsync(ws.w, 0, cells * sizeof(float), s));
-  CU(cudaMemsetAsync(ws.ctrl, 0, sizeof(Ctrl), s));
-  CU(cudaMemsetAsync(ws.stats, 0, (size_t)B * sizeof(ColStats), s));
+  const size_t nt = (size_t)B * ws.tiles;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  // zeroed region
+  const size_t o_dcounter = take((size_t)B * sizeof(int32_t)), o_ncounter = take((size_t)B * sizeof(int32_t)), o_verdict = take((size_t)B * sizeof(int32_t));
+  const size_t o_ctrl = take(sizeof(Ctrl)), o_stats = take((size_t)B * sizeof(ColStats)), o_w = take(cells * sizeof(float));
+  const size_t zero_bytes = off;
+  const size_t o_wn = take(cells * sizeof(float)), o_anc = take(cells * sizeof(int32_t));
+  const size_t o_tilesum = take(nt * sizeof(double)), o_prefix = take(nt * sizeof(double)), o_sin = take(nt * sizeof(double));
+  const size_t o_tileflag = take(nt * sizeof(int32_t)), o_desc = take(nt * sizeof(XsDesc)), o_desc2 = take(nt * sizeof(XsDesc));
+  const size_t o_tables = take(nt * sizeof(SegTable)), o_parts = take((size_t)B * ws.nblk * sizeof(NormPartial));
+  const size_t o_tilemin = take(nt * sizeof(uint32_t)), o_ucol = take((size_t)B * sizeof(float));
+  const size_t o_cbuf = want_cbuf ? take(cells * sizeof(float)) : 0;
+  int dev = 0;
+  CU(cudaGetDevice(&dev));
+  OpSlab& sl = g_slab;
+  if (!sl.base || sl.bytes < off || sl.stream != s || sl.device != dev) {
+    if (sl.base) { cudaFreeAsync(sl.base, sl.stream); sl = OpSlab(); }
+    CU(cudaMallocAsync((void**)&sl.base, off, s));
+    sl.bytes = off; sl.stream = s; sl.device = dev;
+  }
+  char* p = sl.base;
+  CU(cudaMemsetAsync(p, 0, zero_bytes, s));
+  ws.dcounter = (int32_t*)(p + o_dcounter); ws.ncounter = (int32_t*)(p + o_ncounter); ws.verdict = (int32_t*)(p + o_verdict);
+  ws.ctrl = (Ctrl*)(p + o_ctrl); ws.stats = (ColStats*)(p + o_stats); ws.w = (float*)(p + o_w);
+  ws.wn = (float*)(p + o_wn); ws.anc = (int32_t*)(p + o_anc);
+  ws.tilesum = (double*)(p + o_tilesum); ws.prefix = (double*)(p + o_prefix); ws.sin = (double*)(p + o_sin);
+  ws.tileflag = (int32_t*)(p + o_tileflag); ws.desc = (XsDesc*)(p + o_desc); ws.desc2 = (XsDesc*)(p + o_desc2);
+  ws.tables = (SegTable*)(p + o_tables); ws.parts = (NormPartial*)(p + o_parts);
+  ws.tilemin = (uint32_t*)(p + o_tilemin); ws.u_col = (float*)(p + o_ucol);
+  ws.cbuf = want_cbuf ? (float*)(p + o_cbuf) : nullptr;
   return SMCB_OK;
 }
-static void op_free(OpWorkspace& ws, cudaStream_t s) {
-  void* ptrs[] = {ws.w, ws.wn, ws.anc, ws.tilesum, ws.prefix, ws.sin, ws.tileflag, ws.desc, ws.desc2, ws.tables, ws.dcounter, ws.ctrl, ws.stats, ws.parts, ws.cbuf, ws.tilemin, ws.ncounter, ws.verdict,
-                  ws.u_col};
-  for (void* p : ptrs) if (p) cudaFreeAsync(p, s);
-}
+static void op_free(OpWorkspace& ws, cudaStream_t) { ws = OpWorkspace(); }   // the slab stays with the thread for the next call
 
-static int op_prepare(OpWorkspace& ws, const float* w_dev, int64_t n, int B, int64_t sn, int64_t sb, bool need_stats, cudaStream_t s) {
-  int rc = op_alloc(ws, n, B, s);
+static int op_prepare(OpWorkspace& ws, const float* w_dev, int64_t n, int B, int64_t sn, int64_t sb, bool need_stats, cudaStream_t s, bool want_cbuf = false) {
+  int rc = op_alloc(ws, n, B, s, want_cbuf);
   if (rc) return rc;
   op_launch_gather_rows(w_dev, n, B, sn, sb, ws.w, ws.ld, s);
   if (need_stats) op_launch_colstats(ws.w, n, B, ws.ld, ws.nblk, ws.parts, ws.stats, s);
@@ -1003,7 +1014,7 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
   if (kind == SMCB_MULTINOMIAL && n > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");
   if (smcb_device_count() < 1) return fail(SMCB_ENODEVICE, "no CUDA device: libsmcb200 has no CPU fallback");
   OpWorkspace ws;
-  int rc = op_prepare(ws, w_dev, n, B, sn, sb, !normalized, s);
+  int rc = op_prepare(ws, w_dev, n, B, sn, sb, !normalized, s, kind == SMCB_MULTINOMIAL);
   if (rc == SMCB_OK) {
     ResampleArgs r;
     memset(&r, 0, sizeof(r));
@@ -1014,8 +1025,6 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
     r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
     else {
-      cudaError_t e = cudaMallocAsync((void**)&ws.cbuf, (size_t)B * ws.ld * sizeof(float), s);
-      if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
       r.c_out = ws.cbuf;
       if (rc == SMCB_OK) rc = op_launch_multinomial(r, U_dev, n, s);
     }
@@ -1213,18 +1222,20 @@ extern "C" int smcb_residual(const float* w_dev, int64_t n, int32_t B, int64_t s
   cudaStream_t s = (cudaStream_t)stream;
   OpWorkspace ws;
   int32_t *counts = nullptr, *ksum = nullptr;
-  int rc = op_prepare(ws, w_dev, n, B, sn, sb, false, s);
+  int rc = op_prepare(ws, w_dev, n, B, sn, sb, false, s, true);
   if (rc == SMCB_OK) {
     const size_t cells = (size_t)B * ws.ld;
     cudaError_t e = cudaMallocAsync((void**)&counts, cells * sizeof(int32_t), s);
     if (e == cudaSuccess) e = cudaMallocAsync((void**)&ksum, (size_t)B * sizeof(int32_t), s);
-    if (e == cudaSuccess) e = cudaMallocAsync((void**)&ws.cbuf, cells * sizeof(float), s);
     if (e == cudaSuccess) e = cudaMemsetAsync(ws.wn, 0, cells * sizeof(float), s);
     if (e != cudaSuccess) rc = fail(SMCB_ECUDA, cudaGetErrorString(e));
   }
   if (rc == SMCB_OK) {
-    residual_counts_kernel<<<B, 1024, 0, s>>>(ws.w, n, ws.ld, counts, ws.wn, ksum);
-    residual_expand_kernel<<<B, 1024, 0, s>>>(counts, n, ws.ld, ws.anc);
+    int32_t* tile_sum = (int32_t*)ws.tileflag;   // (B, tiles) int32 scratch of the slab, unused until the multinomial pipeline below
+    const dim3 rg(ws.tiles, B);
+    residual_counts_kernel<<<rg, RES_NT, 0, s>>>(ws.w, n, ws.ld, ws.tiles, counts, ws.wn, tile_sum);
+    residual_scan_kernel<<<B, 1024, 0, s>>>(tile_sum, ws.tiles, ksum);
+    residual_expand_kernel<<<rg, RES_NT, 0, s>>>(counts, ws.wn, n, ws.ld, ws.tiles, tile_sum, ksum, ws.anc);
     ResampleArgs r;
     memset(&r, 0, sizeof(r));
     r.w = ws.wn; r.wn = ws.wn; r.n = n; r.ld = ws.ld; r.B = B; r.tiles_per_col = ws.tiles;
