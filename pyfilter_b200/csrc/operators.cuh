@@ -267,6 +267,8 @@ struct MultinomialArgs {
   int32_t* anc;            // (B, ld)
   int32_t stride;          // coarse table: last element of every `stride` cumulative weights (power of two)
   int32_t ncoarse;
+  const float* mid;        // (B, nmid) packed middle level: last element of every MN_MID cumulative weights - the 32+ probes of a chunk
+  int32_t nmid;            //   share one or two 128-byte lines instead of touching a different line of `c` each
   int32_t col0;            // global index of column 0 (Philox counter)
   const int32_t* draw_offset;  // residual resampling: the first draw_offset[col] outputs are the deterministic copies (NULL: none)
 };
@@ -275,6 +277,13 @@ struct MultinomialArgs {
 // threshold on c_k itself once per draw - no division inside the search: with Uc = U rounded up to float32 and Up its predecessor,
 // fl32(c / total) >= Uc  <=>  c >= mid(Up, Uc) * total (exact in fp64: 25 x 24 bits), strictly when the tie rounds to the odd Up.
 // Two-level search: a coarse table of every `stride`-th cumulative weight in shared memory, then one chunk in global memory.
+#define MN_MID 64
+__global__ void __launch_bounds__(256) multinomial_mid_kernel(const float* __restrict__ c, int64_t n, int64_t ld, float* __restrict__ mid, int nmid) {
+  pdl_wait();
+  const int col = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j < nmid) mid[(int64_t)col * nmid + j] = __ldg(c + (int64_t)col * ld + min((int64_t)(j + 1) * MN_MID, n) - 1);
+}
 __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a) {
   extern __shared__ float coarse[];
   pdl_wait();
@@ -314,6 +323,16 @@ __global__ void __launch_bounds__(256) multinomial_draw_kernel(MultinomialArgs a
     int64_t ans = n - 1;
     if (lo < a.ncoarse) {
       int64_t k0 = (int64_t)lo * a.stride, k1 = min(k0 + a.stride, n) - 1;
+      if (a.mid) {  // middle level: first group of MN_MID elements of the chunk whose last element reaches the threshold
+        const float* midp = a.mid + (int64_t)col * a.nmid;
+        int m0 = (int)(k0 / MN_MID), m1 = (int)(k1 / MN_MID);   // groups of the chunk; the last one always qualifies
+        while (m0 < m1) {
+          const int m = (m0 + m1) >> 1;
+          if (__ldg(midp + m) < cthr) m0 = m + 1; else m1 = m;
+        }
+        k0 = (int64_t)m0 * MN_MID;
+        k1 = min(k0 + MN_MID, n) - 1;
+      }
       while (k0 < k1) {
         const int64_t m = (k0 + k1) >> 1;
         if (__ldg(c + m) < cthr) k0 = m + 1; else k1 = m;
@@ -335,6 +354,12 @@ static inline void op_launch_multinomial_after_normalize(const ResampleArgs& r, 
   int stride = 256;  // every block gathers the coarse table itself (one sector per entry): keep it to ~1k entries
   while ((r.n + stride - 1) / stride > 1024) stride *= 2;
   m.stride = stride; m.ncoarse = (int)((r.n + stride - 1) / stride);
+  m.mid = nullptr; m.nmid = 0;
+  if (r.mid_out && stride % MN_MID == 0) {
+    m.nmid = (int)((r.n + MN_MID - 1) / MN_MID);
+    multinomial_mid_kernel<<<dim3((m.nmid + 255) / 256, r.B), 256, 0, s>>>(r.c_out, r.n, r.ld, r.mid_out, m.nmid);
+    m.mid = r.mid_out;
+  }
   int bx = (int)((r.n + 255) / 256);
   const int cap = (smcb_sm_count() * 6 + r.B - 1) / r.B;
   if (bx > cap) bx = cap;

@@ -74,6 +74,7 @@ struct ResampleArgs {
   int32_t t_host;          // resample_fused_kernel: the move index (== ctrl->t), passed by the host to keep it off the critical path
   unsigned long long epoch_host;  // resample_fused_kernel: launch tag of the slots, unique per launch and never 0
   int32_t col0;            // global index of column 0 (smcb_config.column_offset): the Philox counters use col0 + column
+  float* mid_out;          // multinomial: (B, ceil(n / 64)) scratch for the packed middle level of the draw's search (NULL: two levels)
   const int32_t* draw_offset;  // multinomial draws of the residual resampler: column b draws n - draw_offset[b] ancestors into anc[draw_offset[b] ..]
 };
 __device__ __forceinline__ long long rs_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }

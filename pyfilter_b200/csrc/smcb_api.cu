@@ -159,6 +159,7 @@ struct smcb_filter {
   float* y_own = nullptr;
   int y_own_cap = 0;
   float* cbuf = nullptr;  // multinomial: sequential float32 prefix sums (B, ld)
+  float* midbuf = nullptr;  // multinomial: packed middle level of the draw's search (B, ceil(n / 64))
   float* wn = nullptr;    // normalised weights of the current resampling pass (B, ld)
   long long* dbg = nullptr;  // SMCB_DEBUG_TIMELINE=1: per-tile timeline of the scan kernel
   const float *eps_in = nullptr, *u_in = nullptr;
@@ -216,7 +217,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out, f->xch_ticket};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out, f->xch_ticket, f->midbuf};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -299,6 +300,7 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
+  if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->midbuf, (size_t)f->B * ((f->n + MN_MID - 1) / MN_MID)));
   if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)16 * f->B * (f->mv_tiles_cap > f->tiles_per_col ? f->mv_tiles_cap : f->tiles_per_col)));
 #undef A_
   if (e != cudaSuccess) {
@@ -651,10 +653,10 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
     launch_pdl(expand_kernel<53, RS_OUT_ANCESTORS>, rgrid, dim3(RS_NT), s, r);
     f->launches++;
   } else {
-    r.c_out = f->cbuf;
+    r.c_out = f->cbuf; r.mid_out = f->midbuf;
     if (ev) cudaEventRecord(ev[3], s);
     op_launch_multinomial_after_normalize(r, f->U_in, f->ld, s);
-    f->launches += 3;
+    f->launches += 4;
   }
   if (ev) cudaEventRecord(ev[4], s);
   launch_step(f, a, s);  // the block that completes a column also folds its partials (finalize_column, FIN_STEP)
@@ -918,7 +920,7 @@ extern "C" int smcb_filter_sync_stats(smcb_filter* f, void* stream) {
 struct OpWorkspace {
   float* w = nullptr; float* wn = nullptr; int32_t* anc = nullptr; double* tilesum = nullptr; Ctrl* ctrl = nullptr;
   double *prefix = nullptr, *sin = nullptr; int32_t *tileflag = nullptr, *dcounter = nullptr; XsDesc *desc = nullptr, *desc2 = nullptr; SegTable* tables = nullptr;
-  ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr;
+  ColStats* stats = nullptr; NormPartial* parts = nullptr; float* cbuf = nullptr; float* mid = nullptr;
   uint32_t* tilemin = nullptr; int32_t* ncounter = nullptr; int32_t* verdict = nullptr; float* u_col = nullptr;
   int64_t ld = 0; int tiles = 0, nblk = 0;
 };
@@ -949,6 +951,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s, bool want
   const size_t o_tables = take(nt * sizeof(SegTable)), o_parts = take((size_t)B * ws.nblk * sizeof(NormPartial));
   const size_t o_tilemin = take(nt * sizeof(uint32_t)), o_ucol = take((size_t)B * sizeof(float));
   const size_t o_cbuf = want_cbuf ? take(cells * sizeof(float)) : 0;
+  const size_t o_mid = want_cbuf ? take((size_t)B * ((n + MN_MID - 1) / MN_MID) * sizeof(float)) : 0;
   int dev = 0;
   CU(cudaGetDevice(&dev));
   OpSlab& sl = g_slab;
@@ -967,6 +970,7 @@ static int op_alloc(OpWorkspace& ws, int64_t n, int B, cudaStream_t s, bool want
   ws.tables = (SegTable*)(p + o_tables); ws.parts = (NormPartial*)(p + o_parts);
   ws.tilemin = (uint32_t*)(p + o_tilemin); ws.u_col = (float*)(p + o_ucol);
   ws.cbuf = want_cbuf ? (float*)(p + o_cbuf) : nullptr;
+  ws.mid = want_cbuf ? (float*)(p + o_mid) : nullptr;
   return SMCB_OK;
 }
 static void op_free(OpWorkspace& ws, cudaStream_t) { ws = OpWorkspace(); }   // the slab stays with the thread for the next call
@@ -1025,7 +1029,7 @@ static int op_resample(const float* w_dev, int64_t n, int32_t B, int64_t sn, int
     r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
     if (kind == SMCB_SYSTEMATIC) op_launch_systematic(r, s);
     else {
-      r.c_out = ws.cbuf;
+      r.c_out = ws.cbuf; r.mid_out = ws.mid;
       if (rc == SMCB_OK) rc = op_launch_multinomial(r, U_dev, n, s);
     }
     if (rc == SMCB_OK) {
@@ -1243,7 +1247,7 @@ extern "C" int smcb_residual(const float* w_dev, int64_t n, int32_t B, int64_t s
     r.seed = seed; r.tilesum = ws.tilesum; r.anc = ws.anc; r.ctrl = ws.ctrl;
     r.prefix = ws.prefix; r.sin = ws.sin; r.tileflag = ws.tileflag; r.desc = ws.desc; r.desc2 = ws.desc2; r.tables = ws.tables; r.dcounter = ws.dcounter;
     r.tilemin = ws.tilemin; r.ncounter = ws.ncounter; r.verdict = ws.verdict; r.u_col = ws.u_col;
-    r.c_out = ws.cbuf; r.draw_offset = ksum;
+    r.c_out = ws.cbuf; r.mid_out = ws.mid; r.draw_offset = ksum;
     rc = op_launch_multinomial(r, U_dev, n, s);
     if (rc == SMCB_OK) {
       op_launch_scatter_i64(ws.anc, n, B, ws.ld, out_dev, osn, osb, s);
