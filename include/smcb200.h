@@ -30,7 +30,9 @@ extern "C" {
 enum { SMCB_OK = 0, SMCB_EINVAL = -1, SMCB_ECUDA = -2, SMCB_ENODEVICE = -3, SMCB_EUNSUPPORTED = -4, SMCB_ESTATE = -5 };
 
 /* models: the user-supplied stochproc callables of the reference become a compiled zoo */
-enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3 };
+enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3,
+       SMCB_USER_MODEL = 4 /* a build of the library compiled with -DSMCB_USER_MODEL_HEADER=<file>: the user's mean_scale / observation
+                              density as device functions (csrc/models.h); raw parameters: UserModel::NRAW values per column */ };
 /* proposals: filters/particle/proposals/bootstrap.py:4-17, proposals/linear.py:13-89 */
 enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1 };
 /* filters: filters/particle/sisr.py:7-56, filters/particle/apf.py:9-46 */

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmcb200.so")
 _SOURCES = ["smcb_api.cu", "resample.cuh", "step.cuh", "operators.cuh", "common.cuh", "models.h", "philox.h", "scan_tile.h",
-            "exact_scan.h", "column.cuh", "move.cuh"]
+            "exact_scan.h", "column.cuh", "move.cuh", "plugin.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
               "-diag-suppress", "128"]
 
@@ -113,6 +113,63 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+_user_libs = {}
+
+
+def _bind(lib, lib_path, stale_note=None):
+    for name, restype, argtypes in SYMBOLS:
+        try:
+            fn = getattr(lib, name)
+        except AttributeError:
+            raise SmcbError(f"{lib_path} does not export {name}: the binary does not match include/smcb200.h"
+                            + (f" ({stale_note})" if stale_note else ""))
+        fn.restype = restype
+        fn.argtypes = argtypes
+    sig = (C.sizeof(smcb_config) << 16) | C.sizeof(smcb_info)
+    if lib.smcb_version() != ABI_VERSION or lib.smcb_abi_signature() != sig:
+        raise SmcbError(f"{lib_path} was built from another version of include/smcb200.h (version {lib.smcb_version()} vs {ABI_VERSION}, "
+                        f"struct signature {lib.smcb_abi_signature():#x} vs {sig:#x}); rebuild it with pyfilter_b200._lib.build_library(force=True)")
+    return lib
+
+
+def build_user_library(header_path: str, force: bool = False) -> str:
+    """A build of the library that carries a user-supplied model (csrc/models.h: ``SMCB_USER_MODEL_HEADER``): the whole C ABI compiled
+    once more with the user's header, into ``pyfilter_b200/_user/<hash>/libsmcb200_user.so`` (in-tree, so that it travels with the
+    repository snapshot; keyed by the hash of the header and of the library's own sources)."""
+    import hashlib
+
+    h = hashlib.sha256()
+    h.update(open(header_path, "rb").read())
+    for src in _SOURCES:
+        h.update(open(os.path.join(_HERE, "csrc", src), "rb").read())
+    h.update(open(os.path.join(os.path.dirname(_HERE), "include", "smcb200.h"), "rb").read())
+    out_dir = os.path.join(_HERE, "_user", h.hexdigest()[:16])
+    out = os.path.join(out_dir, "libsmcb200_user.so")
+    if os.path.exists(out) and not force:
+        return out
+    os.makedirs(out_dir, exist_ok=True)
+    import shutil
+
+    local = os.path.join(out_dir, "user_model.h")
+    if os.path.abspath(header_path) != os.path.abspath(local):
+        shutil.copyfile(header_path, local)
+    nvcc = os.environ.get("NVCC") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + [f'-DSMCB_USER_MODEL_HEADER="{local}"', "-o", out, os.path.join(_HERE, "csrc", "smcb_api.cu")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise SmcbError(f"nvcc failed on the user model:\n{res.stdout[-2000:]}\n{res.stderr[-4000:]}")
+    return out
+
+
+def load_user_library(so_path: str):
+    with _lock:
+        lib = _user_libs.get(so_path)
+        if lib is None:
+            lib = _bind(C.CDLL(so_path), so_path)
+            _user_libs[so_path] = lib
+        return lib
+
+
 def load_library():
     """Loads the shared library (building it when nvcc is available and the sources are newer) and binds every symbol."""
     global _lib
@@ -155,9 +212,9 @@ def load_library():
         return lib
 
 
-def check(rc: int):
+def check(rc: int, lib=None):
     if rc != 0:
-        msg = load_library().smcb_last_error().decode()
+        msg = (lib or load_library()).smcb_last_error().decode()
         if rc == -4:
             raise NotImplementedError(msg)
         if rc == -1:

@@ -13,7 +13,7 @@
 #define SMCB_NPARAM 32
 #define SMCB_LOG_SQRT_2PI 0.9189385332046727f
 
-enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_NUM_MODELS = 4 };
+enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_MODEL_USER = 4, SMCB_NUM_MODELS = 5 };
 enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1 };
 enum { SMCB_ALG_SISR = 0, SMCB_ALG_APF = 1 };
 enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
@@ -151,3 +151,19 @@ template <> struct Model<SMCB_MODEL_LORENZ63_EM> {
     y[1] = __fadd_rn(__fmul_rn(P[5], x[2]), __fmul_rn(P[P_LGO_OBS_S], v[1]));
   }
 };
+
+// ---- a user-supplied model: the reference takes ANY stochproc callables; here the user writes the same two functions
+//      as device code and the library is compiled once more with that header (pyfilter_b200.timeseries.compile_user_model: nvcc at run
+//      time, the shared object cached by the hash of the source).  The header defines
+//          struct UserModel {
+//            static constexpr int D = ..., OD = ..., NRAW = ...;            // state / observation dimensions, raw parameters per column
+//            static constexpr bool LINEAR_OBS = false;
+//            __device__ static void loc_scale(const float* x, const float* P, float* loc, float& scale);     // mean_scale
+//            __device__ static float obs_lp(const float* y, const float* x, const float* P);                 // build_density().log_prob
+//            __device__ static void obs_sample(const float* x, const float* v, const float* P, float* y);    // build_density().sample
+//            static void derive(const double* raw, float* P);   // HOST: raw parameters -> the row P (P[0 .. NRAW) + any constants), incl.
+//          };                                                   //       P[P_INC_SCALE], P[P_X0_LOC + d], P[P_X0_SCALE + d]
+#ifdef SMCB_USER_MODEL_HEADER
+#include SMCB_USER_MODEL_HEADER
+template <> struct Model<SMCB_MODEL_USER> : UserModel {};
+#endif

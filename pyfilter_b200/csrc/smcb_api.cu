@@ -58,8 +58,15 @@ extern "C" int smcb_device_count(void) {
   return n;
 }
 
-static const int kDims[SMCB_NUM_MODELS][2] = {{1, 1}, {1, 1}, {1, 1}, {3, 2}};
-static const int kRaw[SMCB_NUM_MODELS] = {6, 6, 3, 7};
+#ifdef SMCB_USER_MODEL_HEADER
+static const int kDims[SMCB_NUM_MODELS][2] = {{1, 1}, {1, 1}, {1, 1}, {3, 2}, {UserModel::D, UserModel::OD}};
+static const int kRaw[SMCB_NUM_MODELS] = {6, 6, 3, 7, UserModel::NRAW};
+#define SMCB_USER_CASE(BODY) case 4: { BODY; } break;
+#else
+static const int kDims[SMCB_NUM_MODELS][2] = {{1, 1}, {1, 1}, {1, 1}, {3, 2}, {1, 1}};
+static const int kRaw[SMCB_NUM_MODELS] = {6, 6, 3, 7, 0};
+#define SMCB_USER_CASE(BODY)
+#endif
 
 // ---- host-side parameter row (layout in models.h) -------------------------------------------------------------------------
 static void derive_params(int model, const double* r, float* P) {
@@ -97,6 +104,12 @@ static void derive_params(int model, const double* r, float* P) {
       sigma = r[3]; a = r[5]; s = os; lorenz_lgo = true;
       break;
     }
+#ifdef SMCB_USER_MODEL_HEADER
+    case SMCB_MODEL_USER:
+      P[P_INC_SCALE] = 1.f;
+      UserModel::derive(r, P);
+      return;
+#endif
   }
   P[P_INC_SCALE] = (float)inc;
   if (lorenz_lgo) {
@@ -226,6 +239,10 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
 extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   if (!cfg || !out) return fail(SMCB_EINVAL, "null argument");
   if (cfg->model < 0 || cfg->model >= SMCB_NUM_MODELS) return fail(SMCB_EUNSUPPORTED, "unknown model id (only the compiled zoo is supported; there is no CPU fallback)");
+#ifndef SMCB_USER_MODEL_HEADER
+  if (cfg->model == SMCB_MODEL_USER) return fail(SMCB_EUNSUPPORTED, "this build of libsmcb200 carries no user model (pyfilter_b200.timeseries.compile_user_model builds one)");
+#endif
+  if (cfg->model == SMCB_MODEL_USER && cfg->proposal != SMCB_BOOTSTRAP) return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");
   if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS) return fail(SMCB_EUNSUPPORTED, "unknown proposal");
   if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM || cfg->model == SMCB_LORENZ63_EM))
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
@@ -360,6 +377,7 @@ static StepArgs make_args(smcb_filter* f) {
     case 1: { constexpr int MODEL = 1; BODY; } break;                        \
     case 2: { constexpr int MODEL = 2; BODY; } break;                        \
     case 3: { constexpr int MODEL = 3; BODY; } break;                        \
+    SMCB_USER_CASE(constexpr int MODEL = 4; BODY)                            \
   }
 
 template <int MODEL, int PROP>
@@ -376,6 +394,7 @@ static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
     case 1: if (prop) launch_step_alg<1, 1>(alg, g, s, a); else launch_step_alg<1, 0>(alg, g, s, a); break;
     case 2: launch_step_alg<2, 0>(alg, g, s, a); break;
     case 3: if (prop) launch_step_alg<3, 1>(alg, g, s, a); else launch_step_alg<3, 0>(alg, g, s, a); break;
+    SMCB_USER_CASE((launch_step_alg<4, 0>(alg, g, s, a)))
   }
   f->launches++;
 }
@@ -478,6 +497,7 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
     case 1: e = prop ? launch_move_alg<1, 1>(f, m, s) : launch_move_alg<1, 0>(f, m, s); break;
     case 2: e = launch_move_alg<2, 0>(f, m, s); break;
     case 3: e = prop ? launch_move_alg<3, 1>(f, m, s) : launch_move_alg<3, 0>(f, m, s); break;
+    SMCB_USER_CASE((e = launch_move_alg<4, 0>(f, m, s)))
   }
   if (e != cudaSuccess) return fail(SMCB_ECUDA, std::string("move_kernel: ") + cudaGetErrorString(e));
   f->launches++;
@@ -498,6 +518,7 @@ static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) 
     case 1: if (prop) preweight_kernel<1, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<1, 0><<<g, ST_NT, 0, s>>>(a); break;
     case 2: preweight_kernel<2, 0><<<g, ST_NT, 0, s>>>(a); break;
     case 3: if (prop) preweight_kernel<3, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<3, 0><<<g, ST_NT, 0, s>>>(a); break;
+    SMCB_USER_CASE((preweight_kernel<4, 0><<<g, ST_NT, 0, s>>>(a)))
   }
   f->launches++;
 }
@@ -742,6 +763,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
     case 1: e = prop ? launch_column_alg<1, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, nt, f->B, dyn, s, c); break;
     case 2: e = launch_column_alg<2, 0>(alg, nt, f->B, dyn, s, c); break;
     case 3: e = prop ? launch_column_alg<3, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<3, 0>(alg, nt, f->B, dyn, s, c); break;
+    SMCB_USER_CASE((e = launch_column_alg<4, 0>(alg, nt, f->B, dyn, s, c)))
   }
   if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
   f->launches++;
@@ -1075,6 +1097,7 @@ static int proposal_op(smcb_filter* f, int mode, const float* y_dev, const float
     case 1: if (prop) proposal_op_kernel<1, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<1, 0><<<g, ST_NT, 0, s>>>(c); break;
     case 2: proposal_op_kernel<2, 0><<<g, ST_NT, 0, s>>>(c); break;
     case 3: if (prop) proposal_op_kernel<3, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<3, 0><<<g, ST_NT, 0, s>>>(c); break;
+    SMCB_USER_CASE((proposal_op_kernel<4, 0><<<g, ST_NT, 0, s>>>(c)))
   }
   f->launches++;
   CU(cudaGetLastError());

@@ -12,7 +12,7 @@ class Engine:
                  batch_shape: torch.Size, ess_threshold: float, seed: int, history_rows: int, fold_lookahead: bool = True,
                  exact_weights: bool = False, column_offset: int = 0):
         _lib.require_cuda()
-        self.lib = _lib.load_library()
+        self.lib = model.library() if hasattr(model, "library") else _lib.load_library()   # (a user model lives in its own build)
         self.model = model
         self.batch_shape = torch.Size(batch_shape)
         self.B = int(self.batch_shape[0]) if len(self.batch_shape) else 1
@@ -31,7 +31,7 @@ class Engine:
         cfg.column_offset = int(column_offset)   # global index of column 0: the Philox counters use column_offset + column
         self._params_keepalive = params
         h = C.c_void_p()
-        _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)))
+        _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)), self.lib)
         self.handle = h
         info = self.info()
         self.ld, self.D, self.OD, self.history_rows = info.ld, info.state_dim, info.obs_dim, info.history_rows

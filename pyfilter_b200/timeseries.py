@@ -14,7 +14,7 @@ from typing import Sequence, Tuple
 
 import torch
 
-MODEL_LG_AR1, MODEL_SINE_EM, MODEL_SV_AR1, MODEL_LORENZ63_EM = 0, 1, 2, 3
+MODEL_LG_AR1, MODEL_SINE_EM, MODEL_SV_AR1, MODEL_LORENZ63_EM, MODEL_USER = 0, 1, 2, 3, 4
 
 
 def _t(v) -> torch.Tensor:
@@ -177,6 +177,8 @@ class StateSpaceModel:
             return tuple(h)
         if self.model_id == MODEL_LORENZ63_EM:
             return (*h, _t(self.hidden.dt), *o)
+        if self.model_id == MODEL_USER:
+            return tuple(h)
         raise NotImplementedError
 
     def parameter_matrix(self, batch: int) -> torch.Tensor:
@@ -266,3 +268,57 @@ def build(name: str, **params) -> StateSpaceModel:
         return LinearStateSpaceModel(Lorenz63(p["s"], p["r"], p["b"], p["sigma"], p["dt"]), (p["obs_a"], p["obs_s"]), torch.Size([2]),
                                      observe_every_step=every)
     raise NotImplementedError(f"'{name}' is not in the compiled model zoo")
+
+
+# ---- user-supplied models ---------------------------------------------------------------------------------------
+class UserProcess(HiddenProcess):
+    name = "user"
+
+    def __init__(self, parameters: Sequence, state_dim: int):
+        super().__init__(parameters)
+        self.event_shape = torch.Size([state_dim]) if state_dim > 1 else torch.Size([])
+
+
+class UserStateSpaceModel(StateSpaceModel):
+    """A model whose ``mean_scale`` / observation density the USER wrote as CUDA device functions (``compile_user_model``).  It runs through
+    a build of the library that carries that code; everything else - filters, proposals' Bootstrap path, resamplers, SMC2 / NESS - is the
+    same.  There is no torch evaluation of a user model: ``sample_states`` is not available."""
+
+    def __init__(self, library_path: str, parameters: Sequence, state_dim: int, obs_dim: int, observe_every_step: int = 1):
+        super().__init__(UserProcess(parameters, state_dim), MODEL_USER, (), torch.Size([obs_dim]) if obs_dim > 1 else torch.Size([]),
+                         observe_every_step)
+        self.library_path = library_path
+
+    def library(self):
+        from . import _lib
+
+        return _lib.load_user_library(self.library_path)
+
+    def sample_states(self, *a, **k):
+        raise NotImplementedError("a user model exists as device code only")
+
+
+def compile_user_model(source: str, state_dim: int = 1, obs_dim: int = 1):
+    """Compiles ``source`` - CUDA C++ defining ``struct UserModel`` (see csrc/models.h for the contract: ``D``, ``OD``, ``NRAW``,
+    ``loc_scale``, ``obs_lp``, ``obs_sample`` as ``__device__`` functions and the host function ``derive``) - into its own build of the
+    library (nvcc, about a minute the first time; cached in-tree by the hash of the source) and returns a factory
+    ``make(*parameters, observe_every_step=1) -> UserStateSpaceModel`` (parameters: floats or ``(B,)`` tensors, ``NRAW`` of them)."""
+    import hashlib
+    import os
+
+    from . import _lib
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    tmp_dir = os.path.join(here, "_user", "src")
+    os.makedirs(tmp_dir, exist_ok=True)
+    header = os.path.join(tmp_dir, hashlib.sha256(source.encode()).hexdigest()[:16] + ".h")
+    if not os.path.exists(header):
+        with open(header, "w") as fh:
+            fh.write(source)
+    so = _lib.build_user_library(header)
+
+    def make(*parameters, observe_every_step: int = 1) -> UserStateSpaceModel:
+        return UserStateSpaceModel(so, parameters, state_dim, obs_dim, observe_every_step)
+
+    make.library_path = so
+    return make
