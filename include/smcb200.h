@@ -208,6 +208,17 @@ int smcb_filter_ffbs_step(smcb_filter* f, const float* x_dev, const float* lw_de
 int smcb_filter_resample_columns(smcb_filter* f, const int64_t* idx_dev, int32_t entire_history, void* stream);
 int smcb_filter_exchange_columns(smcb_filter* dst, smcb_filter* src, const uint8_t* mask_dev, void* stream);
 
+/* the columns of a handle as self-contained records, for theta-resampling ACROSS handles / ranks (a sharded SMC2 run: the ancestor of a
+ * column may live on another GPU, particle/state.py:150-158 on a distributed batch).  export: record[b] = everything the handle holds
+ * for column b (particles, both weight rows, ancestors, statistics, running log-likelihood, latest moments, the moment / likelihood
+ * history), smcb_filter_column_record_elems() 4-byte elements each, into buf_dev (B, record).  import: column b of the handle <- record
+ * idx_dev[b] of a buffer holding n_records records (the all-gather of the ranks' exports; idx NULL: identity); both handles must have
+ * been created with the same shapes and stand at the same move index.  `folded` (>= 0) tells whether the imported APF resampling weights
+ * are valid for the coming move.  import synchronises (range check). */
+int64_t smcb_filter_column_record_elems(smcb_filter* f);
+int smcb_filter_export_columns(smcb_filter* f, void* buf_dev, void* stream);
+int smcb_filter_import_columns(smcb_filter* f, const void* buf_dev, int32_t n_records, const int64_t* idx_dev, int32_t folded, void* stream);
+
 /* stand-alone operators ......................................................................................................
  * All take a weight matrix with element strides (stride_n, stride_b): the reference's particle-major (N,B) tensor has
  * (B, 1); a single column has (1, 0).  `out_dev` strides are given the same way. */

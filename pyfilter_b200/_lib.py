@@ -81,6 +81,9 @@ SYMBOLS = [
     ("smcb_residual", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_uint64, _P, C.c_int64, C.c_int64, _P]),
     ("smcb_batched_gather", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     ("smcb_filter_set_seed", C.c_int, [_P, C.c_uint64]),
+    ("smcb_filter_column_record_elems", C.c_int64, [_P]),
+    ("smcb_filter_export_columns", C.c_int, [_P, _P, _P]),
+    ("smcb_filter_import_columns", C.c_int, [_P, _P, C.c_int32, _P, C.c_int32, _P]),
     ("smcb_filter_ffbs_step", C.c_int, [_P, _P, _P, _P, _P, C.c_uint64, C.c_int32, _P, _P, _P]),
 ]
 

@@ -392,3 +392,39 @@ __global__ void __launch_bounds__(256) ffbs_step_kernel(FfbsArgs a) {
     for (int d = 0; d < D; ++d) a.xout[i * D + d] = __ldg(a.x + j * D + d);
   }
 }
+
+// ---- columns of a handle as self-contained records (cross-rank theta-resampling of a sharded SMC2 run) -----------------------------------
+// Every per-column array of a handle is described by (pointer, rows, elements per row, stride between rows, stride between columns, all in
+// 4-byte elements).  pack: record[column] = the column's slices of all arrays, back to back; unpack: column b of the handle <- record
+// [idx[b]] of a buffer that may hold the records of MANY handles (the all-gather of the ranks' packed shards).
+#define SMCB_MAX_COLDESC 16
+struct ColDesc { uint32_t* ptr; int32_t rows, inner; int64_t row_stride, col_stride; int64_t offset; };   // offset: position inside the record
+struct ColPackArgs {
+  ColDesc d[SMCB_MAX_COLDESC];
+  int32_t ndesc, B;
+  int64_t record;          // elements per record
+  uint32_t* buf;           // (columns, record)
+  const int64_t* idx;      // unpack: source record of every local column (NULL: identity)
+  int32_t n_records;       // unpack: records in buf (range check)
+  int32_t* bad;
+};
+template <bool PACK>
+__global__ void __launch_bounds__(256) column_pack_kernel(ColPackArgs a) {
+  const int b = blockIdx.y;
+  int64_t rec = b;
+  if (!PACK && a.idx) {
+    rec = a.idx[b];
+    if (rec < 0 || rec >= a.n_records) { if (a.bad && threadIdx.x == 0 && blockIdx.x == 0) atomicExch(a.bad, 1); return; }
+  }
+  uint32_t* r = a.buf + rec * a.record;
+  for (int k = 0; k < a.ndesc; ++k) {
+    const ColDesc d = a.d[k];
+    const int64_t count = (int64_t)d.rows * d.inner;
+    for (int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x; e < count; e += (int64_t)gridDim.x * 256) {
+      const int64_t row = e / d.inner, in = e - row * d.inner;
+      uint32_t* p = d.ptr + row * d.row_stride + (int64_t)b * d.col_stride + in;
+      if (PACK) r[d.offset + e] = *p;
+      else *p = r[d.offset + e];
+    }
+  }
+}

@@ -1299,3 +1299,69 @@ extern "C" int smcb_filter_ffbs_step(smcb_filter* f, const float* x_dev, const f
   CU(cudaGetLastError());
   return SMCB_OK;
 }
+
+// ---- columns as records: export / import (cross-rank theta-resampling of a sharded batch) -------------------------------------------
+static int64_t column_record_layout(smcb_filter* f, ColPackArgs& a) {
+  memset(&a, 0, sizeof(a));
+  const int cur = f->t_host & 1;
+  int k = 0;
+  int64_t off = 0;
+  auto add = [&](void* ptr, int rows, int64_t inner, int64_t row_stride, int64_t col_stride) {
+    a.d[k].ptr = (uint32_t*)ptr; a.d[k].rows = rows; a.d[k].inner = (int32_t)inner; a.d[k].row_stride = row_stride; a.d[k].col_stride = col_stride;
+    a.d[k].offset = off;
+    off += (int64_t)rows * inner;
+    ++k;
+  };
+  const int64_t plane = (int64_t)f->B * f->ld;
+  add(f->xbuf[cur], f->D, f->ld, plane, f->ld);              // particles (D, B, ld)
+  add(f->lwbuf[cur], 1, f->ld, 0, f->ld);
+  add(f->rwbuf[cur], 1, f->ld, 0, f->ld);
+  add(f->prev_inds, 1, f->ld, 0, f->ld);
+  add(f->stats, 1, sizeof(ColStats) / 4, 0, sizeof(ColStats) / 4);
+  add(f->ll_total, 1, 1, 0, 1);
+  add(f->latest_mean, 1, f->D, 0, f->D);
+  add(f->latest_var, 1, f->D, 0, f->D);
+  add(f->latest_ll, 1, 1, 0, 1);
+  const int rows = f->cfg.history_rows;
+  add(f->hist_mean, rows, f->D, (int64_t)f->B * f->D, f->D);   // (rows, B, D)
+  add(f->hist_var, rows, f->D, (int64_t)f->B * f->D, f->D);
+  add(f->hist_ll, rows, 1, f->B, 1);
+  a.ndesc = k; a.B = f->B; a.record = off;
+  return off;
+}
+extern "C" int64_t smcb_filter_column_record_elems(smcb_filter* f) {
+  if (!f) return 0;
+  ColPackArgs a;
+  return column_record_layout(f, a);
+}
+extern "C" int smcb_filter_export_columns(smcb_filter* f, void* buf_dev, void* stream) {
+  if (!f || !buf_dev) return fail(SMCB_EINVAL, "null argument");
+  ColPackArgs a;
+  column_record_layout(f, a);
+  a.buf = (uint32_t*)buf_dev;
+  column_pack_kernel<true><<<dim3(16, f->B), 256, 0, (cudaStream_t)stream>>>(a);
+  f->launches++;
+  CU(cudaGetLastError());
+  return SMCB_OK;
+}
+extern "C" int smcb_filter_import_columns(smcb_filter* f, const void* buf_dev, int32_t n_records, const int64_t* idx_dev, int32_t folded, void* stream) {
+  if (!f || !buf_dev || n_records < 1) return fail(SMCB_EINVAL, "bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  ColPackArgs a;
+  column_record_layout(f, a);
+  a.buf = (uint32_t*)buf_dev; a.idx = idx_dev; a.n_records = n_records;
+  int* bad = nullptr;
+  CU(cudaMallocAsync((void**)&bad, sizeof(int), s));
+  CU(cudaMemsetAsync(bad, 0, sizeof(int), s));
+  a.bad = bad;
+  column_pack_kernel<false><<<dim3(16, f->B), 256, 0, s>>>(a);
+  f->launches++;
+  int h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, bad, sizeof(int), cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFreeAsync(bad, s);
+  if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
+  if (h) return fail(SMCB_EINVAL, "record index out of range");
+  if (folded >= 0) f->folded_for_next = folded != 0;
+  return SMCB_OK;
+}

@@ -217,6 +217,20 @@ class Engine:
         _lib.check(self.lib.smcb_filter_exchange_columns(self.handle, other.handle, m.data_ptr(), _lib.current_stream()))
         self.stamp += 1
 
+    # ---- columns as records (cross-rank theta-resampling of a sharded batch)
+    def export_columns(self) -> torch.Tensor:
+        n = int(self.lib.smcb_filter_column_record_elems(self.handle))
+        buf = torch.empty((self.B, n), device="cuda", dtype=torch.int32)
+        _lib.check(self.lib.smcb_filter_export_columns(self.handle, buf.data_ptr(), _lib.current_stream()), self.lib)
+        return buf
+
+    def import_columns(self, records: torch.Tensor, indices: torch.Tensor = None, folded: int = -1):
+        assert records.is_cuda and records.dtype == torch.int32 and records.is_contiguous()
+        idx = indices.to(device="cuda", dtype=torch.int64).contiguous() if indices is not None else None
+        _lib.check(self.lib.smcb_filter_import_columns(self.handle, records.data_ptr(), int(records.shape[0]),
+                                                       idx.data_ptr() if idx is not None else None, int(folded), _lib.current_stream()), self.lib)
+        self.stamp += 1
+
     def make_state(self):
         from .state import ParticleFilterCorrection
 

@@ -65,8 +65,8 @@ class SMC2State:
     """``SMC2State`` (inference/sequential/state.py:10-95): theta log-weights, the ESS history, the parsed observations."""
 
     def __init__(self, weights: torch.Tensor, engine: Engine):
-        self.w = weights
-        self.engine = engine
+        self.w = weights          # (B,) theta log-weights of the WHOLE batch (replicated on every rank of a sharded run)
+        self.engine = engine      # the handle that holds this process' columns
         self.ess: List[float] = [float(_utils.get_ess(weights))]
         self.parsed_data: List[torch.Tensor] = []
         self.current_iteration = 0
@@ -103,12 +103,29 @@ class SMC2:
         self._y_dev: torch.Tensor = None
         self._gen = torch.Generator().manual_seed(seed if seed is not None else int(torch.randint(0, 2**62, (1,)).item()))
 
+    # ---- where the columns live: one process holds all of them here; ShardedSMC2 overrides the three hooks
+    def _columns(self) -> slice:
+        """The theta-particles whose filters this process holds."""
+        return slice(0, int(self.particles[0]))
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        """A per-column quantity of this process' columns -> the whole batch's."""
+        return local
+
+    def _migrate(self, engine: Engine, indices: torch.Tensor):
+        """theta-resampling of the filter states: column b <- column indices[b] of the whole batch (state.filter_state.resample)."""
+        engine.resample_columns(indices, entire_history=True)
+
+    def _local_model(self, context: ParameterContext):
+        cols = self._columns()
+        return self._builder({k: v[cols] for k, v in context.constrained().items()})
+
     # ---- filters
     def _make_filter(self, context: ParameterContext, n_state: int, salt: int):
-        model = self._builder(context.constrained())
-        f = self._filter_cls(model, n_state, proposal=self._proposal.copy() if self._proposal is not None else None,
-                             seed=None if self._seed is None else self._seed + 7919 * salt)
-        f.set_batch_shape(self.particles)
+        cols = self._columns()
+        f = self._filter_cls(self._local_model(context), n_state, proposal=self._proposal.copy() if self._proposal is not None else None,
+                             seed=None if self._seed is None else self._seed + 7919 * salt, column_offset=cols.start)
+        f.set_batch_shape(torch.Size([cols.stop - cols.start]))
         return f, f._get_engine(self._rows)
 
     def _draw_seed(self) -> int:
@@ -134,7 +151,7 @@ class SMC2:
         self._y_dev[t] = yt.to("cuda")
         e.set_observations(self._y_dev[: t + 1], 0)
         e.run(1)
-        state.w += e.raw(_lib.PTR_LL, (e.B,))                        # SequentialAlgorithmState.append (state.py:35-44)
+        state.w += self._gather(e.raw(_lib.PTR_LL, (e.B,)))          # SequentialAlgorithmState.append (state.py:35-44)
         ess = float(_utils.get_ess(state.w))
         state.ess.append(ess)
         any_nans = not bool(torch.isfinite(state.w).all())
@@ -154,10 +171,11 @@ class SMC2:
         ctx, e = self.context, state.engine
         B = int(self.particles[0])
         W = state.normalized_weights()
-        indices = self._resampler(W, normalized=True)
-        kernel = construct_mvn(ctx.stack_parameters(), W, scale=1.1)      # SymmetricMH.build (symmetric_mh.py:13-23)
+        u = torch.rand(1, generator=self._gen)                            # the offset from the algorithm's own generator: every rank of a
+        indices = self._resampler(W, normalized=True, u=u.cuda()) if self._resampler is _resampling.systematic else self._resampler(W, normalized=True)
+        kernel = construct_mvn(ctx.stack_parameters(), W, scale=1.1)      # SymmetricMH.build (symmetric_mh.py:13-23)      sharded run draws the same
         ctx.resample(indices)
-        e.resample_columns(indices, entire_history=True)                  # state.filter_state.resample(indices)
+        self._migrate(e, indices)                                         # state.filter_state.resample(indices)
         T = len(state.parsed_data)
         if self._proposal_filter is None or self._proposal_filter[1].N != e.N:
             self._proposal_filter = self._make_filter(ctx, e.N, 1 + self._increases)
@@ -171,7 +189,7 @@ class SMC2:
                 state.acceptance.append(acceptance_rate)
                 return self._increase_states(state)
         state.acceptance.append(acceptance_rate)
-        e.set_params(self._builder(ctx.constrained()))                    # filter_.initialize_model(context)
+        e.set_params(self._local_model(ctx))                              # filter_.initialize_model(context)
         state.w.fill_(0.0)
         state.rejuvenations += 1
         return state
@@ -183,20 +201,22 @@ class SMC2:
         eps = torch.randn(B, mean.shape[0], generator=self._gen).to("cuda")
         rvs = mvn_sample(mean, scale_tril, eps)
         sub_context.unstack_parameters(rvs)
-        pe.set_params(self._builder(sub_context.constrained()))
+        cols = self._columns()
+        pe.set_params(self._local_model(sub_context))
         pe.set_seed(self._draw_seed())                                   # a fresh random stream for every re-filtering
         pe.initialize()
         pe.set_observations(self._y_dev[:T], 0)
         pe.run(T)
-        new_ll = pe.raw(_lib.PTR_LL_TOTAL, (B,))
-        diff_logl = new_ll - state.loglikelihood
-        diff_prior = sub_context.eval_priors() - ctx.eval_priors()
+        new_ll = pe.raw(_lib.PTR_LL_TOTAL, (pe.B,))
+        diff_logl = new_ll - state.loglikelihood                         # this process' columns
+        diff_prior = sub_context.eval_priors() - ctx.eval_priors()       # (B,) arithmetic, replicated
         uniform = torch.full((B,), 1.0 / B, device="cuda")               # state.replicate(new_res): zero log-weights
         new_kernel = construct_mvn(sub_context.stack_parameters(), uniform, scale=1.1)
         diff_prop = mvn_log_prob(*new_kernel, ctx.stack_parameters()) - mvn_log_prob(mean, scale_tril, rvs)
         u = torch.rand(B, generator=self._gen).to("cuda")
-        accepted = pmmh_accept(diff_logl, diff_prior, diff_prop, u)
-        state.engine.exchange_columns(pe, accepted)                       # state.filter_state.exchange(new_res, accepted)
+        accepted_local = pmmh_accept(diff_logl, diff_prior[cols], diff_prop[cols], u[cols])
+        state.engine.exchange_columns(pe, accepted_local)                 # state.filter_state.exchange(new_res, accepted)
+        accepted = self._gather(accepted_local.float()) > 0.5            # the one collective of a sweep on a sharded batch
         ctx.exchange(sub_context, accepted)
         return accepted
 
@@ -211,7 +231,7 @@ class SMC2:
         e.initialize()
         e.set_observations(self._y_dev[:T], 0)
         e.run(T)
-        weight = e.raw(_lib.PTR_LL_TOTAL, (e.B,)) - old_ll
+        weight = self._gather(e.raw(_lib.PTR_LL_TOTAL, (e.B,)) - old_ll)
         res = SMC2State(weight.clone(), e)
         res.ess, res.parsed_data, res.current_iteration = state.ess, state.parsed_data, state.current_iteration
         res.rejuvenations, res.acceptance = state.rejuvenations, state.acceptance
@@ -222,3 +242,42 @@ class SMC2:
     def posterior_mean(self, state: SMC2State) -> Dict[str, torch.Tensor]:
         W = state.normalized_weights()
         return {k: (W * v).sum() for k, v in self.context.constrained().items()}
+
+
+class ShardedSMC2(SMC2):
+    """SMC2 with the theta-particles sharded over the ranks of a ``torch.distributed`` group (one process per GPU):
+    every rank holds a block of the columns (``pyfilter_b200.sharding.column_shard``, Philox streams keyed by the GLOBAL column index),
+    runs the filter moves and the proposal filters of its block, and keeps a replica of the theta-level state - the ``(B,)`` weights and
+    the ``(B, p)`` parameter cloud - which it advances with the same arithmetic from the same generator (``seed`` is mandatory), so no
+    rank ever has to be told what another one decided.  Communication: per step the ``(B_local,)`` likelihood increments (all-gather);
+    per PMMH sweep the accepted flags; per rejuvenation the filter states, because the ancestor of a column may live on another GPU
+    (export of the resident columns as records -> all-gather -> import of the records a rank now owns).  A sharded run reproduces the
+    single-process run of the same seed bit for bit (tools/smc2_sharded_check.py)."""
+
+    def __init__(self, *args, group=None, **kwargs):
+        import torch.distributed as dist
+
+        from ..sharding import column_shard
+
+        if kwargs.get("seed") is None:
+            raise ValueError("a sharded run needs `seed`: every rank replays the same theta-level random numbers")
+        super().__init__(*args, **kwargs)
+        self._dist, self._group = dist, group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self._group), dist.get_rank(self._group)
+        self._lo, self._hi = column_shard(int(self.particles[0]), self.rank, self.world)
+        if (self._hi - self._lo) * self.world != int(self.particles[0]):
+            raise ValueError("the number of theta-particles must be a multiple of the world size")
+
+    def _columns(self) -> slice:
+        return slice(self._lo, self._hi)
+
+    def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        local = local.contiguous()
+        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        self._dist.all_gather_into_tensor(out, local, group=self._group)
+        return out
+
+    def _migrate(self, engine: Engine, indices: torch.Tensor):
+        records = engine.export_columns()                    # (B_local, record)
+        everything = self._gather(records)                   # (B, record): the ranks' blocks in column order
+        engine.import_columns(everything, indices[self._lo:self._hi])

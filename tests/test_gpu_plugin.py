@@ -317,3 +317,30 @@ def test_theta_level_column_operations(pf):
     assert torch.equal(snap(e2)["x"], b["x"])
     with pytest.raises(ValueError):
         e1.resample_columns(torch.tensor([0, 1, 2, 3, 4, 9]).cuda())
+    # columns as records (cross-rank theta-resampling of a sharded batch): export of one handle, import into another with indices ==
+    # the in-place permutation; records of SEVERAL handles concatenated (the all-gather of the ranks' shards) address by global index
+    f3, e3 = make(1)
+    f4, e4 = make(1)
+    torch.cuda.synchronize()
+    rec = e3.export_columns()
+    assert rec.shape[0] == B and rec.dtype == torch.int32
+    e3.resample_columns(idx.cuda(), entire_history=True)
+    e4.import_columns(rec, idx.cuda())
+    torch.cuda.synchronize()
+    s3, s4 = snap(e3), snap(e4)
+    for k in s3:
+        assert torch.equal(s3[k], s4[k]), k
+    both = torch.cat([rec, e2.export_columns()], 0).contiguous()          # "world size 2": records 0..5 of handle 3, 6..11 of handle 2
+    gidx = torch.tensor([7, 0, 11, 6, 2, 2])
+    e4.import_columns(both, gidx.cuda())
+    torch.cuda.synchronize()
+    s4 = snap(e4)
+    a3 = a  # handle 3 before its permutation == handle 1 before its permutation (same seed)
+    for k in ("x", "lw", "pi"):
+        exp = torch.stack([(b[k][:, g - 6] if g >= 6 else a3[k][:, g]) for g in gidx.tolist()], 1)
+        assert torch.equal(s4[k], exp), k
+    e4.run(3)
+    torch.cuda.synchronize()
+    assert torch.isfinite(e4.raw(6, (e4.B,))).all()
+    with pytest.raises(ValueError):
+        e4.import_columns(both, torch.tensor([0, 1, 2, 3, 4, 12]).cuda())
