@@ -25,6 +25,38 @@ class TooManyIncreases(Exception):
     pass
 
 
+class _Phases:
+    """Wall time per phase of the algorithm (diagnostics: SMCB_SMC2_TIMING=1 makes every phase end with a device synchronisation)."""
+
+    def __init__(self):
+        import os
+
+        self.on = bool(os.environ.get("SMCB_SMC2_TIMING"))
+        self.t = {}
+
+    def __call__(self, name):
+        return _Phase(self, name)
+
+
+class _Phase:
+    def __init__(self, owner, name):
+        self.o, self.n = owner, name
+
+    def __enter__(self):
+        if self.o.on:
+            import time
+
+            torch.cuda.synchronize()
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if self.o.on:
+            import time
+
+            torch.cuda.synchronize()
+            self.o.t[self.n] = self.o.t.get(self.n, 0.0) + time.perf_counter() - self.t0
+
+
 # ---- theta-level pieces (each one callable on its own: tests/test_gpu_smc2.py compares them with oracle/smc2_oracle.py) -------------
 def calc_mean_chol(x: torch.Tensor, w: torch.Tensor):
     """``inference/utils.py:42-58``: weighted mean and the Cholesky factor of the weighted covariance of the rows of ``x`` ``(B, p)``;
@@ -102,6 +134,7 @@ class SMC2:
         self._proposal_filter = None
         self._y_dev: torch.Tensor = None
         self._gen = torch.Generator().manual_seed(seed if seed is not None else int(torch.randint(0, 2**62, (1,)).item()))
+        self.phases = _Phases()
 
     # ---- where the columns live: one process holds all of them here; ShardedSMC2 overrides the three hooks
     def _columns(self) -> slice:
@@ -149,14 +182,18 @@ class SMC2:
         yt = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
         state.parsed_data.append(yt)
         self._y_dev[t] = yt.to("cuda")
-        e.set_observations(self._y_dev[: t + 1], 0)
-        e.run(1)
-        state.w += self._gather(e.raw(_lib.PTR_LL, (e.B,)))          # SequentialAlgorithmState.append (state.py:35-44)
-        ess = float(_utils.get_ess(state.w))
+        with self.phases("filter move"):
+            e.set_observations(self._y_dev[: t + 1], 0)
+            e.run(1)
+        with self.phases("gather increments"):
+            state.w += self._gather(e.raw(_lib.PTR_LL, (e.B,)))      # SequentialAlgorithmState.append (state.py:35-44)
+        with self.phases("ess"):
+            ess = float(_utils.get_ess(state.w))
         state.ess.append(ess)
         any_nans = not bool(torch.isfinite(state.w).all())
         if ess < self._threshold * self.particles[0] or any_nans:
-            state = self.rejuvenate(state)
+            with self.phases("rejuvenate (all of it)"):
+                state = self.rejuvenate(state)
         state.current_iteration += 1
         return state
 
@@ -170,15 +207,18 @@ class SMC2:
     def rejuvenate(self, state: SMC2State) -> SMC2State:
         ctx, e = self.context, state.engine
         B = int(self.particles[0])
-        W = state.normalized_weights()
+        with self.phases("theta resample + proposal fit"):
+            W = state.normalized_weights()
         u = torch.rand(1, generator=self._gen)                            # the offset from the algorithm's own generator: every rank of a
         indices = self._resampler(W, normalized=True, u=u.cuda()) if self._resampler is _resampling.systematic else self._resampler(W, normalized=True)
         kernel = construct_mvn(ctx.stack_parameters(), W, scale=1.1)      # SymmetricMH.build (symmetric_mh.py:13-23)      sharded run draws the same
         ctx.resample(indices)
-        self._migrate(e, indices)                                         # state.filter_state.resample(indices)
+        with self.phases("migrate columns"):
+            self._migrate(e, indices)                                     # state.filter_state.resample(indices)
         T = len(state.parsed_data)
         if self._proposal_filter is None or self._proposal_filter[1].N != e.N:
-            self._proposal_filter = self._make_filter(ctx, e.N, 1 + self._increases)
+            with self.phases("create proposal filter"):
+                self._proposal_filter = self._make_filter(ctx, e.N, 1 + self._increases)
         sub_context = ctx.make_new()
         pe = self._proposal_filter[1]
         acceptance_rate = 0.0
@@ -198,15 +238,19 @@ class SMC2:
     def _run_pmmh(self, ctx: ParameterContext, state: SMC2State, kernel, pe: Engine, sub_context: ParameterContext, T: int) -> torch.Tensor:
         B = int(self.particles[0])
         mean, scale_tril = kernel
-        eps = torch.randn(B, mean.shape[0], generator=self._gen).to("cuda")
-        rvs = mvn_sample(mean, scale_tril, eps)
-        sub_context.unstack_parameters(rvs)
+        with self.phases("pmmh propose"):
+            eps = torch.randn(B, mean.shape[0], generator=self._gen).to("cuda")
+            rvs = mvn_sample(mean, scale_tril, eps)
+            sub_context.unstack_parameters(rvs)
         cols = self._columns()
-        pe.set_params(self._local_model(sub_context))
-        pe.set_seed(self._draw_seed())                                   # a fresh random stream for every re-filtering
-        pe.initialize()
-        pe.set_observations(self._y_dev[:T], 0)
-        pe.run(T)
+        with self.phases("proposal filter run"):
+            pe.set_params(self._local_model(sub_context))
+            pe.set_seed(self._draw_seed())                               # a fresh random stream for every re-filtering
+            pe.initialize()
+            pe.set_observations(self._y_dev[:T], 0)
+            pe.run(T)
+        ph = self.phases("pmmh accept arithmetic + exchange")
+        ph.__enter__()
         new_ll = pe.raw(_lib.PTR_LL_TOTAL, (pe.B,))
         diff_logl = new_ll - state.loglikelihood                         # this process' columns
         diff_prior = sub_context.eval_priors() - ctx.eval_priors()       # (B,) arithmetic, replicated
@@ -218,6 +262,7 @@ class SMC2:
         state.engine.exchange_columns(pe, accepted_local)                 # state.filter_state.exchange(new_res, accepted)
         accepted = self._gather(accepted_local.float()) > 0.5            # the one collective of a sweep on a sharded batch
         ctx.exchange(sub_context, accepted)
+        ph.__exit__()
         return accepted
 
     # ---- _increase_states (kernels/mh.py:110-140): twice the state particles, re-filter, weights = change of the log-likelihoods
@@ -267,15 +312,31 @@ class ShardedSMC2(SMC2):
         self._lo, self._hi = column_shard(int(self.particles[0]), self.rank, self.world)
         if (self._hi - self._lo) * self.world != int(self.particles[0]):
             raise ValueError("the number of theta-particles must be a multiple of the world size")
+        self._gather_bufs = {}
+
+    def initialize(self) -> SMC2State:
+        state = super().initialize()
+        # the proposal filter and the migration buffers exist before the first rejuvenation (allocation is slow once the ranks have mapped
+        # each other's memory, see _gather)
+        self._proposal_filter = self._make_filter(self.context, self._n_state, 1)
+        self._proposal_filter[1].initialize()
+        self._gather(state.engine.export_columns())
+        return state
 
     def _columns(self) -> slice:
         return slice(self._lo, self._hi)
 
     def _gather(self, local: torch.Tensor) -> torch.Tensor:
+        # one output buffer per (shape, dtype), kept: with peer access enabled between the GPUs every NEW device allocation is mapped
+        # into all peers and costs milliseconds - the loop must not allocate
         local = local.contiguous()
-        out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+        key = (tuple(local.shape), local.dtype)
+        out = self._gather_bufs.get(key)
+        if out is None:
+            out = torch.empty((self.world * local.shape[0],) + tuple(local.shape[1:]), device=local.device, dtype=local.dtype)
+            self._gather_bufs[key] = out
         self._dist.all_gather_into_tensor(out, local, group=self._group)
-        return out
+        return out.clone() if out.numel() <= 1 << 16 else out   # small results are handed out as copies (the buffer is reused)
 
     def _migrate(self, engine: Engine, indices: torch.Tensor):
         records = engine.export_columns()                    # (B_local, record)
