@@ -411,7 +411,9 @@ static void mv_choose_geometry(smcb_filter* f, int slots) {
   const int64_t Tu = (n + L1 - 1) / L1;
   int bt1 = (int)Tu, bi1 = 16, bi2 = 16, bT = (int)Tu;
   const int64_t total = Tu * B;
-  if (total > slots && total % slots != 0 && total % slots < slots / 4) {
+  // (a single filter only: the cut of a column must not depend on how many columns the handle holds - shards of one batch on
+  // different ranks reproduce the unsharded run bit for bit, and the fold of a column's per-tile records follows its tiles)
+  if (B == 1 && total > slots && total % slots != 0 && total % slots < slots / 4) {
     const int64_t t1 = ((total / slots) * slots) / B;   // whole waves of large tiles
     if (t1 >= 1 && t1 < Tu) {
       const int64_t L2 = (int64_t)MV_NT * 4;
