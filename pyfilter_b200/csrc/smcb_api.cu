@@ -264,7 +264,9 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   {
     const int64_t chunk = ST_NT * ST_VEC;
     const int64_t nchunks = (f->n + chunk - 1) / chunk;
-    int64_t cap = ((int64_t)smcb_sm_count() * SMCB_ST_MINB) / f->B;  // one resident wave of step-kernel blocks
+    // one resident wave of step-kernel blocks PER COLUMN: how a column is cut into blocks (hence the order in which its partial sums are
+    // folded) must not depend on how many columns the handle holds - shards of one batch reproduce the unsharded run bit for bit
+    int64_t cap = (int64_t)smcb_sm_count() * SMCB_ST_MINB;
     if (cap < 1) cap = 1;
     f->iters = (int)((nchunks + cap - 1) / cap);
     f->blocks_per_col = (int)((nchunks + f->iters - 1) / f->iters);

@@ -173,7 +173,9 @@ class BaseOnlineAlgorithm:
         e.set_observations(self._y_dev[: t + 1], 0)
         e.run(1)
         state.w += e.raw(_lib.PTR_LL, (e.B,))
-        state.ess.append(float(_utils.get_ess(state.w)))
+        ess, finite = torch.stack((_utils.get_ess(state.w).reshape(()), torch.isfinite(state.w).all().float())).tolist()   # one synchronisation
+        state.ess.append(ess)
+        state.finite = finite > 0.5
         state.current_iteration += 1
         return state
 
@@ -197,7 +199,7 @@ class NESS(BaseOnlineAlgorithm):
 
     def do_update_particles(self, state):
         ess = state.ess
-        return (any(ess) and ess[-1] < self._threshold) or not bool(torch.isfinite(state.w).all())
+        return (any(ess) and ess[-1] < self._threshold) or not getattr(state, "finite", True)
 
 
 class FixedWidthNESS(BaseOnlineAlgorithm):
@@ -210,4 +212,4 @@ class FixedWidthNESS(BaseOnlineAlgorithm):
 
     def do_update_particles(self, state):
         self._num_iterations += 1
-        return (self._num_iterations % self._bl == 0) or not bool(torch.isfinite(state.w).all())
+        return (self._num_iterations % self._bl == 0) or not getattr(state, "finite", True)

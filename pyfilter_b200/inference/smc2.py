@@ -187,10 +187,10 @@ class SMC2:
             e.run(1)
         with self.phases("gather increments"):
             state.w += self._gather(e.raw(_lib.PTR_LL, (e.B,)))      # SequentialAlgorithmState.append (state.py:35-44)
-        with self.phases("ess"):
-            ess = float(_utils.get_ess(state.w))
+        with self.phases("ess"):   # the ESS and the finiteness flag come to the host together: ONE synchronisation per observation (smc2.py:59-62)
+            ess, finite = torch.stack((_utils.get_ess(state.w).reshape(()), torch.isfinite(state.w).all().float())).tolist()
         state.ess.append(ess)
-        any_nans = not bool(torch.isfinite(state.w).all())
+        any_nans = finite < 0.5
         if ess < self._threshold * self.particles[0] or any_nans:
             with self.phases("rejuvenate (all of it)"):
                 state = self.rejuvenate(state)
