@@ -34,7 +34,8 @@ enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3,
        SMCB_USER_MODEL = 4 /* a build of the library compiled with -DSMCB_USER_MODEL_HEADER=<file>: the user's mean_scale / observation
                               density as device functions (csrc/models.h); raw parameters: UserModel::NRAW values per column */ };
 /* proposals: filters/particle/proposals/bootstrap.py:4-17, proposals/linear.py:13-89 */
-enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1 };
+/*            proposals/linearized.py:9-73 with proposals/utils.py:30-146 (ModeFinder; closed-form derivatives of the zoo's models) */
+enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1, SMCB_LINEARIZED = 2 };
 /* filters: filters/particle/sisr.py:7-56, filters/particle/apf.py:9-46 */
 enum { SMCB_SISR = 0, SMCB_APF = 1 };
 /* resamplers: resampling.py:24-52 (systematic), :55-65 (multinomial) */
@@ -71,6 +72,9 @@ typedef struct smcb_config {
                              move, purpose): shards of ONE batch of filters on different ranks (or handles) pass the offset of their
                              first column so that no two columns of the batch share a random stream, and the result does not depend
                              on how the batch is split */
+  int32_t lin_steps;      /* SMCB_LINEARIZED: `n_steps`, `alpha`, `use_second_order` of proposals/linearized.py:22 (the default functorch  */
+  float lin_alpha;        /* path of ModeFinder.find_mode, proposals/utils.py:96-146)                                                   */
+  int32_t lin_second_order;
 } smcb_config;
 
 typedef struct smcb_filter smcb_filter;

@@ -42,7 +42,11 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
     ref_params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in params.items()}
     ssm = build_reference_model(model_name, {**O.DEFAULT_PARAMS[model_name], **ref_params})
     cls = {"sisr": SISR, "apf": APF}[alg]
-    prop = {"bootstrap": pr.Bootstrap, "linear_gaussian": pr.LinearGaussianObservations}[proposal]()
+    if proposal.startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>" (proposals/linearized.py:22)
+        parts = proposal.split(":")
+        prop = pr.Linearized(n_steps=int(parts[1]), alpha=float(parts[2]), use_second_order=bool(int(parts[3])))
+    else:
+        prop = {"bootstrap": pr.Bootstrap, "linear_gaussian": pr.LinearGaussianObservations}[proposal]()
     filt = cls(ssm, N, proposal=prop, resampling={"systematic": RR.systematic, "multinomial": RR.multinomial}[resampler])
     bshape = torch.Size([B]) if B else torch.Size([])
     filt.set_batch_shape(bshape)
@@ -179,8 +183,22 @@ def oracle_only_cases():
     filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132)
 
 
+def linearized_cases():
+    """f2: the ``Linearized`` proposal (proposals/linearized.py, proposals/utils.py:30-146) - first order (the default) and second order,
+    scalar and vector state, batched and not."""
+    filter_case("c3_sisr_lin1", "sv_ar1", {}, "sisr", "linearized:1:0.0001:0", "systematic", 500, 0, 6, 141)
+    filter_case("c3_apf_lin2nd", "sv_ar1", {}, "apf", "linearized:3:0.0001:1", "systematic", 500, 0, 6, 142)
+    filter_case("c1_sisr_lin2nd_b3", "lg_ar1", {}, "sisr", "linearized:2:0.0001:1", "systematic", 400, 3, 6, 143)
+    filter_case("c2_apf_lin_alpha", "sine_em", {}, "apf", "linearized:2:0.01:0", "systematic", 400, 0, 6, 144)
+    filter_case("c4_sisr_lin2nd", "lorenz63_em", {}, "sisr", "linearized:2:0.0001:1", "systematic", 300, 0, 6, 145)
+    filter_case("c4_apf_lin1", "lorenz63_em", {}, "apf", "linearized:1:0.0001:0", "systematic", 300, 0, 6, 146)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "linearized":   # added later: leaves the other files as they are
+        linearized_cases()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "residual":   # added later: leaves the other files as they are
         residual_cases()
         return

@@ -531,10 +531,114 @@ def _lgo_pre_weight_nd(model: Model, y, x_prev):
     return MultivariateNormal(o_loc, scale_tril=cholesky_ex(cov)[0], validate_args=False).log_prob(y)
 
 
+def transition_log_prob(model: Model, x_new, x_prev):
+    """``model.hidden.build_density(state).log_prob(x_new)`` (stochproc ``AffineProcess.build_density``): the increment distribution
+    ``N(0, inc_scale)`` pushed through ``AffineTransform(loc, scale)``, summed over the event dimension."""
+    loc, scale = model.mean_scale(x_prev)
+    inc_std = _t(model.inc_scale)
+    lp = normal_log_prob((x_new - loc) / scale, 0.0, inc_std) - scale.abs().log()
+    return lp.sum(-1) if model.state_dim else lp
+
+
+def linearized_sample_and_weight(model: Model, y, x_prev, z, n_steps: int = 1, alpha: float = 1e-4, second_order: bool = False):
+    """``Linearized.sample_and_weight`` (``proposals/linearized.py:53-70``) with ``ModeFinder.find_mode`` (``proposals/utils.py:96-146``, the
+    default functorch path), as written: starting from ``x = mean``, ``n_steps`` times ``x += step`` where ``step`` is the CONSTANT
+    ``alpha`` for the first-order variant (the gradient is evaluated but not used: proposals/utils.py:119,137) and the Newton-like
+    ``cov * gradient`` with ``cov = -(H - clip(2 H, 0))^-1`` (scalar state) / ``-pinv(H - clip(2 lambda_min, 0) I)`` (vector state) for
+    ``use_second_order``, ``H`` and the gradient those of ``log p(y | x) + log p(x | x_prev)`` at the current ``x`` (torch.func here,
+    functorch there).  Kernel ``N(x, std)`` with ``std`` the hidden scale (first order) or ``sqrt(cov)`` / ``chol(cov)`` of the LAST step;
+    weight ``log p(y|x') + log p(x'|x_prev) - kernel.log_prob(x')`` (``proposals/base.py:45-50``)."""
+    from torch.func import grad, hessian, vmap
+
+    d = model.state_dim
+    mean, std0 = model.mean_scale(x_prev)
+    mean, std0 = torch.broadcast_tensors(mean, std0)
+    shape = x_prev.shape
+    flat = lambda t: t.reshape((-1, d) if d else (-1,))
+    # per-particle parameters: models with (B,) parameters are evaluated column by column through a tiny per-particle model
+    n_part = flat(mean).shape[0]
+
+    def joint(xi, xpi, col):
+        mo = model if col is None else _column_model(model, col)
+        return mo.obs_log_prob(y, xi) + transition_log_prob(mo, xi, xpi)
+
+    batched = x_prev.dim() - (1 if d else 0) == 2
+    B = shape[1] if batched else 1
+    x = mean.clone()
+    std = std0.clone()
+    chol = None
+    for _ in range(n_steps):
+        if second_order:
+            cols = []
+            for b in range(B):
+                xb = x[:, b] if batched else x
+                pb = x_prev[:, b] if batched else x_prev
+                fn = lambda xi, xpi: joint(xi, xpi, b if batched else None)
+                g = vmap(grad(fn))(xb, pb).to(xb.dtype)
+                H = vmap(hessian(fn))(xb, pb).to(xb.dtype)   # (float32 like the reference's: python-float constants of this module upcast it)
+                if d == 0:
+                    d_h = (2.0 * H).clip(min=0.0)
+                    cov = -(H - d_h).pow(-1)
+                    cols.append((cov * g, cov.sqrt(), None))
+                else:
+                    lam = torch.linalg.eigvalsh(H).real.min(dim=-1).values
+                    d_h = (2.0 * lam).clip(min=0.0).view(-1, 1, 1) * torch.eye(d)
+                    cov = -torch.linalg.pinv(H - d_h)
+                    cols.append(((cov @ g.unsqueeze(-1)).squeeze(-1), None, torch.linalg.cholesky_ex(cov)[0]))
+            step = torch.stack([c[0] for c in cols], 1) if batched else cols[0][0]
+            if d == 0:
+                std = torch.stack([c[1] for c in cols], 1) if batched else cols[0][1]
+            else:
+                chol = torch.stack([c[2] for c in cols], 1) if batched else cols[0][2]
+            x = x + step
+        else:
+            x = x + alpha   # (sic) proposals/utils.py:119,137
+    if d and second_order:
+        kernel = torch.distributions.MultivariateNormal(x, scale_tril=chol, validate_args=False)
+        x_new = x + (chol @ z.unsqueeze(-1)).squeeze(-1)
+        k_lp = kernel.log_prob(x_new)
+    else:
+        x_new = x + std * z
+        k_lp = normal_log_prob(x_new, x, std)
+        if d:
+            k_lp = k_lp.sum(-1)
+    w = model.obs_log_prob(y, x_new) + transition_log_prob(model, x_new, x_prev) - k_lp
+    return x_new, w
+
+
+def _column_model(model: Model, b: int) -> Model:
+    """The same model with every ``(B,)`` parameter reduced to its ``b``-th entry (per-particle autograd wants scalars)."""
+    import copy
+
+    mo = copy.copy(model)
+    for k, v in vars(model).items():
+        if isinstance(v, torch.Tensor) and v.dim() == 1 and v.shape[0] > 1 and k not in ("x0_mean", "x0_scale"):
+            setattr(mo, k, v[b])
+    return mo
+
+
 PROPOSALS = {
     "bootstrap": (bootstrap_sample_and_weight, affine_pre_weight),
     "linear_gaussian": (lgo_sample_and_weight, lgo_pre_weight),
 }
+
+
+class _ProposalTable(dict):
+    """``"linearized:<n_steps>:<alpha>:<0|1 second order>"`` names a configured ``Linearized`` proposal (default pre-weight)."""
+
+    def __missing__(self, key):
+        if isinstance(key, str) and key.startswith("linearized"):
+            parts = key.split(":")
+            n_steps = int(parts[1]) if len(parts) > 1 else 1
+            alpha = float(parts[2]) if len(parts) > 2 else 1e-4
+            second = bool(int(parts[3])) if len(parts) > 3 else False
+            fn = lambda model, y, x_prev, z: linearized_sample_and_weight(model, y, x_prev, z, n_steps, alpha, second)
+            self[key] = (fn, affine_pre_weight)
+            return self[key]
+        raise KeyError(key)
+
+
+PROPOSALS = _ProposalTable(PROPOSALS)
 
 
 # ----------------------------------------------------------------------------------------------------------------------

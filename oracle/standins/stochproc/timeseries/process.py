@@ -88,6 +88,9 @@ class StateSpaceModel(object):
     def build_density(self, x: TimeseriesState) -> Distribution:
         return self._f(x, *self.parameters)
 
+    def yield_parameters(self):   # (call site: proposals/utils.py:70-71, ModeFinder.initialize)
+        return {"parameters": self.parameters}
+
     @property
     def event_shape(self):
         if self._event_shape is None:

@@ -30,7 +30,7 @@ class smcb_config(C.Structure):
         ("particles", C.c_int64), ("batch", C.c_int32), ("n_raw_params", C.c_int32),
         ("params_host", C.POINTER(C.c_float)), ("param_cols", C.c_int32), ("ess_threshold", C.c_float),
         ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_weights", C.c_int32),
-        ("column_offset", C.c_int32),
+        ("column_offset", C.c_int32), ("lin_steps", C.c_int32), ("lin_alpha", C.c_float), ("lin_second_order", C.c_int32),
     ]
 
 

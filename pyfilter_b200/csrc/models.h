@@ -10,11 +10,11 @@
 #pragma once
 #include <cuda_runtime.h>
 
-#define SMCB_NPARAM 32
+#define SMCB_NPARAM 40
 #define SMCB_LOG_SQRT_2PI 0.9189385332046727f
 
 enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_MODEL_USER = 4, SMCB_NUM_MODELS = 5 };
-enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1 };
+enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1, SMCB_PROPOSAL_LINEARIZED = 2 };
 enum { SMCB_ALG_SISR = 0, SMCB_ALG_APF = 1 };
 enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 
@@ -49,6 +49,14 @@ enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 #define P_LGO_K1_INV2VAR 29
 #define P_LGO_K1_LOGNORM 30
 #define P_LGO_OBS_S 31        // Lorenz: obs_s itself (slots 6, 7 hold the derived constants of its density)
+// Linearized proposal (proposals/linearized.py:22, proposals/utils.py:30-146): its three settings and the constants of the transition
+// density log p(x' | x) = sum_d -((x'_d - loc_d) / scale)^2 / (2 inc^2) - log(inc |scale|) - log sqrt(2 pi)
+#define P_LIN_STEPS 32        // n_steps (as float)
+#define P_LIN_ALPHA 33        // alpha
+#define P_LIN_SECOND 34       // use_second_order (0 / 1)
+#define P_LIN_T_INV2VAR 35    // 1 / (2 (scale inc)^2)
+#define P_LIN_T_LOGNORM 36    // log(inc |scale|) + log sqrt(2 pi)
+#define P_LIN_T_INVVAR 37     // 1 / (scale inc)^2
 
 // sin(v) for the drift of the sine diffusion: explicit two-constant reduction to [-pi, pi] (exact products through fma), then the SFU.
 // Absolute error <= 2^-20.9 ~ 5e-7 on the reduced argument (PTX sin.approx.ftz.f32) against ~27 instructions of sinf() with its slow
@@ -85,6 +93,13 @@ template <> struct Model<SMCB_MODEL_LG_AR1> {
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
   }
+  // d/dx and d2/dx2 of obs_lp (Linearized proposal: proposals/utils.py:52-62 takes them by automatic differentiation)
+  __device__ static __forceinline__ void obs_grad_hess(const float* y, const float* x, const float* P, float* g, float* h) {
+    const float r = __fsub_rn(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])));
+    const float ivar = __fmul_rn(2.0f, P[P_OBS_INV2VAR]);
+    g[0] = __fmul_rn(__fmul_rn(P[P_OBS_A], r), ivar);
+    h[0] = -__fmul_rn(__fmul_rn(P[P_OBS_A], P[P_OBS_A]), ivar);
+  }
   // y = b + a x + s v   (sample of build_density(x): ParticleFilterCorrection.predict_path, particle/state.py:173-174)
   __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
     y[0] = __fadd_rn(__fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), __fmul_rn(P[P_OBS_S], v[0]));
@@ -101,6 +116,13 @@ template <> struct Model<SMCB_MODEL_SINE_EM> {
   }
   __device__ static __forceinline__ float obs_lp(const float* y, const float* x, const float* P) {
     return smcb_normal_lp(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), P[P_OBS_INV2VAR], P[P_OBS_LOGNORM]);
+  }
+  // d/dx and d2/dx2 of obs_lp (Linearized proposal: proposals/utils.py:52-62 takes them by automatic differentiation)
+  __device__ static __forceinline__ void obs_grad_hess(const float* y, const float* x, const float* P, float* g, float* h) {
+    const float r = __fsub_rn(y[0], __fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])));
+    const float ivar = __fmul_rn(2.0f, P[P_OBS_INV2VAR]);
+    g[0] = __fmul_rn(__fmul_rn(P[P_OBS_A], r), ivar);
+    h[0] = -__fmul_rn(__fmul_rn(P[P_OBS_A], P[P_OBS_A]), ivar);
   }
   __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
     y[0] = __fadd_rn(__fadd_rn(P[P_OBS_B], __fmul_rn(P[P_OBS_A], x[0])), __fmul_rn(P[P_OBS_S], v[0]));
@@ -121,6 +143,11 @@ template <> struct Model<SMCB_MODEL_SV_AR1> {
     float e;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(__fmul_rn(-x[0], 1.4426950408889634f)));
     return fmaf(-hy2, e, fmaf(-0.5f, x[0], -SMCB_LOG_SQRT_2PI));  // explicit fma: the same bits at every call site
+  }
+  __device__ static __forceinline__ void obs_grad_hess(const float* y, const float* x, const float* P, float* g, float* h) {
+    const float hy2e = __fmul_rn(__fmul_rn(0.5f, __fmul_rn(y[0], y[0])), __expf(-x[0]));   // y^2 exp(-x) / 2
+    g[0] = __fsub_rn(hy2e, 0.5f);
+    h[0] = -hy2e;
   }
   __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
     y[0] = __fmul_rn(__expf(__fmul_rn(0.5f, x[0])), v[0]);
@@ -145,6 +172,13 @@ template <> struct Model<SMCB_MODEL_LORENZ63_EM> {
     float l0 = smcb_normal_lp(y[0], __fmul_rn(P[5], x[0]), P[6], P[7]);
     float l1 = smcb_normal_lp(y[1], __fmul_rn(P[5], x[2]), P[6], P[7]);
     return __fadd_rn(l0, l1);
+  }
+  __device__ static __forceinline__ void obs_grad_hess(const float* y, const float* x, const float* P, float* g, float* h) {
+    const float ivar = __fmul_rn(2.0f, P[6]);   // 1 / obs_s^2; the Hessian of this model is diagonal (each observation reads one coordinate)
+    g[0] = __fmul_rn(__fmul_rn(P[5], __fsub_rn(y[0], __fmul_rn(P[5], x[0]))), ivar);
+    g[1] = 0.f;
+    g[2] = __fmul_rn(__fmul_rn(P[5], __fsub_rn(y[1], __fmul_rn(P[5], x[2]))), ivar);
+    h[0] = -__fmul_rn(__fmul_rn(P[5], P[5]), ivar); h[1] = 0.f; h[2] = h[0];
   }
   __device__ static __forceinline__ void obs_sample(const float* x, const float* v, const float* P, float* y) {
     y[0] = __fadd_rn(__fmul_rn(P[5], x[0]), __fmul_rn(P[P_LGO_OBS_S], v[0]));

@@ -69,7 +69,7 @@ static const int kRaw[SMCB_NUM_MODELS] = {6, 6, 3, 7, 0};
 #endif
 
 // ---- host-side parameter row (layout in models.h) -------------------------------------------------------------------------
-static void derive_params(int model, const double* r, float* P) {
+static void derive_params(int model, const double* r, float* P, const smcb_config& cfg) {
   const double c = 0.91893853320467274178;  // log sqrt(2 pi)
   for (int i = 0; i < SMCB_NPARAM; ++i) P[i] = 0.f;
   double inc = 1.0, sigma = 1.0, a = 0, s = 1;
@@ -87,6 +87,7 @@ static void derive_params(int model, const double* r, float* P) {
       P[P_X0_LOC] = 0.f; P[P_X0_SCALE] = 1.f;
       break;
     case SMCB_MODEL_SV_AR1:
+      sigma = r[2];
       for (int i = 0; i < 3; ++i) P[i] = (float)r[i];
       P[P_X0_LOC] = (float)r[0];
       P[P_X0_SCALE] = (float)(r[2] / sqrt(1.0 - r[1] * r[1]));
@@ -112,6 +113,13 @@ static void derive_params(int model, const double* r, float* P) {
 #endif
   }
   P[P_INC_SCALE] = (float)inc;
+  {  // Linearized proposal: its settings and the constants of the transition density (models.h)
+    const double tv = sigma * inc;
+    P[P_LIN_STEPS] = (float)cfg.lin_steps; P[P_LIN_ALPHA] = cfg.lin_alpha; P[P_LIN_SECOND] = cfg.lin_second_order ? 1.f : 0.f;
+    P[P_LIN_T_INVVAR] = (float)(1.0 / (tv * tv));
+    P[P_LIN_T_INV2VAR] = (float)(1.0 / (2.0 * tv * tv));
+    P[P_LIN_T_LOGNORM] = (float)(log(fabs(tv)) + c);
+  }
   if (lorenz_lgo) {
     const double hvi = 1.0 / (sigma * sigma), ovi = 1.0 / (s * s);
     const double cov = 1.0 / (hvi + a * a * ovi), cov1 = 1.0 / hvi;
@@ -218,7 +226,7 @@ static int upload_params(smcb_filter* f, const float* params_host, int n_raw, in
   for (int b = 0; b < f->B; ++b) {
     double r[SMCB_MAX_RAW_PARAMS];
     for (int k = 0; k < n_raw; ++k) r[k] = params_host[(size_t)k * cols + (cols == 1 ? 0 : b)];
-    derive_params(f->cfg.model, r, &P[(size_t)b * SMCB_NPARAM]);
+    derive_params(f->cfg.model, r, &P[(size_t)b * SMCB_NPARAM], f->cfg);
   }
   CU(cudaMemcpyAsync(f->P_dev, P.data(), P.size() * sizeof(float), cudaMemcpyHostToDevice, s));
   CU(cudaStreamSynchronize(s));  // P is a stack/heap temporary
@@ -243,7 +251,9 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   if (cfg->model == SMCB_MODEL_USER) return fail(SMCB_EUNSUPPORTED, "this build of libsmcb200 carries no user model (pyfilter_b200.timeseries.compile_user_model builds one)");
 #endif
   if (cfg->model == SMCB_MODEL_USER && cfg->proposal != SMCB_BOOTSTRAP) return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");
-  if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS) return fail(SMCB_EUNSUPPORTED, "unknown proposal");
+  if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && cfg->proposal != SMCB_LINEARIZED)
+    return fail(SMCB_EUNSUPPORTED, "unknown proposal");
+  if (cfg->proposal == SMCB_LINEARIZED && cfg->lin_steps < 1) return fail(SMCB_EINVAL, "``n_steps`` must be >= 1");   // proposals/linearized.py:39
   if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM || cfg->model == SMCB_LORENZ63_EM))
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
   if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
@@ -382,6 +392,28 @@ static StepArgs make_args(smcb_filter* f) {
     SMCB_USER_CASE(constexpr int MODEL = 4; BODY)                            \
   }
 
+// every compiled (model, proposal) pair: LinearGaussianObservations needs linear-Gaussian observations, a user model takes Bootstrap
+#ifdef SMCB_USER_MODEL_HEADER
+#define SMCB_USER_PAIR(BODY) case 16: { constexpr int MODEL = 4, PROP = 0; BODY; } break;
+#else
+#define SMCB_USER_PAIR(BODY)
+#endif
+#define FOR_MODEL_PROP(M, PR, BODY)                                                   \
+  switch ((M) * 4 + (PR)) {                                                           \
+    case 0: { constexpr int MODEL = 0, PROP = 0; BODY; } break;                        \
+    case 1: { constexpr int MODEL = 0, PROP = 1; BODY; } break;                        \
+    case 2: { constexpr int MODEL = 0, PROP = 2; BODY; } break;                        \
+    case 4: { constexpr int MODEL = 1, PROP = 0; BODY; } break;                        \
+    case 5: { constexpr int MODEL = 1, PROP = 1; BODY; } break;                        \
+    case 6: { constexpr int MODEL = 1, PROP = 2; BODY; } break;                        \
+    case 8: { constexpr int MODEL = 2, PROP = 0; BODY; } break;                        \
+    case 10: { constexpr int MODEL = 2, PROP = 2; BODY; } break;                       \
+    case 12: { constexpr int MODEL = 3, PROP = 0; BODY; } break;                       \
+    case 13: { constexpr int MODEL = 3, PROP = 1; BODY; } break;                       \
+    case 14: { constexpr int MODEL = 3, PROP = 2; BODY; } break;                       \
+    SMCB_USER_PAIR(BODY)                                                              \
+  }
+
 template <int MODEL, int PROP>
 static void launch_step_alg(int alg, dim3 g, cudaStream_t s, const StepArgs& a) {
   if (alg == SMCB_SISR) launch_pdl(step_kernel<MODEL, PROP, SMCB_ALG_SISR>, g, dim3(ST_NT), s, a);
@@ -391,13 +423,7 @@ static void launch_step_alg(int alg, dim3 g, cudaStream_t s, const StepArgs& a) 
 static void launch_step(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   dim3 g(f->blocks_per_col, f->B);
   const int prop = f->cfg.proposal, alg = f->cfg.algorithm;
-  switch (f->cfg.model) {
-    case 0: if (prop) launch_step_alg<0, 1>(alg, g, s, a); else launch_step_alg<0, 0>(alg, g, s, a); break;
-    case 1: if (prop) launch_step_alg<1, 1>(alg, g, s, a); else launch_step_alg<1, 0>(alg, g, s, a); break;
-    case 2: launch_step_alg<2, 0>(alg, g, s, a); break;
-    case 3: if (prop) launch_step_alg<3, 1>(alg, g, s, a); else launch_step_alg<3, 0>(alg, g, s, a); break;
-    SMCB_USER_CASE((launch_step_alg<4, 0>(alg, g, s, a)))
-  }
+  FOR_MODEL_PROP(f->cfg.model, prop, (launch_step_alg<MODEL, PROP>(alg, g, s, a)));
   f->launches++;
 }
 
@@ -496,13 +522,7 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   }
   const int prop = f->cfg.proposal;
   cudaError_t e = cudaSuccess;
-  switch (f->cfg.model) {
-    case 0: e = prop ? launch_move_alg<0, 1>(f, m, s) : launch_move_alg<0, 0>(f, m, s); break;
-    case 1: e = prop ? launch_move_alg<1, 1>(f, m, s) : launch_move_alg<1, 0>(f, m, s); break;
-    case 2: e = launch_move_alg<2, 0>(f, m, s); break;
-    case 3: e = prop ? launch_move_alg<3, 1>(f, m, s) : launch_move_alg<3, 0>(f, m, s); break;
-    SMCB_USER_CASE((e = launch_move_alg<4, 0>(f, m, s)))
-  }
+  FOR_MODEL_PROP(f->cfg.model, prop, (e = launch_move_alg<MODEL, PROP>(f, m, s)));
   if (e != cudaSuccess) return fail(SMCB_ECUDA, std::string("move_kernel: ") + cudaGetErrorString(e));
   f->launches++;
   return SMCB_OK;
@@ -517,13 +537,7 @@ static bool move_path_ok(const smcb_filter* f) {
 static void launch_preweight(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
   dim3 g(f->blocks_per_col, f->B);
   const int prop = f->cfg.proposal;
-  switch (f->cfg.model) {
-    case 0: if (prop) preweight_kernel<0, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<0, 0><<<g, ST_NT, 0, s>>>(a); break;
-    case 1: if (prop) preweight_kernel<1, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<1, 0><<<g, ST_NT, 0, s>>>(a); break;
-    case 2: preweight_kernel<2, 0><<<g, ST_NT, 0, s>>>(a); break;
-    case 3: if (prop) preweight_kernel<3, 1><<<g, ST_NT, 0, s>>>(a); else preweight_kernel<3, 0><<<g, ST_NT, 0, s>>>(a); break;
-    SMCB_USER_CASE((preweight_kernel<4, 0><<<g, ST_NT, 0, s>>>(a)))
-  }
+  FOR_MODEL_PROP(f->cfg.model, prop, (preweight_kernel<MODEL, PROP><<<g, ST_NT, 0, s>>>(a)));
   f->launches++;
 }
 
@@ -762,13 +776,7 @@ static int run_column(smcb_filter* f, int steps, cudaStream_t s) {
   int nt = (f->B <= smcb_sm_count()) ? 1 : 2;
   if (const char* v = getenv("SMCB_COLUMN_MINB")) nt = atoi(v);   // diagnostics: 0 = 1024 threads x 4, 1 = 512 x 8 one block per SM, 2 = 512 x 8 two per SM
   cudaError_t e = cudaSuccess;
-  switch (f->cfg.model) {
-    case 0: e = prop ? launch_column_alg<0, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<0, 0>(alg, nt, f->B, dyn, s, c); break;
-    case 1: e = prop ? launch_column_alg<1, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<1, 0>(alg, nt, f->B, dyn, s, c); break;
-    case 2: e = launch_column_alg<2, 0>(alg, nt, f->B, dyn, s, c); break;
-    case 3: e = prop ? launch_column_alg<3, 1>(alg, nt, f->B, dyn, s, c) : launch_column_alg<3, 0>(alg, nt, f->B, dyn, s, c); break;
-    SMCB_USER_CASE((e = launch_column_alg<4, 0>(alg, nt, f->B, dyn, s, c)))
-  }
+  FOR_MODEL_PROP(f->cfg.model, prop, (e = launch_column_alg<MODEL, PROP>(alg, nt, f->B, dyn, s, c)));
   if (e != cudaSuccess) return fail(SMCB_ECUDA, cudaGetErrorString(e));
   f->launches++;
   const int t1 = t + steps;
@@ -1096,13 +1104,7 @@ static int proposal_op(smcb_filter* f, int mode, const float* y_dev, const float
   const int64_t chunk = ST_NT * ST_VEC;
   dim3 g((unsigned)((f->n + chunk - 1) / chunk), f->B);
   const int prop = f->cfg.proposal;
-  switch (f->cfg.model) {
-    case 0: if (prop) proposal_op_kernel<0, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<0, 0><<<g, ST_NT, 0, s>>>(c); break;
-    case 1: if (prop) proposal_op_kernel<1, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<1, 0><<<g, ST_NT, 0, s>>>(c); break;
-    case 2: proposal_op_kernel<2, 0><<<g, ST_NT, 0, s>>>(c); break;
-    case 3: if (prop) proposal_op_kernel<3, 1><<<g, ST_NT, 0, s>>>(c); else proposal_op_kernel<3, 0><<<g, ST_NT, 0, s>>>(c); break;
-    SMCB_USER_CASE((proposal_op_kernel<4, 0><<<g, ST_NT, 0, s>>>(c)))
-  }
+  FOR_MODEL_PROP(f->cfg.model, prop, (proposal_op_kernel<MODEL, PROP><<<g, ST_NT, 0, s>>>(c)));
   f->launches++;
   CU(cudaGetLastError());
   return SMCB_OK;

@@ -327,6 +327,76 @@ struct ProposalLGO<MODEL, SMCB_PROPOSAL_LINEAR_GAUSS, false> {
   }
 };
 
+// Linearized (proposals/linearized.py:53-70 with ModeFinder.find_mode, proposals/utils.py:96-146, the default functorch path, as
+// written): from x = mean, n_steps times x += step, step = the CONSTANT alpha for the first-order variant (the gradient is evaluated
+// there but not used: utils.py:119,137) or cov * gradient with cov = -(H - clip(2 H, 0))^-1 for use_second_order (vector state:
+// -pinv(H - clip(2 lambda_min, 0) I); the Hessians of the zoo's models are diagonal, so eigenvalues, pseudo-inverse and Cholesky factor
+// are per coordinate); gradient and H are those of log p(y | x) + log p(x | x_prev) - closed forms here (Model::obs_grad_hess),
+// automatic differentiation there.  Kernel N(x, std), std = the hidden scale (first order) / sqrt(cov) of the last step.
+template <int MODEL>
+struct Proposal<MODEL, SMCB_PROPOSAL_LINEARIZED> {
+  typedef Model<MODEL> M;
+  __device__ static __forceinline__ float pre_weight(const float* y, const float* x, const float* P) {   // proposals/base.py:69-85
+    float loc[M::D], sc;
+    M::loc_scale(x, P, loc, sc);
+    return M::obs_lp(y, loc, P);
+  }
+  __device__ static __forceinline__ void sample_and_weight(const float* y, const float* xa, const float* z, const float* P,
+                                                           bool observed, float* xn, float& inc, float& g_anc) {
+    constexpr int D = M::D;
+    float m[D], sc;
+    M::loc_scale(xa, P, m, sc);
+    inc = 0.f; g_anc = 0.f;
+    if (!observed) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) xn[d] = __fadd_rn(m[d], __fmul_rn(sc, __fmul_rn(z[d], P[P_INC_SCALE])));
+      return;
+    }
+    float x[D], sd[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { x[d] = m[d]; sd[d] = sc; }
+    const int steps = (int)P[P_LIN_STEPS];
+    const bool second = P[P_LIN_SECOND] != 0.f;
+    const float tiv = P[P_LIN_T_INVVAR];
+    for (int it = 0; it < steps; ++it) {
+      if (second) {
+        float g[D], h[D];
+        M::obs_grad_hess(y, x, P, g, h);
+        float lam = INFINITY;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          g[d] = __fsub_rn(g[d], __fmul_rn(__fsub_rn(x[d], m[d]), tiv));
+          h[d] = __fsub_rn(h[d], tiv);
+          lam = fminf(lam, h[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const float dh = fmaxf(__fmul_rn(2.0f, (D == 1) ? h[d] : lam), 0.f);
+          const float den = __fsub_rn(h[d], dh);
+          const float cov = (den == 0.f && D > 1) ? 0.f : -__frcp_rn(den);   // pinv of a diagonal matrix; the scalar case divides as written
+          x[d] = __fadd_rn(x[d], __fmul_rn(cov, g[d]));
+          sd[d] = __fsqrt_rn(cov);
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < D; ++d) x[d] = __fadd_rn(x[d], P[P_LIN_ALPHA]);
+      }
+    }
+    float x_lp = 0.f, k_lp = 0.f;
+    const float rsc = __frcp_rn(sc);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xn[d] = __fadd_rn(x[d], __fmul_rn(sd[d], z[d]));
+      const float e = __fsub_rn(xn[d], m[d]);
+      x_lp = __fadd_rn(x_lp, __fsub_rn(__fmul_rn(-__fmul_rn(e, e), P[P_LIN_T_INV2VAR]), P[P_LIN_T_LOGNORM]));
+      k_lp = __fadd_rn(k_lp, smcb_normal_lp_scale(xn[d], x[d], sd[d]));
+    }
+    (void)rsc;
+    inc = __fsub_rn(__fadd_rn(M::obs_lp(y, xn, P), x_lp), k_lp);
+    g_anc = pre_weight(y, xa, P);
+  }
+};
+
 // ---- helpers -----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ const float* st_obs(const Ctrl* c, int t, int od) {
   int k = t - c->y_base;

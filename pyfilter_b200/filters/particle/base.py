@@ -173,7 +173,7 @@ class ParticleFilter:
             n = int(self._base_particles[0])
             e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS[self._resampler], n,
                        self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_weights,
-                       self._column_offset)
+                       self._column_offset, proposal_config=self._proposal.config())
             self._engine = e
         return e
 

@@ -10,7 +10,7 @@ from ...timeseries import StateSpaceModel, TimeseriesState
 class Engine:
     def __init__(self, model: StateSpaceModel, proposal_id: int, algorithm_id: int, resampler_id: int, particles: int,
                  batch_shape: torch.Size, ess_threshold: float, seed: int, history_rows: int, fold_lookahead: bool = True,
-                 exact_weights: bool = False, column_offset: int = 0):
+                 exact_weights: bool = False, column_offset: int = 0, proposal_config: dict = None):
         _lib.require_cuda()
         self.lib = model.library() if hasattr(model, "library") else _lib.load_library()   # (a user model lives in its own build)
         self.model = model
@@ -29,6 +29,9 @@ class Engine:
         cfg.fold_lookahead = int(bool(fold_lookahead))
         cfg.exact_weights = int(bool(exact_weights))
         cfg.column_offset = int(column_offset)   # global index of column 0: the Philox counters use column_offset + column
+        pc = proposal_config or {}
+        cfg.lin_steps, cfg.lin_alpha = int(pc.get("n_steps", 1)), float(pc.get("alpha", 1e-4))
+        cfg.lin_second_order = int(bool(pc.get("use_second_order", False)))
         self._params_keepalive = params
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)), self.lib)

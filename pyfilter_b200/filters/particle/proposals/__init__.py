@@ -27,6 +27,10 @@ class Proposal:
     def copy(self) -> "Proposal":
         return type(self)()
 
+    def config(self) -> dict:
+        """Settings the compiled proposal reads (smcb_config)."""
+        return {}
+
     # ---- the plug-in methods
     def _engine_for(self, x: torch.Tensor):
         """A handle of the right shape for the stand-alone passes (kept until the shape or the model changes)."""
@@ -38,7 +42,8 @@ class Proposal:
         batch = torch.Size(x.shape[1: x.dim() - d])
         e = self._op_engine
         if e is None or e.N != n or e.batch_shape != batch:
-            e = Engine(self._model, self.proposal_id, 0, 0, n, batch, 0.9, int(torch.randint(0, 2**62, (1,)).item()), 1)
+            e = Engine(self._model, self.proposal_id, 0, 0, n, batch, 0.9, int(torch.randint(0, 2**62, (1,)).item()), 1,
+                       proposal_config=self.config())
             self._op_engine = e
         return e
 
@@ -75,6 +80,33 @@ class LinearGaussianObservations(Proposal):
         return super().set_model(model)
 
 
+class Linearized(Proposal):
+    """``proposals/linearized.py:9-73``: a Gaussian kernel around a (few-step) ascent of ``log p(y | x) + log p(x | x_prev)`` from the
+    transition mean, first order (``x += alpha`` per step, as the reference's ``ModeFinder.find_mode`` does it) or with second-order
+    information.  The derivatives are the closed forms of the compiled models (``Model::obs_grad_hess``, csrc/models.h) instead of
+    functorch's; the legacy ``torch.autograd`` path (``use_functorch=False``) is not built."""
+
+    proposal_id = 2
+
+    def __init__(self, n_steps=1, alpha: float = 1e-4, use_second_order: bool = False, use_functorch: bool = True):
+        assert n_steps > 0, "``n_steps`` must be >= 1"
+        super().__init__()
+        if not use_functorch:
+            raise NotImplementedError("the legacy autograd path of ModeFinder (find_mode_legacy) is not compiled")
+        self._alpha, self._n_steps, self._use_second_order = alpha, n_steps, use_second_order
+
+    def set_model(self, model):
+        if getattr(model, "model_id", None) == 4:   # a user model brings no derivatives
+            raise ValueError("Hidden must be of type AffineProcess with compiled derivatives!")
+        return super().set_model(model)
+
+    def config(self) -> dict:
+        return {"n_steps": self._n_steps, "alpha": self._alpha, "use_second_order": self._use_second_order}
+
+    def copy(self) -> "Proposal":
+        return Linearized(self._n_steps, self._alpha, self._use_second_order)
+
+
 def _out_of_scope(name):
     class _Missing(Proposal):
         def __init__(self, *a, **k):
@@ -84,7 +116,6 @@ def _out_of_scope(name):
     return _Missing
 
 
-Linearized = _out_of_scope("Linearized")
 NestedProposal = _out_of_scope("NestedProposal")
 GaussianLinear = _out_of_scope("GaussianLinear")
 GaussianLinearized = _out_of_scope("GaussianLinearized")

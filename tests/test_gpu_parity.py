@@ -156,7 +156,11 @@ def _make_filter(pf, g, N, B, model=None, **kw):
     params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in g["params"].items()}
     m = ts.build(g["model"], **params)
     cls = {"sisr": SISR, "apf": APF}[g["alg"]]
-    prop = {"bootstrap": proposals.Bootstrap, "linear_gaussian": proposals.LinearGaussianObservations}[g["proposal"]]()
+    if g["proposal"].startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>"
+        parts = g["proposal"].split(":")
+        prop = proposals.Linearized(n_steps=int(parts[1]), alpha=float(parts[2]), use_second_order=bool(int(parts[3])))
+    else:
+        prop = {"bootstrap": proposals.Bootstrap, "linear_gaussian": proposals.LinearGaussianObservations}[g["proposal"]]()
     res = {"systematic": pf.resampling.systematic, "multinomial": pf.resampling.multinomial}[g["resampler"]]
     f = cls(m, N, proposal=prop, resampling=res, seed=1234, **kw)
     f.set_batch_shape(torch.Size([B]) if B else torch.Size([]))
@@ -186,7 +190,7 @@ def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights, smc_pa
     N, B, T = g["N"], g["B"], g["T"]
     f = _make_filter(pf, g, N, B, exact_weights=exact_weights)
     e = f._get_engine(2)
-    lgo = g["proposal"] == "linear_gaussian"
+    lgo = g["proposal"] != "bootstrap"   # the proposals with a kernel density in the weight: three log-densities, 3e-5
     wdump = torch.zeros(e.B, e.ld, device="cuda")
     e.dump_noise(None, None, wdump)
     model = O.build_model(g["model"], model_params(g))

@@ -22,11 +22,16 @@ def pf():
 def _proposal(pf, name):
     from pyfilter_b200.filters.particle import proposals
 
+    if name.startswith("linearized"):
+        parts = name.split(":")
+        return proposals.Linearized(n_steps=int(parts[1]), alpha=float(parts[2]), use_second_order=bool(int(parts[3])))
     return {"bootstrap": proposals.Bootstrap, "linear_gaussian": proposals.LinearGaussianObservations}[name]()
 
 
 CASES = [("lg_ar1", "bootstrap"), ("lg_ar1", "linear_gaussian"), ("sine_em", "linear_gaussian"), ("sv_ar1", "bootstrap"),
-         ("lorenz63_em", "bootstrap"), ("lorenz63_em", "linear_gaussian")]
+         ("lorenz63_em", "bootstrap"), ("lorenz63_em", "linear_gaussian"),
+         ("sv_ar1", "linearized:1:0.0001:0"), ("sv_ar1", "linearized:4:0.0001:1"), ("sine_em", "linearized:3:0.01:0"),
+         ("lg_ar1", "linearized:2:0.0001:1"), ("lorenz63_em", "linearized:2:0.0001:1"), ("lorenz63_em", "linearized:2:0.001:0")]
 
 
 @pytest.mark.parametrize("B", [0, 3])
@@ -51,7 +56,7 @@ def test_proposal_plugin_methods_vs_oracle(pf, name, prop, B):
     xs = ts.TimeseriesState(4, x.cuda(), torch.Size(ev))
     # pre_weight
     got = p.pre_weight(y, xs).cpu()
-    ref = O.PROPOSALS[prop][1](mo, y, x) if prop == "linear_gaussian" else O.affine_pre_weight(mo, y, x)
+    ref = O.PROPOSALS[prop][1](mo, y, x)
     assert got.shape == ref.shape
     assert torch.allclose(got, ref, rtol=0, atol=3e-5 + 4e-6 * float(ref.abs().max())), (got - ref).abs().max()
     # sample_and_weight
