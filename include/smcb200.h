@@ -35,7 +35,8 @@ enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3,
                               density as device functions (csrc/models.h); raw parameters: UserModel::NRAW values per column */ };
 /* proposals: filters/particle/proposals/bootstrap.py:4-17, proposals/linear.py:13-89 */
 /*            proposals/linearized.py:9-73 with proposals/utils.py:30-146 (ModeFinder; closed-form derivatives of the zoo's models) */
-enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1, SMCB_LINEARIZED = 2 };
+/*            proposals/nested.py:8-50 (num_samples inner draws per particle, one of them proposed) */
+enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1, SMCB_LINEARIZED = 2, SMCB_NESTED = 3 };
 /* filters: filters/particle/sisr.py:7-56, filters/particle/apf.py:9-46 */
 enum { SMCB_SISR = 0, SMCB_APF = 1 };
 /* resamplers: resampling.py:24-52 (systematic), :55-65 (multinomial) */
@@ -75,6 +76,7 @@ typedef struct smcb_config {
   int32_t lin_steps;      /* SMCB_LINEARIZED: `n_steps`, `alpha`, `use_second_order` of proposals/linearized.py:22 (the default functorch  */
   float lin_alpha;        /* path of ModeFinder.find_mode, proposals/utils.py:96-146)                                                   */
   int32_t lin_second_order;
+  int32_t nested_samples; /* SMCB_NESTED: `num_samples` of proposals/nested.py:17 (1 .. 256) */
 } smcb_config;
 
 typedef struct smcb_filter smcb_filter;
@@ -158,6 +160,10 @@ int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* stream);
  * switches a hook off. */
 int smcb_filter_set_noise(smcb_filter* f, const float* eps_dev, const float* u_dev, const double* U_dev);
 int smcb_filter_dump_noise(smcb_filter* f, float* eps_dev, float* u_dev, float* w_dev);
+/* NestedProposal: inject the N(0,1) values of the inner samples (num_samples, D, B, ld) and the Exp(1) values (num_samples, B, ld) of
+ * the categorical draw - hidden_density.sample(num_samples) and Categorical.sample in proposals/nested.py:29,40; torch.multinomial
+ * picks its single sample per row as argmax(probs / Exp(1)).  NULL: Philox (one uniform per particle inverts the prefix sums). */
+int smcb_filter_set_nested_noise(smcb_filter* f, const float* z_dev, const float* e_dev);
 
 /* borrowed device pointers into the handle's state (valid until destroy) ........ ParticleFilterCorrection (particle/state.py:72-211) */
 enum {

@@ -42,7 +42,10 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
     ref_params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in params.items()}
     ssm = build_reference_model(model_name, {**O.DEFAULT_PARAMS[model_name], **ref_params})
     cls = {"sisr": SISR, "apf": APF}[alg]
-    if proposal.startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>" (proposals/linearized.py:22)
+    nested_m = int(proposal.split(":")[1]) if proposal.startswith("nested") else 0
+    if nested_m:                            # "nested:<num_samples>" (proposals/nested.py:17)
+        prop = pr.NestedProposal(nested_m)
+    elif proposal.startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>" (proposals/linearized.py:22)
         parts = proposal.split(":")
         prop = pr.Linearized(n_steps=int(parts[1]), alpha=float(parts[2]), use_second_order=bool(int(parts[3])))
     else:
@@ -54,6 +57,8 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
     d = ssm.hidden.event_shape
     nb = B if B else 1
     rec = {k: [] for k in ("x_prev", "lw_prev", "inds_prev", "u", "U", "z", "x", "lw", "ll", "mean", "var", "prev_inds", "drew")}
+    if nested_m:
+        rec["Un"] = []
     x0 = _np(state.timeseries_state.value)
     for t in range(T):
         x_prev, lw_prev = state.timeseries_state.value.clone(), state.weights.clone()
@@ -79,7 +84,13 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
                 Uf = np.zeros((N, nb))
                 Uf[:, mask.numpy()] = torch.empty((k, N), dtype=torch.float64).uniform_().numpy().T
                 U = Uf
-        z = torch.empty(tuple(filt.particles) + tuple(d)).normal_()
+        if nested_m:   # hidden_density.sample(num_samples), then Categorical.sample: torch.multinomial's Exp(1) race (nested.py:29,40)
+            z = torch.empty((nested_m,) + tuple(filt.particles) + tuple(d)).normal_()
+            # (Categorical normalises the moved-axis view, which keeps its strides: the race's Exp(1) tensor is laid out sample-major)
+            Un = torch.empty(nested_m, int(np.prod(tuple(filt.particles)))).exponential_(1).t().reshape(tuple(filt.particles) + (nested_m,))
+            rec["Un"].append(_np(Un))
+        else:
+            z = torch.empty(tuple(filt.particles) + tuple(d)).normal_()
         assert torch.equal(torch.get_rng_state(), after), f"{tag}: draw replay out of sync at step {t}"
         for k_, v in (("x_prev", x_prev), ("lw_prev", lw_prev), ("inds_prev", inds_prev), ("z", z),
                       ("x", new_state.timeseries_state.value), ("lw", new_state.weights),
@@ -183,6 +194,14 @@ def oracle_only_cases():
     filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132)
 
 
+def nested_cases():
+    """f2: ``NestedProposal`` (proposals/nested.py) - scalar and vector state, batched and not, SISR and APF."""
+    filter_case("c3_sisr_nested", "sv_ar1", {}, "sisr", "nested:20", "systematic", 400, 0, 6, 151)
+    filter_case("c1_apf_nested_b3", "lg_ar1", {}, "apf", "nested:50", "systematic", 300, 3, 6, 152)
+    filter_case("c4_sisr_nested", "lorenz63_em", {}, "sisr", "nested:12", "systematic", 300, 0, 6, 153)
+    filter_case("c2_apf_nested", "sine_em", {}, "apf", "nested:8", "systematic", 400, 0, 6, 154)
+
+
 def linearized_cases():
     """f2: the ``Linearized`` proposal (proposals/linearized.py, proposals/utils.py:30-146) - first order (the default) and second order,
     scalar and vector state, batched and not."""
@@ -198,6 +217,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "linearized":   # added later: leaves the other files as they are
         linearized_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "nested":
+        nested_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "residual":   # added later: leaves the other files as they are
         residual_cases()

@@ -623,6 +623,27 @@ PROPOSALS = {
 }
 
 
+def nested_sample_and_weight(model: Model, y, x_prev, noise, num_samples: int):
+    """``NestedProposal.sample_and_weight`` (``proposals/nested.py:27-47``) on replayed draws: ``noise = (zs, E)`` with ``zs`` the standard
+    normals behind ``hidden_density.sample(num_samples)`` - shape ``(M, N, [B], [d])`` - and ``E`` the float32 Exp(1) values behind
+    ``Categorical(probs).sample()``, shape ``(N, [B], M)``: ``torch.multinomial`` draws a single sample per row as
+    ``argmax(probs / q)``, ``q ~ Exp(1)`` (aten/src/ATen/native/Distributions.cpp, the n_sample == 1 path)."""
+    zs, E = noise
+    d = model.state_dim
+    mean, scale = model.mean_scale(x_prev)
+    samples = mean + scale * (zs * _t(model.inc_scale))
+    log_prob = model.obs_log_prob(y, samples).nan_to_num(-float("inf"), -float("inf"))
+    probs = log_prob.softmax(dim=0)
+    probs = probs.masked_fill(probs.isnan(), 1.0 / num_samples)
+    rows = probs.moveaxis(0, -1)
+    best = (rows / torch.as_tensor(E, dtype=rows.dtype).reshape(rows.shape)).argmax(dim=-1)
+    idx = best.unsqueeze(0)
+    if d:
+        idx = idx.unsqueeze(-1).expand((1,) + tuple(samples.shape[1:]))
+    x_new = samples.gather(0, idx).squeeze(0)
+    return x_new, log_prob.exp().mean(dim=0).log()
+
+
 class _ProposalTable(dict):
     """``"linearized:<n_steps>:<alpha>:<0|1 second order>"`` names a configured ``Linearized`` proposal (default pre-weight)."""
 
@@ -634,6 +655,10 @@ class _ProposalTable(dict):
             second = bool(int(parts[3])) if len(parts) > 3 else False
             fn = lambda model, y, x_prev, z: linearized_sample_and_weight(model, y, x_prev, z, n_steps, alpha, second)
             self[key] = (fn, affine_pre_weight)
+            return self[key]
+        if isinstance(key, str) and key.startswith("nested"):   # "nested:<num_samples>"; the step's noise argument is (zs, U)
+            m = int(key.split(":")[1])
+            self[key] = (lambda model, y, x_prev, noise: nested_sample_and_weight(model, y, x_prev, noise, m), affine_pre_weight)
             return self[key]
         raise KeyError(key)
 
@@ -703,7 +728,7 @@ def sisr_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, ess_t
         x_new, inc = PROPOSALS[proposal][0](model, y, x_res, z)
         lw_new = inc + lw_res  # sisr.py:52
         ll = log_likelihood(inc, W)  # sisr.py:55
-    mean, var = filter_mean_and_variance(x_new, normalize(lw_new.clone()), model.state_dim)
+    mean, var = filter_mean_and_variance(x_new, normalize(lw_new), model.state_dim)
     out.update(x=x_new, lw=lw_new, ll=ll, mean=mean, var=var)
     return out
 
@@ -728,7 +753,7 @@ def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resamp
     x_new, inc = sample_and_weight(model, y, x_res, z)  # apf.py:41
     lw_new = inc - g.gather(0, idx)  # apf.py:43
     ll = log_likelihood(lw_new) + (W * g.exp()).sum(dim=0).log()  # apf.py:44
-    mean, var = filter_mean_and_variance(x_new, normalize(lw_new.clone()), model.state_dim)
+    mean, var = filter_mean_and_variance(x_new, normalize(lw_new), model.state_dim)
     return {"x": x_new, "lw": lw_new, "ll": ll, "mean": mean, "var": var, "prev_inds": idx, "resample_W": rw,
             "pre_weight": g, "x_resampled": x_res}
 

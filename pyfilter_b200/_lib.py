@@ -31,6 +31,7 @@ class smcb_config(C.Structure):
         ("params_host", C.POINTER(C.c_float)), ("param_cols", C.c_int32), ("ess_threshold", C.c_float),
         ("seed", C.c_uint64), ("history_rows", C.c_int32), ("fold_lookahead", C.c_int32), ("exact_weights", C.c_int32),
         ("column_offset", C.c_int32), ("lin_steps", C.c_int32), ("lin_alpha", C.c_float), ("lin_second_order", C.c_int32),
+        ("nested_samples", C.c_int32),
     ]
 
 
@@ -64,6 +65,7 @@ SYMBOLS = [
     ("smcb_filter_exchange_wait", C.c_int, [_P, C.POINTER(_P), _P]),
     ("smcb_filter_set_noise", C.c_int, [_P, _P, _P, _P]),
     ("smcb_filter_dump_noise", C.c_int, [_P, _P, _P, _P]),
+    ("smcb_filter_set_nested_noise", C.c_int, [_P, _P, _P]),
     ("smcb_filter_ptr", C.c_int, [_P, C.c_int32, C.POINTER(_P)]),
     ("smcb_filter_sync_stats", C.c_int, [_P, _P]),
     ("smcb_normalize", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int64, C.c_int64, _P, C.c_int64, C.c_int64, _P, _P]),

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(NT, MINB) column_kernel(ColumnArgs c) {
           float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
           for (int d = 0; d < D; ++d) { xk[d] = xa[d][q]; zk[d] = z[d][q]; }
-          Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+          prop_sample_and_weight<MODEL, PROP>(a, col, (int64_t)i0 + q, t, y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
           for (int d = 0; d < D; ++d) xn[d][q] = xo[d];
           float lwv;

@@ -14,7 +14,7 @@
 #define SMCB_LOG_SQRT_2PI 0.9189385332046727f
 
 enum { SMCB_MODEL_LG_AR1 = 0, SMCB_MODEL_SINE_EM = 1, SMCB_MODEL_SV_AR1 = 2, SMCB_MODEL_LORENZ63_EM = 3, SMCB_MODEL_USER = 4, SMCB_NUM_MODELS = 5 };
-enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1, SMCB_PROPOSAL_LINEARIZED = 2 };
+enum { SMCB_PROPOSAL_BOOTSTRAP = 0, SMCB_PROPOSAL_LINEAR_GAUSS = 1, SMCB_PROPOSAL_LINEARIZED = 2, SMCB_PROPOSAL_NESTED = 3 };
 enum { SMCB_ALG_SISR = 0, SMCB_ALG_APF = 1 };
 enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 
@@ -57,6 +57,8 @@ enum { SMCB_RESAMPLE_SYSTEMATIC = 0, SMCB_RESAMPLE_MULTINOMIAL = 1 };
 #define P_LIN_T_INV2VAR 35    // 1 / (2 (scale inc)^2)
 #define P_LIN_T_LOGNORM 36    // log(inc |scale|) + log sqrt(2 pi)
 #define P_LIN_T_INVVAR 37     // 1 / (scale inc)^2
+#define P_NESTED_M 38         // NestedProposal: num_samples (as float), proposals/nested.py:17
+#define SMCB_NESTED_MAX 256   // largest num_samples (the per-particle log-densities of the inner samples sit in local memory)
 
 // sin(v) for the drift of the sine diffusion: explicit two-constant reduction to [-pi, pi] (exact products through fma), then the SFU.
 // Absolute error <= 2^-20.9 ~ 5e-7 on the reduced argument (PTX sin.approx.ftz.f32) against ~27 instructions of sinf() with its slow

@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(MV_NT, (Model<MODEL>::D == 1 ? SMCB_MV_MINB : 
         float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
         for (int d = 0; d < D; ++d) { xk[d] = xa[d][k]; zk[d] = z[d][k]; }
-        Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+        prop_sample_and_weight<MODEL, PROP>(a, col, (int64_t)s0 + k, t, y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
         for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
         float lw;

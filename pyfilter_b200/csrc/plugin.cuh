@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(ST_NT) proposal_op_kernel(ProposalOpArgs c) {
       float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
       for (int d = 0; d < D; ++d) { xk[d] = x[d][k]; zk[d] = z[d][k]; }
-      Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+      prop_sample_and_weight<MODEL, PROP>(a, col, i0 + k, c.t, y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
       for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
       w[k] = inc;

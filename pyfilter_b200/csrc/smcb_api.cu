@@ -119,6 +119,7 @@ static void derive_params(int model, const double* r, float* P, const smcb_confi
     P[P_LIN_T_INVVAR] = (float)(1.0 / (tv * tv));
     P[P_LIN_T_INV2VAR] = (float)(1.0 / (2.0 * tv * tv));
     P[P_LIN_T_LOGNORM] = (float)(log(fabs(tv)) + c);
+    P[P_NESTED_M] = (float)cfg.nested_samples;
   }
   if (lorenz_lgo) {
     const double hvi = 1.0 / (sigma * sigma), ovi = 1.0 / (s * s);
@@ -183,6 +184,8 @@ struct smcb_filter {
   float* midbuf = nullptr;  // multinomial: packed middle level of the draw's search (B, ceil(n / 64))
   float* wn = nullptr;    // normalised weights of the current resampling pass (B, ld)
   long long* dbg = nullptr;  // SMCB_DEBUG_TIMELINE=1: per-tile timeline of the scan kernel
+  const float* nest_z = nullptr;   // NestedProposal: injected inner draws (smcb_filter_set_nested_noise)
+  const float* nest_e = nullptr;
   const float *eps_in = nullptr, *u_in = nullptr;
   const double* U_in = nullptr;
   float *eps_out = nullptr, *u_out = nullptr, *w_out = nullptr;
@@ -251,8 +254,11 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   if (cfg->model == SMCB_MODEL_USER) return fail(SMCB_EUNSUPPORTED, "this build of libsmcb200 carries no user model (pyfilter_b200.timeseries.compile_user_model builds one)");
 #endif
   if (cfg->model == SMCB_MODEL_USER && cfg->proposal != SMCB_BOOTSTRAP) return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");
-  if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && cfg->proposal != SMCB_LINEARIZED)
+  if (cfg->proposal != SMCB_BOOTSTRAP && cfg->proposal != SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && cfg->proposal != SMCB_LINEARIZED &&
+      cfg->proposal != SMCB_NESTED)
     return fail(SMCB_EUNSUPPORTED, "unknown proposal");
+  if (cfg->proposal == SMCB_NESTED && (cfg->nested_samples < 1 || cfg->nested_samples > SMCB_NESTED_MAX))
+    return fail(SMCB_EINVAL, "NestedProposal: num_samples must be in 1 .. 256");
   if (cfg->proposal == SMCB_LINEARIZED && cfg->lin_steps < 1) return fail(SMCB_EINVAL, "``n_steps`` must be >= 1");   // proposals/linearized.py:39
   if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM || cfg->model == SMCB_LORENZ63_EM))
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
@@ -376,6 +382,7 @@ static StepArgs make_args(smcb_filter* f) {
   philox_round_keys((uint32_t)f->cfg.seed, (uint32_t)(f->cfg.seed >> 32), a.pkeys);
   a.fold = f->cfg.fold_lookahead; a.store_lw = 1; a.sample_x0 = 0; a.ess_threshold = f->cfg.ess_threshold;
   a.col0 = f->cfg.column_offset;
+  a.nest_z = f->nest_z; a.nest_e = f->nest_e;
   a.xch = f->xch; a.xch.seq = 0;   // set by the launch that finalises the last move of a run
   a.hist_mean = f->hist_mean; a.hist_var = f->hist_var; a.hist_ll = f->hist_ll; a.hist_rows = f->cfg.history_rows;
   a.dbg = f->dbg;
@@ -403,14 +410,18 @@ static StepArgs make_args(smcb_filter* f) {
     case 0: { constexpr int MODEL = 0, PROP = 0; BODY; } break;                        \
     case 1: { constexpr int MODEL = 0, PROP = 1; BODY; } break;                        \
     case 2: { constexpr int MODEL = 0, PROP = 2; BODY; } break;                        \
+    case 3: { constexpr int MODEL = 0, PROP = 3; BODY; } break;                        \
     case 4: { constexpr int MODEL = 1, PROP = 0; BODY; } break;                        \
     case 5: { constexpr int MODEL = 1, PROP = 1; BODY; } break;                        \
     case 6: { constexpr int MODEL = 1, PROP = 2; BODY; } break;                        \
+    case 7: { constexpr int MODEL = 1, PROP = 3; BODY; } break;                        \
     case 8: { constexpr int MODEL = 2, PROP = 0; BODY; } break;                        \
     case 10: { constexpr int MODEL = 2, PROP = 2; BODY; } break;                       \
+    case 11: { constexpr int MODEL = 2, PROP = 3; BODY; } break;                       \
     case 12: { constexpr int MODEL = 3, PROP = 0; BODY; } break;                       \
     case 13: { constexpr int MODEL = 3, PROP = 1; BODY; } break;                       \
     case 14: { constexpr int MODEL = 3, PROP = 2; BODY; } break;                       \
+    case 15: { constexpr int MODEL = 3, PROP = 3; BODY; } break;                       \
     SMCB_USER_PAIR(BODY)                                                              \
   }
 
@@ -906,6 +917,11 @@ extern "C" int smcb_filter_exchange_wait(smcb_filter* f, float** out_dev, void* 
 extern "C" int smcb_filter_set_noise(smcb_filter* f, const float* eps_dev, const float* u_dev, const double* U_dev) {
   if (!f) return fail(SMCB_EINVAL, "null handle");
   f->eps_in = eps_dev; f->u_in = u_dev; f->U_in = U_dev;
+  return SMCB_OK;
+}
+extern "C" int smcb_filter_set_nested_noise(smcb_filter* f, const float* z_dev, const float* e_dev) {
+  if (!f) return fail(SMCB_EINVAL, "null handle");
+  f->nest_z = z_dev; f->nest_e = e_dev;
   return SMCB_OK;
 }
 extern "C" int smcb_filter_dump_noise(smcb_filter* f, float* eps_dev, float* u_dev, float* w_dev) {

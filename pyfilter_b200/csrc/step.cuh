@@ -56,6 +56,10 @@ struct StepArgs {
   uint32_t pkeys[20];                // Philox round keys of `seed` (philox_round_keys)
   ExchangeArgs xch;                  // peer-memory exchange of the per-column log-likelihoods (common.cuh); xch.seq == 0: none
   int32_t col0;                      // global index of column 0 (smcb_config.column_offset): the Philox counters use col0 + column
+  // NestedProposal (proposals/nested.py): optional injected draws - the inner samples' N(0,1) values (M, D, B, ld) and the float64
+  // uniform of every particle's categorical draw (B, ld); NULL: Philox
+  const float* nest_z;
+  const float* nest_e;
 };
 __device__ __forceinline__ long long st_now() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 enum { FIN_STATE = 0, FIN_PREWEIGHT = 1, FIN_STEP = 2 };
@@ -396,6 +400,126 @@ struct Proposal<MODEL, SMCB_PROPOSAL_LINEARIZED> {
     g_anc = pre_weight(y, xa, P);
   }
 };
+
+// NestedProposal (proposals/nested.py:27-47, Naesseth et al.): M inner samples from the transition density per particle; the proposed
+// particle is one of them, drawn from Categorical(softmax of their observation log-densities), the weight is log mean exp of those
+// log-densities.  torch semantics reproduced: nan_to_num(nan = -inf, posinf = -inf) on the log-densities, a float32 soft-max accumulated
+// in sample order, NaN probabilities -> 1 / M, and torch.multinomial's single-sample rule for the draw (argmax of probs / Exp(1)) when the
+// exponentials are injected; the library's own draw inverts the prefix sums at one uniform.  The inner samples are never stored: their
+// log-densities sit in a local array, the chosen sample is regenerated from its Philox counter (particle, column, move, group of four).
+#define SMCB_RNG_NESTED 0x100u
+#define SMCB_RNG_NESTED_U 0x80u
+template <int MODEL>
+struct Proposal<MODEL, SMCB_PROPOSAL_NESTED> {
+  typedef Model<MODEL> M;
+  __device__ static __forceinline__ float pre_weight(const float* y, const float* x, const float* P) {   // proposals/base.py:69-85
+    float loc[M::D], sc;
+    M::loc_scale(x, P, loc, sc);
+    return M::obs_lp(y, loc, P);
+  }
+  // standard normals of the four inner samples 4 g .. 4 g + 3 of particle i: one Philox block per state dimension
+  __device__ static __forceinline__ void inner_normals4(const StepArgs& a, int col, int64_t i, int t, int g, int Ms, float (&z)[M::D][4]) {
+#pragma unroll
+    for (int d = 0; d < M::D; ++d) {
+      if (a.nest_z) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int s = min(4 * g + q, Ms - 1);
+          z[d][q] = a.nest_z[(((int64_t)s * M::D + d) * a.B + col) * a.ld + i];
+        }
+      } else {
+        const Philox4 r = philox4x32_10_keys((uint32_t)i, (uint32_t)(col + a.col0), (uint32_t)t, SMCB_RNG_NESTED + (uint32_t)g * 4u + d, a.pkeys);
+        smcb_normal4(r, z[d]);
+      }
+    }
+  }
+  __device__ static __noinline__ void sample_and_weight(const StepArgs& a, int col, int64_t i, int t, const float* y, const float* xa,
+                                                        const float* zk, const float* P, bool observed, float* xn, float& inc, float& g_anc) {
+    constexpr int D = M::D;
+    float m[D], sc;
+    M::loc_scale(xa, P, m, sc);
+    inc = 0.f; g_anc = 0.f;
+    if (!observed) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) xn[d] = __fadd_rn(m[d], __fmul_rn(sc, __fmul_rn(zk[d], P[P_INC_SCALE])));
+      return;
+    }
+    const int Ms = min((int)P[P_NESTED_M], SMCB_NESTED_MAX);
+    float lp[SMCB_NESTED_MAX];
+    float mx = -INFINITY;
+    for (int g = 0; 4 * g < Ms; ++g) {
+      float z[D][4];
+      inner_normals4(a, col, i, t, g, Ms, z);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        float xs[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xs[d] = __fadd_rn(m[d], __fmul_rn(sc, __fmul_rn(z[d][q], P[P_INC_SCALE])));
+        float l = M::obs_lp(y, xs, P);
+        if (l != l || l == INFINITY) l = -INFINITY;          // nan_to_num(-inf, -inf): -inf itself becomes the lowest finite float
+        else if (l == -INFINITY) l = -SMCB_FLT_MAX;
+        if (4 * g + q < Ms) {
+          lp[4 * g + q] = l;
+          mx = fmaxf(mx, l);
+        }
+      }
+    }
+    // soft-max over the samples (float32, in sample order) and the mean of exp(log-density)
+    float se = 0.f, sw = 0.f;
+    for (int s = 0; s < Ms; ++s) {
+      se += expf(lp[s] - mx);
+      sw += expf(lp[s]);
+    }
+    inc = logf(sw / (float)Ms);                              // log_prob.exp().mean(dim=0).log()
+    // Categorical(probs).sample(): torch.multinomial draws ONE sample per row as argmax(probs / Exp(1)) (its n_sample == 1 path); with
+    // injected exponentials that rule is followed, the library's own draw inverts the prefix sums at one Philox uniform
+    const float fill = 1.0f / (float)Ms;
+    int best = Ms - 1;
+    if (a.nest_e) {
+      float top = -INFINITY;
+      best = 0;
+      for (int s = 0; s < Ms; ++s) {
+        float pr = __fdiv_rn(expf(lp[s] - mx), se);
+        if (pr != pr) pr = fill;
+        const float q = __fdiv_rn(pr, a.nest_e[((int64_t)s * a.B + col) * a.ld + i]);
+        if (q > top) { top = q; best = s; }
+      }
+    } else {
+      const Philox4 r = philox4x32_10_keys((uint32_t)i, (uint32_t)(col + a.col0), (uint32_t)t, SMCB_RNG_NESTED_U, a.pkeys);
+      const double U = smcb_u01_double(r.x, r.y);
+      float total = 0.f;
+      for (int s = 0; s < Ms; ++s) {
+        float pr = expf(lp[s] - mx) / se;
+        if (pr != pr) pr = fill;
+        total = __fadd_rn(total, pr);
+      }
+      float c = 0.f;
+      for (int s = 0; s < Ms; ++s) {
+        float pr = expf(lp[s] - mx) / se;
+        if (pr != pr) pr = fill;
+        c = __fadd_rn(c, pr);
+        if ((double)__fdiv_rn(c, total) >= U) { best = s; break; }
+      }
+    }
+    float z[D][4];
+    inner_normals4(a, col, i, t, best >> 2, Ms, z);
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const int q = best & 3;
+      const float zb = q == 0 ? z[d][0] : q == 1 ? z[d][1] : q == 2 ? z[d][2] : z[d][3];
+      xn[d] = __fadd_rn(m[d], __fmul_rn(sc, __fmul_rn(zb, P[P_INC_SCALE])));
+    }
+    g_anc = pre_weight(y, xa, P);
+  }
+};
+
+// one entry point for every proposal: the nested one draws its own inner samples and needs to know which particle it is working on
+template <int MODEL, int PROP>
+__device__ __forceinline__ void prop_sample_and_weight(const StepArgs& a, int col, int64_t i, int t, const float* y, const float* xa,
+                                                       const float* zk, const float* P, bool observed, float* xn, float& inc, float& g_anc) {
+  if constexpr (PROP == SMCB_PROPOSAL_NESTED) Proposal<MODEL, PROP>::sample_and_weight(a, col, i, t, y, xa, zk, P, observed, xn, inc, g_anc);
+  else Proposal<MODEL, PROP>::sample_and_weight(y, xa, zk, P, observed, xn, inc, g_anc);
+}
 
 // ---- helpers -----------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ const float* st_obs(const Ctrl* c, int t, int od) {
@@ -885,7 +1009,7 @@ __global__ void __launch_bounds__(ST_NT, SMCB_ST_MINB) step_kernel(StepArgs a) {
         float xk[D], zk[D], xo[D], inc, g_anc;
 #pragma unroll
         for (int d = 0; d < D; ++d) { xk[d] = xa[d][k]; zk[d] = z[d][k]; }
-        Proposal<MODEL, PROP>::sample_and_weight(y, xk, zk, Ps, observed, xo, inc, g_anc);
+        prop_sample_and_weight<MODEL, PROP>(a, col, (int64_t)i0 + k, t, y, xk, zk, Ps, observed, xo, inc, g_anc);
 #pragma unroll
         for (int d = 0; d < D; ++d) xn[d][k] = xo[d];
         float lw;

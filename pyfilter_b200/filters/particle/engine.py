@@ -32,6 +32,7 @@ class Engine:
         pc = proposal_config or {}
         cfg.lin_steps, cfg.lin_alpha = int(pc.get("n_steps", 1)), float(pc.get("alpha", 1e-4))
         cfg.lin_second_order = int(bool(pc.get("use_second_order", False)))
+        cfg.nested_samples = int(pc.get("num_samples", 0))
         self._params_keepalive = params
         h = C.c_void_p()
         _lib.check(self.lib.smcb_filter_create(C.byref(cfg), C.byref(h)), self.lib)
@@ -134,6 +135,22 @@ class Engine:
         self._noise_keep = (eps, u, U)
         _lib.check(self.lib.smcb_filter_set_noise(self.handle, eps.data_ptr() if eps is not None else None,
                                                   u.data_ptr() if u is not None else None, U.data_ptr() if U is not None else None))
+
+    def set_nested_noise(self, z=None, e=None):
+        """NestedProposal parity hook: ``z`` (num_samples, N, [B], [d]) standard normals of the inner samples, ``e`` (N, [B], num_samples)
+        the Exp(1) values of ``torch.multinomial``'s single-sample draw."""
+        zs = es = None
+        if z is not None:
+            m = z.shape[0]
+            zs = torch.zeros((m, self.D, self.B, self.ld), device="cuda", dtype=torch.float32)
+            zs[..., : self.N] = z.to("cuda", torch.float32).reshape(m, self.N, self.B, self.D).permute(0, 3, 2, 1)
+        if e is not None:
+            m = e.shape[-1]
+            es = torch.ones((m, self.B, self.ld), device="cuda", dtype=torch.float32)
+            es[..., : self.N] = e.to("cuda", torch.float32).reshape(self.N, self.B, m).permute(2, 1, 0)
+        self._nested_keep = (zs, es)
+        _lib.check(self.lib.smcb_filter_set_nested_noise(self.handle, zs.data_ptr() if zs is not None else None,
+                                                         es.data_ptr() if es is not None else None), self.lib)
 
     def dump_noise(self, eps=None, u=None, w=None):
         self._dump_keep = (eps, u, w)

@@ -107,6 +107,29 @@ class Linearized(Proposal):
         return Linearized(self._n_steps, self._alpha, self._use_second_order)
 
 
+class NestedProposal(Proposal):
+    """``proposals/nested.py:8-50`` (Naesseth et al.): ``num_samples`` draws from the transition density per particle, one of them -
+    chosen with probabilities proportional to their observation densities - becomes the particle, the weight is the log of their mean
+    observation density.  Compiled into the fused kernels (csrc/step.cuh); at most 256 inner samples."""
+
+    proposal_id = 3
+
+    def __init__(self, num_samples: int, **kwargs):
+        super().__init__(**kwargs)
+        self._num_samples = torch.Size([int(num_samples)])
+
+    def set_model(self, model):
+        if getattr(model, "model_id", None) == 4:
+            raise ValueError("NestedProposal is compiled for the models of the zoo")
+        return super().set_model(model)
+
+    def config(self) -> dict:
+        return {"num_samples": int(self._num_samples[0])}
+
+    def copy(self) -> "Proposal":
+        return NestedProposal(self._num_samples[0])
+
+
 def _out_of_scope(name):
     class _Missing(Proposal):
         def __init__(self, *a, **k):
@@ -116,7 +139,6 @@ def _out_of_scope(name):
     return _Missing
 
 
-NestedProposal = _out_of_scope("NestedProposal")
 GaussianLinear = _out_of_scope("GaussianLinear")
 GaussianLinearized = _out_of_scope("GaussianLinearized")
 GaussianProposal = _out_of_scope("GaussianProposal")

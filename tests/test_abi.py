@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(_lib.smcb_config) == 88
+    assert C.sizeof(_lib.smcb_config) == 88   # (the last two int32 fields fill the padding of the 8-byte aligned struct)
     assert C.sizeof(_lib.smcb_info) == 64
 
 

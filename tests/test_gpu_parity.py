@@ -156,7 +156,9 @@ def _make_filter(pf, g, N, B, model=None, **kw):
     params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in g["params"].items()}
     m = ts.build(g["model"], **params)
     cls = {"sisr": SISR, "apf": APF}[g["alg"]]
-    if g["proposal"].startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>"
+    if g["proposal"].startswith("nested"):       # "nested:<num_samples>"
+        prop = proposals.NestedProposal(int(g["proposal"].split(":")[1]))
+    elif g["proposal"].startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>"
         parts = g["proposal"].split(":")
         prop = proposals.Linearized(n_steps=int(parts[1]), alpha=float(parts[2]), use_second_order=bool(int(parts[3])))
     else:
@@ -198,7 +200,12 @@ def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights, smc_pa
     for t in range(T):
         x_prev, lw_prev = torch.from_numpy(g["x_prev"][t]), torch.from_numpy(g["lw_prev"][t])
         e.load_state(x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), t)
-        eps, u, U = _noise_buffers(e, g["z"][t], g["u"][t], g["U"][t])
+        nested = g["proposal"].startswith("nested")
+        if nested:   # the inner samples' normals and the Exp(1) values of torch.multinomial's single-sample draw
+            e.set_nested_noise(torch.from_numpy(g["z"][t]), torch.from_numpy(g["Un"][t]))
+            eps, u, U = _noise_buffers(e, np.zeros(g["x"][t].shape, np.float32), g["u"][t], g["U"][t])
+        else:
+            eps, u, U = _noise_buffers(e, g["z"][t], g["u"][t], g["U"][t])
         e.set_noise(eps, u, U)
         y = torch.as_tensor(g["y"][t]).float().reshape(1, -1).cuda()
         e.set_observations(y, t)
@@ -222,11 +229,20 @@ def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights, smc_pa
         total_flips += flips
         assert flips <= max(2, N * max(B, 1) // 200), (tag, t, flips)  # ulp-level weight differences only
         sx = same if x.dim() == same.dim() else same.unsqueeze(-1).expand_as(x)
-        assert torch.allclose(x[sx], gx[sx], rtol=0, atol=2e-6 * max(1.0, float(gx.abs().max()))), (tag, t, (x - gx)[sx].abs().max())
+        xtol = 2e-6 * max(1.0, float(gx.abs().max()))
+        picks = 0
+        if nested:
+            # the pick is argmax(softmax(lp) / E) in float32: where two quotients tie within an ulp of the soft-max the device may
+            # take the other inner sample (same rule as for ancestors: a handful per step at most)
+            bad = ((x - gx).abs() > xtol) & sx
+            picks = int((bad if bad.dim() == same.dim() else bad.any(-1)).sum())
+            assert picks <= max(2, N * max(B, 1) // 200), (tag, t, picks)
+            sx = sx & ~bad
+        assert torch.allclose(x[sx], gx[sx], rtol=0, atol=xtol), (tag, t, (x - gx)[sx].abs().max())
         tol = 3e-5 if lgo else 1e-5
         fin = torch.isfinite(glw) & same
         assert ((lw[fin] - glw[fin]).abs() <= tol + 4e-6 * glw[fin].abs()).all(), (tag, t, (lw - glw)[fin].abs().max())
-        if flips == 0:
+        if flips == 0 and picks == 0:
             for key, got in (("ll", st.get_loglikelihood()), ("mean", st.get_mean()), ("var", st.get_variance())):
                 a, b = got.cpu().numpy().reshape(-1), g[key][t].reshape(-1)
                 assert np.allclose(a, b, rtol=2e-5, atol=2e-5), (tag, t, key, a, b)
@@ -235,13 +251,22 @@ def test_teacher_forced_steps_vs_reference_golden(pf, tag, exact_weights, smc_pa
         kw = dict(force_idx=inds.reshape(gx.shape[:ginds.dim()]))
         yt = torch.as_tensor(g["y"][t]).float()
         ut = torch.from_numpy(g["u"][t]).reshape(-1)
+        zt = torch.from_numpy(g["z"][t])
+        if nested:
+            zt = (zt, torch.from_numpy(g["Un"][t]))
         if g["alg"] == "sisr":
-            ref = O.sisr_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, torch.from_numpy(g["z"][t]),
+            ref = O.sisr_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, zt,
                               ut, resampler=g["resampler"], **kw)
         else:
-            ref = O.apf_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, torch.from_numpy(g["z"][t]),
+            ref = O.apf_step(model, g["proposal"], x_prev, lw_prev, torch.from_numpy(g["inds_prev"][t]), yt, zt,
                              ut, resampler=g["resampler"], **kw)
-        assert torch.allclose(x, ref["x"], rtol=0, atol=2e-6 * max(1.0, float(gx.abs().max()))), (tag, t, "x vs oracle on device ancestors")
+        if nested:
+            badr = (x - ref["x"]).abs() > xtol
+            nb_ = int((badr if badr.dim() == same.dim() else badr.any(-1)).sum())
+            assert nb_ <= max(2, N * max(B, 1) // 200), (tag, t, "picks vs oracle on device ancestors", nb_)
+            if nb_:
+                continue   # the moments below depend on the picks
+        assert torch.allclose(x, ref["x"], rtol=0, atol=xtol), (tag, t, "x vs oracle on device ancestors")
         finr = torch.isfinite(ref["lw"])
         assert ((lw[finr] - ref["lw"][finr]).abs() <= tol + 4e-6 * ref["lw"][finr].abs()).all(), (tag, t, "lw vs oracle on device ancestors")
         for key, got in (("ll", st.get_loglikelihood()), ("mean", st.get_mean()), ("var", st.get_variance())):

@@ -73,6 +73,68 @@ def test_proposal_plugin_methods_vs_oracle(pf, name, prop, B):
     assert not torch.equal(a1.value.cpu(), rx)
 
 
+@pytest.mark.parametrize("name", ["lg_ar1", "lorenz63_em"])
+def test_nested_proposal_stand_alone_pass(pf, name):
+    """``NestedProposal.sample_and_weight`` (proposals/nested.py:27-47) as a stand-alone pass: exact against the oracle when the inner
+    normals and the Exp(1) values of the categorical draw are injected; with the inner normals injected and the library's own pick, every
+    new particle is one of its inner samples and the picks follow the soft-max probabilities; with the library's own draws throughout,
+    the law of the result (shift and spread of the chosen normal, mean weight) is the oracle's."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import proposals
+    from pyfilter_b200.filters.particle.state import ParticleFilterPrediction
+
+    M, N = 50, 4096
+    torch.manual_seed(5)
+    mo = O.build_model(name)
+    gen = torch.Generator().manual_seed(3)
+    ev = (mo.state_dim,) if mo.state_dim else ()
+    loc, scale = mo.initial_loc_scale()
+    if name == "lorenz63_em":   # a tight cloud and an observation it can explain (the inner samples spread by 0.1, the noise is 0.32)
+        x = loc + 0.1 * torch.randn((N,) + ev, generator=gen)
+        y = mo.obs_loc(mo.mean_scale(loc)[0]).float() + 0.2
+    else:
+        x = loc + scale * torch.randn((N,) + ev, generator=gen)
+        y = mo.simulate(3)[1][2].float()
+    p = proposals.NestedProposal(M).set_model(ts.build(name))
+    xs = ts.TimeseriesState(4, x.cuda(), torch.Size(ev))
+    pred = ParticleFilterPrediction(xs, torch.zeros(N).cuda(), torch.full((N,), 1.0 / N).cuda(), None)
+    zs = torch.randn((M, N) + ev, generator=gen)
+    E = torch.empty(N, M).exponential_(1, generator=gen)
+    rx, rw = O.nested_sample_and_weight(mo, y, x, (zs, E), M)
+    e = p._engine_for(xs.value)
+    e.set_nested_noise(zs, E)
+    new, w = p.sample_and_weight(y, pred)
+    xtol = 2e-6 * max(1.0, float(rx.abs().max()))
+    bad = (new.value.cpu() - rx).abs() > xtol
+    assert int((bad if bad.dim() == 1 else bad.any(-1)).sum()) <= 4          # near-ties of the race only
+    fin = rw > -1e30
+    assert ((w.cpu() - rw)[fin].abs() <= 3e-5 + 4e-6 * rw[fin].abs()).all()
+    # the library's pick on injected inner normals
+    e.set_nested_noise(zs, None)
+    new, w2 = p.sample_and_weight(y, pred)
+    mean, sc = mo.mean_scale(x)
+    samples = mean + sc * (zs * mo.inc_scale)
+    nv = new.value.cpu()
+    dist = (samples - nv).abs() if not ev else (samples - nv).abs().amax(-1)
+    best = dist.argmin(0)
+    assert float(dist.gather(0, best[None]).max()) <= xtol
+    assert torch.equal(w2, w)
+    lp = mo.obs_log_prob(y, samples).nan_to_num(-float("inf"), -float("inf"))
+    probs = lp.softmax(0)
+    c = probs.double().cumsum(0)
+    hi = c.gather(0, best[None])[0]
+    mid = hi - probs.double().gather(0, best[None])[0] / 2                  # the uniform that picked lies around here: U(0, 1) overall
+    assert abs(float(mid.mean()) - 0.5) < 0.03 and abs(float(mid.var()) - 1 / 12) < 0.01
+    # the library's own draws throughout
+    e.set_nested_noise(None, None)
+    new, w3 = p.sample_and_weight(y, pred)
+    zb, zr = (new.value.cpu() - mean) / (sc * mo.inc_scale), (rx - mean) / (sc * mo.inc_scale)
+    assert (zb.mean(0) - zr.mean(0)).abs().max() < 0.1 and (zb.var(0) - zr.var(0)).abs().max() < 0.2, (zb.mean(0), zr.mean(0), zb.var(0), zr.var(0))
+    f3 = (w3.cpu() > -1e30) & fin
+    assert abs(float(f3.float().mean()) - float(fin.float().mean())) < 0.05
+    assert abs(float(w3.cpu()[f3].mean()) - float(rw[f3].mean())) < 0.05 * max(1.0, abs(float(rw[f3].mean())))
+
+
 @pytest.mark.parametrize("alg", ["sisr", "apf"])
 @pytest.mark.parametrize("B", [0, 4])
 def test_split_predict_correct_matches_oracle_statistics(pf, alg, B):

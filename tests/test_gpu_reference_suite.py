@@ -33,6 +33,7 @@ def _filters(particles=1_500, **kwargs):
             prop = part.proposals.Linearized(n_steps=5, use_second_order=second)
             out.append(("%s-linearized%d" % (pt.__name__, second), partial(pt, particles=particles, proposal=prop, **kwargs)))
         out.append(("%s-lgo" % pt.__name__, partial(pt, particles=particles, proposal=part.proposals.LinearGaussianObservations(), **kwargs)))
+        out.append(("%s-nested50" % pt.__name__, partial(pt, particles=particles, proposal=part.proposals.NestedProposal(50), **kwargs)))
     return out
 
 

@@ -102,6 +102,8 @@ def test_teacher_forced_steps_match_reference(tag):
         inds = torch.from_numpy(g["inds_prev"][t])
         y = torch.as_tensor(g["y"][t])
         z = torch.from_numpy(g["z"][t])
+        if g["proposal"].startswith("nested"):   # the inner normals and the Exp(1) values of the categorical draw
+            z = (z, torch.from_numpy(g["Un"][t]))
         u = torch.from_numpy(g["u"][t])
         U = g["U"][t]
         U = (U if B else U[:, 0]) if U.size else None
