@@ -118,7 +118,8 @@ class BaseOnlineAlgorithm:
         self._kernel = kernel or NonShrinkingKernel()
         self._disc = bool(discrete)
         self._seed = seed
-        self._rows = int(max_observations) + 2
+        self._max_obs, self._oes = int(max_observations), 1
+        self._rows = self._max_obs + 2
         self._resampler = resampling
         self._gen = torch.Generator().manual_seed(seed if seed is not None else int(torch.randint(0, 2**62, (1,)).item()))
         self._y_dev = None
@@ -131,6 +132,9 @@ class BaseOnlineAlgorithm:
                              proposal=self._proposal.copy() if self._proposal is not None else None, seed=self._seed)
         f.set_batch_shape(self.particles)
         self._filter = f
+        # filters/base.py:204-210: observation k >= 1 is consumed by move k * observe_every_step, the moves in between only propagate
+        self._oes = int(getattr(f.ssm, "observe_every_step", 1))
+        self._rows = self._max_obs * self._oes + 2
         e = f._get_engine(self._rows)
         e.initialize()
         self._y_dev = torch.full((self._rows, e.OD), float("nan"), device="cuda", dtype=torch.float32)
@@ -165,13 +169,15 @@ class BaseOnlineAlgorithm:
             state = self._update(state)
         e = state.engine
         t = len(state.parsed_data)
-        if t + 2 > self._rows:
+        if t + 1 > self._max_obs:
             raise ValueError("more observations than `max_observations`")
         yt = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
         state.parsed_data.append(yt)
-        self._y_dev[t] = yt.to("cuda")
-        e.set_observations(self._y_dev[: t + 1], 0)
-        e.run(1)
+        done = 0 if t == 0 else (t - 1) * self._oes + 1
+        upto = t * self._oes + 1
+        self._y_dev[upto - 1] = yt.to("cuda")                            # the rows of the propagate-only moves stay NaN
+        e.set_observations(self._y_dev[:upto], 0)
+        e.run(upto - done)
         state.w += e.raw(_lib.PTR_LL, (e.B,))
         ess, finite = torch.stack((_utils.get_ess(state.w).reshape(()), torch.isfinite(state.w).all().float())).tolist()   # one synchronisation
         state.ess.append(ess)

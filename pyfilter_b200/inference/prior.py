@@ -66,6 +66,26 @@ class LogNormal(Prior):
         return _normal_lp(u, self.loc, self.scale)
 
 
+class Exponential(Prior):
+    """``Exponential(rate)``: positive support, bijection ``exp``; the unconstrained parameter ``u = log x`` has the density
+    ``rate exp(u - rate exp(u))``."""
+
+    def __init__(self, rate: float):
+        self.rate = float(rate)
+
+    def sample(self, n, generator=None):
+        return torch.empty(n).exponential_(self.rate, generator=generator)
+
+    def get_constrained(self, u):
+        return u.exp()
+
+    def get_unconstrained(self, x):
+        return x.log()
+
+    def eval_unconstrained(self, u):
+        return math.log(self.rate) - self.rate * u.exp() + u
+
+
 class ParameterContext:
     """The parameters of the theta-particles: ``values`` is the ``(B, p)`` matrix of UNCONSTRAINED values
     (``stack_parameters(constrained=False)``, inference/context.py), one column per named prior in declaration order."""

@@ -128,7 +128,8 @@ class SMC2:
         self._acceptance_threshold = float(acceptance_threshold)
         self._max_increases, self._increases = int(max_increases), 0
         self._seed = seed
-        self._rows = int(max_observations) + 2
+        self._max_obs, self._oes = int(max_observations), 1
+        self._rows = self._max_obs + 2
         self._resampler = resampling                    # kernels/base.py:15-23
         self._filter = None
         self._proposal_filter = None
@@ -159,7 +160,14 @@ class SMC2:
         f = self._filter_cls(self._local_model(context), n_state, proposal=self._proposal.copy() if self._proposal is not None else None,
                              seed=None if self._seed is None else self._seed + 7919 * salt, column_offset=cols.start)
         f.set_batch_shape(torch.Size([cols.stop - cols.start]))
+        # filters/base.py:204-210: observation k >= 1 is consumed by move k * observe_every_step, the moves in between only propagate
+        self._oes = int(getattr(f.ssm, "observe_every_step", 1))
+        self._rows = self._max_obs * self._oes + 2
         return f, f._get_engine(self._rows)
+
+    def _moves(self, n_obs: int) -> int:
+        """Moves the filter has made once ``n_obs`` observations are in."""
+        return 0 if n_obs == 0 else (n_obs - 1) * self._oes + 1
 
     def _draw_seed(self) -> int:
         return int(torch.randint(0, 2**62, (1,), generator=self._gen).item())
@@ -177,14 +185,15 @@ class SMC2:
     def step(self, y: torch.Tensor, state: SMC2State) -> SMC2State:
         e = state.engine
         t = len(state.parsed_data)
-        if t + 2 > self._rows:
+        if t + 1 > self._max_obs:
             raise ValueError("more observations than `max_observations`")
         yt = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
         state.parsed_data.append(yt)
-        self._y_dev[t] = yt.to("cuda")
+        done, upto = self._moves(t), self._moves(t + 1)
+        self._y_dev[upto - 1] = yt.to("cuda")                            # the rows of the propagate-only moves stay NaN
         with self.phases("filter move"):
-            e.set_observations(self._y_dev[: t + 1], 0)
-            e.run(1)
+            e.set_observations(self._y_dev[:upto], 0)
+            e.run(upto - done)
         with self.phases("gather increments"):
             state.w += self._gather(e.raw(_lib.PTR_LL, (e.B,)))      # SequentialAlgorithmState.append (state.py:35-44)
         with self.phases("ess"):   # the ESS and the finiteness flag come to the host together: ONE synchronisation per observation (smc2.py:59-62)
@@ -215,7 +224,7 @@ class SMC2:
         ctx.resample(indices)
         with self.phases("migrate columns"):
             self._migrate(e, indices)                                     # state.filter_state.resample(indices)
-        T = len(state.parsed_data)
+        T = self._moves(len(state.parsed_data))
         if self._proposal_filter is None or self._proposal_filter[1].N != e.N:
             with self.phases("create proposal filter"):
                 self._proposal_filter = self._make_filter(ctx, e.N, 1 + self._increases)
@@ -271,7 +280,7 @@ class SMC2:
         if self._increases > self._max_increases:
             raise TooManyIncreases(f"Configuration only allows {self._max_increases}!")
         old_ll = state.loglikelihood.clone()
-        T = len(state.parsed_data)
+        T = self._moves(len(state.parsed_data))
         self._filter, e = self._make_filter(self.context, 2 * state.engine.N, 100 + self._increases)
         e.initialize()
         e.set_observations(self._y_dev[:T], 0)

@@ -112,6 +112,77 @@ def test_user_model_outside_the_zoo_vs_oracle():
     assert abs(dev.mean() - ora.mean()) < 4.0 * se + 0.05, (dev.mean(), ora.mean(), se, dev, ora)
 
 
+def test_notebook_stochastic_volatility_model_vs_oracle():
+    """The model of examples/stochastic-volatility.ipynb:60-83 (Verhulst volatility observed through a sinh-arcsinh transformed normal,
+    ``observe_every_step = 1 / dt = 5``, days without a price change masked to NaN) as a user model: teacher-forced APF / SISR moves and a
+    free-running filter against the oracle's restatement, then the notebook's SMC2 fit (six parameters with its priors) on a small cloud."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR
+    from pyfilter_b200.inference import SMC2, Exponential, LogNormal, Normal
+
+    make = ts.compile_user_model(_src("verhulst_sas_user.h"), state_dim=1, obs_dim=1)
+    p = O.DEFAULT_PARAMS["verhulst_sas"]
+    pars = (p["kappa"], p["gamma"], p["sigma"], p["mu"], p["nu"], p["tau"], p["dt"])
+    mo = O.build_model("verhulst_sas")
+    gen = torch.Generator().manual_seed(3)
+    N = 20_000
+    loc, sc = mo.initial_loc_scale()
+    x0 = loc + sc * torch.randn(N, generator=gen)
+    lw0 = torch.randn(N, generator=gen) * 0.3
+    z = torch.randn(N, generator=gen)
+    y = torch.tensor(-1.3)
+    for alg, cls in (("apf", APF), ("sisr", SISR)):
+        f = cls(make(*pars), N, seed=5)
+        e = f._get_engine(4)
+        e.load_state(x0, lw0, torch.arange(N), 0)
+        u = torch.tensor([0.61])
+        eps = torch.zeros(e.D, e.B, e.ld)
+        eps[0, 0, :N] = z
+        e.set_noise(eps.cuda(), u.cuda(), None)
+        e.set_observations(y.reshape(1, 1).cuda(), 0)
+        e.run(1)
+        torch.cuda.synchronize()
+        st = e.make_state()
+        inds = st.previous_indices.cpu()
+        step = O.apf_step if alg == "apf" else O.sisr_step
+        kw = {"ess_threshold": 0.9} if alg == "sisr" else {}
+        ref = step(mo, "bootstrap", x0, lw0, torch.arange(N), y, z, u, resampler="systematic", force_idx=inds, **kw)
+        ref0 = step(mo, "bootstrap", x0, lw0, torch.arange(N), y, z, u, resampler="systematic", **kw)
+        assert int((ref0["prev_inds"] != inds).sum()) <= N // 200, alg
+        assert torch.allclose(st.timeseries_state.value.cpu(), ref["x"], rtol=0, atol=2e-5), alg
+        fin = torch.isfinite(ref["lw"])
+        assert ((st.weights.cpu()[fin] - ref["lw"][fin]).abs() <= 2e-4 + 1e-5 * ref["lw"][fin].abs()).all(), alg
+        assert np.allclose(st.get_loglikelihood().cpu().numpy(), ref["ll"].numpy(), rtol=1e-4, atol=1e-4), alg
+    # data on the filter's schedule (filters/base.py:204-210): the first observation after one step, then one every five steps
+    torch.manual_seed(9)
+    x, ys = mo.initial_sample(()), []
+    for k in range(40):
+        for _ in range(1 if k == 0 else 5):
+            x = mo.propagate(x, torch.randn(()))
+        ys.append(mo.sample_obs(x, None))
+    yv = torch.stack(ys)
+    yv[[7, 19, 20]] = float("nan")
+    dev = np.array([float(APF(make(*pars, observe_every_step=5), 20_000, seed=100 + k).batch_filter(yv, bar=False).loglikelihood) for k in range(8)])
+    ora = []
+    for k in range(8):
+        torch.manual_seed(200 + k)
+        ora.append(float(O.batch_filter(mo, "apf", "bootstrap", yv, 20_000, observe_every_step=5)["loglikelihood"]))
+    ora = np.array(ora)
+    se = math.sqrt(dev.var(ddof=1) / 8 + ora.var(ddof=1) / 8)
+    assert abs(dev.mean() - ora.mean()) < 4.0 * se + 0.05, (dev.mean(), ora.mean(), se, dev, ora)
+    # the notebook's fit, small: APF(build_model, 400) under SMC2 with the notebook's priors
+    priors = {"kappa": Exponential(10.0), "gamma": LogNormal(0.0, 1.0), "sigma": LogNormal(math.log(0.05), 1.0),
+              "mu": Normal(0.0, 0.5), "nu": Normal(0.0, 0.15), "tau": LogNormal(0.0, 0.1)}
+    alg = SMC2(lambda q: make(q["kappa"], q["gamma"], q["sigma"], q["mu"], q["nu"], q["tau"], 0.2, observe_every_step=5), priors,
+               particles=256, state_particles=400, threshold=0.2, num_steps=2, seed=4, max_observations=64, max_increases=8)
+    state = alg.fit(yv)
+    ll = state.loglikelihood
+    assert state.engine.t == (len(yv) - 1) * 5 + 1 and torch.isfinite(ll).all()
+    post = {k: float(v) for k, v in alg.posterior_mean(state).items()}
+    assert all(math.isfinite(v) for v in post.values()) and post["gamma"] > 0 and post["tau"] > 0, post
+    assert len(state.ess) == len(yv) + 1 and state.ess[-1] > 1.0        # the initial cloud's ESS, then one per observation
+
+
 def test_user_model_rejects_unsupported_pairings():
     from pyfilter_b200 import timeseries as ts
     from pyfilter_b200.filters.particle import APF, proposals

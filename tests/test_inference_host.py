@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import smc2_oracle as S
-from pyfilter_b200.inference import LogNormal, Normal, ParameterContext
+from pyfilter_b200.inference import Exponential, LogNormal, Normal, ParameterContext
 from pyfilter_b200.inference import ness as NS
 from pyfilter_b200.inference import smc2 as M
 
@@ -67,3 +67,17 @@ def test_jitter_kernels_vs_reference_golden_and_oracle(kind):
     # the weighted quartiles: a triangular product here, a sequential sum in the reference - a quartile may land on the neighbouring order statistic
     assert torch.allclose(torch.as_tensor(sc).float(), g[f"jit_{kind}_scale"], rtol=5e-3, atol=1e-7)
     assert torch.allclose(torch.as_tensor(sc).float(), torch.as_tensor(osc).float(), rtol=5e-3, atol=1e-7)
+
+
+def test_exponential_prior_in_the_unconstrained_space():
+    """``Exponential(rate)`` (examples/stochastic-volatility.ipynb:75): the prior of ``log x`` is what torch's
+    ``TransformedDistribution(Exponential, biject_to(positive).inv)`` evaluates (inference/prior.py:33-44, 81-90)."""
+    import torch.distributions as D
+
+    u = torch.linspace(-6.0, 2.0, 41)
+    ref = D.TransformedDistribution(D.Exponential(10.0), D.biject_to(D.constraints.positive).inv).log_prob(u)
+    p = Exponential(10.0)
+    assert torch.allclose(p.eval_unconstrained(u), ref, rtol=1e-5, atol=1e-5)
+    x = p.sample(20_000, torch.Generator().manual_seed(1))
+    assert (x > 0).all() and abs(float(x.mean()) - 0.1) < 0.005
+    assert torch.allclose(p.get_constrained(p.get_unconstrained(x)), x, rtol=1e-5)
