@@ -38,7 +38,7 @@ enum { SMCB_LG_AR1 = 0, SMCB_SINE_EM = 1, SMCB_SV_AR1 = 2, SMCB_LORENZ63_EM = 3,
 /*            proposals/nested.py:8-50 (num_samples inner draws per particle, one of them proposed) */
 enum { SMCB_BOOTSTRAP = 0, SMCB_LINEAR_GAUSSIAN_OBSERVATIONS = 1, SMCB_LINEARIZED = 2, SMCB_NESTED = 3 };
 /* filters: filters/particle/sisr.py:7-56, filters/particle/apf.py:9-46 */
-enum { SMCB_SISR = 0, SMCB_APF = 1 };
+enum { SMCB_SISR = 0, SMCB_APF = 1, SMCB_GPF = 2 };   /* GPF: filters/particle/gpf.py with its default GaussianProposal */
 /* resamplers: resampling.py:24-52 (systematic), :55-65 (multinomial) */
 enum { SMCB_SYSTEMATIC = 0, SMCB_MULTINOMIAL = 1 };
 
@@ -53,7 +53,7 @@ enum { SMCB_SYSTEMATIC = 0, SMCB_MULTINOMIAL = 1 };
 typedef struct smcb_config {
   int32_t model;          /* SMCB_LG_AR1 ...                                              (the `model` argument, filters/base.py:22) */
   int32_t proposal;       /* SMCB_BOOTSTRAP ...                                           (`proposal`, filters/particle/base.py:24) */
-  int32_t algorithm;      /* SMCB_SISR / SMCB_APF                                          (the filter class) */
+  int32_t algorithm;      /* SMCB_SISR / SMCB_APF / SMCB_GPF                                          (the filter class) */
   int32_t resampler;      /* SMCB_SYSTEMATIC / SMCB_MULTINOMIAL                            (`resampling`, filters/particle/base.py:23) */
   int64_t particles;      /* N                                                            (`particles`, filters/particle/base.py:22) */
   int32_t batch;          /* B >= 1 independent filters                                    (set_batch_shape, filters/base.py:93-119) */

@@ -30,7 +30,7 @@ def _np(t):
 
 def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed, nan_steps=(), prefix="filter"):
     pf = load_reference()
-    from pyfilter.filters.particle import APF, SISR, proposals as pr
+    from pyfilter.filters.particle import APF, GPF, SISR, proposals as pr
     from pyfilter import resampling as RR
     from pyfilter.utils import get_ess, normalize
 
@@ -41,9 +41,11 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
         y[s] = float("nan")
     ref_params = {k: (torch.tensor(v) if isinstance(v, (list, tuple)) else v) for k, v in params.items()}
     ssm = build_reference_model(model_name, {**O.DEFAULT_PARAMS[model_name], **ref_params})
-    cls = {"sisr": SISR, "apf": APF}[alg]
+    cls = {"sisr": SISR, "apf": APF, "gpf": GPF}[alg]
     nested_m = int(proposal.split(":")[1]) if proposal.startswith("nested") else 0
-    if nested_m:                            # "nested:<num_samples>" (proposals/nested.py:17)
+    if alg == "gpf":                        # gpf.py:24: the default GaussianProposal
+        prop = None
+    elif nested_m:                          # "nested:<num_samples>" (proposals/nested.py:17)
         prop = pr.NestedProposal(nested_m)
     elif proposal.startswith("linearized"):   # "linearized:<n_steps>:<alpha>:<second order>" (proposals/linearized.py:22)
         parts = proposal.split(":")
@@ -59,6 +61,8 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
     rec = {k: [] for k in ("x_prev", "lw_prev", "inds_prev", "u", "U", "z", "x", "lw", "ll", "mean", "var", "prev_inds", "drew")}
     if nested_m:
         rec["Un"] = []
+    if alg == "gpf":
+        rec["z2"] = []
     x0 = _np(state.timeseries_state.value)
     for t in range(T):
         x_prev, lw_prev = state.timeseries_state.value.clone(), state.weights.clone()
@@ -72,6 +76,8 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
         isnan = bool(torch.isnan(y[t]).all())
         if alg == "sisr":
             mask = (get_ess(normalize(lw_prev.clone()), True) < 0.9 * N).reshape(-1)
+        elif alg == "gpf":
+            mask = torch.zeros(nb, dtype=torch.bool)   # nothing resamples
         else:
             mask = torch.full((nb,), not isnan)
         u = np.zeros(nb, dtype=np.float32)
@@ -91,6 +97,9 @@ def filter_case(tag, model_name, params, alg, proposal, resampler, N, B, T, seed
             rec["Un"].append(_np(Un))
         else:
             z = torch.empty(tuple(filt.particles) + tuple(d)).normal_()
+        if alg == "gpf":   # the sample from the Gaussian approximation (approximate.py:26), none on a propagate-only move
+            z2 = torch.zeros(tuple(filt.particles) + tuple(d)) if isnan else torch.empty(tuple(filt.particles) + tuple(d)).normal_()
+            rec["z2"].append(_np(z2))
         assert torch.equal(torch.get_rng_state(), after), f"{tag}: draw replay out of sync at step {t}"
         for k_, v in (("x_prev", x_prev), ("lw_prev", lw_prev), ("inds_prev", inds_prev), ("z", z),
                       ("x", new_state.timeseries_state.value), ("lw", new_state.weights),
@@ -194,6 +203,14 @@ def oracle_only_cases():
     filter_case("c4_sisr_lgo_sys", "lorenz63_em", {}, "sisr", "linear_gaussian", "systematic", 400, 0, 8, 132)
 
 
+def gpf_cases():
+    """f4: the Gaussian particle filter (filters/particle/gpf.py) - scalar and vector state, batched and not, a NaN observation."""
+    filter_case("c1_gpf", "lg_ar1", {}, "gpf", "bootstrap", "systematic", 500, 0, 8, 161, nan_steps=(3,))
+    filter_case("c3_gpf_b3", "sv_ar1", {}, "gpf", "bootstrap", "systematic", 400, 3, 6, 162)
+    filter_case("c4_gpf", "lorenz63_em", {}, "gpf", "bootstrap", "systematic", 600, 0, 6, 163)
+    filter_case("c4_gpf_b2", "lorenz63_em", {}, "gpf", "bootstrap", "systematic", 300, 2, 5, 164, nan_steps=(2,))
+
+
 def nested_cases():
     """f2: ``NestedProposal`` (proposals/nested.py) - scalar and vector state, batched and not, SISR and APF."""
     filter_case("c3_sisr_nested", "sv_ar1", {}, "sisr", "nested:20", "systematic", 400, 0, 6, 151)
@@ -217,6 +234,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "linearized":   # added later: leaves the other files as they are
         linearized_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "gpf":
+        gpf_cases()
         return
     if len(sys.argv) > 1 and sys.argv[1] == "nested":
         nested_cases()

@@ -799,7 +799,38 @@ def apf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resamp
             "pre_weight": g, "x_resampled": x_res}
 
 
-STEPS = {"sisr": sisr_step, "apf": apf_step}
+def gpf_step(model: Model, proposal: str, x, lw, prev_inds, y, z, u=None, resampler="systematic", U=None, force_idx=None, **_):
+    """One move of the Gaussian particle filter: ``GPF.predict`` / ``.correct`` (``filters/particle/gpf.py:27-36``) with the default
+    ``GaussianProposal.sample_and_weight`` (``proposals/approximate.py:19-35``) and ``get_predictive_density(approximate=True)``
+    (``particle/state.py:59-70``).  ``z = (z1, z2)``: the N(0, 1) draws of ``hidden.propagate`` and of the sample from the Gaussian
+    approximation (one draw for a propagate-only move: ``z`` may then be ``z1`` alone).  The weights are replaced, not accumulated;
+    the ancestors stay what they were."""
+    z1, z2 = z if isinstance(z, (tuple, list)) else (z, None)
+    lw = lw.clone()
+    W = normalize(lw)                                  # state.normalized_weights() (mutates like the reference)
+    d = model.state_dim
+    x_prop = model.propagate(x, z1)
+    if bool(torch.isnan(torch.as_tensor(y)).all()):     # filters/base.py:213-214 -> particle/state.py:38-42
+        x_new, lw_new, ll = x_prop, lw, torch.zeros(lw.shape[1:])
+    else:
+        values = x_prop if d else x_prop.unsqueeze(-1)  # particle/utils.py:42-58 with covariance=True, keep_dim=False
+        w = W.unsqueeze(-1)
+        mean = (w * values).sum(dim=0)
+        centered = values - mean
+        if d == 0:
+            var = (w * centered.pow(2.0)).sum(dim=0).squeeze(-1)
+            x_new = mean.squeeze(-1) + var.sqrt() * z2  # Normal(mean, var.sqrt()).expand(...).sample()
+        else:
+            cov = torch.einsum("b...,b...ij->...ij", W, centered.unsqueeze(-1) @ centered.unsqueeze(-2))
+            L = torch.linalg.cholesky(cov)              # MultivariateNormal(mean, covariance_matrix=cov).sample()
+            x_new = mean + (L @ z2.unsqueeze(-1)).squeeze(-1)
+        lw_new = model.obs_log_prob(y, x_new)
+        ll = log_likelihood(lw_new)
+    fm, fv = filter_mean_and_variance(x_new, normalize(lw_new), d)
+    return dict(x=x_new, lw=lw_new, ll=ll, mean=fm, var=fv, prev_inds=prev_inds)
+
+
+STEPS = {"sisr": sisr_step, "apf": apf_step, "gpf": gpf_step}
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -834,6 +865,17 @@ def batch_filter(model: Model, algorithm: str, proposal: str, y: torch.Tensor, p
         time_index += 1
     for y_t, recorded in moves:
         # which columns draw resampling randomness (reference order: u first, then the transition noise)
+        if algorithm == "gpf":   # gpf.py: nothing resamples; the propagation's draws, then (observed moves) the Gaussian sample's
+            z1 = torch.empty(shape + d).normal_()
+            z2 = None if bool(torch.isnan(y_t).all()) else torch.empty(shape + d).normal_()
+            out = gpf_step(model, proposal, x, lw, inds, y_t, (z1, z2))
+            x, lw, inds = out["x"], out["lw"], out["prev_inds"]
+            if recorded:
+                ll_total = ll_total + out["ll"]
+                means.append(out["mean"])
+                variances.append(out["var"])
+                states.append((x, lw, inds))
+            continue
         if algorithm == "sisr":
             mask = (get_ess(normalize(lw.clone()), True) < ess_threshold * n).reshape(-1)  # sisr.py:16-19
         else:

@@ -12,7 +12,7 @@ import threading
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsmcb200.so")
 _SOURCES = ["smcb_api.cu", "resample.cuh", "step.cuh", "operators.cuh", "common.cuh", "models.h", "philox.h", "scan_tile.h",
-            "exact_scan.h", "column.cuh", "move.cuh", "plugin.cuh"]
+            "exact_scan.h", "column.cuh", "move.cuh", "plugin.cuh", "gpf.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
               "-diag-suppress", "128"]
 

@@ -15,6 +15,7 @@
 #include "move.cuh"
 #include "operators.cuh"
 #include "plugin.cuh"
+#include "gpf.cuh"
 
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -184,6 +185,8 @@ struct smcb_filter {
   float* midbuf = nullptr;  // multinomial: packed middle level of the draw's search (B, ceil(n / 64))
   float* wn = nullptr;    // normalised weights of the current resampling pass (B, ld)
   long long* dbg = nullptr;  // SMCB_DEBUG_TIMELINE=1: per-tile timeline of the scan kernel
+  float* gpf_partial = nullptr;    // GPF: block sums of the predictive moments, (B, blocks_per_col, 10)
+  float* gpf_dist = nullptr;       //      mean and Cholesky factor of the Gaussian approximation, (B, 12)
   const float* nest_z = nullptr;   // NestedProposal: injected inner draws (smcb_filter_set_nested_noise)
   const float* nest_e = nullptr;
   const float *eps_in = nullptr, *u_in = nullptr;
@@ -241,7 +244,7 @@ extern "C" int smcb_filter_destroy(smcb_filter* f) {
   void* ptrs[] = {f->P_dev, f->xbuf[0], f->xbuf[1], f->lwbuf[0], f->lwbuf[1], f->rwbuf[0], f->rwbuf[1], f->anc, f->prev_inds, f->stats, f->partials, f->ctrl,
                   f->tilesum, f->prefix, f->sin, f->tileflag, f->desc, f->desc2, f->tables, f->dcounter, f->hist_mean, f->hist_var, f->hist_ll, f->latest_mean, f->latest_var, f->latest_ll,
                   f->ll_total, f->ess_packed, f->y_own, f->cbuf, f->col_ticket, f->wn, f->dbg, f->tilemin, f->ncounter, f->verdict, f->fslots,
-                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out, f->xch_ticket, f->midbuf};
+                  f->u_col, f->tile_partials, f->tile_counter, f->wd, f->mslots, f->gwords, f->xch_out, f->xch_ticket, f->midbuf, f->gpf_partial, f->gpf_dist};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete f;
   return SMCB_OK;
@@ -262,7 +265,9 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   if (cfg->proposal == SMCB_LINEARIZED && cfg->lin_steps < 1) return fail(SMCB_EINVAL, "``n_steps`` must be >= 1");   // proposals/linearized.py:39
   if (cfg->proposal == SMCB_LINEAR_GAUSSIAN_OBSERVATIONS && !(cfg->model == SMCB_LG_AR1 || cfg->model == SMCB_SINE_EM || cfg->model == SMCB_LORENZ63_EM))
     return fail(SMCB_EUNSUPPORTED, "Model combination not supported!");  // same condition as proposals/linear.py:32-36
-  if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
+  if (cfg->algorithm != SMCB_SISR && cfg->algorithm != SMCB_APF && cfg->algorithm != SMCB_GPF) return fail(SMCB_EUNSUPPORTED, "unknown filter algorithm");
+  if (cfg->algorithm == SMCB_GPF && cfg->proposal != SMCB_BOOTSTRAP)   // the GaussianProposal of gpf.py:24 is the one compiled
+    return fail(SMCB_EUNSUPPORTED, "GPF runs with its default GaussianProposal");
   if (cfg->resampler != SMCB_SYSTEMATIC && cfg->resampler != SMCB_MULTINOMIAL) return fail(SMCB_EUNSUPPORTED, "unknown resampler");
   if (cfg->particles < 1 || cfg->particles >= ((int64_t)1 << 31) - (1 << 21)) return fail(SMCB_EINVAL, "particles out of range");
   if (cfg->resampler == SMCB_MULTINOMIAL && cfg->particles > (1 << 24)) return fail(SMCB_EINVAL, "number of categories cannot exceed 2^24");  // torch.multinomial's limit
@@ -334,6 +339,11 @@ extern "C" int smcb_filter_create(const smcb_config* cfg, smcb_filter** out) {
   A_(dalloc(&f->latest_ll, (size_t)f->B));
   A_(dalloc(&f->ll_total, (size_t)f->B));
   A_(dalloc(&f->ess_packed, (size_t)f->B * 2));
+  if (cfg->algorithm == SMCB_GPF) {
+    A_(dalloc(&f->gpf_partial, (size_t)f->B * f->blocks_per_col * 10));
+    A_(dalloc(&f->gpf_dist, (size_t)f->B * 12));
+    f->cfg.ess_threshold = 0.f;   // nothing resamples (gpf.py:27-30): the propagate-only moves never see a resampling flag
+  }
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->cbuf, cells));
   if (cfg->resampler == SMCB_MULTINOMIAL) A_(dalloc(&f->midbuf, (size_t)f->B * ((f->n + MN_MID - 1) / MN_MID)));
   if (getenv("SMCB_DEBUG_TIMELINE")) A_(dalloc(&f->dbg, (size_t)32 + (size_t)16 * f->B * (f->mv_tiles_cap > f->tiles_per_col ? f->mv_tiles_cap : f->tiles_per_col)));
@@ -541,7 +551,7 @@ static int launch_move(smcb_filter* f, const StepArgs& a, cudaStream_t s) {
 // the move kernel serves systematic resampling with rounding-free weights of at most 2^23 particles (the lean probe count)
 static bool move_path_ok(const smcb_filter* f) {
   const bool off = getenv("SMCB_NO_MOVE") != nullptr;  // diagnostics / tests: force the two-kernel pipeline
-  return !off && f->cfg.resampler == SMCB_SYSTEMATIC && !f->cfg.exact_weights && f->n <= (1 << 23) &&
+  return !off && f->cfg.algorithm != SMCB_GPF && f->cfg.resampler == SMCB_SYSTEMATIC && !f->cfg.exact_weights && f->n <= (1 << 23) &&
          (int64_t)f->mv_tiles_cap * f->B < (1 << 30);
 }
 
@@ -640,6 +650,22 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
   a.t_host = t;
   a.y_t = f->y_dev ? f->y_dev + (int64_t)(t - f->y_base) * f->OD : nullptr;
   a.y_next = (f->y_dev && t + 1 - f->y_base < f->y_count) ? f->y_dev + (int64_t)(t + 1 - f->y_base) * f->OD : nullptr;
+  if (f->cfg.algorithm == SMCB_GPF) {   // gpf.cuh: propagate + predictive moments, Gaussian fit, draw + weight, fold
+    GpfArgs g;
+    g.s = a; g.partial = f->gpf_partial; g.dist = f->gpf_dist;
+    g.s.fin_host = 1;
+    const dim3 grid(f->blocks_per_col, f->B);
+    FOR_MODEL(f->cfg.model, (gpf_predict_kernel<MODEL><<<grid, ST_NT, 0, s>>>(g)));
+    if (f->D == 1) gpf_moments_kernel<1><<<f->B, ST_NT, 0, s>>>(g);
+    else if (f->D == 2) gpf_moments_kernel<2><<<f->B, ST_NT, 0, s>>>(g);
+    else gpf_moments_kernel<3><<<f->B, ST_NT, 0, s>>>(g);
+    FOR_MODEL(f->cfg.model, (gpf_correct_kernel<MODEL><<<grid, ST_NT, 0, s>>>(g)));
+    f->launches += 3;
+    launch_finalize(f, g.s, FIN_STEP, s);
+    if (ev) for (int k = 0; k <= 5; ++k) cudaEventRecord(ev[k], s);
+    f->t_host = t + 1;
+    return SMCB_OK;
+  }
   if (ev) cudaEventRecord(ev[0], s);
   if (apf && !f->folded_for_next) {  // apf.py:27-29 evaluated now because the previous move could not fold it
     launch_preweight(f, a, s);
@@ -719,6 +745,7 @@ static int run_one(smcb_filter* f, cudaStream_t s, cudaEvent_t* ev, bool last = 
 // ---- resident-column path: one block per column runs all `steps` moves in one launch (column.cuh) -----------------------------------
 static bool column_path_ok(const smcb_filter* f) {
   if (getenv("SMCB_NO_COLUMN")) return false;   // diagnostics / tests: force the multi-kernel pipeline
+  if (f->cfg.algorithm == SMCB_GPF) return false;
   if (f->n > RS_TILE || f->cfg.resampler != SMCB_SYSTEMATIC || f->cfg.exact_weights) return false;
   if (f->cfg.algorithm == SMCB_APF && !f->cfg.fold_lookahead) return false;
   return true;

@@ -62,3 +62,27 @@ class APF(ParticleFilter):
         """``apf.py:25-46``: pre-weight, resample on ``g + log w``, propagate, second-stage weights - one fused move."""
         x = prediction.get_timeseries_state()
         return self._move_from(y, x.value, prediction.weights, prediction.indices, int(x.time_index), resample=True)
+
+
+class GPF(ParticleFilter):
+    """Gaussian particle filter of Kotecha and Djuric (reference filters/particle/gpf.py:10-36) with its default ``GaussianProposal``: per
+    move the cloud is propagated, a Gaussian is fitted to it under the previous weights, every particle is redrawn from that Gaussian and
+    weighted by the observation density (the weights are replaced); nothing resamples.  One difference from the reference: the time index
+    of the state advances with every move (the reference's ``GaussianProposal`` copies the previous state's index, approximate.py:28)."""
+
+    algorithm_id = 2
+
+    def __init__(self, model, particles: int, proposal=None, **kwargs):
+        proposal = proposal if proposal is not None else proposals.GaussianProposal()
+        if not getattr(proposal, "gaussian", False):
+            raise NotImplementedError("GPF is compiled with its default GaussianProposal (GaussianLinearized / GaussianLinear are not built)")
+        super().__init__(model, particles, proposal=proposal, **kwargs)
+
+    def predict(self, state):
+        """``gpf.py:27-30``."""
+        return ParticleFilterPrediction(state.timeseries_state, state.weights, state.normalized_weights(), state.previous_indices)
+
+    def correct(self, y, prediction):
+        """``gpf.py:32-36``: one move of csrc/gpf.cuh from the prediction's state."""
+        x = prediction.get_timeseries_state()
+        return self._move_from(y, x.value, prediction.weights, prediction.indices, int(x.time_index), resample=True)

@@ -38,6 +38,8 @@ class ParticleFilter:
             raise NotImplementedError("only pyfilter_b200.resampling.systematic / multinomial run inside the device loop")
         self._resampler = resampling
         self._proposal: Proposal = proposal if proposal is not None else Bootstrap()
+        if getattr(self._proposal, "gaussian", False) and self.algorithm_id != 2:
+            raise NotImplementedError("GaussianProposal is the proposal of GPF")
         self._seed = seed
         self._fold = fold_lookahead
         self._engine: Engine = None

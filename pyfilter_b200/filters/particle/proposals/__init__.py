@@ -130,6 +130,21 @@ class NestedProposal(Proposal):
         return NestedProposal(self._num_samples[0])
 
 
+class GaussianProposal(Proposal):
+    """``proposals/approximate.py:13-37``: the proposal of the Gaussian particle filter - every particle is a draw from the Gaussian fitted
+    to the propagated, weighted cloud, weighted by the observation density.  It is the fit over the WHOLE cloud that makes it a step of
+    the filter rather than a per-particle pass: it runs inside ``GPF``'s move (csrc/gpf.cuh) and has no stand-alone form."""
+
+    proposal_id = 0
+    gaussian = True
+
+    def pre_weight(self, y, x):
+        raise NotImplementedError("GaussianProposal belongs to GPF, which does not pre-weight")
+
+    def sample_and_weight(self, y, prediction, eps=None):
+        raise NotImplementedError("GaussianProposal runs inside GPF's move: use GPF.filter / GPF.correct")
+
+
 def _out_of_scope(name):
     class _Missing(Proposal):
         def __init__(self, *a, **k):
@@ -141,5 +156,4 @@ def _out_of_scope(name):
 
 GaussianLinear = _out_of_scope("GaussianLinear")
 GaussianLinearized = _out_of_scope("GaussianLinearized")
-GaussianProposal = _out_of_scope("GaussianProposal")
 LocalLinearization = _out_of_scope("LocalLinearization")

@@ -34,11 +34,12 @@ def _filters(particles=1_500, **kwargs):
             out.append(("%s-linearized%d" % (pt.__name__, second), partial(pt, particles=particles, proposal=prop, **kwargs)))
         out.append(("%s-lgo" % pt.__name__, partial(pt, particles=particles, proposal=part.proposals.LinearGaussianObservations(), **kwargs)))
         out.append(("%s-nested50" % pt.__name__, partial(pt, particles=particles, proposal=part.proposals.NestedProposal(50), **kwargs)))
+    out.append(("GPF-gaussian", partial(part.GPF, particles=particles, **kwargs)))   # tests/filters/test_particle.py:22-23
     return out
 
 
 FILTERS = _filters()
-SMOOTH_FILTERS = _filters(particles=1_500, record_states=True)
+SMOOTH_FILTERS = _filters(particles=1_500, record_states=True)[:-1]   # skip_gpf=True (test_particle.py:172)
 
 
 def _data(missing_perc):

@@ -104,6 +104,8 @@ def test_teacher_forced_steps_match_reference(tag):
         z = torch.from_numpy(g["z"][t])
         if g["proposal"].startswith("nested"):   # the inner normals and the Exp(1) values of the categorical draw
             z = (z, torch.from_numpy(g["Un"][t]))
+        if g["alg"] == "gpf":                     # the propagation's draws and the draws of the sample from the Gaussian approximation
+            z = (z, torch.from_numpy(g["z2"][t]))
         u = torch.from_numpy(g["u"][t])
         U = g["U"][t]
         U = (U if B else U[:, 0]) if U.size else None
