@@ -34,8 +34,15 @@ class ParticleFilter:
         self._base_particles = torch.Size([int(particles)])
         self._ess_threshold_arg = ess_threshold
         self._resample_threshold = ess_threshold * particles  # filters/particle/base.py:42
-        if resampling not in _RESAMPLERS:
-            raise NotImplementedError("only pyfilter_b200.resampling.systematic / multinomial run inside the device loop")
+        # systematic / multinomial run inside the fused move.  Any other resampler - `residual`, a user's callable
+        # `(weights, normalized=False) -> indices` (filters/particle/base.py:23,43) - is served by the SPLIT step: `predict` calls it
+        # between the stand-alone device passes, `correct` is one fused move with the resampling rule switched off.  SISR only: the
+        # APF resamples inside its correction.
+        self._split = resampling not in _RESAMPLERS
+        if self._split and not callable(resampling):
+            raise ValueError("`resampling` must be a callable")
+        if self._split and self.algorithm_id == 1:
+            raise NotImplementedError("APF resamples inside the fused move: pyfilter_b200.resampling.systematic / multinomial only")
         self._resampler = resampling
         self._proposal: Proposal = proposal if proposal is not None else Bootstrap()
         if getattr(self._proposal, "gaussian", False) and self.algorithm_id != 2:
@@ -121,6 +128,28 @@ class ParticleFilter:
             e.set_ess_threshold(self._resample_threshold / n)
         return state
 
+    def _filter_split(self, y, correction: ParticleFilterCorrection, result: FilterResult = None) -> ParticleFilterCorrection:
+        """``BaseFilter.filter`` as the reference writes it (filters/base.py:201-221): predict, the propagate-only moves of
+        ``observe_every_step``, then ``correct`` - or another propagate-only move when the observation is all NaN."""
+        y = torch.as_tensor(y, dtype=torch.float32)
+        k = int(getattr(self._model, "observe_every_step", 1))
+        nan_y = torch.full_like(y.reshape(-1), float("nan"))
+
+        def propagate_only(pred):   # ParticleFilterPrediction.create_state_from_prediction (particle/state.py:38-42)
+            x = pred.get_timeseries_state()
+            return self._move_from(nan_y, x.value, pred.weights, pred.indices, int(x.time_index), resample=False)
+
+        prediction = self.predict(correction)
+        while int(prediction.get_timeseries_state().time_index) % k != 0:
+            correction = propagate_only(prediction)
+            if result is not None and self._record_intermediary:
+                result.append(correction)
+            prediction = self.predict(correction)
+        correction = propagate_only(prediction) if bool(torch.isnan(y).all()) else self.correct(y, prediction)
+        if result is not None:
+            result.append(correction)
+        return correction
+
     def _do_sample_fl(self, states):
         """Fixed-lag smoothing = ancestral tracing over the recorded states (filters/particle/base.py:130-146)."""
         from ..utils import trace_back
@@ -173,7 +202,7 @@ class ParticleFilter:
                 seed = self._seed if self._generation == 0 else self._derive_seed(self._generation)
             self._generation += 1
             n = int(self._base_particles[0])
-            e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS[self._resampler], n,
+            e = Engine(self._model, self._proposal.proposal_id, self.algorithm_id, _RESAMPLERS.get(self._resampler, 0), n,
                        self.batch_shape, self._resample_threshold / n, seed, history_rows, self._fold, self._exact_weights,
                        self._column_offset, proposal_config=self._proposal.config())
             self._engine = e
@@ -217,6 +246,12 @@ class ParticleFilter:
     def batch_filter(self, y, bar=True, init_state=None) -> FilterResult:
         """``BaseFilter.batch_filter`` (filters/base.py:140-158): the whole time loop stays on the device."""
         y = torch.as_tensor(y)
+        if self._split:   # a resampler the fused loop does not hold: the reference's own loop over filter() (filters/base.py:140-158)
+            state = init_state if init_state is not None else self.initialize().detach_copy()
+            result = FilterResult(state, self.record_states, self.record_moments)
+            for yt in y:
+                state = self.filter(yt, state, result=result)
+            return result
         T = int(y.shape[0])
         k = int(getattr(self._model, "observe_every_step", 1))
         t_start = 0 if init_state is None else int(init_state.timeseries_state.time_index)
@@ -263,6 +298,8 @@ class ParticleFilter:
     def filter(self, y, correction: ParticleFilterCorrection, result: FilterResult = None) -> ParticleFilterCorrection:
         """``BaseFilter.filter`` (filters/base.py:188-221): one observation - the propagate-only moves ``observe_every_step`` asks
         for, then the observed move."""
+        if self._split:
+            return self._filter_split(y, correction, result)
         e = self._get_engine(2)
         self._adopt(e, correction)
         y_moves, _ = self._expand_observations(torch.as_tensor(y).reshape(1, -1), e.t)

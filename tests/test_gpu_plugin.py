@@ -336,6 +336,48 @@ def test_residual_resampler_golden_and_restated(pf):
         pf.resampling.residual(torch.zeros(8, 2).cuda())
 
 
+def test_any_resampler_runs_through_the_split_step(pf):
+    """``resampling=`` takes any callable in the reference (filters/particle/base.py:23,43).  systematic / multinomial live inside the
+    fused move; ``residual`` or a user's function is called between the stand-alone passes of ``SISR.predict`` and the fused correction
+    (the reference's own loop, filters/base.py:201-221) - same accuracy criterion as the reference's tests, NaN observations included."""
+    from pyfilter_b200 import timeseries as ts
+    from pyfilter_b200.filters.particle import APF, SISR
+
+    torch.manual_seed(123)
+    mo = O.build_model("lg_ar1")
+    _, y = mo.simulate(60)
+    y = y.float()
+    y[[11, 30]] = float("nan")
+    p = O.DEFAULT_PARAMS["lg_ar1"]
+    _, _, kll = O.kalman_filter_1d(y.numpy(), p["alpha"], p["beta"], p["sigma"], p["a"], p["b"], p["s"], p["alpha"],
+                                   p["sigma"] ** 2 / (1 - p["beta"] ** 2))
+    calls = []
+
+    def mine(w, normalized=False):
+        calls.append(tuple(w.shape))
+        return pf.resampling.systematic(w, normalized=normalized)
+
+    fused = SISR(ts.build("lg_ar1"), 2000, seed=5).batch_filter(y, bar=False)
+    for res in (pf.resampling.residual, mine):
+        f = SISR(ts.build("lg_ar1"), 2000, resampling=res, seed=5)
+        r = f.batch_filter(y, bar=False)
+        assert r.filter_means.shape == fused.filter_means.shape and len(r.states) == 1
+        assert abs(float(r.loglikelihood) - float(fused.loglikelihood)) < 0.05 * abs(float(fused.loglikelihood))
+        assert abs(float(r.loglikelihood) - kll) < 0.1 * abs(kll)          # tests/filters/test_particle.py:105
+        assert int(r.latest_state.timeseries_state.time_index) == 60
+        g = f.copy()
+        assert g._resampler is res
+    assert calls and all(c == (2000,) for c in calls)
+    # batched filters hand the callable the columns that resample
+    calls.clear()
+    fb = SISR(ts.build("lg_ar1"), 1000, resampling=mine, seed=6)
+    fb.set_batch_shape(torch.Size([3]))
+    rb = fb.batch_filter(y[:20], bar=False)
+    assert rb.loglikelihood.shape == (3,) and torch.isfinite(rb.loglikelihood).all() and all(c[0] == 1000 and len(c) == 2 for c in calls)
+    with pytest.raises(NotImplementedError):
+        APF(ts.build("lg_ar1"), 100, resampling=pf.resampling.residual)
+
+
 def test_theta_level_column_operations(pf):
     """``FilterResult.resample`` / ``.exchange`` on the resident state (filters/result.py:76-117, particle/state.py:150-168): the device
     permutation / masked copy of columns against torch indexing of the same tensors, and the filter keeps running afterwards exactly as
