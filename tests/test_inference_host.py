@@ -81,3 +81,22 @@ def test_exponential_prior_in_the_unconstrained_space():
     x = p.sample(20_000, torch.Generator().manual_seed(1))
     assert (x > 0).all() and abs(float(x.mean()) - 0.1) < 0.005
     assert torch.allclose(p.get_constrained(p.get_unconstrained(x)), x, rtol=1e-5)
+
+
+def test_smc2_move_schedule_is_the_filters():
+    """``observe_every_step`` (filters/base.py:204-210): the move that consumes observation k is the one the filter's own expansion of
+    the observations puts it on - SMC2 / NESS advance their resident filters by that many moves per observation."""
+    import types
+
+    from pyfilter_b200.filters.particle.base import ParticleFilter
+    from pyfilter_b200.inference.smc2 import SMC2
+
+    for every in (1, 3, 5):
+        alg = SMC2.__new__(SMC2)
+        alg._oes = every
+        dummy = types.SimpleNamespace(_model=types.SimpleNamespace(observe_every_step=every))
+        y = torch.arange(7.0)
+        y_moves, observed = ParticleFilter._expand_observations(dummy, y, 0)
+        assert observed == [alg._moves(k + 1) - 1 for k in range(7)]
+        assert int(y_moves.shape[0]) == alg._moves(7) and alg._moves(0) == 0
+        assert torch.equal(y_moves[observed, 0], y) and torch.isnan(y_moves).sum() == y_moves.shape[0] - 7
